@@ -1,0 +1,174 @@
+/* pgb200_ert.h -- C ABI of the B200-native ERT forward + Jacobian path.
+ *
+ * Drop-in target: the work pyGIMLi does inside
+ *   DCSRMultiElectrodeModelling::response(model)      core/src/bert/dcfemmodelling.cpp:1085
+ *   DCSRMultiElectrodeModelling::createJacobian(model) core/src/bert/dcfemmodelling.cpp:1446
+ * reached from pygimli/physics/ert/ertModelling.py:213 (`self._core.response(mod)`) and :238
+ * (`self._core.createJacobian(mod)`).  Plain pointers and sizes only; no torch types.
+ *
+ * Life cycle:  build a pgb200_plan on the host (geometry-only, once per mesh/scheme)
+ *   -> pgb200_ert_create()  uploads it, assembles the rho=1 matrices and the analytic primary
+ *      potentials (both geometry-only, cached like primPot_ in dcfemmodelling.cpp:1991-1999)
+ *   -> pgb200_ert_response() / pgb200_ert_create_jacobian() per Gauss-Newton step
+ *   -> pgb200_ert_destroy().
+ * All functions return 0 on success, non-zero on failure; pgb200_last_error() gives the text.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef PGB200_ERT_H
+#define PGB200_ERT_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pgb200_ert pgb200_ert; /* opaque handle */
+
+/* Host-side plan.  All pointers are HOST pointers, copied during create.  Index arrays are
+ * int32 (the reference keeps CSR indices in `int` "to be cholmod compatible",
+ * core/src/sparsematrix.h:1112-1116). */
+typedef struct pgb200_plan {
+    int dim;            /* 2 or 3                                                           */
+    int nloc;           /* nodes per cell: 3 Tri3, 6 Tri6, 4 Tet4, 10 Tet10                 */
+    int n_nodes;        /* N                                                                */
+    int n_cells;        /* C                                                                */
+    int nnz;            /* CSR entries                                                      */
+    int n_elec;         /* nE electrodes = current patterns (pole sources, :1518-1523)      */
+    int n_k;            /* wavenumbers (1 in 3-D)                                           */
+    int n_model;        /* M = max cell marker + 1 (bertJacobian.cpp:280)                   */
+    int n_data;         /* D                                                                */
+    int sr;             /* 1: singularity removal (DCSRMultiElectrodeModelling), 0: total field */
+    int fullspace;      /* 1: no surface found -> full-space analytic potentials            */
+    double surface_z;   /* mirror plane of the analytic primary potential (bertMisc.cpp:196)*/
+
+    const double *pos;          /* [N*3] node coordinates                                   */
+    const int *cells;           /* [C*nloc] node ids, original cell order                   */
+    const int *cell_marker;     /* [C]                                                      */
+    const int *rowptr;          /* [N+1]   CSR pattern == SparseMatrix::buildSparsityPattern */
+    const int *colidx;          /* [nnz]   (sparsematrix.h:966-1032), columns ascending      */
+    const int *diag_pos;        /* [N]     CSR slot of the diagonal                          */
+
+    int n_colors;               /* conflict-free cell colours for the atomic-free scatter    */
+    const int *color_ptr;       /* [n_colors+1] ranges into the colour-ordered cell list     */
+    const int *color_order;     /* [C]     original cell id of colour-ordered slot           */
+    const int *cells_col;       /* [nloc*C]      SoA node ids in colour order                */
+    const int *pos_col;         /* [nloc*nloc*C] SoA CSR slot of local entry (i,j)           */
+
+    const double *k_values;     /* [n_k]  (bertMisc.cpp:87-105 or setkValues)                */
+    const double *k_weights;    /* [n_k]                                                     */
+
+    int n_bc_slots;             /* mixed-BC faces (marker -2, dcfemmodelling.cpp:243-299)    */
+    int n_bc_entries;
+    const int *bc_slot;         /* [n_bc_slots]   CSR slot                                   */
+    const int *bc_ptr;          /* [n_bc_slots+1] range into entries                         */
+    const int *bc_owner;        /* [n_bc_entries] owner cell (1/rho of that cell)            */
+    const double *bc_coef;      /* [n_k*n_bc_entries] beta_b(k) * |face| * Uhat_ij           */
+
+    int n_dir_zero;             /* homogeneous Dirichlet rows/cols (marker -3, :141-161)     */
+    int n_dir_nodes;
+    const int *dir_zero_slots;  /* [n_dir_zero]  CSR slots forced to 0                       */
+    const int *dir_diag_slots;  /* [n_dir_nodes] CSR slots forced to 1                       */
+    const int *dir_nodes;       /* [n_dir_nodes] rows whose RHS is forced to 0               */
+
+    const double *el_pos;       /* [nE*3] electrode positions                                */
+    const int *sing_node;       /* [nE]   node whose analytic value is patched, -1 none      */
+    const double *sing_val;     /* [n_k*nE] patched value (electrode.cpp:154-189)            */
+    const int *pick_ptr;        /* [nE+1] potential pick-up / delta-RHS stencil              */
+    const int *pick_idx;        /*        node ids                                           */
+    const double *pick_w;       /*        shape-function weights (1 for node electrodes)     */
+    const int *src_cell_ptr;    /* [nE+1] cells around the electrode (rho at the source,     */
+    const int *src_cells;       /*        geometric mean, electrode.cpp:102-120)             */
+
+    int n_pro_levels;           /* background prolongation (mesh.cpp:2247-2316)              */
+    int pro_nf;                 /* faces per cell                                            */
+    const int *pro_level_ptr;   /* [n_pro_levels+1] ranges into pro_cells                    */
+    const int *pro_cells;       /* cells filled at each level                                */
+    const int *pro_nb;          /* [n*pro_nf] neighbour cells                                */
+    const double *pro_w;        /* [n*pro_nf] normalised weights (0 = unused)                */
+
+    int n_jac_cells;            /* cells with marker >= 0, sorted by marker (:298-299)       */
+    const int *jac_cells;       /* [n_jac_cells]                                             */
+    const int *jac_col_ptr;     /* [M+1] ranges into jac_cells                               */
+
+    const int *abmn;            /* [D*4] electrode indices, -1 = unused                      */
+    const double *k_fac;        /* [D] geometric factors                                     */
+} pgb200_plan;
+
+/* ---- host-only helpers (no GPU needed) -------------------------------------------- */
+const char *pgb200_last_error(void);
+int pgb200_version(void);
+/* Greedy conflict colouring: cells sharing a node get different colours.
+ * Returns the number of colours (<= 0 on failure); color[C] receives the colour per cell. */
+int pgb200_color_cells(int n_cells, int nloc, const int *cells, int n_nodes, int *color);
+
+/* ---- life cycle ------------------------------------------------------------------- */
+int pgb200_ert_create(const pgb200_plan *plan, int device, pgb200_ert **out);
+int pgb200_ert_destroy(pgb200_ert *h);
+/* CUDA stream (cudaStream_t) all work is enqueued on; 0/NULL = legacy default stream.   */
+int pgb200_ert_set_stream(pgb200_ert *h, void *stream);
+/* Block-PCG controls: relative residual tolerance ||r||/||b|| per source column,
+ * iteration cap, and how many iterations run between convergence checks.               */
+int pgb200_ert_set_solver(pgb200_ert *h, double rel_tol, int max_iter, int check_every);
+/* Restrict this handle to a shard: current sources [src_begin, src_end) are solved here,
+ * data rows [row_begin, row_end) are written by the Jacobian (multi-GPU).               */
+int pgb200_ert_set_shard(pgb200_ert *h, int src_begin, int src_end, int row_begin, int row_end);
+/* Replace geometric factors (token "k" of the data container).                          */
+int pgb200_ert_set_kfac(pgb200_ert *h, const double *k_fac_host);
+
+/* ---- the path: HOST buffers (what a reference-side binding calls) ------------------- */
+/* response: model_host[n_model_in] (n_model_in == M: per marker, == C: per cell,
+ * dcfemmodelling.cpp:1211-1218)  ->  rhoa_host[D] = sqrt(|resp * respRez|) (:1196).     */
+int pgb200_ert_response(pgb200_ert *h, const double *model_host, int n_model_in, double *rhoa_host);
+/* createJacobian: uses the potentials of the last response() if present (:1262), else
+ * solves (analytic branch for homogeneous models, :1272-1301).  J stays in HBM.          */
+int pgb200_ert_create_jacobian(pgb200_ert *h, const double *model_host, int n_model_in);
+/* copy J to the host, row-major [D_local x M].                                           */
+int pgb200_ert_jacobian_copy(pgb200_ert *h, double *j_host);
+/* y = J x  and  y = J^T x  with host vectors (jacobian().mult / transMult).              */
+int pgb200_ert_jacobian_mult(pgb200_ert *h, const double *x_host, double *y_host);
+int pgb200_ert_jacobian_tmult(pgb200_ert *h, const double *x_host, double *y_host);
+
+/* ---- the path: DEVICE buffers (inputs already resident in HBM) ---------------------- */
+int pgb200_ert_response_dev(pgb200_ert *h, const double *model_dev, int n_model_in, double *rhoa_dev);
+int pgb200_ert_create_jacobian_dev(pgb200_ert *h, const double *model_dev, int n_model_in);
+/* J in HBM is stored column-major: element (d, j) at ptr[j * ld + d] (each model column is a
+ * contiguous run of data rows, written with coalesced 128-bit stores).                    */
+int pgb200_ert_jacobian_info(pgb200_ert *h, void **dev_ptr, int *rows, int *cols, long long *ld);
+/* drop cached potentials (mesh/data change semantics, dcfemmodelling.cpp:712, :777)       */
+int pgb200_ert_clear_potentials(pgb200_ert *h);
+/* device pointer + leading dimension of the k-resolved potentials U[node][ld], column
+ * s = electrode + nE * kIdx (subSolutions_ transposed, :1681); used for the NCCL all-gather */
+int pgb200_ert_potentials_info(pgb200_ert *h, void **dev_ptr, int *n_nodes, int *n_src, long long *ld);
+int pgb200_ert_mark_potentials_valid(pgb200_ert *h);
+
+/* ---- multi-GPU staging (one handle per GPU; the exchange itself is NCCL in the caller) - */
+/* solve this shard's sources; leaves U[:, shard] and the PARTIAL electrode matrix in HBM    */
+int pgb200_ert_forward_dev(pgb200_ert *h, const double *model_dev, int n_model_in);
+/* device pointer of the nE x nE electrode-potential matrix (all-reduce SUM across shards)   */
+int pgb200_ert_pm_info(pgb200_ert *h, void **dev_ptr, int *n);
+/* ABMN + reciprocity combine from the (reduced) electrode matrix -> rhoa_dev[D]             */
+int pgb200_ert_finish_response_dev(pgb200_ert *h, double *rhoa_dev);
+/* pack (unpack=0) / unpack (unpack=1) the potential columns [c0,c1) to/from a contiguous
+ * [N x (c1-c0)] device buffer, the unit of the all-gather of potentials                     */
+int pgb200_ert_pack_potentials(pgb200_ert *h, int c0, int c1, double *buf_dev, int unpack);
+
+/* ---- introspection for parity tests / bench ----------------------------------------- */
+/* what: "vals" [nK*nnz], "vals1" [nK*nnz] (rho=1), "rho" [C], "rho_src" [nE], "prim" [nS*N]
+ * (row = e + nE*k), "pots" [nS*N], "solutions" [nE*N], "pm" [nE*nE], "resp" [D], "resp_rez" [D],
+ * "rel_res" [nS].  Returns the number of doubles written (or needed when out == NULL), < 0 on error. */
+long long pgb200_ert_get(pgb200_ert *h, const char *what, double *out_host, long long capacity);
+/* stats[0]=PCG iterations of the last solve, [1]=max relative residual, [2]=kernel launches
+ * since create/reset, [3..8] = ms of the last call: map, assemble, rhs, solve, epilogue, jacobian,
+ * [9]=SpMM launches timed, [10]=their total ms, [11]=Jacobian kernel ms                     */
+int pgb200_ert_stats(pgb200_ert *h, double *stats, int n);
+int pgb200_ert_reset_stats(pgb200_ert *h);
+int pgb200_ert_set_profile(pgb200_ert *h, int on);
+
+/* ---- single-kernel entry points (device pointers; unit tests and micro-benchmarks) --- */
+/* Y[N x ld] = A X with per-wavenumber values: column s uses vals[(s / nE) * nnz + .]       */
+int pgb200_spmm(const int *rowptr, const int *colidx, const double *vals, long long nnz,
+                const double *X, double *Y, int n_rows, int n_elec, int n_k, long long ld, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGB200_ERT_H */

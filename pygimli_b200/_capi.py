@@ -1,0 +1,176 @@
+"""ctypes binding of the C ABI in include/pgb200_ert.h (libpgb200_ert.so, built in-tree).
+
+The product path has no CPU fallback: if the shared library is missing, importing the
+compute entry points raises; if it is present but no CUDA device exists, ``create`` fails
+with the library's error text.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libpgb200_ert.so")
+
+c_int_p = C.POINTER(C.c_int)
+c_dbl_p = C.POINTER(C.c_double)
+
+
+class Plan(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int), ("nloc", C.c_int), ("n_nodes", C.c_int), ("n_cells", C.c_int), ("nnz", C.c_int),
+        ("n_elec", C.c_int), ("n_k", C.c_int), ("n_model", C.c_int), ("n_data", C.c_int), ("sr", C.c_int),
+        ("fullspace", C.c_int), ("surface_z", C.c_double),
+        ("pos", c_dbl_p), ("cells", c_int_p), ("cell_marker", c_int_p), ("rowptr", c_int_p), ("colidx", c_int_p),
+        ("diag_pos", c_int_p),
+        ("n_colors", C.c_int), ("color_ptr", c_int_p), ("color_order", c_int_p), ("cells_col", c_int_p), ("pos_col", c_int_p),
+        ("k_values", c_dbl_p), ("k_weights", c_dbl_p),
+        ("n_bc_slots", C.c_int), ("n_bc_entries", C.c_int), ("bc_slot", c_int_p), ("bc_ptr", c_int_p), ("bc_owner", c_int_p),
+        ("bc_coef", c_dbl_p),
+        ("n_dir_zero", C.c_int), ("n_dir_nodes", C.c_int), ("dir_zero_slots", c_int_p), ("dir_diag_slots", c_int_p),
+        ("dir_nodes", c_int_p),
+        ("el_pos", c_dbl_p), ("sing_node", c_int_p), ("sing_val", c_dbl_p), ("pick_ptr", c_int_p), ("pick_idx", c_int_p),
+        ("pick_w", c_dbl_p), ("src_cell_ptr", c_int_p), ("src_cells", c_int_p),
+        ("n_pro_levels", C.c_int), ("pro_nf", C.c_int), ("pro_level_ptr", c_int_p), ("pro_cells", c_int_p), ("pro_nb", c_int_p),
+        ("pro_w", c_dbl_p),
+        ("n_jac_cells", C.c_int), ("jac_cells", c_int_p), ("jac_col_ptr", c_int_p),
+        ("abmn", c_int_p), ("k_fac", c_dbl_p),
+    ]
+
+
+# every symbol include/pgb200_ert.h declares (checked by tests/test_capi_symbols.py)
+EXPORTS = [
+    "pgb200_last_error", "pgb200_version", "pgb200_color_cells",
+    "pgb200_ert_create", "pgb200_ert_destroy", "pgb200_ert_set_stream", "pgb200_ert_set_solver", "pgb200_ert_set_shard",
+    "pgb200_ert_set_kfac", "pgb200_ert_response", "pgb200_ert_create_jacobian", "pgb200_ert_jacobian_copy",
+    "pgb200_ert_jacobian_mult", "pgb200_ert_jacobian_tmult", "pgb200_ert_response_dev", "pgb200_ert_create_jacobian_dev",
+    "pgb200_ert_jacobian_info", "pgb200_ert_clear_potentials", "pgb200_ert_potentials_info",
+    "pgb200_ert_mark_potentials_valid", "pgb200_ert_forward_dev", "pgb200_ert_pm_info", "pgb200_ert_finish_response_dev",
+    "pgb200_ert_pack_potentials", "pgb200_ert_get", "pgb200_ert_stats", "pgb200_ert_reset_stats", "pgb200_ert_set_profile",
+    "pgb200_spmm",
+]
+
+_lib = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LibraryMissing(
+                f"{LIB_PATH} is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). The B200 ERT path has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.pgb200_last_error.restype = C.c_char_p
+        L.pgb200_ert_get.restype = C.c_longlong
+        L.pgb200_ert_get.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]
+        L.pgb200_ert_create.argtypes = [C.POINTER(Plan), C.c_int, C.POINTER(C.c_void_p)]
+        for name in ("pgb200_ert_destroy", "pgb200_ert_clear_potentials", "pgb200_ert_mark_potentials_valid",
+                     "pgb200_ert_reset_stats"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.pgb200_ert_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.pgb200_ert_set_solver.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int]
+        L.pgb200_ert_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.pgb200_ert_set_kfac.argtypes = [C.c_void_p, C.c_void_p]
+        L.pgb200_ert_response.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.pgb200_ert_response_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.pgb200_ert_create_jacobian.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.pgb200_ert_create_jacobian_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.pgb200_ert_jacobian_copy.argtypes = [C.c_void_p, C.c_void_p]
+        L.pgb200_ert_jacobian_mult.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pgb200_ert_jacobian_tmult.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pgb200_ert_jacobian_info.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), c_int_p, c_int_p, C.POINTER(C.c_longlong)]
+        L.pgb200_ert_potentials_info.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), c_int_p, c_int_p, C.POINTER(C.c_longlong)]
+        L.pgb200_ert_forward_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.pgb200_ert_pm_info.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), c_int_p]
+        L.pgb200_ert_finish_response_dev.argtypes = [C.c_void_p, C.c_void_p]
+        L.pgb200_ert_pack_potentials.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.pgb200_ert_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.pgb200_ert_set_profile.argtypes = [C.c_void_p, C.c_int]
+        L.pgb200_color_cells.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.pgb200_spmm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
+                                  C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return lib().pgb200_last_error().decode()
+
+
+class PGB200Error(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise PGB200Error(last_error())
+
+
+def color_cells(cells: np.ndarray, n_nodes: int):
+    """C++ greedy colouring (host helper of the library, no GPU needed)."""
+    cells = np.ascontiguousarray(cells, np.int32)
+    color = np.zeros(cells.shape[0], np.int32)
+    n = lib().pgb200_color_cells(cells.shape[0], cells.shape[1], cells.ctypes.data, int(n_nodes), color.ctypes.data)
+    if n <= 0:
+        raise PGB200Error(last_error())
+    return color, int(n)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_int_p)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dbl_p)
+
+
+def make_plan_struct(P, sr: bool):
+    """ERTPlan (host_setup.build_plan) -> (ctypes Plan, keep-alive list of arrays)."""
+    keep = []
+
+    def I(a):
+        a = np.ascontiguousarray(a, np.int32)
+        keep.append(a)
+        return _ip(a)
+
+    def D(a):
+        a = np.ascontiguousarray(a, np.float64)
+        keep.append(a)
+        return _dp(a)
+
+    s = Plan()
+    s.dim, s.nloc, s.n_nodes, s.n_cells, s.nnz = P.dim, P.nloc, P.N, P.C, P.nnz
+    s.n_elec, s.n_k, s.n_model, s.n_data, s.sr = P.nE, P.nK, P.M, P.scheme.size, 1 if sr else 0
+    s.fullspace = 1 if P.surface_z <= -1e300 else 0
+    s.surface_z = 0.0 if s.fullspace else P.surface_z
+    s.pos, s.cells, s.cell_marker = D(P.mesh.pos), I(P.mesh.cells), I(P.cell_marker)
+    s.rowptr, s.colidx, s.diag_pos = I(P.rowptr), I(P.colidx), I(P.diag_pos)
+    s.n_colors, s.color_ptr, s.color_order = P.n_colors, I(P.color_ptr), I(P.color_order)
+    s.cells_col, s.pos_col = I(P.cells_col), I(P.pos_col)
+    s.k_values, s.k_weights = D(P.k), D(P.w)
+    s.n_bc_slots, s.n_bc_entries = int(P.bc_slot.size), int(P.bc_owner.size)
+    s.bc_slot, s.bc_ptr, s.bc_owner, s.bc_coef = I(P.bc_slot), I(P.bc_ptr), I(P.bc_owner), D(P.bc_coef)
+    s.n_dir_zero, s.n_dir_nodes = int(P.dir_zero_slots.size), int(P.dir_nodes.size)
+    s.dir_zero_slots, s.dir_diag_slots, s.dir_nodes = I(P.dir_zero_slots), I(P.dir_diag_slots), I(P.dir_nodes)
+    s.el_pos, s.sing_node, s.sing_val = D(P.el_pos), I(P.sing_node), D(P.sing_val)
+    s.pick_ptr, s.pick_idx, s.pick_w = I(P.pick_ptr), I(P.pick_idx), D(P.pick_w)
+    s.src_cell_ptr, s.src_cells = I(P.src_cell_ptr), I(P.src_cells)
+    lv = P.pro_levels
+    s.n_pro_levels = len(lv)
+    s.pro_nf = int(getattr(P, "pro_nf", 0)) if lv else 0
+    lp = np.concatenate([[0], np.cumsum([len(c) for c, _, _ in lv])]).astype(np.int32) if lv else np.zeros(1, np.int32)
+    s.pro_level_ptr = I(lp)
+    s.pro_cells = I(np.concatenate([c for c, _, _ in lv]) if lv else np.zeros(0, np.int32))
+    s.pro_nb = I(np.concatenate([n for _, n, _ in lv]).ravel() if lv else np.zeros(0, np.int32))
+    s.pro_w = D(np.concatenate([w for _, _, w in lv]).ravel() if lv else np.zeros(0))
+    s.n_jac_cells, s.jac_cells, s.jac_col_ptr = int(P.jac_cells.size), I(P.jac_cells), I(P.jac_col_ptr)
+    s.abmn = I(P.scheme.abmn())
+    kf = P.scheme.k if P.scheme.k is not None else np.zeros(P.scheme.size)
+    s.k_fac = D(kf)
+    return s, keep

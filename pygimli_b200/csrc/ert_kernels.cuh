@@ -1,0 +1,609 @@
+// CUDA kernels of the B200 ERT forward + Jacobian path (FP64, sm_100a, no tensor cores:
+// per-cell 3x3..10x10 contractions and CSR work, HBM/L2-bound -- see DESIGN.md).
+//
+// Layout conventions
+//   * block vectors (potentials, PCG state) are node-major  X[node * ld + s],
+//     s = electrode + nE * kIdx  (the reference's subSolutions_ row index,
+//     dcfemmodelling.cpp:1681) -- one node's values for all sources are contiguous, so the
+//     SpMM gathers whole rows and the Jacobian gathers a cell's nodes with coalesced loads.
+//   * CSR values are stored per wavenumber: vals[kIdx * nnz + slot].
+//   * J is written column-major Jt[col * ldJ + d].
+#pragma once
+#include "ert_device.cuh"
+#include <stdint.h>
+
+namespace pgb {
+
+// ---------------------------------------------------------------------------------
+// model mapping: rho_cell = model[marker]   (modellingbase.cpp:424-440) or cell-wise copy
+// ---------------------------------------------------------------------------------
+__global__ void k_map_model(const double *__restrict__ model, int n_model_in, const int *__restrict__ marker,
+                            int C, double *__restrict__ rho) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    if (n_model_in == C) { rho[c] = model[c]; return; }
+    int m = marker[c];
+    rho[c] = (m >= 0 && m < n_model_in) ? model[m] : 0.0;
+}
+// one prolongation level (mesh.cpp:2276-2306): weighted mean of already filled neighbours
+__global__ void k_prolong_level(const int *__restrict__ cells, const int *__restrict__ nb, const double *__restrict__ w,
+                                int n, int nf, double *__restrict__ rho) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double acc = 0.0;
+    for (int f = 0; f < nf; f++) {
+        double wf = w[(size_t)t * nf + f];
+        if (wf != 0.0) acc += wf * rho[nb[(size_t)t * nf + f]];
+    }
+    rho[cells[t]] = acc;
+}
+__global__ void k_check_model(const double *__restrict__ v, int n, int *flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !(v[i] >= 1e-12)) atomicOr(flag, 1);   // min(model) < TOLERANCE -> error (:1133)
+}
+// std-dev test for the analytic branch of createJacobian (:1272-1274) on the host-visible scalars
+__global__ void k_mean_var(const double *__restrict__ v, int n, double *out /* sum, sumsq */) {
+    __shared__ double s0[256], s1[256];
+    double a = 0.0, b = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { a += v[i]; b += v[i] * v[i]; }
+    s0[threadIdx.x] = a; s1[threadIdx.x] = b; __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) { s0[threadIdx.x] += s0[threadIdx.x + o]; s1[threadIdx.x] += s1[threadIdx.x + o]; } __syncthreads(); }
+    if (threadIdx.x == 0) { atomicAdd(out, s0[0]); atomicAdd(out + 1, s1[0]); }
+}
+
+// ---------------------------------------------------------------------------------
+// K1: coloured, atomic-free stiffness assembly (dcfemmodelling.cpp:163-228)
+//   one thread per cell of ONE colour; cells of a colour share no node, so no two threads of a
+//   launch touch the same CSR slot.  Node ids, scatter slots and rho are SoA in colour order
+//   -> fully coalesced; the nK wavenumber matrices are produced in the same pass.
+//   S(k) += (1/rho_c) (K_c + k^2 M_c);   rho == nullptr -> rho = 1 (the S1 matrix of the SR scheme)
+// ---------------------------------------------------------------------------------
+template <int E>
+__global__ void __launch_bounds__(128)
+k_assemble(const double *__restrict__ pos, const int *__restrict__ cells_col, const int *__restrict__ pos_col,
+           const int *__restrict__ color_order, const double *__restrict__ rho, int C, int first, int count,
+           const double *__restrict__ kvals, int nK, size_t nnz, double *__restrict__ vals) {
+    constexpr int NV = ElemTraits<E>::NV, NL = ElemTraits<E>::NL, DIM = ElemTraits<E>::DIM;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int slot = first + t;
+    double r = 1.0;
+    if (rho) r = rho[color_order[slot]];
+    if (fabs(r) <= 1e-12) return;                       // :185 skip |rho| <= TOLERANCE
+    const double inv_rho = 1.0 / r;
+    double X[NV][3];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        const int n = cells_col[(size_t)v * C + slot];
+        X[v][0] = pos[3 * (size_t)n]; X[v][1] = pos[3 * (size_t)n + 1]; X[v][2] = pos[3 * (size_t)n + 2];
+    }
+    double size, G[NV][NV];
+    simplex_gram<DIM>(X, size, G);
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+#pragma unroll
+        for (int j = 0; j < NL; j++) {
+            const double kij = stiff_entry<E>(i, j, size, G);
+            const double mij = size * mass_unit<E>(i, j);
+            const int p = pos_col[(size_t)(i * NL + j) * C + slot];
+            for (int kk = 0; kk < nK; kk++) {
+                const double k = kvals[kk];
+                const double v = (k > 0.0) ? (mij * (k * k) + kij) : kij;    // :186-196
+                vals[(size_t)kk * nnz + p] += v * inv_rho;
+            }
+        }
+    }
+}
+
+// mixed boundary faces (:243-299): vals[k][slot] += sum_e coef[k][e] / rho[owner[e]]
+__global__ void k_boundary_add(const int *__restrict__ slot, const int *__restrict__ ptr, const int *__restrict__ owner,
+                               const double *__restrict__ coef, int n_slots, int n_entries, const double *__restrict__ rho,
+                               int nK, size_t nnz, double *__restrict__ vals) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_slots) return;
+    const int p = slot[t];
+    for (int kk = 0; kk < nK; kk++) {
+        double acc = 0.0;
+        for (int e = ptr[t]; e < ptr[t + 1]; e++) {
+            const double r = rho ? rho[owner[e]] : 1.0;
+            acc += coef[(size_t)kk * n_entries + e] / r;
+        }
+        vals[(size_t)kk * nnz + p] += acc;
+    }
+}
+// homogeneous Dirichlet rows/cols (:141-161)
+__global__ void k_dirichlet_zero(const int *__restrict__ zero_slots, int nz, int nK, size_t nnz, double *__restrict__ vals) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nz) for (int kk = 0; kk < nK; kk++) vals[(size_t)kk * nnz + zero_slots[t]] = 0.0;
+}
+__global__ void k_dirichlet_diag(const int *__restrict__ diag_slots, int nd, int nK, size_t nnz, double *__restrict__ vals) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nd) for (int kk = 0; kk < nK; kk++) vals[(size_t)kk * nnz + diag_slots[t]] = 1.0;
+}
+// :209-218 rows whose diagonal is < TOLERANCE would be forced to identity by the reference;
+// we count them (the host refuses such a model rather than silently diverging)
+__global__ void k_count_singular(const int *__restrict__ diag_pos, int N, int nK, size_t nnz, const double *__restrict__ vals, int *count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    for (int kk = 0; kk < nK; kk++) if (vals[(size_t)kk * nnz + diag_pos[i]] < 1e-12) atomicAdd(count, 1);
+}
+__global__ void k_inv_diag(const int *__restrict__ diag_pos, int N, int nK, size_t nnz, const double *__restrict__ vals,
+                           double *__restrict__ dinv /* [nK*N] */) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    for (int kk = 0; kk < nK; kk++) dinv[(size_t)kk * N + i] = 1.0 / vals[(size_t)kk * nnz + diag_pos[i]];
+}
+
+// ---------------------------------------------------------------------------------
+// analytic primary potentials (bertMisc.cpp:186-260 + singular patch electrode.cpp:154-189)
+//   prim[node * ld + (e + nE*kIdx)]
+// ---------------------------------------------------------------------------------
+__global__ void k_primary(const double *__restrict__ pos, int N, const double *__restrict__ el_pos, int nE,
+                          const int *__restrict__ sing_node, const double *__restrict__ sing_val,
+                          const double *__restrict__ kvals, int nK, double surface_z, int fullspace,
+                          double *__restrict__ prim, size_t ld) {
+    const int s = blockIdx.y * blockDim.x + threadIdx.x;     // columns fastest -> coalesced
+    const int node = blockIdx.x * blockDim.y + threadIdx.y;
+    if (s >= nE * nK || node >= N) return;
+    const int kk = s / nE, e = s - kk * nE;
+    const double k = kvals[kk];
+    const int md = (k > 0.0) ? 1 : 2;                         // mirrored coordinate (:241)
+    const double px = pos[3 * (size_t)node], py = pos[3 * (size_t)node + 1], pz = pos[3 * (size_t)node + 2];
+    const double sx = el_pos[3 * e], sy = el_pos[3 * e + 1], sz = el_pos[3 * e + 2];
+    double val;
+    if (sing_node[e] == node) {
+        val = sing_val[kk * nE + e];
+    } else {
+        const double dx = px - sx, dy = py - sy, dz = pz - sz;
+        const double r = sqrt(dx * dx + dy * dy + dz * dz);
+        if (r < 1e-12) {
+            val = 0.0;                                        // fallback (:235)
+        } else {
+            double mx = sx, my = sy, mz = sz;
+            if (md == 1) my = 2.0 * surface_z - sy; else mz = 2.0 * surface_z - sz;
+            const double ex = px - mx, ey = py - my, ez = pz - mz;
+            const double rm = sqrt(ex * ex + ey * ey + ez * ez);
+            const double PI_ = 3.14159265358979323846;
+            if (fullspace) {
+                val = (k == 0.0) ? 1.0 / (4.0 * PI_ * r) : as_bessel_k0(r * k) / (2.0 * PI_);
+            } else if (k == 0.0) {
+                val = (1.0 / r + 1.0 / rm) / (4.0 * PI_);
+            } else {
+                const double d2 = (sx - mx) * (sx - mx) + (sy - my) * (sy - my) + (sz - mz) * (sz - mz);
+                if (d2 < 1e-12) val = as_bessel_k0(r * k) / PI_;                        // source == mirror (:220)
+                else val = (as_bessel_k0(r * k) + as_bessel_k0(rm * k)) / (2.0 * PI_);
+            }
+        }
+    }
+    prim[(size_t)node * ld + s] = val;
+}
+
+// rho at the source: geometric mean over the cells around the electrode (electrode.cpp:102-120)
+__global__ void k_rho_src(const int *__restrict__ ptr, const int *__restrict__ cells, const double *__restrict__ rho,
+                          int nE, double *__restrict__ rho_src) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nE) return;
+    double acc = 0.0; int n = ptr[e + 1] - ptr[e];
+    for (int i = ptr[e]; i < ptr[e + 1]; i++) acc += log(rho[cells[i]]);
+    rho_src[e] = exp(acc / (double)n);
+}
+
+// ---------------------------------------------------------------------------------
+// K2: CSR x dense-block SpMM  Y = A X  (block of all sources; per-wavenumber values)
+//   CTA = ROWS rows x (16*CPT) columns; a half-warp reads 16 consecutive doubles (128 B) of a
+//   gathered X row, every thread carries CPT independent accumulators.  Optionally fuses
+//   the per-column dot  sum_i X[i][s] * Y[i][s]  (p.Ap of PCG): serial over the thread's rows,
+//   shared-memory tree over the row lanes, one atomicAdd per column and CTA.
+//   MODE 0: Y = A X            MODE 1: Y = A1 X - rho_src[e] * A X  (the SR right-hand side,
+//   dcfemmodelling.cpp:2252-2254, both products in one pass over the pattern)
+// ---------------------------------------------------------------------------------
+constexpr int SPMM_TX = 16, SPMM_TY = 8, SPMM_ROWS = 32;
+
+template <int CPT, int MODE, bool DOT>
+__global__ void __launch_bounds__(SPMM_TX * SPMM_TY)
+k_spmm(const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals,
+       const double *__restrict__ vals1, const double *__restrict__ rho_src, size_t nnz,
+       const double *__restrict__ X, double *__restrict__ Y, int N, int nE, int c0, int c1, size_t ld,
+       double *__restrict__ dots) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int cbase = c0 + blockIdx.y * (SPMM_TX * CPT) + tx;
+    int col[CPT]; size_t voff[CPT]; double rs[CPT]; bool ok[CPT];
+#pragma unroll
+    for (int m = 0; m < CPT; m++) {
+        col[m] = cbase + m * SPMM_TX;
+        ok[m] = col[m] < c1;
+        const int cc = ok[m] ? col[m] : c0;
+        const int kk = cc / nE;
+        voff[m] = (size_t)kk * nnz;
+        rs[m] = (MODE == 1) ? rho_src[cc - kk * nE] : 0.0;
+        col[m] = cc;
+    }
+    double part[CPT];
+#pragma unroll
+    for (int m = 0; m < CPT; m++) part[m] = 0.0;
+    const int row0 = blockIdx.x * SPMM_ROWS;
+    for (int r = ty; r < SPMM_ROWS; r += SPMM_TY) {
+        const int row = row0 + r;
+        if (row >= N) break;
+        const int pb = rowptr[row], pe = rowptr[row + 1];
+        double acc[CPT];
+#pragma unroll
+        for (int m = 0; m < CPT; m++) acc[m] = 0.0;
+        for (int p = pb; p < pe; p++) {
+            const size_t xo = (size_t)colidx[p] * ld;
+#pragma unroll
+            for (int m = 0; m < CPT; m++) {
+                double a = __ldg(vals + voff[m] + p);
+                if (MODE == 1) a = __ldg(vals1 + voff[m] + p) - rs[m] * a;
+                acc[m] = fma(a, __ldg(X + xo + col[m]), acc[m]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < CPT; m++) {
+            if (ok[m]) {
+                Y[(size_t)row * ld + col[m]] = acc[m];
+                if (DOT) part[m] = fma(acc[m], __ldg(X + (size_t)row * ld + col[m]), part[m]);
+            }
+        }
+    }
+    if (DOT) {
+        __shared__ double red[SPMM_TY][SPMM_TX * CPT];
+#pragma unroll
+        for (int m = 0; m < CPT; m++) red[ty][m * SPMM_TX + tx] = part[m];
+        __syncthreads();
+        if (ty == 0) {
+#pragma unroll
+            for (int m = 0; m < CPT; m++) {
+                double s = 0.0;
+#pragma unroll
+                for (int y = 0; y < SPMM_TY; y++) s += red[y][m * SPMM_TX + tx];
+                if (ok[m]) atomicAdd(dots + col[m], s);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// block-PCG vector kernels (Jacobi preconditioner; one independent CG per source column,
+// all columns advance in the same launches).  Thread = 1 column x strided rows; per-column
+// partial dot products stay in registers, then a shared-memory tree + one atomic per CTA.
+// ---------------------------------------------------------------------------------
+constexpr int VEC_TX = 32, VEC_TY = 8, VEC_ROWS = 64;
+
+__device__ __forceinline__ void block_col_reduce(double v0, double v1, double *d0, double *d1, int col, bool ok) {
+    __shared__ double red0[VEC_TY][VEC_TX], red1[VEC_TY][VEC_TX];
+    red0[threadIdx.y][threadIdx.x] = v0; red1[threadIdx.y][threadIdx.x] = v1;
+    __syncthreads();
+    if (threadIdx.y == 0 && ok) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int y = 0; y < VEC_TY; y++) { a += red0[y][threadIdx.x]; b += red1[y][threadIdx.x]; }
+        if (d0) atomicAdd(d0 + col, a);
+        if (d1) atomicAdd(d1 + col, b);
+    }
+}
+
+// r = b - (x == 0); z = Dinv r; p = z; rz = r.z; bb = b.b
+__global__ void __launch_bounds__(VEC_TX * VEC_TY)
+k_pcg_init(const double *__restrict__ B, const double *__restrict__ dinv, double *__restrict__ Xv, double *__restrict__ R,
+           double *__restrict__ P, int N, int nE, int c0, int c1, size_t ld, double *__restrict__ rz, double *__restrict__ bb) {
+    const int col = c0 + blockIdx.y * VEC_TX + threadIdx.x;
+    const bool ok = col < c1;
+    double s0 = 0.0, s1 = 0.0;
+    if (ok) {
+        const double *dk = dinv + (size_t)(col / nE) * N;
+        const int row0 = blockIdx.x * VEC_ROWS;
+        for (int r = threadIdx.y; r < VEC_ROWS; r += VEC_TY) {
+            const int row = row0 + r; if (row >= N) break;
+            const size_t o = (size_t)row * ld + col;
+            const double b = B[o];
+            const double z = dk[row] * b;
+            Xv[o] = 0.0; R[o] = b; P[o] = z;
+            s0 = fma(b, z, s0); s1 = fma(b, b, s1);
+        }
+    }
+    block_col_reduce(s0, s1, rz, bb, col, ok);
+}
+// alpha = rz/pAp;  x += alpha p;  r -= alpha Ap;  rz_new = r.Dinv r;  rr = r.r
+__global__ void __launch_bounds__(VEC_TX * VEC_TY)
+k_pcg_update_xr(const double *__restrict__ P, const double *__restrict__ AP, const double *__restrict__ dinv,
+                double *__restrict__ Xv, double *__restrict__ R, int N, int nE, int c0, int c1, size_t ld,
+                const double *__restrict__ rz, const double *__restrict__ pAp, double *__restrict__ rz_new, double *__restrict__ rr) {
+    const int col = c0 + blockIdx.y * VEC_TX + threadIdx.x;
+    const bool ok = col < c1;
+    double s0 = 0.0, s1 = 0.0;
+    if (ok) {
+        const double den = pAp[col], num = rz[col];
+        const double alpha = (den > 0.0 && num > 0.0) ? num / den : 0.0;
+        const double *dk = dinv + (size_t)(col / nE) * N;
+        const int row0 = blockIdx.x * VEC_ROWS;
+        for (int r = threadIdx.y; r < VEC_ROWS; r += VEC_TY) {
+            const int row = row0 + r; if (row >= N) break;
+            const size_t o = (size_t)row * ld + col;
+            const double rn = fma(-alpha, AP[o], R[o]);
+            Xv[o] = fma(alpha, P[o], Xv[o]);
+            R[o] = rn;
+            s0 = fma(rn * dk[row], rn, s0); s1 = fma(rn, rn, s1);
+        }
+    }
+    block_col_reduce(s0, s1, rz_new, rr, col, ok);
+}
+// beta = rz_new/rz;  p = Dinv r + beta p   (p = 0 once the column has converged: it freezes)
+// also clears the accumulators of the next iteration (buffers nobody reads in this launch)
+__global__ void __launch_bounds__(VEC_TX * VEC_TY)
+k_pcg_update_p(const double *__restrict__ R, const double *__restrict__ dinv, double *__restrict__ P, int N, int nE,
+               int c0, int c1, size_t ld, const double *__restrict__ rz, const double *__restrict__ rz_new,
+               const double *__restrict__ rr, const double *__restrict__ bb, double tol2,
+               double *__restrict__ zero_a, double *__restrict__ zero_b, double *__restrict__ zero_c) {
+    const int col = c0 + blockIdx.y * VEC_TX + threadIdx.x;
+    if (col >= c1) return;
+    if (blockIdx.x == 0 && threadIdx.y == 0) { zero_a[col] = 0.0; zero_b[col] = 0.0; zero_c[col] = 0.0; }
+    const bool done = !(rr[col] > tol2 * bb[col]);
+    const double den = rz[col];
+    const double beta = (den > 0.0) ? rz_new[col] / den : 0.0;
+    const double *dk = dinv + (size_t)(col / nE) * N;
+    const int row0 = blockIdx.x * VEC_ROWS;
+    for (int r = threadIdx.y; r < VEC_ROWS; r += VEC_TY) {
+        const int row = row0 + r; if (row >= N) break;
+        const size_t o = (size_t)row * ld + col;
+        P[o] = done ? 0.0 : fma(beta, P[o], dk[row] * R[o]);
+    }
+}
+
+// total field  U = X + rho_src * prim   (:2287)  /  analytic branch  U = scale * prim (:1295-1300)
+__global__ void k_finalize_pots(const double *__restrict__ Xv, const double *__restrict__ prim, const double *__restrict__ rho_src,
+                                double scale, int N, int nE, int c0, int c1, size_t ld, double *__restrict__ U) {
+    const int col = c0 + blockIdx.y * blockDim.x + threadIdx.x;
+    const int row = blockIdx.x * blockDim.y + threadIdx.y;
+    if (col >= c1 || row >= N) return;
+    const size_t o = (size_t)row * ld + col;
+    if (Xv) {
+        const int e = col % nE;
+        U[o] = prim ? Xv[o] + rho_src[e] * prim[o] : Xv[o];
+    } else {
+        U[o] = scale * prim[o];
+    }
+}
+// zero the RHS rows of Dirichlet nodes (:2281-2283)
+__global__ void k_zero_rows(const int *__restrict__ rows, int n, int c0, int c1, size_t ld, double *__restrict__ B) {
+    const int col = c0 + blockIdx.y * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x;
+    if (col < c1 && i < n) B[(size_t)rows[i] * ld + col] = 0.0;
+}
+// total-field right-hand side: delta at the electrode (electrode.cpp:133-151, :274-287)
+__global__ void k_delta_rhs(const int *__restrict__ pick_ptr, const int *__restrict__ pick_idx, const double *__restrict__ pick_w,
+                            int nE, int c0, int c1, size_t ld, double *__restrict__ B) {
+    const int col = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= c1) return;
+    const int e = col % nE;
+    for (int t = pick_ptr[e]; t < pick_ptr[e + 1]; t++) B[(size_t)pick_idx[t] * ld + col] = pick_w[t];
+}
+
+// ---------------------------------------------------------------------------------
+// forward epilogue (dcfemmodelling.cpp:1707-1729, datamap.cpp:57-97, :159-231, :1140-1196)
+// ---------------------------------------------------------------------------------
+// pM[e][e'] = sum_k w_k * sum_t pick_w[t] U[pick_idx[t]][e + nE k]   (potential of source e at electrode e')
+__global__ void k_pickup(const double *__restrict__ U, size_t ld, const double *__restrict__ w, int nK, int nE,
+                         const int *__restrict__ pick_ptr, const int *__restrict__ pick_idx, const double *__restrict__ pick_w,
+                         int c0, int c1, double *__restrict__ pM) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;      // source
+    const int ep = blockIdx.y;                                 // receiving electrode
+    if (e >= nE) return;
+    double acc = 0.0;
+    for (int kk = 0; kk < nK; kk++) {
+        const int s = e + nE * kk;
+        if (s < c0 || s >= c1) continue;                       // other shards add their part (all-reduce)
+        double u = 0.0;
+        for (int t = pick_ptr[ep]; t < pick_ptr[ep + 1]; t++) u += pick_w[t] * U[(size_t)pick_idx[t] * ld + e + nE * kk];
+        acc += u * w[kk];
+    }
+    pM[(size_t)e * nE + ep] = acc;
+}
+__global__ void k_response(const double *__restrict__ pM, int nE, const int *__restrict__ abmn, const double *__restrict__ kfac, int D,
+                           double *__restrict__ resp, double *__restrict__ resp_rez, double *__restrict__ rhoa) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    const int a = abmn[4 * d], b = abmn[4 * d + 1], m = abmn[4 * d + 2], n = abmn[4 * d + 3];
+    auto P = [&](int s, int r) -> double { return (s >= 0 && r >= 0) ? pM[(size_t)s * nE + r] : 0.0; };
+    const double u  = (P(a, m) - P(a, n)) - (P(b, m) - P(b, n));
+    const double ur = (P(m, a) - P(m, b)) - (P(n, a) - P(n, b));           // reciprocity: a<->m, b<->n
+    const double r1 = rint(u / 1e-10) * 1e-10 * kfac[d];                   // round(u, 1e-10) * k
+    const double r2 = rint(ur / 1e-10) * 1e-10 * kfac[d];
+    resp[d] = r1; resp_rez[d] = r2;
+    rhoa[d] = sqrt(fabs(r1 * r2));
+}
+// solutions_[e][node] = sum_k w_k U[node][e + nE k]  (only for introspection)
+__global__ void k_ksum(const double *__restrict__ U, size_t ld, const double *__restrict__ w, int nK, int nE, int N, double *__restrict__ out) {
+    const int e = blockIdx.y * blockDim.x + threadIdx.x;
+    const int node = blockIdx.x * blockDim.y + threadIdx.y;
+    if (e >= nE || node >= N) return;
+    double acc = 0.0;
+    for (int kk = 0; kk < nK; kk++) acc += w[kk] * U[(size_t)node * ld + e + nE * kk];
+    out[(size_t)e * N + node] = acc;
+}
+// transposed copy for introspection: out[s][node] = U[node][s]
+__global__ void k_transpose_out(const double *__restrict__ U, size_t ld, int N, int nS, double *__restrict__ out) {
+    __shared__ double tile[32][33];
+    int s = blockIdx.x * 32 + threadIdx.x, node = blockIdx.y * 32 + threadIdx.y;
+    for (int j = 0; j < 32; j += 8) if (s < nS && node + j < N) tile[threadIdx.y + j][threadIdx.x] = U[(size_t)(node + j) * ld + s];
+    __syncthreads();
+    int node2 = blockIdx.y * 32 + threadIdx.x, s2 = blockIdx.x * 32 + threadIdx.y;
+    for (int j = 0; j < 32; j += 8) if (s2 + j < nS && node2 < N) out[(size_t)(s2 + j) * N + node2] = tile[threadIdx.x][threadIdx.y + j];
+}
+
+// ---------------------------------------------------------------------------------
+// K3: Jacobian (bertJacobian.cpp:70-119, elementmatrix.h:280-293, dcfemmodelling.cpp:1377-1383)
+//   J[d][col] = k_d / rho_col^2 * sum_{cells c of col} sum_k w_k (u_a-u_b)^T (K_c + k^2 M_c) (u_m-u_n)
+//
+//   One CTA per model column.  For every cell of the column and every wavenumber the CTA
+//   gathers the cell's nodal potentials for the "current-side" electrode list P and the
+//   "potential-side" list Q (coalesced: one node's values for all sources are contiguous),
+//   forms V = E U_Q, and accumulates the electrode-pair Gram block
+//       G[p][q] += w_k * sum_i U_P[i][p] * V[i][q]
+//   in registers (4x4 micro-tiles per thread, FP64 FMA pipe).  G is then dropped to shared
+//   memory once per column and every datum is the 4-term ABMN combination
+//       G[a][m] - G[a][n] - G[b][m] + G[b][n],
+//   scaled and stored to the column-major J with consecutive threads writing consecutive rows.
+// ---------------------------------------------------------------------------------
+constexpr int JAC_THREADS = 256;
+constexpr int JAC_MAX_TILES = 4;     // micro-tiles per thread
+
+struct JacArgs {
+    const double *pos; const int *cells; int nloc;
+    const int *jac_cells; const int *jac_col_ptr; int col_begin, col_end;
+    const double *U; size_t ld; int nE; int nK; const double *kvals; const double *kw;
+    const int *plist; int nP, nPp;            // current-side electrodes, padded to a multiple of 4
+    const int *qlist; int nQ, nQp;
+    const int *ia, *ib, *im, *in;             // [nd] indices into plist / qlist (-1 unused)
+    const int *out_row; const double *kfac; int nd;
+    const double *rho_col;                    // [M] model value per column or nullptr (no scaling)
+    double *Jt; size_t ldJ;
+};
+
+template <int E>
+__global__ void __launch_bounds__(JAC_THREADS)
+k_jacobian(const JacArgs A) {
+    constexpr int NV = ElemTraits<E>::NV, NL = ElemTraits<E>::NL, DIM = ElemTraits<E>::DIM;
+    extern __shared__ __align__(16) double sm[];
+    double *sUp = sm;                               // [NL][nPp]
+    double *sUq = sUp + NL * A.nPp;                 // [NL][nQp]
+    double *sV  = sUq + NL * A.nQp;                 // [NL][nQp]
+    double *sK  = sV + NL * A.nQp;                  // [NL*NL] stiffness
+    double *sM  = sK + NL * NL;                     // [NL*NL] mass
+    double *sG  = sM + NL * NL;                     // [nPp][nQp + 1]
+    __shared__ int snode[NL];
+    const int tid = threadIdx.x;
+    const int tilesQ = A.nQp / 4, tilesP = A.nPp / 4, ntiles = tilesP * tilesQ;
+    const int gstride = A.nQp + 1;
+
+    for (int col = A.col_begin + blockIdx.x; col < A.col_end; col += gridDim.x) {
+        double acc[JAC_MAX_TILES][16];
+#pragma unroll
+        for (int t = 0; t < JAC_MAX_TILES; t++)
+#pragma unroll
+            for (int x = 0; x < 16; x++) acc[t][x] = 0.0;
+
+        const int cb = A.jac_col_ptr[col], ce = A.jac_col_ptr[col + 1];
+        for (int ci = cb; ci < ce; ci++) {
+            const int cell = A.jac_cells[ci];
+            __syncthreads();                         // previous cell fully consumed
+            if (tid < NL) snode[tid] = A.cells[(size_t)cell * NL + tid];
+            if (tid < NL * NL) {
+                double X[NV][3];
+#pragma unroll
+                for (int v = 0; v < NV; v++) {
+                    const int n = A.cells[(size_t)cell * NL + v];
+                    X[v][0] = A.pos[3 * (size_t)n]; X[v][1] = A.pos[3 * (size_t)n + 1]; X[v][2] = A.pos[3 * (size_t)n + 2];
+                }
+                double size, G[NV][NV];
+                simplex_gram<DIM>(X, size, G);
+                const int i = tid / NL, j = tid - i * NL;
+                sK[tid] = stiff_entry<E>(i, j, size, G);
+                sM[tid] = size * mass_unit<E>(i, j);
+            }
+            __syncthreads();
+            for (int kk = 0; kk < A.nK; kk++) {
+                const double k = A.kvals[kk], wk = A.kw[kk];
+                const double k2 = k * k;
+                if (kk > 0) __syncthreads();         // tiles of the previous k consumed
+                // gather nodal potentials (coalesced along the electrode index)
+                for (int x = tid; x < NL * A.nPp; x += JAC_THREADS) {
+                    const int i = x / A.nPp, p = x - i * A.nPp;
+                    sUp[x] = (p < A.nP) ? A.U[(size_t)snode[i] * A.ld + A.plist[p] + A.nE * kk] : 0.0;
+                }
+                for (int x = tid; x < NL * A.nQp; x += JAC_THREADS) {
+                    const int i = x / A.nQp, q = x - i * A.nQp;
+                    sUq[x] = (q < A.nQ) ? A.U[(size_t)snode[i] * A.ld + A.qlist[q] + A.nE * kk] : 0.0;
+                }
+                __syncthreads();
+                // V = w_k (K + k^2 M) U_Q
+                for (int x = tid; x < NL * A.nQp; x += JAC_THREADS) {
+                    const int i = x / A.nQp, q = x - i * A.nQp;
+                    double v = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NL; j++) v = fma(fma(k2, sM[i * NL + j], sK[i * NL + j]), sUq[j * A.nQp + q], v);
+                    sV[x] = v * wk;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int t = 0; t < JAC_MAX_TILES; t++) {
+                    const int tile = tid + t * JAC_THREADS;
+                    if (tile < ntiles) {
+                        const int tp = tile / tilesQ, tq = tile - tp * tilesQ;
+#pragma unroll
+                        for (int i = 0; i < NL; i++) {
+                            const double2 u01 = *reinterpret_cast<const double2 *>(sUp + i * A.nPp + 4 * tp);
+                            const double2 u23 = *reinterpret_cast<const double2 *>(sUp + i * A.nPp + 4 * tp + 2);
+                            const double2 v01 = *reinterpret_cast<const double2 *>(sV + i * A.nQp + 4 * tq);
+                            const double2 v23 = *reinterpret_cast<const double2 *>(sV + i * A.nQp + 4 * tq + 2);
+                            const double u[4] = {u01.x, u01.y, u23.x, u23.y};
+                            const double v[4] = {v01.x, v01.y, v23.x, v23.y};
+#pragma unroll
+                            for (int a = 0; a < 4; a++)
+#pragma unroll
+                                for (int b = 0; b < 4; b++) acc[t][a * 4 + b] = fma(u[a], v[b], acc[t][a * 4 + b]);
+                        }
+                    }
+                }
+            }
+        }
+        // drop G to shared memory
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < JAC_MAX_TILES; t++) {
+            const int tile = tid + t * JAC_THREADS;
+            if (tile < ntiles) {
+                const int tp = tile / tilesQ, tq = tile - tp * tilesQ;
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) sG[(4 * tp + a) * gstride + 4 * tq + b] = acc[t][a * 4 + b];
+            }
+        }
+        __syncthreads();
+        double scale = 1.0;
+        if (A.rho_col) { const double r = A.rho_col[col]; scale = 1.0 / (r * r); }
+        double *out = A.Jt + (size_t)col * A.ldJ;
+        for (int d = tid; d < A.nd; d += JAC_THREADS) {
+            const int a = A.ia[d], b = A.ib[d], m = A.im[d], n = A.in[d];
+            double v = 0.0;
+            if (a >= 0 && m >= 0) v += sG[a * gstride + m];
+            if (a >= 0 && n >= 0) v -= sG[a * gstride + n];
+            if (b >= 0 && m >= 0) v -= sG[b * gstride + m];
+            if (b >= 0 && n >= 0) v += sG[b * gstride + n];
+            out[A.out_row[d]] = v * scale * A.kfac[d];
+        }
+    }
+}
+
+// y = J x  (J column-major [cols][ld]):  y[d] = sum_j Jt[j][d] x[j]
+__global__ void k_jac_mult(const double *__restrict__ Jt, size_t ld, int rows, int cols, const double *__restrict__ x, double *__restrict__ y) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= rows) return;
+    const int j0 = blockIdx.y * 256, j1 = min(cols, j0 + 256);
+    double acc = 0.0;
+    for (int j = j0; j < j1; j++) acc = fma(Jt[(size_t)j * ld + d], x[j], acc);
+    atomicAdd(y + d, acc);
+}
+// y = J^T x:  y[j] = sum_d Jt[j][d] x[d]   (one warp per column)
+__global__ void k_jac_tmult(const double *__restrict__ Jt, size_t ld, int rows, int cols, const double *__restrict__ x, double *__restrict__ y) {
+    const int j = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    if (j >= cols) return;
+    const int lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int d = lane; d < rows; d += 32) acc = fma(Jt[(size_t)j * ld + d], x[d], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[j] = acc;
+}
+// row-major copy of the column-major J: out[d][j] = Jt[j][d]
+__global__ void k_jac_to_rowmajor(const double *__restrict__ Jt, size_t ld, int rows, int cols, double *__restrict__ out) {
+    __shared__ double tile[32][33];
+    int d = blockIdx.x * 32 + threadIdx.x, j = blockIdx.y * 32 + threadIdx.y;
+    for (int t = 0; t < 32; t += 8) if (d < rows && j + t < cols) tile[threadIdx.y + t][threadIdx.x] = Jt[(size_t)(j + t) * ld + d];
+    __syncthreads();
+    int j2 = blockIdx.y * 32 + threadIdx.x, d2 = blockIdx.x * 32 + threadIdx.y;
+    for (int t = 0; t < 32; t += 8) if (d2 + t < rows && j2 < cols) out[(size_t)(d2 + t) * cols + j2] = tile[threadIdx.x][threadIdx.y + t];
+}
+
+} // namespace pgb

@@ -1,0 +1,836 @@
+// pgb200_ert.cu -- host side of the C ABI declared in include/pgb200_ert.h.
+// Owns the device memory of one (mesh, scheme) plan and sequences the kernels of
+// ert_kernels.cuh on one CUDA stream.  No CPU fallback anywhere: every compute entry
+// point needs a CUDA device and fails loudly otherwise.
+#include "../../include/pgb200_ert.h"
+#include "ert_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <initializer_list>
+#include <string>
+#include <vector>
+
+using namespace pgb;
+
+namespace {
+
+thread_local std::string g_err;
+
+#define PGB_FAIL(msg) do { g_err = std::string(msg) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"; return 1; } while (0)
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    g_err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"; return 1; } } while (0)
+#define CKR(call) do { int r_ = (call); if (r_) return r_; } while (0)
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+template <class T> struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    int alloc(size_t count) {
+        release(); n = count;
+        if (count == 0) return 0;
+        CK(cudaMalloc((void **)&p, count * sizeof(T)));
+        return 0;
+    }
+    int upload(const T *host, size_t count, cudaStream_t st) {
+        CKR(alloc(count));
+        if (count) CK(cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+};
+
+struct JacChunk {
+    int nP, nPp, nd;
+    size_t plist_off, data_off;   // offsets into the concatenated device arrays
+    size_t smem;
+};
+
+enum Phase { PH_MAP = 0, PH_ASM, PH_RHS, PH_SOLVE, PH_EPI, PH_JAC, PH_COUNT };
+
+} // namespace
+
+struct pgb200_ert {
+    // sizes
+    int dim = 0, nloc = 0, elem = 0, N = 0, C = 0, nE = 0, nK = 0, nS = 0, M = 0, D = 0, sr = 1, fullspace = 0;
+    size_t nnz = 0, ld = 0;
+    double surface_z = 0.0;
+    int device = 0;
+    cudaStream_t st = 0;
+    // solver controls
+    double tol = 1e-12; int max_iter = 20000; int check_every = 25;
+    // shard
+    int c0 = 0, c1 = 0, row0 = 0, row1 = 0;
+    // plan (device)
+    DevBuf<double> pos, kvals, kw, bc_coef, el_pos, sing_val, pick_w, pro_w, kfac;
+    DevBuf<int> cells, cell_marker, rowptr, colidx, diag_pos, color_order, cells_col, pos_col, bc_slot, bc_ptr, bc_owner,
+        dir_zero, dir_diag, dir_nodes, sing_node, pick_ptr, pick_idx, src_cell_ptr, src_cells, pro_cells, pro_nb,
+        jac_cells, jac_col_ptr, abmn;
+    std::vector<int> color_ptr, pro_level_ptr;
+    std::vector<double> h_kvals;
+    int n_colors = 0, n_bc_slots = 0, n_bc_entries = 0, n_dir_zero = 0, n_dir_nodes = 0, pro_nf = 0, n_jac_cells = 0;
+    std::vector<int> h_abmn; std::vector<double> h_kfac;
+    // state (device)
+    DevBuf<double> model, rho, rho_src, vals, vals1, dinv, prim, B, X, R, P, AP, U, scal, pM, resp, resp_rez, rhoa, Jt, tmp, xin, yout;
+    DevBuf<int> flags;
+    bool pots_valid = false, have_vals = false;
+    int model_len = 0;
+    std::vector<double> h_model;
+    // jacobian plan
+    DevBuf<int> j_plist, j_qlist, j_ia, j_ib, j_im, j_in, j_out;
+    DevBuf<double> j_kfac;
+    std::vector<JacChunk> chunks; int nQ = 0, nQp = 0;
+    size_t ldJ = 0; int j_rows = 0; bool jac_valid = false;
+    // stats
+    int last_iters = 0; double last_relres = 0.0; long long launches = 0;
+    cudaEvent_t ev[PH_COUNT + 1]; bool ev_ok = false; float ph_ms[PH_COUNT] = {0};
+    bool ph_rec[PH_COUNT + 1] = {false};
+    int prof = 0; std::vector<cudaEvent_t> pev; int n_pev = 0; double spmm_ms = 0.0; int spmm_timed = 0; double jac_ms = 0.0;
+    cudaEvent_t jev[2];
+    double *h_pinned = nullptr; size_t h_pinned_n = 0;
+    int num_sms = 148;
+};
+
+#define LAUNCH(h) ((h)->launches++)
+
+namespace {
+
+int ensure_pinned(pgb200_ert *h, size_t n) {
+    if (h->h_pinned_n >= n) return 0;
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    h->h_pinned = nullptr; h->h_pinned_n = 0;
+    CK(cudaMallocHost((void **)&h->h_pinned, n * sizeof(double)));
+    h->h_pinned_n = n;
+    return 0;
+}
+
+template <int E>
+int launch_assemble(pgb200_ert *h, const double *rho, double *vals) {
+    CK(cudaMemsetAsync(vals, 0, sizeof(double) * h->nnz * h->nK, h->st));
+    for (int c = 0; c < h->n_colors; c++) {
+        const int first = h->color_ptr[c], count = h->color_ptr[c + 1] - first;
+        if (count <= 0) continue;
+        k_assemble<E><<<cdiv(count, 128), 128, 0, h->st>>>(h->pos.p, h->cells_col.p, h->pos_col.p, h->color_order.p, rho,
+                                                          h->C, first, count, h->kvals.p, h->nK, h->nnz, vals);
+        LAUNCH(h);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int assemble(pgb200_ert *h, const double *rho, double *vals) {
+    switch (h->elem) {
+        case TRI3:  CKR(launch_assemble<TRI3>(h, rho, vals)); break;
+        case TRI6:  CKR(launch_assemble<TRI6>(h, rho, vals)); break;
+        case TET4:  CKR(launch_assemble<TET4>(h, rho, vals)); break;
+        case TET10: CKR(launch_assemble<TET10>(h, rho, vals)); break;
+        default: PGB_FAIL("unknown element type");
+    }
+    if (h->n_bc_slots) {
+        k_boundary_add<<<cdiv(h->n_bc_slots, 128), 128, 0, h->st>>>(h->bc_slot.p, h->bc_ptr.p, h->bc_owner.p, h->bc_coef.p,
+                                                                   h->n_bc_slots, h->n_bc_entries, rho, h->nK, h->nnz, vals);
+        LAUNCH(h);
+    }
+    if (h->n_dir_zero) {
+        k_dirichlet_zero<<<cdiv(h->n_dir_zero, 128), 128, 0, h->st>>>(h->dir_zero.p, h->n_dir_zero, h->nK, h->nnz, vals); LAUNCH(h);
+        k_dirichlet_diag<<<cdiv(h->n_dir_nodes, 128), 128, 0, h->st>>>(h->dir_diag.p, h->n_dir_nodes, h->nK, h->nnz, vals); LAUNCH(h);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <int MODE, bool DOT>
+int launch_spmm(pgb200_ert *h, const double *vals, const double *vals1, const double *rho_src, const double *X, double *Y,
+                int c0, int c1, double *dots) {
+    const int ncols = c1 - c0;
+    if (ncols <= 0) return 0;
+    // choose columns per thread to minimise idle lanes in the last column block
+    int best = 1; double beste = 0.0;
+    for (int cpt : {4, 2, 1}) {
+        const int w = SPMM_TX * cpt; const double eff = (double)ncols / (double)(cdiv(ncols, w) * w);
+        if (eff > beste + 0.05) { beste = eff; best = cpt; }
+    }
+    dim3 block(SPMM_TX, SPMM_TY), grid(cdiv(h->N, SPMM_ROWS), cdiv(ncols, SPMM_TX * best));
+#define SPMM_GO(CPT) k_spmm<CPT, MODE, DOT><<<grid, block, 0, h->st>>>(h->rowptr.p, h->colidx.p, vals, vals1, rho_src, h->nnz, X, Y, h->N, h->nE, c0, c1, h->ld, dots)
+    if (best == 4) SPMM_GO(4); else if (best == 2) SPMM_GO(2); else SPMM_GO(1);
+#undef SPMM_GO
+    LAUNCH(h);
+    return 0;
+}
+
+// scal layout: [0] rz_a [1] rz_b [2] rz_c [3] pAp [4] rr_a [5] rr_b [6] bb   (each ld doubles)
+int pcg_solve(pgb200_ert *h) {
+    const int c0 = h->c0, c1 = h->c1, ncols = c1 - c0;
+    h->last_iters = 0; h->last_relres = 0.0;
+    if (ncols <= 0) return 0;
+    const size_t ld = h->ld;
+    double *S = h->scal.p;
+    auto sc = [&](int i) { return S + (size_t)i * ld; };
+    CK(cudaMemsetAsync(S, 0, sizeof(double) * 7 * ld, h->st));
+    dim3 vb(VEC_TX, VEC_TY), vg(cdiv(h->N, VEC_ROWS), cdiv(ncols, VEC_TX));
+    k_pcg_init<<<vg, vb, 0, h->st>>>(h->B.p, h->dinv.p, h->X.p, h->R.p, h->P.p, h->N, h->nE, c0, c1, ld, sc(0), sc(6)); LAUNCH(h);
+    CK(cudaGetLastError());
+    CKR(ensure_pinned(h, 2 * ld));
+    const double tol2 = h->tol * h->tol;
+    int it = 0; bool converged = false;
+    // initial residual == b: a zero right-hand side needs no iteration
+    while (it < h->max_iter) {
+        const int rz_old = it % 3, rz_new = (it + 1) % 3, rz_nxt = (it + 2) % 3;
+        const int rr_cur = 4 + (it % 2), rr_nxt = 4 + ((it + 1) % 2);
+        const bool timed = h->prof && h->n_pev + 2 <= (int)h->pev.size();
+        if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
+        CKR((launch_spmm<0, true>(h, h->vals.p, nullptr, nullptr, h->P.p, h->AP.p, c0, c1, sc(3))));
+        if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
+        k_pcg_update_xr<<<vg, vb, 0, h->st>>>(h->P.p, h->AP.p, h->dinv.p, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
+                                             sc(rz_old), sc(3), sc(rz_new), sc(rr_cur)); LAUNCH(h);
+        it++;
+        const bool check = (it % h->check_every == 0) || it >= h->max_iter;
+        if (check) {
+            CK(cudaMemcpyAsync(h->h_pinned, sc(rr_cur), sizeof(double) * ld, cudaMemcpyDeviceToHost, h->st));
+            CK(cudaMemcpyAsync(h->h_pinned + ld, sc(6), sizeof(double) * ld, cudaMemcpyDeviceToHost, h->st));
+        }
+        k_pcg_update_p<<<vg, vb, 0, h->st>>>(h->R.p, h->dinv.p, h->P.p, h->N, h->nE, c0, c1, ld, sc(rz_old), sc(rz_new),
+                                            sc(rr_cur), sc(6), tol2, sc(3), sc(rr_nxt), sc(rz_nxt)); LAUNCH(h);
+        if (check) {
+            CK(cudaStreamSynchronize(h->st));
+            double worst = 0.0;
+            for (int c = c0; c < c1; c++) {
+                const double bb = h->h_pinned[ld + c], rr = h->h_pinned[c];
+                if (bb > 0.0) worst = std::max(worst, std::sqrt(rr / bb));
+                else if (rr > 0.0) worst = INFINITY;
+                if (!(rr == rr)) worst = INFINITY;
+            }
+            h->last_relres = worst;
+            if (worst <= h->tol) { converged = true; break; }
+        }
+    }
+    CK(cudaGetLastError());
+    h->last_iters = it;
+    if (!converged) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "block-PCG did not reach rel. residual %.1e in %d iterations (worst column %.3e)", h->tol, it, h->last_relres);
+        PGB_FAIL(buf);
+    }
+    return 0;
+}
+
+void phase_begin(pgb200_ert *h, int ph) { cudaEventRecord(h->ev[ph], h->st); h->ph_rec[ph] = true; }
+
+int map_model(pgb200_ert *h, const double *model_dev, int n_in) {
+    if (n_in != h->M && n_in != h->C) PGB_FAIL("model length must equal the number of model cells (max marker + 1) or the cell count");
+    CK(cudaMemsetAsync(h->flags.p, 0, sizeof(int) * 4, h->st));
+    k_check_model<<<cdiv(n_in, 256), 256, 0, h->st>>>(model_dev, n_in, h->flags.p); LAUNCH(h);
+    k_map_model<<<cdiv(h->C, 256), 256, 0, h->st>>>(model_dev, n_in, h->cell_marker.p, h->C, h->rho.p); LAUNCH(h);
+    if (n_in != h->C) {
+        const int nl = (int)h->pro_level_ptr.size() - 1;
+        for (int l = 0; l < nl; l++) {
+            const int b = h->pro_level_ptr[l], n = h->pro_level_ptr[l + 1] - b;
+            if (n <= 0) continue;
+            k_prolong_level<<<cdiv(n, 128), 128, 0, h->st>>>(h->pro_cells.p + b, h->pro_nb.p + (size_t)b * h->pro_nf,
+                                                            h->pro_w.p + (size_t)b * h->pro_nf, n, h->pro_nf, h->rho.p); LAUNCH(h);
+        }
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// assemble S(rho), right-hand sides, solve, total potentials  (calculateK, dcfemmodelling.cpp:2152-2296)
+int forward_solve(pgb200_ert *h) {
+    phase_begin(h, PH_ASM);
+    CKR(assemble(h, h->rho.p, h->vals.p));
+    k_count_singular<<<cdiv(h->N, 256), 256, 0, h->st>>>(h->diag_pos.p, h->N, h->nK, h->nnz, h->vals.p, h->flags.p + 1); LAUNCH(h);
+    k_inv_diag<<<cdiv(h->N, 256), 256, 0, h->st>>>(h->diag_pos.p, h->N, h->nK, h->nnz, h->vals.p, h->dinv.p); LAUNCH(h);
+    h->have_vals = true;
+    phase_begin(h, PH_RHS);
+    const int c0 = h->c0, c1 = h->c1;
+    if (h->sr) {
+        k_rho_src<<<cdiv(h->nE, 64), 64, 0, h->st>>>(h->src_cell_ptr.p, h->src_cells.p, h->rho.p, h->nE, h->rho_src.p); LAUNCH(h);
+        CKR((launch_spmm<1, false>(h, h->vals.p, h->vals1.p, h->rho_src.p, h->prim.p, h->B.p, c0, c1, nullptr)));
+    } else {
+        CK(cudaMemsetAsync(h->B.p, 0, sizeof(double) * h->N * h->ld, h->st));
+        if (c1 > c0) { k_delta_rhs<<<cdiv(c1 - c0, 128), 128, 0, h->st>>>(h->pick_ptr.p, h->pick_idx.p, h->pick_w.p, h->nE, c0, c1, h->ld, h->B.p); LAUNCH(h); }
+    }
+    if (h->n_dir_nodes && c1 > c0) {
+        k_zero_rows<<<dim3(h->n_dir_nodes, cdiv(c1 - c0, 128)), 128, 0, h->st>>>(h->dir_nodes.p, h->n_dir_nodes, c0, c1, h->ld, h->B.p); LAUNCH(h);
+    }
+    CK(cudaGetLastError());
+    // model / matrix sanity before iterating
+    int hf[4];
+    CK(cudaMemcpyAsync(hf, h->flags.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    if (hf[0]) PGB_FAIL("response for model with negative or zero resistivity is not defined");
+    if (hf[1]) PGB_FAIL("stiffness matrix has rows with diagonal < 1e-12 (the reference would force them to homogeneous Dirichlet); unsupported model");
+    phase_begin(h, PH_SOLVE);
+    CKR(pcg_solve(h));
+    phase_begin(h, PH_EPI);
+    if (c1 > c0) {
+        dim3 b(32, 8), g(cdiv(h->N, 8), cdiv(c1 - c0, 32));
+        k_finalize_pots<<<g, b, 0, h->st>>>(h->X.p, h->sr ? h->prim.p : nullptr, h->rho_src.p, 0.0, h->N, h->nE, c0, c1, h->ld, h->U.p); LAUNCH(h);
+    }
+    CK(cudaGetLastError());
+    h->pots_valid = true;
+    return 0;
+}
+
+int analytic_pots(pgb200_ert *h, double scale) {
+    const int c0 = h->c0, c1 = h->c1;
+    if (c1 > c0) {
+        dim3 b(32, 8), g(cdiv(h->N, 8), cdiv(c1 - c0, 32));
+        k_finalize_pots<<<g, b, 0, h->st>>>(nullptr, h->prim.p, nullptr, scale, h->N, h->nE, c0, c1, h->ld, h->U.p); LAUNCH(h);
+    }
+    CK(cudaGetLastError());
+    h->pots_valid = true;
+    return 0;
+}
+
+// partial electrode-potential matrix of this shard's sources
+int pickup(pgb200_ert *h) {
+    CK(cudaMemsetAsync(h->pM.p, 0, sizeof(double) * h->nE * h->nE, h->st));
+    // only this shard's source columns [c0,c1) are summed; other ranks add theirs by all-reduce
+    k_pickup<<<dim3(cdiv(h->nE, 64), h->nE), 64, 0, h->st>>>(h->U.p, h->ld, h->kw.p, h->nK, h->nE, h->pick_ptr.p, h->pick_idx.p,
+                                                              h->pick_w.p, h->c0, h->c1, h->pM.p); LAUNCH(h);
+    CK(cudaGetLastError());
+    return 0;
+}
+int finish_response(pgb200_ert *h, double *rhoa_dev) {
+    k_response<<<cdiv(h->D, 128), 128, 0, h->st>>>(h->pM.p, h->nE, h->abmn.p, h->kfac.p, h->D, h->resp.p, h->resp_rez.p, rhoa_dev); LAUNCH(h);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+size_t jac_smem(int NL, int nPp, int nQp) {
+    return sizeof(double) * ((size_t)NL * nPp + 2 * (size_t)NL * nQp + 2 * (size_t)NL * NL + (size_t)nPp * (nQp + 1));
+}
+
+// Build the chunked electrode-pair plan of the Jacobian for data rows [row0,row1)
+int build_jac_plan(pgb200_ert *h) {
+    const int NL = h->nloc;
+    const int r0 = h->row0, r1 = h->row1, nd = r1 - r0;
+    h->chunks.clear(); h->j_rows = nd; h->jac_valid = false;
+    if (nd <= 0) return 0;
+    std::vector<int> qmap(h->nE, -1), qlist;
+    for (int d = r0; d < r1; d++) for (int t = 2; t < 4; t++) { int e = h->h_abmn[4 * d + t]; if (e >= 0 && qmap[e] < 0) qmap[e] = 1; }
+    for (int e = 0; e < h->nE; e++) if (qmap[e] > 0) { qmap[e] = (int)qlist.size(); qlist.push_back(e); }
+    h->nQ = (int)qlist.size(); h->nQp = std::max(4, (h->nQ + 3) / 4 * 4);
+    std::vector<int> order(nd);
+    for (int i = 0; i < nd; i++) order[i] = r0 + i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        const int ax = h->h_abmn[4 * x], ay = h->h_abmn[4 * y];
+        if (ax != ay) return ax < ay;
+        return h->h_abmn[4 * x + 1] < h->h_abmn[4 * y + 1];
+    });
+    int dev_smem = 0;
+    CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    const size_t smem_cap = std::min<size_t>((size_t)dev_smem, 200 * 1024) - 64;
+    const int max_tiles = JAC_MAX_TILES * JAC_THREADS;
+    std::vector<int> plist_all, ia, ib, im, in, outr; std::vector<double> kf;
+    size_t i = 0;
+    while (i < (size_t)nd) {
+        std::vector<int> pmap(h->nE, -1), plist;
+        JacChunk ch; ch.plist_off = plist_all.size(); ch.data_off = ia.size(); ch.nd = 0;
+        while (i < (size_t)nd) {
+            const int d = order[i];
+            const int a = h->h_abmn[4 * d], b = h->h_abmn[4 * d + 1];
+            int add = 0;
+            if (a >= 0 && pmap[a] < 0) add++;
+            if (b >= 0 && b != a && pmap[b] < 0) add++;
+            const int nPp_new = std::max(4, ((int)plist.size() + add + 3) / 4 * 4);
+            const bool fits = jac_smem(NL, nPp_new, h->nQp) <= smem_cap && (nPp_new / 4) * (h->nQp / 4) <= max_tiles;
+            if (!fits) {
+                if (plist.empty()) PGB_FAIL("Jacobian tile does not fit shared memory (too many potential electrodes)");
+                break;
+            }
+            if (a >= 0 && pmap[a] < 0) { pmap[a] = (int)plist.size(); plist.push_back(a); }
+            if (b >= 0 && pmap[b] < 0) { pmap[b] = (int)plist.size(); plist.push_back(b); }
+            const int m = h->h_abmn[4 * d + 2], n = h->h_abmn[4 * d + 3];
+            ia.push_back(a >= 0 ? pmap[a] : -1); ib.push_back(b >= 0 ? pmap[b] : -1);
+            im.push_back(m >= 0 ? qmap[m] : -1); in.push_back(n >= 0 ? qmap[n] : -1);
+            outr.push_back(d - r0); kf.push_back(h->h_kfac[d]);
+            ch.nd++; i++;
+        }
+        ch.nP = (int)plist.size(); ch.nPp = std::max(4, (ch.nP + 3) / 4 * 4);
+        ch.smem = jac_smem(NL, ch.nPp, h->nQp);
+        plist_all.insert(plist_all.end(), plist.begin(), plist.end());
+        h->chunks.push_back(ch);
+    }
+    CKR(h->j_plist.upload(plist_all.data(), plist_all.size(), h->st));
+    CKR(h->j_qlist.upload(qlist.data(), qlist.size(), h->st));
+    CKR(h->j_ia.upload(ia.data(), ia.size(), h->st)); CKR(h->j_ib.upload(ib.data(), ib.size(), h->st));
+    CKR(h->j_im.upload(im.data(), im.size(), h->st)); CKR(h->j_in.upload(in.data(), in.size(), h->st));
+    CKR(h->j_out.upload(outr.data(), outr.size(), h->st));
+    CKR(h->j_kfac.upload(kf.data(), kf.size(), h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->ldJ = ((size_t)nd + 1) / 2 * 2;
+    return 0;
+}
+
+template <int E>
+int launch_jacobian(pgb200_ert *h, const double *rho_col) {
+    size_t maxsm = 0;
+    for (auto &c : h->chunks) maxsm = std::max(maxsm, c.smem);
+    CK(cudaFuncSetAttribute(k_jacobian<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxsm));
+    for (auto &c : h->chunks) {
+        JacArgs A;
+        A.pos = h->pos.p; A.cells = h->cells.p; A.nloc = h->nloc;
+        A.jac_cells = h->jac_cells.p; A.jac_col_ptr = h->jac_col_ptr.p; A.col_begin = 0; A.col_end = h->M;
+        A.U = h->U.p; A.ld = h->ld; A.nE = h->nE; A.nK = h->nK; A.kvals = h->kvals.p; A.kw = h->kw.p;
+        A.plist = h->j_plist.p + c.plist_off; A.nP = c.nP; A.nPp = c.nPp;
+        A.qlist = h->j_qlist.p; A.nQ = h->nQ; A.nQp = h->nQp;
+        A.ia = h->j_ia.p + c.data_off; A.ib = h->j_ib.p + c.data_off; A.im = h->j_im.p + c.data_off; A.in = h->j_in.p + c.data_off;
+        A.out_row = h->j_out.p + c.data_off; A.kfac = h->j_kfac.p + c.data_off; A.nd = c.nd;
+        A.rho_col = rho_col; A.Jt = h->Jt.p; A.ldJ = h->ldJ;
+        int occ = 1;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_jacobian<E>, JAC_THREADS, c.smem));
+        const int grid = std::max(1, std::min(h->M, h->num_sms * std::max(1, occ)));
+        k_jacobian<E><<<grid, JAC_THREADS, c.smem, h->st>>>(A); LAUNCH(h);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int jacobian(pgb200_ert *h, const double *rho_col) {
+    if (h->j_rows <= 0) { h->jac_valid = true; return 0; }
+    if (h->Jt.n < (size_t)h->M * h->ldJ) CKR(h->Jt.alloc((size_t)h->M * h->ldJ));
+    phase_begin(h, PH_JAC);
+    if (h->prof) CK(cudaEventRecord(h->jev[0], h->st));
+    switch (h->elem) {
+        case TRI3:  CKR(launch_jacobian<TRI3>(h, rho_col)); break;
+        case TRI6:  CKR(launch_jacobian<TRI6>(h, rho_col)); break;
+        case TET4:  CKR(launch_jacobian<TET4>(h, rho_col)); break;
+        case TET10: CKR(launch_jacobian<TET10>(h, rho_col)); break;
+        default: PGB_FAIL("unknown element type");
+    }
+    if (h->prof) CK(cudaEventRecord(h->jev[1], h->st));
+    h->jac_valid = true;
+    return 0;
+}
+
+int finish_timing(pgb200_ert *h) {
+    CK(cudaEventRecord(h->ev[PH_COUNT], h->st));
+    CK(cudaStreamSynchronize(h->st));
+    int order[PH_COUNT + 1], n = 0;
+    for (int p = 0; p < PH_COUNT; p++) { h->ph_ms[p] = 0.f; if (h->ph_rec[p]) order[n++] = p; }
+    order[n] = PH_COUNT;
+    for (int i = 0; i < n; i++) { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev[order[i]], h->ev[order[i + 1]]); h->ph_ms[order[i]] = ms; }
+    for (int p = 0; p <= PH_COUNT; p++) h->ph_rec[p] = false;
+    if (h->prof) {
+        for (int i = 0; i + 1 < h->n_pev; i += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, h->pev[i], h->pev[i + 1]); h->spmm_ms += ms; h->spmm_timed++; }
+        h->n_pev = 0;
+        if (h->jac_valid && h->ph_ms[PH_JAC] > 0.f) { float ms = 0.f; if (cudaEventElapsedTime(&ms, h->jev[0], h->jev[1]) == cudaSuccess) h->jac_ms = ms; }
+    }
+    return 0;
+}
+
+double host_stddev(const std::vector<double> &v) {
+    if (v.size() < 2) return 0.0;
+    double mean = 0.0; for (double x : v) mean += x; mean /= (double)v.size();
+    double s = 0.0; for (double x : v) s += (x - mean) * (x - mean);
+    return std::sqrt(s / (double)(v.size() - 1));
+}
+
+} // namespace
+
+// =====================================================================================
+extern "C" {
+
+const char *pgb200_last_error(void) { return g_err.c_str(); }
+int pgb200_version(void) { return 100; }
+
+int pgb200_color_cells(int n_cells, int nloc, const int *cells, int n_nodes, int *color) {
+    // sequential greedy with a 256-bit "colours used around this node" mask per node
+    struct Mask { unsigned long long w[4]; };
+    std::vector<Mask> used((size_t)n_nodes, Mask{{0, 0, 0, 0}});
+    int ncol = 0;
+    for (int c = 0; c < n_cells; c++) {
+        Mask f{{0, 0, 0, 0}};
+        for (int j = 0; j < nloc; j++) { const Mask &u = used[cells[(size_t)c * nloc + j]]; for (int w = 0; w < 4; w++) f.w[w] |= u.w[w]; }
+        int col = -1;
+        for (int w = 0; w < 4 && col < 0; w++) if (~f.w[w]) col = w * 64 + __builtin_ctzll(~f.w[w]);
+        if (col < 0) { g_err = "colouring needs more than 256 colours"; return -1; }
+        color[c] = col; ncol = std::max(ncol, col + 1);
+        for (int j = 0; j < nloc; j++) used[cells[(size_t)c * nloc + j]].w[col >> 6] |= 1ull << (col & 63);
+    }
+    return ncol;
+}
+
+int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
+    if (!p || !out) PGB_FAIL("null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) PGB_FAIL("no CUDA device: the B200 ERT path has no CPU fallback");
+    if (device < 0 || device >= ndev) PGB_FAIL("invalid CUDA device index");
+    CK(cudaSetDevice(device));
+    pgb200_ert *h = new pgb200_ert();
+    *out = h;
+    h->device = device;
+    CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
+    h->dim = p->dim; h->nloc = p->nloc; h->N = p->n_nodes; h->C = p->n_cells; h->nnz = (size_t)p->nnz;
+    h->nE = p->n_elec; h->nK = p->n_k; h->nS = h->nE * h->nK; h->M = p->n_model; h->D = p->n_data; h->sr = p->sr;
+    h->fullspace = p->fullspace; h->surface_z = p->surface_z;
+    if (p->dim == 2 && p->nloc == 3) h->elem = TRI3; else if (p->dim == 2 && p->nloc == 6) h->elem = TRI6;
+    else if (p->dim == 3 && p->nloc == 4) h->elem = TET4; else if (p->dim == 3 && p->nloc == 10) h->elem = TET10;
+    else PGB_FAIL("unsupported cell type (need Tri3/Tri6/Tet4/Tet10)");
+    h->ld = ((size_t)h->nS + 3) / 4 * 4;
+    h->c0 = 0; h->c1 = h->nS; h->row0 = 0; h->row1 = h->D;
+    cudaStream_t st = h->st;
+    const int N = h->N, C = h->C, nE = h->nE, nK = h->nK, NL = h->nloc;
+    CKR(h->pos.upload(p->pos, (size_t)N * 3, st));
+    CKR(h->cells.upload(p->cells, (size_t)C * NL, st));
+    CKR(h->cell_marker.upload(p->cell_marker, C, st));
+    CKR(h->rowptr.upload(p->rowptr, (size_t)N + 1, st));
+    CKR(h->colidx.upload(p->colidx, h->nnz, st));
+    CKR(h->diag_pos.upload(p->diag_pos, N, st));
+    h->n_colors = p->n_colors; h->color_ptr.assign(p->color_ptr, p->color_ptr + p->n_colors + 1);
+    CKR(h->color_order.upload(p->color_order, C, st));
+    CKR(h->cells_col.upload(p->cells_col, (size_t)C * NL, st));
+    CKR(h->pos_col.upload(p->pos_col, (size_t)C * NL * NL, st));
+    CKR(h->kvals.upload(p->k_values, nK, st)); CKR(h->kw.upload(p->k_weights, nK, st));
+    h->h_kvals.assign(p->k_values, p->k_values + nK);
+    h->n_bc_slots = p->n_bc_slots; h->n_bc_entries = p->n_bc_entries;
+    CKR(h->bc_slot.upload(p->bc_slot, p->n_bc_slots, st)); CKR(h->bc_ptr.upload(p->bc_ptr, (size_t)p->n_bc_slots + 1, st));
+    CKR(h->bc_owner.upload(p->bc_owner, p->n_bc_entries, st)); CKR(h->bc_coef.upload(p->bc_coef, (size_t)nK * p->n_bc_entries, st));
+    h->n_dir_zero = p->n_dir_zero; h->n_dir_nodes = p->n_dir_nodes;
+    CKR(h->dir_zero.upload(p->dir_zero_slots, p->n_dir_zero, st)); CKR(h->dir_diag.upload(p->dir_diag_slots, p->n_dir_nodes, st));
+    CKR(h->dir_nodes.upload(p->dir_nodes, p->n_dir_nodes, st));
+    CKR(h->el_pos.upload(p->el_pos, (size_t)nE * 3, st)); CKR(h->sing_node.upload(p->sing_node, nE, st));
+    CKR(h->sing_val.upload(p->sing_val, (size_t)nK * nE, st));
+    CKR(h->pick_ptr.upload(p->pick_ptr, (size_t)nE + 1, st));
+    CKR(h->pick_idx.upload(p->pick_idx, p->pick_ptr[nE], st)); CKR(h->pick_w.upload(p->pick_w, p->pick_ptr[nE], st));
+    CKR(h->src_cell_ptr.upload(p->src_cell_ptr, (size_t)nE + 1, st)); CKR(h->src_cells.upload(p->src_cells, p->src_cell_ptr[nE], st));
+    h->pro_nf = p->pro_nf; h->pro_level_ptr.assign(p->pro_level_ptr, p->pro_level_ptr + p->n_pro_levels + 1);
+    const size_t npro = p->n_pro_levels ? (size_t)p->pro_level_ptr[p->n_pro_levels] : 0;
+    CKR(h->pro_cells.upload(p->pro_cells, npro, st)); CKR(h->pro_nb.upload(p->pro_nb, npro * p->pro_nf, st));
+    CKR(h->pro_w.upload(p->pro_w, npro * p->pro_nf, st));
+    h->n_jac_cells = p->n_jac_cells;
+    CKR(h->jac_cells.upload(p->jac_cells, p->n_jac_cells, st)); CKR(h->jac_col_ptr.upload(p->jac_col_ptr, (size_t)h->M + 1, st));
+    CKR(h->abmn.upload(p->abmn, (size_t)h->D * 4, st)); CKR(h->kfac.upload(p->k_fac, h->D, st));
+    h->h_abmn.assign(p->abmn, p->abmn + (size_t)h->D * 4); h->h_kfac.assign(p->k_fac, p->k_fac + h->D);
+    for (int d = 0; d < h->D * 4; d++) if (h->h_abmn[d] >= nE || h->h_abmn[d] < -1) PGB_FAIL("Collect matrix too small: electrode index out of range in the data (datamap.cpp:184-194)");
+
+    // state
+    const size_t blk = (size_t)N * h->ld;
+    CKR(h->model.alloc(std::max(h->M, C))); CKR(h->rho.alloc(C)); CKR(h->rho_src.alloc(nE));
+    CKR(h->vals.alloc(h->nnz * nK)); CKR(h->dinv.alloc((size_t)N * nK));
+    CKR(h->B.alloc(blk)); CKR(h->X.alloc(blk)); CKR(h->R.alloc(blk)); CKR(h->P.alloc(blk)); CKR(h->AP.alloc(blk)); CKR(h->U.alloc(blk));
+    CK(cudaMemsetAsync(h->U.p, 0, blk * sizeof(double), st));
+    CK(cudaMemsetAsync(h->P.p, 0, blk * sizeof(double), st)); CK(cudaMemsetAsync(h->AP.p, 0, blk * sizeof(double), st));
+    CKR(h->scal.alloc(7 * h->ld)); CKR(h->pM.alloc((size_t)nE * nE)); CKR(h->resp.alloc(h->D)); CKR(h->resp_rez.alloc(h->D)); CKR(h->rhoa.alloc(h->D));
+    CKR(h->flags.alloc(4)); CKR(h->xin.alloc(std::max(h->M, h->D))); CKR(h->yout.alloc(std::max(h->M, h->D)));
+    for (int i = 0; i <= PH_COUNT; i++) CK(cudaEventCreate(&h->ev[i]));
+    CK(cudaEventCreate(&h->jev[0])); CK(cudaEventCreate(&h->jev[1]));
+    h->ev_ok = true;
+    // geometry-only device work: primary potentials and the rho = 1 matrices
+    CKR(h->prim.alloc(blk));
+    CK(cudaMemsetAsync(h->prim.p, 0, blk * sizeof(double), st));
+    {
+        dim3 b(32, 8), g(cdiv(N, 8), cdiv(h->nS, 32));
+        k_primary<<<g, b, 0, st>>>(h->pos.p, N, h->el_pos.p, nE, h->sing_node.p, h->sing_val.p, h->kvals.p, nK, h->surface_z,
+                                  h->fullspace, h->prim.p, h->ld); LAUNCH(h);
+        CK(cudaGetLastError());
+    }
+    if (h->sr) { CKR(h->vals1.alloc(h->nnz * nK)); CKR(assemble(h, nullptr, h->vals1.p)); }
+    CKR(build_jac_plan(h));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int pgb200_ert_destroy(pgb200_ert *h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (h->ev_ok) { for (int i = 0; i <= PH_COUNT; i++) cudaEventDestroy(h->ev[i]); cudaEventDestroy(h->jev[0]); cudaEventDestroy(h->jev[1]); }
+    for (auto e : h->pev) cudaEventDestroy(e);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    delete h;
+    return 0;
+}
+
+int pgb200_ert_set_stream(pgb200_ert *h, void *stream) { if (!h) PGB_FAIL("null handle"); h->st = (cudaStream_t)stream; return 0; }
+
+int pgb200_ert_set_solver(pgb200_ert *h, double rel_tol, int max_iter, int check_every) {
+    if (!h) PGB_FAIL("null handle");
+    if (!(rel_tol > 0.0) || max_iter <= 0 || check_every <= 0) PGB_FAIL("invalid solver parameters");
+    h->tol = rel_tol; h->max_iter = max_iter; h->check_every = check_every;
+    return 0;
+}
+
+int pgb200_ert_set_shard(pgb200_ert *h, int src_begin, int src_end, int row_begin, int row_end) {
+    if (!h) PGB_FAIL("null handle");
+    if (src_begin < 0 || src_end > h->nS || src_begin > src_end || row_begin < 0 || row_end > h->D || row_begin > row_end) PGB_FAIL("invalid shard");
+    CK(cudaSetDevice(h->device));
+    h->c0 = src_begin; h->c1 = src_end; h->pots_valid = false;
+    if (row_begin != h->row0 || row_end != h->row1) { h->row0 = row_begin; h->row1 = row_end; CKR(build_jac_plan(h)); }
+    return 0;
+}
+
+int pgb200_ert_set_kfac(pgb200_ert *h, const double *k) {
+    if (!h || !k) PGB_FAIL("null argument");
+    CK(cudaSetDevice(h->device));
+    h->h_kfac.assign(k, k + h->D);
+    CK(cudaMemcpyAsync(h->kfac.p, k, sizeof(double) * h->D, cudaMemcpyHostToDevice, h->st));
+    CKR(build_jac_plan(h));
+    return 0;
+}
+
+int pgb200_ert_clear_potentials(pgb200_ert *h) { if (!h) PGB_FAIL("null handle"); h->pots_valid = false; return 0; }
+int pgb200_ert_mark_potentials_valid(pgb200_ert *h) { if (!h) PGB_FAIL("null handle"); h->pots_valid = true; return 0; }
+
+// ---- forward --------------------------------------------------------------------------
+static int response_common(pgb200_ert *h, int n_in, double *rhoa_dev) {
+    phase_begin(h, PH_MAP);
+    CKR(map_model(h, h->model.p, n_in));
+    CKR(forward_solve(h));
+    CKR(pickup(h));
+    CKR(finish_response(h, rhoa_dev));
+    return 0;
+}
+
+int pgb200_ert_response_dev(pgb200_ert *h, const double *model_dev, int n_in, double *rhoa_dev) {
+    if (!h || !model_dev || !rhoa_dev) PGB_FAIL("null argument");
+    CK(cudaSetDevice(h->device));
+    if (n_in != h->M && n_in != h->C) PGB_FAIL("model length must equal the number of model cells (max marker + 1) or the cell count");
+    CK(cudaMemcpyAsync(h->model.p, model_dev, sizeof(double) * n_in, cudaMemcpyDeviceToDevice, h->st));
+    h->model_len = n_in;
+    CKR(response_common(h, n_in, rhoa_dev));
+    CKR(finish_timing(h));
+    return 0;
+}
+
+int pgb200_ert_response(pgb200_ert *h, const double *model_host, int n_in, double *rhoa_host) {
+    if (!h || !model_host || !rhoa_host) PGB_FAIL("null argument");
+    CK(cudaSetDevice(h->device));
+    if (n_in != h->M && n_in != h->C) PGB_FAIL("model length must equal the number of model cells (max marker + 1) or the cell count");
+    h->h_model.assign(model_host, model_host + n_in);
+    CK(cudaMemcpyAsync(h->model.p, model_host, sizeof(double) * n_in, cudaMemcpyHostToDevice, h->st));
+    h->model_len = n_in;
+    CKR(response_common(h, n_in, h->rhoa.p));
+    CK(cudaMemcpyAsync(rhoa_host, h->rhoa.p, sizeof(double) * h->D, cudaMemcpyDeviceToHost, h->st));
+    CKR(finish_timing(h));
+    return 0;
+}
+
+// multi-GPU staging: solve this shard's sources and leave the partial electrode matrix in HBM
+int pgb200_ert_forward_dev(pgb200_ert *h, const double *model_dev, int n_in) {
+    if (!h || !model_dev) PGB_FAIL("null argument");
+    CK(cudaSetDevice(h->device));
+    if (n_in != h->M && n_in != h->C) PGB_FAIL("model length must equal the number of model cells (max marker + 1) or the cell count");
+    CK(cudaMemcpyAsync(h->model.p, model_dev, sizeof(double) * n_in, cudaMemcpyDeviceToDevice, h->st));
+    h->model_len = n_in;
+    phase_begin(h, PH_MAP);
+    CKR(map_model(h, h->model.p, n_in));
+    CKR(forward_solve(h));
+    CKR(pickup(h));
+    CKR(finish_timing(h));
+    return 0;
+}
+int pgb200_ert_pm_info(pgb200_ert *h, void **dev_ptr, int *n) { if (!h) PGB_FAIL("null handle"); *dev_ptr = h->pM.p; *n = h->nE * h->nE; return 0; }
+int pgb200_ert_finish_response_dev(pgb200_ert *h, double *rhoa_dev) {
+    if (!h || !rhoa_dev) PGB_FAIL("null argument");
+    CK(cudaSetDevice(h->device));
+    CKR(finish_response(h, rhoa_dev));
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+// contiguous [N x (c1-c0)] copy of this shard's potential columns and its inverse (NCCL all-gather)
+__global__ void k_pack_cols(const double *__restrict__ U, size_t ld, int N, int c0, int c1, double *__restrict__ buf, int unpack, double *__restrict__ Uw) {
+    const int w = c1 - c0;
+    const int c = blockIdx.y * blockDim.x + threadIdx.x, row = blockIdx.x * blockDim.y + threadIdx.y;
+    if (c >= w || row >= N) return;
+    if (unpack) Uw[(size_t)row * ld + c0 + c] = buf[(size_t)row * w + c];
+    else buf[(size_t)row * w + c] = U[(size_t)row * ld + c0 + c];
+}
+int pgb200_ert_pack_potentials(pgb200_ert *h, int c0, int c1, double *buf_dev, int unpack) {
+    if (!h || !buf_dev) PGB_FAIL("null argument");
+    if (c0 < 0 || c1 > h->nS || c0 >= c1) return 0;
+    CK(cudaSetDevice(h->device));
+    dim3 b(32, 8), g(cdiv(h->N, 8), cdiv(c1 - c0, 32));
+    k_pack_cols<<<g, b, 0, h->st>>>(h->U.p, h->ld, h->N, c0, c1, buf_dev, unpack, h->U.p); LAUNCH(h);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---- Jacobian -------------------------------------------------------------------------
+static int create_jacobian_common(pgb200_ert *h, int n_in) {
+    const double *rho_col = (n_in == h->M) ? h->model.p : nullptr;      // scaling only if len(model) == J.cols (:1377)
+    if (!h->pots_valid) {
+        // prepareJacobianT_ (:1246-1309): no potentials yet -> solve, analytically for a homogeneous model
+        const bool hetero = host_stddev(h->h_model) > 1e-12 * 1e5;
+        phase_begin(h, PH_MAP);
+        CKR(map_model(h, h->model.p, n_in));
+        if (!hetero) { CKR(analytic_pots(h, h->h_model[0])); }
+        else { CKR(forward_solve(h)); }
+    }
+    CKR(jacobian(h, rho_col));
+    return 0;
+}
+
+int pgb200_ert_create_jacobian(pgb200_ert *h, const double *model_host, int n_in) {
+    if (!h || !model_host) PGB_FAIL("null argument");
+    CK(cudaSetDevice(h->device));
+    if (n_in != h->M && n_in != h->C) PGB_FAIL("model length must equal the number of model cells (max marker + 1) or the cell count");
+    h->h_model.assign(model_host, model_host + n_in);
+    CK(cudaMemcpyAsync(h->model.p, model_host, sizeof(double) * n_in, cudaMemcpyHostToDevice, h->st));
+    h->model_len = n_in;
+    CKR(create_jacobian_common(h, n_in));
+    CKR(finish_timing(h));
+    return 0;
+}
+
+int pgb200_ert_create_jacobian_dev(pgb200_ert *h, const double *model_dev, int n_in) {
+    if (!h || !model_dev) PGB_FAIL("null argument");
+    CK(cudaSetDevice(h->device));
+    if (n_in != h->M && n_in != h->C) PGB_FAIL("model length must equal the number of model cells (max marker + 1) or the cell count");
+    CK(cudaMemcpyAsync(h->model.p, model_dev, sizeof(double) * n_in, cudaMemcpyDeviceToDevice, h->st));
+    h->model_len = n_in;
+    if (!h->pots_valid) {
+        h->h_model.resize(n_in);
+        CK(cudaMemcpyAsync(h->h_model.data(), model_dev, sizeof(double) * n_in, cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+    }
+    CKR(create_jacobian_common(h, n_in));
+    CKR(finish_timing(h));
+    return 0;
+}
+
+int pgb200_ert_jacobian_info(pgb200_ert *h, void **dev_ptr, int *rows, int *cols, long long *ld) {
+    if (!h) PGB_FAIL("null handle");
+    if (!h->jac_valid) PGB_FAIL("no Jacobian: call createJacobian first");
+    if (dev_ptr) *dev_ptr = h->Jt.p;
+    if (rows) *rows = h->j_rows;
+    if (cols) *cols = h->M;
+    if (ld) *ld = (long long)h->ldJ;
+    return 0;
+}
+
+int pgb200_ert_jacobian_copy(pgb200_ert *h, double *j_host) {
+    if (!h || !j_host) PGB_FAIL("null argument");
+    if (!h->jac_valid) PGB_FAIL("no Jacobian: call createJacobian first");
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->j_rows * h->M;
+    if (n == 0) return 0;
+    if (h->tmp.n < n) CKR(h->tmp.alloc(n));
+    dim3 b(32, 8), g(cdiv(h->j_rows, 32), cdiv(h->M, 32));
+    k_jac_to_rowmajor<<<g, b, 0, h->st>>>(h->Jt.p, h->ldJ, h->j_rows, h->M, h->tmp.p); LAUNCH(h);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(j_host, h->tmp.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int pgb200_ert_jacobian_mult(pgb200_ert *h, const double *x_host, double *y_host) {
+    if (!h || !x_host || !y_host) PGB_FAIL("null argument");
+    if (!h->jac_valid) PGB_FAIL("no Jacobian: call createJacobian first");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->xin.p, x_host, sizeof(double) * h->M, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemsetAsync(h->yout.p, 0, sizeof(double) * std::max(1, h->j_rows), h->st));
+    if (h->j_rows) { k_jac_mult<<<dim3(cdiv(h->j_rows, 128), cdiv(h->M, 256)), 128, 0, h->st>>>(h->Jt.p, h->ldJ, h->j_rows, h->M, h->xin.p, h->yout.p); LAUNCH(h); }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(y_host, h->yout.p, sizeof(double) * h->j_rows, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int pgb200_ert_jacobian_tmult(pgb200_ert *h, const double *x_host, double *y_host) {
+    if (!h || !x_host || !y_host) PGB_FAIL("null argument");
+    if (!h->jac_valid) PGB_FAIL("no Jacobian: call createJacobian first");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->xin.p, x_host, sizeof(double) * std::max(1, h->j_rows), cudaMemcpyHostToDevice, h->st));
+    k_jac_tmult<<<cdiv(h->M, 8), 256, 0, h->st>>>(h->Jt.p, h->ldJ, h->j_rows, h->M, h->xin.p, h->yout.p); LAUNCH(h);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(y_host, h->yout.p, sizeof(double) * h->M, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+int pgb200_ert_potentials_info(pgb200_ert *h, void **dev_ptr, int *n_nodes, int *n_src, long long *ld) {
+    if (!h) PGB_FAIL("null handle");
+    if (dev_ptr) *dev_ptr = h->U.p;
+    if (n_nodes) *n_nodes = h->N;
+    if (n_src) *n_src = h->nS;
+    if (ld) *ld = (long long)h->ld;
+    return 0;
+}
+
+// ---- introspection ----------------------------------------------------------------------
+long long pgb200_ert_get(pgb200_ert *h, const char *what, double *out, long long cap) {
+    if (!h || !what) { g_err = "null argument"; return -1; }
+    if (cudaSetDevice(h->device) != cudaSuccess) { g_err = "cudaSetDevice failed"; return -1; }
+    const std::string w(what);
+    const double *src = nullptr; long long n = 0; bool transposed = false;
+    if (w == "vals") { src = h->vals.p; n = (long long)h->nnz * h->nK; }
+    else if (w == "vals1") { src = h->vals1.p; n = h->vals1.p ? (long long)h->nnz * h->nK : 0; }
+    else if (w == "rho") { src = h->rho.p; n = h->C; }
+    else if (w == "rho_src") { src = h->rho_src.p; n = h->nE; }
+    else if (w == "pm") { src = h->pM.p; n = (long long)h->nE * h->nE; }
+    else if (w == "resp") { src = h->resp.p; n = h->D; }
+    else if (w == "resp_rez") { src = h->resp_rez.p; n = h->D; }
+    else if (w == "rel_res") { n = h->nS; }
+    else if (w == "prim" || w == "pots" || w == "rhs" || w == "sec") { n = (long long)h->nS * h->N; transposed = true; }
+    else if (w == "solutions") { n = (long long)h->nE * h->N; }
+    else { g_err = "unknown quantity: " + w; return -1; }
+    if (!out) return n;
+    if (cap < n) { g_err = "output buffer too small"; return -1; }
+    if (n == 0) return 0;
+    cudaError_t e = cudaSuccess;
+    if (w == "rel_res") {
+        std::vector<double> rr(h->ld), bb(h->ld);
+        // the buffer holding the last residual norms alternates; take the larger (the other one is zeroed)
+        std::vector<double> ra(h->ld), rb(h->ld);
+        cudaStreamSynchronize(h->st);
+        cudaMemcpy(ra.data(), h->scal.p + 4 * h->ld, sizeof(double) * h->ld, cudaMemcpyDeviceToHost);
+        cudaMemcpy(rb.data(), h->scal.p + 5 * h->ld, sizeof(double) * h->ld, cudaMemcpyDeviceToHost);
+        e = cudaMemcpy(bb.data(), h->scal.p + 6 * h->ld, sizeof(double) * h->ld, cudaMemcpyDeviceToHost);
+        for (int c = 0; c < h->nS; c++) { const double r = std::max(ra[c], rb[c]); out[c] = bb[c] > 0 ? std::sqrt(r / bb[c]) : 0.0; }
+    } else if (transposed || w == "solutions") {
+        if (h->tmp.n < (size_t)n) { if (h->tmp.alloc((size_t)n)) return -1; }
+        if (w == "solutions") {
+            dim3 b(32, 8), g(cdiv(h->N, 8), cdiv(h->nE, 32));
+            k_ksum<<<g, b, 0, h->st>>>(h->U.p, h->ld, h->kw.p, h->nK, h->nE, h->N, h->tmp.p);
+        } else {
+            const double *Usrc = w == "prim" ? h->prim.p : w == "pots" ? h->U.p : w == "rhs" ? h->B.p : h->X.p;
+            dim3 b(32, 8), g(cdiv(h->nS, 32), cdiv(h->N, 32));
+            k_transpose_out<<<g, b, 0, h->st>>>(Usrc, h->ld, h->N, h->nS, h->tmp.p);
+        }
+        cudaStreamSynchronize(h->st);
+        e = cudaMemcpy(out, h->tmp.p, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    } else {
+        cudaStreamSynchronize(h->st);
+        e = cudaMemcpy(out, src, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    }
+    if (e != cudaSuccess) { g_err = std::string("copy failed: ") + cudaGetErrorString(e); return -1; }
+    return n;
+}
+
+int pgb200_ert_stats(pgb200_ert *h, double *s, int n) {
+    if (!h || !s) PGB_FAIL("null argument");
+    double v[12] = {(double)h->last_iters, h->last_relres, (double)h->launches, h->ph_ms[PH_MAP], h->ph_ms[PH_ASM], h->ph_ms[PH_RHS],
+                    h->ph_ms[PH_SOLVE], h->ph_ms[PH_EPI], h->ph_ms[PH_JAC], (double)h->spmm_timed, h->spmm_ms, h->jac_ms};
+    for (int i = 0; i < n && i < 12; i++) s[i] = v[i];
+    return 0;
+}
+int pgb200_ert_reset_stats(pgb200_ert *h) {
+    if (!h) PGB_FAIL("null handle");
+    h->launches = 0; h->spmm_ms = 0.0; h->spmm_timed = 0; h->jac_ms = 0.0; h->n_pev = 0;
+    return 0;
+}
+int pgb200_ert_set_profile(pgb200_ert *h, int on) {
+    if (!h) PGB_FAIL("null handle");
+    CK(cudaSetDevice(h->device));
+    h->prof = on;
+    if (on && h->pev.empty()) { h->pev.resize(4096); for (auto &e : h->pev) CK(cudaEventCreate(&e)); }
+    return 0;
+}
+
+int pgb200_spmm(const int *rowptr, const int *colidx, const double *vals, long long nnz, const double *X, double *Y,
+                int n_rows, int n_elec, int n_k, long long ld, void *stream) {
+    const int ncols = n_elec * n_k;
+    dim3 block(SPMM_TX, SPMM_TY), grid(cdiv(n_rows, SPMM_ROWS), cdiv(ncols, SPMM_TX * 4));
+    k_spmm<4, 0, false><<<grid, block, 0, (cudaStream_t)stream>>>(rowptr, colidx, vals, nullptr, nullptr, (size_t)nnz, X, Y, n_rows,
+                                                                  n_elec, 0, ncols, (size_t)ld, nullptr);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+} // extern "C"

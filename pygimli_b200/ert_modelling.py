@@ -1,0 +1,362 @@
+"""Host-side mirror of the reference's ERT forward operator for the B200 path.
+
+``ERTModellingB200`` has the call surface of ``pygimli.physics.ert.ERTModelling``
+(pygimli/physics/ert/ertModelling.py:73-246) for the forward + Jacobian path:
+
+    fop = ERTModellingB200(sr=True)
+    fop.setMesh(mesh)          # MeshArrays or pg.Mesh (when pygimli is importable)
+    fop.setData(scheme)        # SchemeArrays or pg.DataContainerERT      (fop.data = scheme works too)
+    rhoa = fop.response(model)
+    fop.createJacobian(model)
+    J = fop.jacobian()         # rows() cols() mult(x) transMult(y)  -- J stays in HBM
+
+``CoreB200`` is the replacement for ``pg.core.DCSRMultiElectrodeModelling`` behind
+``ERTModelling._core`` (same method names: setMesh, setData, response, createJacobian, jacobian,
+setkValues, setWeights, kValues, weights, calcGeometricFactor, solution, mapERTModel,
+setThreadCount, setVerbose).  Everything numeric runs in libpgb200_ert.so (CUDA, sm_100a);
+there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import numpy as np
+
+from . import _capi
+from .host_setup import build_plan, TOLERANCE
+from .mesh import MeshArrays, from_pg_mesh
+from .scheme import SchemeArrays, geometric_factors
+
+
+def _as_mesh(mesh) -> MeshArrays:
+    if isinstance(mesh, MeshArrays):
+        return mesh
+    if hasattr(mesh, "cellCount") and hasattr(mesh, "positions"):
+        return from_pg_mesh(mesh)
+    raise TypeError("mesh must be a pygimli_b200.MeshArrays or a pg.Mesh")
+
+
+def _as_scheme(data) -> SchemeArrays:
+    if isinstance(data, SchemeArrays):
+        return data
+    if hasattr(data, "sensorPositions") or hasattr(data, "sensors"):
+        sens = np.asarray(data.sensors() if hasattr(data, "sensors") else data.sensorPositions(), float)
+        tok = {t: np.asarray(data[t]).astype(np.int32) for t in "abmn"}
+        k = np.asarray(data["k"], float) if data.haveData("k") else None
+        return SchemeArrays(sens, tok["a"], tok["b"], tok["m"], tok["n"], k)
+    raise TypeError("data must be a pygimli_b200.SchemeArrays or a pg.DataContainerERT")
+
+
+class JacobianB200:
+    """The Jacobian as the inversion sees it (``ModellingBase::jacobian()``,
+    core/src/modellingbase.h:118-121): rows(), cols(), mult(x), transMult(y).
+    The matrix lives in HBM (column-major); ``numpy()`` copies it out row-major."""
+
+    def __init__(self, core: "CoreB200"):
+        self._core = core
+
+    def rows(self) -> int:
+        return self._core._jac_shape()[0]
+
+    def cols(self) -> int:
+        return self._core._jac_shape()[1]
+
+    @property
+    def shape(self):
+        return self._core._jac_shape()[:2]
+
+    def mult(self, x):
+        x = np.ascontiguousarray(x, np.float64)
+        if x.size != self.cols():
+            raise ValueError("mult: vector length must equal cols()")
+        y = np.zeros(self.rows())
+        _capi.check(_capi.lib().pgb200_ert_jacobian_mult(self._core._h, x.ctypes.data, y.ctypes.data))
+        return y
+
+    def transMult(self, y):
+        y = np.ascontiguousarray(y, np.float64)
+        if y.size != self.rows():
+            raise ValueError("transMult: vector length must equal rows()")
+        x = np.zeros(self.cols())
+        _capi.check(_capi.lib().pgb200_ert_jacobian_tmult(self._core._h, y.ctypes.data, x.ctypes.data))
+        return x
+
+    def numpy(self) -> np.ndarray:
+        r, c = self.shape
+        out = np.zeros((r, c))
+        _capi.check(_capi.lib().pgb200_ert_jacobian_copy(self._core._h, out.ctypes.data))
+        return out
+
+    __array__ = lambda self, dtype=None, copy=None: self.numpy()  # noqa: E731
+
+    def torch(self):
+        """zero-copy torch view of logical shape (rows, cols) onto the column-major HBM buffer"""
+        import torch
+        ptr, rows, cols, ld = self._core._jac_info()
+
+        class _Iface:
+            __cuda_array_interface__ = dict(shape=(cols, ld), typestr="<f8", data=(ptr, False), version=3, strides=None)
+        t = torch.as_tensor(_Iface(), device=f"cuda:{self._core.device}")
+        return t[:, :rows].t()
+
+
+class CoreB200:
+    """Replacement for ``pg.core.DCSRMultiElectrodeModelling`` (sr=True) /
+    ``DCMultiElectrodeModelling`` (sr=False) on one B200."""
+
+    def __init__(self, sr: bool = True, verbose: bool = False, device: int = 0):
+        self.sr = bool(sr)
+        self.verbose = bool(verbose)
+        self.device = int(device)
+        self._mesh = None
+        self._scheme = None
+        self._plan = None
+        self._h = None
+        self._keep = None
+        self._k = None
+        self._w = None
+        self._tol, self._maxit, self._check = 1e-12, 50000, 25
+        self._stream = None
+        self._shard = None
+        self._J = JacobianB200(self)
+
+    # ---- reference-style setters -----------------------------------------------------
+    def setVerbose(self, v):
+        self.verbose = bool(v)
+
+    def setThreadCount(self, n):   # CPU threads of the reference's sensitivity loop; nothing to do on the GPU
+        pass
+
+    def setMesh(self, mesh, ignoreRegionManager=True):
+        self._mesh = _as_mesh(mesh)
+        self._invalidate()
+
+    def setData(self, data):
+        self._scheme = _as_scheme(data)
+        self._invalidate()
+
+    def setkValues(self, k):
+        self._k = np.asarray(k, float).copy()
+        self._invalidate()
+
+    def setWeights(self, w):
+        self._w = np.asarray(w, float).copy()
+        self._invalidate()
+
+    def kValues(self):
+        self._ensure_plan()
+        return self._plan.k.copy()
+
+    def weights(self):
+        self._ensure_plan()
+        return self._plan.w.copy()
+
+    def setSolverTolerance(self, rel_tol=1e-12, max_iter=50000, check_every=25):
+        """block-PCG controls (replaces the reference's direct CHOLMOD solve; stated tolerance)"""
+        self._tol, self._maxit, self._check = float(rel_tol), int(max_iter), int(check_every)
+        if self._h:
+            _capi.check(_capi.lib().pgb200_ert_set_solver(self._h, self._tol, self._maxit, self._check))
+
+    def setStream(self, stream_ptr):
+        """CUDA stream handle (int, e.g. torch.cuda.current_stream().cuda_stream)"""
+        self._stream = int(stream_ptr) if stream_ptr else None
+        if self._h:
+            _capi.check(_capi.lib().pgb200_ert_set_stream(self._h, C.c_void_p(self._stream or 0)))
+
+    def setShard(self, src_begin, src_end, row_begin, row_end):
+        self._shard = (int(src_begin), int(src_end), int(row_begin), int(row_end))
+        if self._h:
+            _capi.check(_capi.lib().pgb200_ert_set_shard(self._h, *self._shard))
+
+    def calcGeometricFactor(self, data=None, nModel=0):
+        """analytic geometric factors (dcfemmodelling.cpp:1527-1533; numeric ones need topography support)"""
+        sch = self._scheme if data is None else _as_scheme(data)
+        return geometric_factors(sch, self._mesh.dim if self._mesh is not None else 3)
+
+    # ---- life cycle -------------------------------------------------------------------
+    def _invalidate(self):
+        if self._h:
+            _capi.lib().pgb200_ert_destroy(self._h)
+        self._h = None
+        self._plan = None
+        self._keep = None
+
+    def close(self):
+        self._invalidate()
+
+    def __del__(self):
+        try:
+            self._invalidate()
+        except Exception:
+            pass
+
+    def _ensure_plan(self):
+        if self._plan is None:
+            if self._mesh is None:
+                raise RuntimeError("Found no mesh, so cannot calculate a response.")
+            if self._scheme is None:
+                raise RuntimeError("no response without data container")
+            sch = self._scheme
+            if sch.k is None or np.min(np.abs(sch.k)) < TOLERANCE:
+                # response() computes missing k-factors analytically for flat earth (:1088-1093)
+                sch.k = geometric_factors(sch, self._mesh.dim)
+            self._plan = build_plan(self._mesh, sch, self._k, self._w, color_fn=_capi.color_cells)
+        return self._plan
+
+    def _ensure_handle(self):
+        if self._h is None:
+            P = self._ensure_plan()
+            s, keep = _capi.make_plan_struct(P, self.sr)
+            h = C.c_void_p()
+            rc = _capi.lib().pgb200_ert_create(C.byref(s), self.device, C.byref(h))
+            if rc != 0:
+                msg = _capi.last_error()
+                if h:
+                    _capi.lib().pgb200_ert_destroy(h)
+                raise _capi.PGB200Error(msg)
+            self._h, self._keep = h, keep
+            _capi.check(_capi.lib().pgb200_ert_set_solver(h, self._tol, self._maxit, self._check))
+            if self._stream:
+                _capi.check(_capi.lib().pgb200_ert_set_stream(h, C.c_void_p(self._stream)))
+            if self._shard:
+                _capi.check(_capi.lib().pgb200_ert_set_shard(h, *self._shard))
+        return self._h
+
+    # ---- the path ---------------------------------------------------------------------
+    def response(self, model):
+        h = self._ensure_handle()
+        m = np.ascontiguousarray(model, np.float64)
+        out = np.zeros(self._scheme.size)
+        _capi.check(_capi.lib().pgb200_ert_response(h, m.ctypes.data, int(m.size), out.ctypes.data))
+        return out
+
+    def createJacobian(self, model):
+        h = self._ensure_handle()
+        m = np.ascontiguousarray(model, np.float64)
+        _capi.check(_capi.lib().pgb200_ert_create_jacobian(h, m.ctypes.data, int(m.size)))
+        return None
+
+    def response_dev(self, model_ptr: int, n: int, out_ptr: int):
+        _capi.check(_capi.lib().pgb200_ert_response_dev(self._ensure_handle(), C.c_void_p(model_ptr), int(n), C.c_void_p(out_ptr)))
+
+    def createJacobian_dev(self, model_ptr: int, n: int):
+        _capi.check(_capi.lib().pgb200_ert_create_jacobian_dev(self._ensure_handle(), C.c_void_p(model_ptr), int(n)))
+
+    def jacobian(self):
+        return self._J
+
+    def clearPotentials(self):
+        if self._h:
+            _capi.check(_capi.lib().pgb200_ert_clear_potentials(self._h))
+
+    def solution(self):
+        """k-summed potentials, one row per electrode (ModellingBase::solution())"""
+        P = self._ensure_plan()
+        return self.get("solutions").reshape(P.nE, P.N)
+
+    def mapERTModel(self, model, background=-9e99):
+        raise NotImplementedError("use get('rho') after response(); the mapping runs on the GPU")
+
+    # ---- introspection ------------------------------------------------------------------
+    def get(self, what: str) -> np.ndarray:
+        h = self._ensure_handle()
+        n = _capi.lib().pgb200_ert_get(h, what.encode(), None, 0)
+        if n < 0:
+            raise _capi.PGB200Error(_capi.last_error())
+        out = np.zeros(int(n))
+        if n:
+            r = _capi.lib().pgb200_ert_get(h, what.encode(), out.ctypes.data, int(n))
+            if r < 0:
+                raise _capi.PGB200Error(_capi.last_error())
+        return out
+
+    def stats(self) -> dict:
+        s = np.zeros(12)
+        _capi.check(_capi.lib().pgb200_ert_stats(self._ensure_handle(), s.ctypes.data, 12))
+        keys = ["pcg_iterations", "max_rel_residual", "launches", "ms_map", "ms_assemble", "ms_rhs", "ms_solve",
+                "ms_epilogue", "ms_jacobian", "spmm_timed", "spmm_ms_total", "jacobian_kernel_ms"]
+        return dict(zip(keys, s.tolist()))
+
+    def resetStats(self):
+        _capi.check(_capi.lib().pgb200_ert_reset_stats(self._ensure_handle()))
+
+    def setProfile(self, on=True):
+        _capi.check(_capi.lib().pgb200_ert_set_profile(self._ensure_handle(), 1 if on else 0))
+
+    def _jac_info(self):
+        ptr, rows, cols, ld = C.c_void_p(), C.c_int(), C.c_int(), C.c_longlong()
+        _capi.check(_capi.lib().pgb200_ert_jacobian_info(self._ensure_handle(), C.byref(ptr), C.byref(rows), C.byref(cols), C.byref(ld)))
+        return int(ptr.value or 0), rows.value, cols.value, ld.value
+
+    def _jac_shape(self):
+        _, r, c, ld = self._jac_info()
+        return r, c, ld
+
+    def _pots_info(self):
+        ptr, n, s, ld = C.c_void_p(), C.c_int(), C.c_int(), C.c_longlong()
+        _capi.check(_capi.lib().pgb200_ert_potentials_info(self._ensure_handle(), C.byref(ptr), C.byref(n), C.byref(s), C.byref(ld)))
+        return int(ptr.value or 0), n.value, s.value, ld.value
+
+
+class ERTModellingB200:
+    """Drop-in for ``pg.physics.ert.ERTModelling`` on the forward + Jacobian path."""
+
+    def __init__(self, sr=True, verbose=False, device=0):
+        self._core = CoreB200(sr=sr, verbose=verbose, device=device)
+        self._data = None
+        # forwarded attributes, as in ertModelling.py:115-120
+        self.solution = self._core.solution
+        self.calcGeometricFactor = self._core.calcGeometricFactor
+        self.mapERTModel = self._core.mapERTModel
+
+    def complex(self):
+        return False
+
+    def setComplex(self, c):
+        if c:
+            raise NotImplementedError("complex resistivity is outside the B200 path (SURVEY §8(f) item 3)")
+
+    def setVerbose(self, v):
+        self._core.setVerbose(v)
+
+    # data / mesh ------------------------------------------------------------------------
+    @property
+    def data(self):
+        return self._data
+
+    @data.setter
+    def data(self, d):
+        self.setData(d)
+
+    def setData(self, data):
+        self._data = data
+        self.setDataPost(data)
+
+    def setDataPost(self, data):
+        self._core.setData(data)
+
+    def setMesh(self, mesh, ignoreRegionManager=False):
+        self._mesh = mesh
+        self.setMeshPost(mesh)
+
+    def setMeshPost(self, mesh):
+        self._core.setMesh(mesh, ignoreRegionManager=True)
+
+    def mesh(self):
+        return self._mesh
+
+    @property
+    def parameterCount(self):
+        return int(self._core._ensure_plan().M)
+
+    def createStartModel(self, dataVals):
+        return np.full(self.parameterCount, float(np.median(np.asarray(dataVals, float))))
+
+    # the path ---------------------------------------------------------------------------
+    def response(self, mod):
+        return self._core.response(mod)
+
+    def createJacobian(self, mod):
+        return self._core.createJacobian(mod)
+
+    def jacobian(self):
+        return self._core.jacobian()

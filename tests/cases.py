@@ -1,0 +1,49 @@
+"""Seeded small test cases shared by the parity tests, smoke() and the golden-vector generator.
+Sizes are chosen so that the compiled reference finishes each case in seconds."""
+import numpy as np
+
+from pygimli_b200.mesh import (graded_axis, grid_mesh_2d, grid_mesh_3d, create_p2, create_h2, mark_electrode_nodes)
+from pygimli_b200.scheme import create_dd, create_slm, create_grid_dd, geometric_factors
+
+CASES = ("2d_p1", "2d_p2", "3d_p1", "3d_p2", "2d_p1_h2", "3d_p1_cellmodel")
+
+
+def _model(M, seed=1234):
+    rng = np.random.default_rng(seed)
+    return 10.0 ** (2.0 + 0.5 * rng.standard_normal(M))
+
+
+def make_case(name: str):
+    """-> (MeshArrays, SchemeArrays with analytic k, model vector)"""
+    if name.startswith("2d"):
+        ne, sp = 11, 1.0
+        xs = graded_axis(0.0, (ne - 1) * sp, sp / 2, 1.4, 60.0)
+        ys = -graded_axis(0.0, 4.0, sp / 2, 1.4, 60.0, both=False)
+        mesh = grid_mesh_2d(xs, ys, para_box=(-2.0, (ne - 1) * sp + 2.0, -5.0))
+        sens = np.zeros((ne, 3))
+        sens[:, 0] = np.arange(ne) * sp
+        if name == "2d_p1_h2":
+            mesh = create_h2(mesh)
+        mark_electrode_nodes(mesh, sens)
+        if name == "2d_p2":
+            mesh = create_p2(mesh)
+        scheme = create_dd(sens) if name != "2d_p2" else create_slm(sens)
+        scheme.k = geometric_factors(scheme, 2)
+    else:
+        nx = 5
+        sp = 2.0
+        h = sp if name == "3d_p2" else sp / 2
+        xs = graded_axis(0.0, (nx - 1) * sp, h, 1.6, 50.0)
+        zs = -graded_axis(0.0, 4.0, h, 1.6, 50.0, both=False)
+        pb = (-2.5, (nx - 1) * sp + 2.5, -2.5, (nx - 1) * sp + 2.5, -4.5)
+        mesh = grid_mesh_3d(xs, xs, zs, para_box=pb, marker_per="cube")
+        gx, gy = np.meshgrid(np.arange(nx) * sp, np.arange(nx) * sp)
+        sens = np.stack([gx.ravel(), gy.ravel(), np.zeros(nx * nx)], 1)
+        mark_electrode_nodes(mesh, sens)
+        if name == "3d_p2":
+            mesh = create_p2(mesh)
+        scheme = create_grid_dd(nx, nx, sens)
+        scheme.k = geometric_factors(scheme, 3)
+    M = int(mesh.cell_marker.max()) + 1
+    model = _model(mesh.cell_count if name.endswith("cellmodel") else M)
+    return mesh, scheme, model
