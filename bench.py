@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- ERT forward + Jacobian seconds per iteration on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c1] [--scale S]
+    python bench.py --impl reference ...        # the reference's own CPU code (oracle/_ref)
+
+A "step" is one Gauss-Newton-style pass of the hot path on one resistivity model:
+response(model) followed by createJacobian(model) (the Jacobian reuses the potentials of the
+forward solve, dcfemmodelling.cpp:1262).  `value` is timed with the model already resident in
+HBM; `e2e` goes through the host-buffer C ABI (H2D model, D2H apparent resistivities, plus one
+J.x and one J^T.y with host vectors, which is how the inversion consumes J while it stays in HBM).
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu=0):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(name, scale):
+    from pygimli_b200.workloads import WORKLOADS, model_for
+    mesh, scheme, desc = WORKLOADS[name](scale)
+    ok = np.isfinite(scheme.k) & (np.abs(scheme.k) < 1e9)
+    if not ok.all():
+        scheme = scheme.subset(np.nonzero(ok)[0])
+    M = int(mesh.cell_marker.max()) + 1
+    return mesh, scheme, model_for(M), desc
+
+
+# ----------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU implementation (oracle/_ref = libgimli compiled from source),
+    timed on this box's host cores on a bounded sample and scaled to the full workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgimli_ref.so not built"}))
+        return
+    mesh, scheme, model, desc = build_workload(args.workload, args.scale)
+    cores = os.cpu_count() or 1
+    threads = max(1, min(8, cores - 2))          # reference default (modellingbase.cpp:77)
+    samples = []
+    info = {}
+    for step in range(args.warmup + args.steps):
+        t, info = reference_sample(ref, mesh, scheme, model, threads, args)
+        if step >= args.warmup:
+            samples.append(t)
+    val = float(np.mean(samples))
+    line = {"metric": "ert_forward_jacobian_s_per_iter", "value": val, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": val * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": args.workload + ": " + desc, "cells": mesh.cell_count, "nodes": mesh.node_count,
+                       "electrodes": scheme.sensor_count, "data": scheme.size, "model_cells": int(model.size)},
+            "cpu_baseline": {"value": val, "unit": "s", "cores": threads, "kind": "reference", "sample": info["sample"],
+                             "stages_s": info["stages"]},
+            "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def reference_sample(ref, mesh, scheme, model, threads, args):
+    """One bounded sample of the reference path, extrapolated to the whole workload:
+      (i)  pattern + assembly of S(rho) and S(1) for every wavenumber: full, unmodified reference code
+           (dcfemmodelling.cpp:2175-2192)
+      (ii) linear solves: the reference hands S to CHOLMOD, which this image does not have; the stand-in is a
+           Jacobi-PCG (1e-12) inside oracle/ref_driver.cpp run for `n_src` sources and scaled by nS / n_src
+      (iii) createSensitivityCol: unmodified reference code on `d_sub` data rows, scaled by D / d_sub
+           (cost is linear in nData x nCells)."""
+    nE, D = scheme.sensor_count, scheme.size
+    d_sub = min(D, args.ref_rows)
+    n_src = min(nE, args.ref_sources)
+    sub = scheme.subset(np.linspace(0, D - 1, d_sub).astype(int))
+    R = ref.RefERT(mesh, sub, sr=True, solver="pcg")
+    R.set_threads(threads)
+    R.set_pcg_tol(args.tol)
+    k, _ = R.kw()
+    nK = k.size
+    t0 = time.perf_counter()
+    rho = R.mapped_model(model)                   # mapERTModel incl. background prolongation (:1211)
+    t_map = time.perf_counter() - t0
+    # (i)
+    t_asm = 0.0
+    for kk in range(nK if nK <= 2 else 2):
+        _, sec = R.assemble(float(k[kk]), rho, boundary=True, want=False)
+        t_asm += 2.0 * (sec[0] + sec[1])          # S(rho) and S(1), pattern rebuilt for both (:2175, :2186)
+    t_asm *= nK / float(min(nK, 2))
+    # (ii)
+    t_solve = R.time_partial_solve(model, n_src) * (nE / float(n_src))
+    # (iii)
+    pots = np.zeros((nE * nK, mesh.node_count)) + 1.0
+    t0 = time.perf_counter()
+    R.sensitivity_only(pots, n_threads=threads, want=False)
+    t_sens = (time.perf_counter() - t0) * (D / float(d_sub))
+    R.close()
+    total = t_map + t_asm + t_solve + t_sens
+    return total, {"sample": f"assembly: {min(nK, 2)} of {nK} wavenumbers x2 matrices (full mesh); solves: {n_src} of {nE} sources x "
+                             f"{nK} k with a Jacobi-PCG stand-in for CHOLMOD; sensitivity: {d_sub} of {D} rows on {threads} threads; "
+                             "each stage scaled linearly to the full workload",
+                   "stages": {"map_model": t_map, "assembly": t_asm, "solve_substitute": t_solve, "sensitivity": t_sens}}
+
+
+# ----------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from pygimli_b200.dist import ShardedERT
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    t_setup = time.perf_counter()
+    mesh, scheme, model, desc = build_workload(args.workload, args.scale)
+    fop = ShardedERT(mesh, scheme, device=local, rank=rank, world=world, sr=True)
+    fop.set_solver(args.tol, 100000, 25)
+    stream = torch.cuda.current_stream()
+    fop.set_stream(stream.cuda_stream)
+    t_setup = time.perf_counter() - t_setup
+    D, M = scheme.size, int(model.size)
+
+    model_dev = torch.from_numpy(model).cuda()
+    rhoa_dev = torch.zeros(D, dtype=torch.float64, device="cuda")
+    model_pin = torch.from_numpy(model).pin_memory()
+    x_host = np.random.default_rng(3).standard_normal(M)
+    y_host = np.random.default_rng(4).standard_normal(D)
+
+    def step_dev():
+        fop.response_dev(model_dev, rhoa_dev)
+        fop.create_jacobian_dev(model_dev)
+
+    def step_e2e():
+        r = fop.response(model_pin.numpy())
+        fop.create_jacobian(model_pin.numpy())
+        jx = fop.jac_mult(x_host)
+        jty = fop.jac_tmult(y_host)
+        return r, jx, jty
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_dev()
+    fop.core.setProfile(True)
+    fop.core.resetStats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    st = fop.core.stats()
+    clocks = sampler.stop() if rank == 0 else None
+    fop.core.setProfile(False)
+
+    # end-to-end through the host-buffer API
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank == 0:
+        P = fop.core._plan
+        peak, peak_src = _peaks()
+        sec = ms / 1e3 / args.steps
+        # dominant kernel: the SpMM inside block-PCG.  Algorithmic bytes per launch:
+        # 12 nnz + 4 (N+1) + 16 N s  (values + column indices + row pointers; X read once, Y written once)
+        ncols = fop.n_local_sources
+        spmm_bytes = 12.0 * P.nnz * (P.nK if ncols >= P.nS else max(1, ncols // P.nE)) + 4.0 * (P.N + 1) + 16.0 * P.N * ncols
+        spmm_ms = st["spmm_ms_total"] / max(1.0, st["spmm_timed"])
+        ach = spmm_bytes / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0
+        jac_bytes = 8.0 * D * M + 8.0 * P.nS * P.N + P.C * (4.0 * P.nloc + 4.0) + 24.0 * P.N + 16.0 * D
+        jac_ms = st["jacobian_kernel_ms"]
+        line = {
+            "metric": "ert_forward_jacobian_s_per_iter", "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + desc, "cells": P.C, "nodes": P.N, "nnz": P.nnz, "electrodes": P.nE,
+                       "wavenumbers": P.nK, "sources": P.nS, "data": D, "model_cells": M, "pcg_rel_tol": args.tol,
+                       "l2": "working set (PCG block vectors) larger than L2", "parallelism": f"sources+rows sharded x{world}",
+                       "setup_s": t_setup},
+            "pcg_iterations": st["pcg_iterations"], "pcg_max_rel_residual": st["max_rel_residual"],
+            "phase_ms_last_step": {k: st[k] for k in ("ms_map", "ms_assemble", "ms_rhs", "ms_solve", "ms_epilogue", "ms_jacobian")},
+            "roofline": {"kernel": "k_spmm (CSR x dense block, inside block-PCG)", "bound": "hbm", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                         "launches_timed": st["spmm_timed"], "avg_launch_ms": spmm_ms, "algorithmic_bytes_per_launch": spmm_bytes},
+            "roofline_jacobian": {"kernel": "k_jacobian", "bound": "hbm", "achieved": jac_bytes / (jac_ms * 1e-3) / 1e9 if jac_ms > 0 else None,
+                                  "peak": peak, "unit": "GB/s", "launch_ms": jac_ms, "algorithmic_bytes_per_launch": jac_bytes},
+            "e2e": {"value": ms_e2e / 1e3 / args.steps, "unit": "s", "h2d_bytes_per_step": 8 * (2 * M + M + D),
+                    "d2h_bytes_per_step": 8 * (D + D + M),
+                    "note": "host-buffer C ABI: response + createJacobian + one J.x and one J^T.y; J stays in HBM"},
+            "gpu_launches": int(st["launches"]),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle import ref
+                if ref.available():
+                    cores = os.cpu_count() or 1
+                    threads = max(1, min(8, cores - 2))
+                    tv, info = reference_sample(ref, mesh, scheme, model, threads, args)
+                    line["cpu_baseline"] = {"value": tv, "unit": "s", "cores": threads, "kind": "reference",
+                                            "sample": info["sample"], "stages_s": info["stages"]}
+                else:
+                    line["cpu_baseline"] = {"value": None, "unit": "s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+            except Exception as exc:  # the baseline must never take the bench line down
+                line["cpu_baseline"] = {"value": None, "unit": "s", "cores": 0, "kind": "reference", "sample": f"failed: {exc}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3"])
+    ap.add_argument("--scale", type=float, default=1.0, help="mesh refinement factor (1.0 = the named size)")
+    ap.add_argument("--tol", type=float, default=1e-12, help="block-PCG relative residual tolerance")
+    ap.add_argument("--ref-rows", type=int, default=24, help="data rows in the CPU sensitivity sample")
+    ap.add_argument("--ref-sources", type=int, default=1, help="sources in the CPU solve sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

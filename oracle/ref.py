@@ -235,6 +235,16 @@ class RefERT:
         lib().ref_time_forward_jacobian(self.h, C.c_int(m.size), _d(m), C.c_int(n_threads), _d(out))
         return out
 
+    def set_pcg_tol(self, tol):
+        lib().ref_set_pcg_tol(self.h, C.c_double(tol))
+
+    def time_partial_solve(self, model, n_src, detail=False):
+        """seconds the reference spends in SolverWrapper::solve for the first n_src sources (all k)"""
+        m = np.ascontiguousarray(model, np.float64)
+        out = np.zeros(4)
+        lib().ref_time_partial_solve(self.h, C.c_int(m.size), _d(m), C.c_int(int(n_src)), _d(out))
+        return out if detail else float(out[1])
+
     def solver_stats(self):
         out = np.zeros(4)
         lib().ref_solver_stats(self.h, _d(out))

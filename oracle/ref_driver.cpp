@@ -54,7 +54,7 @@ namespace {
 class InjectedSolver : public SolverWrapper {
 public:
     InjectedSolver() : SolverWrapper(false), S_(0), setCb_(0), solveCb_(0),
-        nSetMatrix(0), nSolve(0), tSetMatrix(0.0), tSolve(0.0) { name_ = "oracleInjected"; }
+        nSetMatrix(0), nSolve(0), tSetMatrix(0.0), tSolve(0.0), tol_(1e-14), iters_(0) { name_ = "oracleInjected"; }
 
     virtual void setMatrix(const RSparseMatrix & S){
         Stopwatch sw(true);
@@ -90,7 +90,8 @@ public:
             RVector Ap(A * p);
             double a = rz / dot(p, Ap);
             x += p * a; r -= Ap * a;
-            if (std::sqrt(dot(r, r)) <= 1e-14 * b2) break;
+            iters_++;
+            if (std::sqrt(dot(r, r)) <= tol_ * b2) break;
             z = r / diag_; double rzn = dot(r, z);
             p = z + p * (rzn / rz); rz = rzn;
         }
@@ -101,6 +102,8 @@ public:
     solve_cb solveCb_;
     long nSetMatrix, nSolve;
     double tSetMatrix, tSolve;
+    double tol_;
+    long iters_;
 };
 
 struct RefHandle {
@@ -171,6 +174,24 @@ void ref_solver_stats(void * vh, double * out4){
     RefHandle * h = (RefHandle *)vh;
     out4[0] = (double)h->solver->nSetMatrix; out4[1] = h->solver->tSetMatrix;
     out4[2] = (double)h->solver->nSolve;     out4[3] = h->solver->tSolve;
+}
+void ref_set_pcg_tol(void * vh, double tol){ ((RefHandle *)vh)->solver->tol_ = tol; }
+// Time the linear-solve stage of calculateK (dcfemmodelling.cpp:2152-2296) for the first nSrc current
+// patterns and all wavenumbers: out = {seconds in setMatrix, seconds in solve, seconds total calculateK, iterations}
+void ref_time_partial_solve(void * vh, int nModel, const double * model, int nSrc, double * out){
+    RefHandle * h = (RefHandle *)vh;
+    RVector m(nModel); for (int i = 0; i < nModel; i++) m[i] = model[i];
+    h->fop->mapERTModel(m, -9e99);
+    std::vector < ElectrodeShape * > eA, eB;
+    h->fop->createCurrentPattern(eA, eB, true);
+    eA.resize(nSrc); eB.resize(nSrc);
+    h->fop->preCalculate(eA, eB);
+    RMatrix sol(nSrc * h->fop->kValues().size(), h->fop->mesh()->nodeCount());
+    double t0s = h->solver->tSetMatrix, t0v = h->solver->tSolve; long it0 = h->solver->iters_;
+    Stopwatch sw(true);
+    for (Index k = 0; k < h->fop->kValues().size(); k++) h->fop->calculateK(eA, eB, sol, k);
+    out[2] = sw.duration();
+    out[0] = h->solver->tSetMatrix - t0s; out[1] = h->solver->tSolve - t0v; out[3] = (double)(h->solver->iters_ - it0);
 }
 void ref_set_threads(void * vh, int n){ ((RefHandle *)vh)->fop->setThreadCount(n); }
 

@@ -571,7 +571,7 @@ k_jacobian(const JacArgs A) {
             if (a >= 0 && n >= 0) v -= sG[a * gstride + n];
             if (b >= 0 && m >= 0) v -= sG[b * gstride + m];
             if (b >= 0 && n >= 0) v += sG[b * gstride + n];
-            out[A.out_row[d]] = v * scale * A.kfac[d];
+            out[A.out_row[d]] = A.rho_col ? v * scale * A.kfac[d] : v;   // k_i / rho_j^2 only if len(model) == cols (:1377)
         }
     }
 }
