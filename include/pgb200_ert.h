@@ -85,6 +85,14 @@ typedef struct pgb200_plan {
     const int *pro_nb;          /* [n*pro_nf] neighbour cells                                */
     const double *pro_w;        /* [n*pro_nf] normalised weights (0 = unused)                */
 
+    int n_panels;               /* row panels of the staged SpMM (0 = use the plain kernel)  */
+    int max_halo;               /* largest halo (distinct columns) of a panel                */
+    const int *panel_ptr;       /* [n_panels+1] row ranges                                   */
+    const int *halo_ptr;        /* [n_panels+1] ranges into halo_cols                        */
+    const int *halo_cols;       /* distinct columns touched by each panel                    */
+    const unsigned short *lidx; /* [nnz] column of every entry as offset into its halo list  */
+    const unsigned short *self_idx; /* [N] offset of the row's own column (diagonal)         */
+
     int n_jac_cells;            /* cells with marker >= 0, sorted by marker (:298-299)       */
     const int *jac_cells;       /* [n_jac_cells]                                             */
     const int *jac_col_ptr;     /* [M+1] ranges into jac_cells                               */
@@ -99,6 +107,10 @@ int pgb200_version(void);
 /* Greedy conflict colouring: cells sharing a node get different colours.
  * Returns the number of colours (<= 0 on failure); color[C] receives the colour per cell. */
 int pgb200_color_cells(int n_cells, int nloc, const int *cells, int n_nodes, int *color);
+/* Row panels of the staged SpMM: consecutive rows grouped while rows <= rmax and distinct
+ * columns <= hmax.  Returns the number of panels (< 0 on failure).                          */
+int pgb200_build_panels(int n_rows, const int *rowptr, const int *colidx, int rmax, int hmax,
+                        int *panel_ptr, int *halo_ptr, int *halo_cols, unsigned short *lidx, unsigned short *self_idx);
 
 /* ---- life cycle ------------------------------------------------------------------- */
 int pgb200_ert_create(const pgb200_plan *plan, int device, pgb200_ert **out);
@@ -162,6 +174,8 @@ long long pgb200_ert_get(pgb200_ert *h, const char *what, double *out_host, long
 int pgb200_ert_stats(pgb200_ert *h, double *stats, int n);
 int pgb200_ert_reset_stats(pgb200_ert *h);
 int pgb200_ert_set_profile(pgb200_ert *h, int on);
+/* 1 (default): panel-staged TMA SpMM inside PCG; 0: plain gather kernel (for A/B measurements) */
+int pgb200_ert_set_spmm_variant(pgb200_ert *h, int panel_staged);
 
 /* ---- single-kernel entry points (device pointers; unit tests and micro-benchmarks) --- */
 /* Y[N x ld] = A X with per-wavenumber values: column s uses vals[(s / nE) * nnz + .]       */

@@ -34,6 +34,8 @@ class Plan(C.Structure):
         ("pick_w", c_dbl_p), ("src_cell_ptr", c_int_p), ("src_cells", c_int_p),
         ("n_pro_levels", C.c_int), ("pro_nf", C.c_int), ("pro_level_ptr", c_int_p), ("pro_cells", c_int_p), ("pro_nb", c_int_p),
         ("pro_w", c_dbl_p),
+        ("n_panels", C.c_int), ("max_halo", C.c_int), ("panel_ptr", c_int_p), ("halo_ptr", c_int_p), ("halo_cols", c_int_p),
+        ("lidx", C.POINTER(C.c_ushort)), ("self_idx", C.POINTER(C.c_ushort)),
         ("n_jac_cells", C.c_int), ("jac_cells", c_int_p), ("jac_col_ptr", c_int_p),
         ("abmn", c_int_p), ("k_fac", c_dbl_p),
     ]
@@ -41,7 +43,7 @@ class Plan(C.Structure):
 
 # every symbol include/pgb200_ert.h declares (checked by tests/test_capi_symbols.py)
 EXPORTS = [
-    "pgb200_last_error", "pgb200_version", "pgb200_color_cells",
+    "pgb200_last_error", "pgb200_version", "pgb200_color_cells", "pgb200_build_panels", "pgb200_ert_set_spmm_variant",
     "pgb200_ert_create", "pgb200_ert_destroy", "pgb200_ert_set_stream", "pgb200_ert_set_solver", "pgb200_ert_set_shard",
     "pgb200_ert_set_kfac", "pgb200_ert_response", "pgb200_ert_create_jacobian", "pgb200_ert_jacobian_copy",
     "pgb200_ert_jacobian_mult", "pgb200_ert_jacobian_tmult", "pgb200_ert_response_dev", "pgb200_ert_create_jacobian_dev",
@@ -93,6 +95,8 @@ def lib():
         L.pgb200_ert_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.pgb200_ert_set_profile.argtypes = [C.c_void_p, C.c_int]
         L.pgb200_color_cells.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.pgb200_build_panels.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
+        L.pgb200_ert_set_spmm_variant.argtypes = [C.c_void_p, C.c_int]
         L.pgb200_spmm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p]
         _lib = L
@@ -120,6 +124,26 @@ def color_cells(cells: np.ndarray, n_nodes: int):
     if n <= 0:
         raise PGB200Error(last_error())
     return color, int(n)
+
+
+def build_panels(rowptr: np.ndarray, colidx: np.ndarray, rmax: int = 64, hmax: int = 320):
+    """row panels + halo lists + 16-bit local column indices for the staged SpMM (C++ host helper)"""
+    rowptr = np.ascontiguousarray(rowptr, np.int32)
+    colidx = np.ascontiguousarray(colidx, np.int32)
+    n = rowptr.size - 1
+    panel_ptr = np.zeros(n + 1, np.int32)
+    halo_ptr = np.zeros(n + 1, np.int32)
+    halo_cols = np.zeros(max(1, colidx.size), np.int32)
+    lidx = np.zeros(max(1, colidx.size), np.uint16)
+    self_idx = np.zeros(n, np.uint16)
+    npan = lib().pgb200_build_panels(n, rowptr.ctypes.data, colidx.ctypes.data, int(rmax), int(hmax), panel_ptr.ctypes.data,
+                                     halo_ptr.ctypes.data, halo_cols.ctypes.data, lidx.ctypes.data, self_idx.ctypes.data)
+    if npan < 0:
+        raise PGB200Error(last_error())
+    panel_ptr = panel_ptr[: npan + 1].copy()
+    halo_ptr = halo_ptr[: npan + 1].copy()
+    return dict(n_panels=int(npan), panel_ptr=panel_ptr, halo_ptr=halo_ptr, halo_cols=halo_cols[: halo_ptr[-1]].copy(),
+                lidx=lidx, self_idx=self_idx, max_halo=int(np.diff(halo_ptr).max()))
 
 
 def _ip(a):
@@ -169,6 +193,15 @@ def make_plan_struct(P, sr: bool):
     s.pro_cells = I(np.concatenate([c for c, _, _ in lv]) if lv else np.zeros(0, np.int32))
     s.pro_nb = I(np.concatenate([n for _, n, _ in lv]).ravel() if lv else np.zeros(0, np.int32))
     s.pro_w = D(np.concatenate([w for _, _, w in lv]).ravel() if lv else np.zeros(0))
+    pan = getattr(P, "panels", None)
+    if pan:
+        s.n_panels, s.max_halo = pan["n_panels"], pan["max_halo"]
+        s.panel_ptr, s.halo_ptr, s.halo_cols = I(pan["panel_ptr"]), I(pan["halo_ptr"]), I(pan["halo_cols"])
+        l16, s16 = np.ascontiguousarray(pan["lidx"], np.uint16), np.ascontiguousarray(pan["self_idx"], np.uint16)
+        keep.extend([l16, s16])
+        s.lidx, s.self_idx = l16.ctypes.data_as(C.POINTER(C.c_ushort)), s16.ctypes.data_as(C.POINTER(C.c_ushort))
+    else:
+        s.n_panels, s.max_halo = 0, 0
     s.n_jac_cells, s.jac_cells, s.jac_col_ptr = int(P.jac_cells.size), I(P.jac_cells), I(P.jac_col_ptr)
     s.abmn = I(P.scheme.abmn())
     kf = P.scheme.k if P.scheme.k is not None else np.zeros(P.scheme.size)

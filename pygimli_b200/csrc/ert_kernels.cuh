@@ -264,6 +264,102 @@ k_spmm(const int *__restrict__ rowptr, const int *__restrict__ colidx, const dou
 }
 
 // ---------------------------------------------------------------------------------
+// K2': panel-staged SpMM  Y = A X  (+ fused p.Ap), the PCG hot kernel.
+//   Rows are renumbered along a space-filling curve at set-up, so R consecutive rows form a
+//   compact patch of the mesh whose matrix rows touch only a small "halo" set of distinct
+//   columns (about 3 per row instead of 15 for Kuhn tetrahedra).  One CTA = one row panel x one
+//   tile of TW source columns:
+//     1. one thread arms an mbarrier with the byte count, then the CTA issues one TMA bulk copy
+//        (cp.async.bulk.shared.global, SASS UBLKCP) per halo row: X[halo][tile] -> shared memory;
+//     2. every warp takes rows of the panel; lane = source column.  Column indices were
+//        re-encoded at set-up as 16-bit offsets into the halo list, so the inner loop is
+//        one broadcast load of (value, local index) + one conflict-free shared-memory read
+//        of X + one DFMA;
+//     3. Y is written with coalesced stores; the p.Ap partials are reduced over the warps in
+//        shared memory and leave the CTA as one atomicAdd per column.
+//   Each gathered X row is read from L2/HBM once per panel instead of once per touching row.
+// ---------------------------------------------------------------------------------
+constexpr int PANEL_THREADS = 256;
+constexpr int PANEL_WARPS = PANEL_THREADS / 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <bool DOT>
+__global__ void __launch_bounds__(PANEL_THREADS)
+k_spmm_panel(const int *__restrict__ rowptr, const unsigned short *__restrict__ lidx, const unsigned short *__restrict__ self_idx,
+             const int *__restrict__ panel_ptr, const int *__restrict__ halo_ptr, const int *__restrict__ halo_cols,
+             const double *__restrict__ vals, size_t nnz, const double *__restrict__ X, double *__restrict__ Y,
+             int nE, int c0, int c1, int tw, size_t ld, double *__restrict__ dots) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ double red[PANEL_WARPS][32];
+    const int panel = blockIdx.x;
+    const int tile0 = c0 + blockIdx.y * tw;                   // first column of this tile (even)
+    const int w = min(tw, (int)ld - tile0);                    // copied width (even; may include zero padding)
+    const int r0 = panel_ptr[panel], r1 = panel_ptr[panel + 1];
+    const int h0 = halo_ptr[panel], hn = halo_ptr[panel + 1] - h0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    if (threadIdx.x == 0) mbar_expect_tx(&bar, (uint32_t)(hn * w * 8));
+    __syncthreads();
+    // the bulk copies are issued from all warps (the issue itself is serialised per warp)
+    for (int i = threadIdx.x; i < hn; i += PANEL_THREADS)
+        tma_bulk_g2s(sm + (size_t)i * tw, X + (size_t)halo_cols[h0 + i] * ld + tile0, (uint32_t)(w * 8), &bar);
+    const int col = tile0 + lane;
+    const bool ok = lane < w && col < c1;
+    const size_t voff = (size_t)((ok ? col : c0) / nE) * nnz;
+    mbar_wait(&bar, 0);
+
+    double part = 0.0;
+    for (int row = r0 + warp; row < r1; row += PANEL_WARPS) {
+        const int pb = rowptr[row], pe = rowptr[row + 1];
+        double acc = 0.0;
+        if (lane < w) {
+#pragma unroll 4
+            for (int p = pb; p < pe; p++)
+                acc = fma(__ldg(vals + voff + p), sm[(size_t)__ldg(lidx + p) * tw + lane], acc);
+        }
+        if (ok) {
+            Y[(size_t)row * ld + col] = acc;
+            if (DOT) part = fma(acc, sm[(size_t)self_idx[row] * tw + lane], part);
+        }
+    }
+    if (DOT) {
+        red[warp][lane] = part;
+        __syncthreads();
+        if (warp == 0 && ok) {
+            double s = 0.0;
+#pragma unroll
+            for (int y = 0; y < PANEL_WARPS; y++) s += red[y][lane];
+            atomicAdd(dots + col, s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // block-PCG vector kernels (Jacobi preconditioner; one independent CG per source column,
 // all columns advance in the same launches).  Thread = 1 column x strided rows; per-column
 // partial dot products stay in registers, then a shared-memory tree + one atomic per CTA.

@@ -70,6 +70,7 @@ struct pgb200_ert {
         dir_zero, dir_diag, dir_nodes, sing_node, pick_ptr, pick_idx, src_cell_ptr, src_cells, pro_cells, pro_nb,
         jac_cells, jac_col_ptr, abmn;
     std::vector<int> color_ptr, pro_level_ptr;
+    DevBuf<int> panel_ptr, halo_ptr, halo_cols; DevBuf<unsigned short> lidx, self_idx; int n_panels = 0, max_halo = 0; int use_panels = 1;
     std::vector<double> h_kvals;
     int n_colors = 0, n_bc_slots = 0, n_bc_entries = 0, n_dir_zero = 0, n_dir_nodes = 0, pro_nf = 0, n_jac_cells = 0;
     std::vector<int> h_abmn; std::vector<double> h_kfac;
@@ -161,6 +162,30 @@ int launch_spmm(pgb200_ert *h, const double *vals, const double *vals1, const do
     return 0;
 }
 
+// panel-staged SpMM (the PCG hot kernel): Y = A X on columns [c0,c1), fused p.Ap
+int launch_spmm_panel(pgb200_ert *h, const double *vals, const double *X, double *Y, int c0, int c1, double *dots) {
+    const int ncols = c1 - c0;
+    if (ncols <= 0) return 0;
+    const int c0e = c0;                                        // even by construction (16-byte aligned copies)
+    const int span = c1 - c0e;
+    const int ntile = cdiv(span, 32);
+    int tw = cdiv(span, ntile); tw += tw & 1;                  // even tile width <= 32
+    const size_t smem = (size_t)h->max_halo * tw * sizeof(double);
+    static size_t configured = 0;
+    if (smem > configured) {
+        CK(cudaFuncSetAttribute(k_spmm_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_spmm_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid(h->n_panels, ntile);
+    if (dots) k_spmm_panel<true><<<grid, PANEL_THREADS, smem, h->st>>>(h->rowptr.p, h->lidx.p, h->self_idx.p, h->panel_ptr.p, h->halo_ptr.p,
+                                                                       h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0e, c1, tw, h->ld, dots);
+    else k_spmm_panel<false><<<grid, PANEL_THREADS, smem, h->st>>>(h->rowptr.p, h->lidx.p, h->self_idx.p, h->panel_ptr.p, h->halo_ptr.p,
+                                                                    h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0e, c1, tw, h->ld, nullptr);
+    LAUNCH(h);
+    return 0;
+}
+
 // scal layout: [0] rz_a [1] rz_b [2] rz_c [3] pAp [4] rr_a [5] rr_b [6] bb   (each ld doubles)
 int pcg_solve(pgb200_ert *h) {
     const int c0 = h->c0, c1 = h->c1, ncols = c1 - c0;
@@ -182,7 +207,8 @@ int pcg_solve(pgb200_ert *h) {
         const int rr_cur = 4 + (it % 2), rr_nxt = 4 + ((it + 1) % 2);
         const bool timed = h->prof && h->n_pev + 2 <= (int)h->pev.size();
         if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
-        CKR((launch_spmm<0, true>(h, h->vals.p, nullptr, nullptr, h->P.p, h->AP.p, c0, c1, sc(3))));
+        if (h->use_panels && h->n_panels > 0 && !(c0 & 1)) CKR(launch_spmm_panel(h, h->vals.p, h->P.p, h->AP.p, c0, c1, sc(3)));
+        else CKR((launch_spmm<0, true>(h, h->vals.p, nullptr, nullptr, h->P.p, h->AP.p, c0, c1, sc(3))));
         if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
         k_pcg_update_xr<<<vg, vb, 0, h->st>>>(h->P.p, h->AP.p, h->dinv.p, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
                                              sc(rz_old), sc(3), sc(rz_new), sc(rr_cur)); LAUNCH(h);
@@ -456,6 +482,41 @@ int pgb200_color_cells(int n_cells, int nloc, const int *cells, int n_nodes, int
     return ncol;
 }
 
+// Row panels for the staged SpMM: consecutive rows are grouped while the panel has at most rmax rows
+// and its halo (distinct columns) at most hmax entries.  Outputs: panel_ptr[<=N+1], halo_ptr[<=N+1],
+// halo_cols[<=nnz], lidx[nnz] (16-bit offset of every entry's column in its panel's halo list),
+// self_idx[N] (offset of the row itself).  Returns the number of panels (< 0 on failure).
+int pgb200_build_panels(int n_rows, const int *rowptr, const int *colidx, int rmax, int hmax,
+                        int *panel_ptr, int *halo_ptr, int *halo_cols, unsigned short *lidx, unsigned short *self_idx) {
+    if (hmax > 65535 || rmax < 1) { g_err = "invalid panel limits"; return -1; }
+    std::vector<int> stamp((size_t)n_rows, -1), slot((size_t)n_rows, 0);
+    int np = 0, hcount = 0, row = 0;
+    panel_ptr[0] = 0; halo_ptr[0] = 0;
+    while (row < n_rows) {
+        const int start = row, hstart = hcount;
+        int h = 0;
+        while (row < n_rows && row - start < rmax) {
+            int add = 0;
+            for (int p = rowptr[row]; p < rowptr[row + 1]; p++) if (stamp[colidx[p]] != np) add++;
+            if (h + add > hmax) {
+                if (row == start) { g_err = "a single matrix row exceeds the halo limit"; return -1; }
+                break;
+            }
+            for (int p = rowptr[row]; p < rowptr[row + 1]; p++) {
+                const int c = colidx[p];
+                if (stamp[c] != np) { stamp[c] = np; slot[c] = h; halo_cols[hstart + h] = c; h++; }
+                lidx[p] = (unsigned short)slot[c];
+            }
+            if (stamp[row] != np) { g_err = "matrix row without diagonal entry"; return -1; }
+            self_idx[row] = (unsigned short)slot[row];
+            row++;
+        }
+        hcount += h; np++;
+        panel_ptr[np] = row; halo_ptr[np] = hcount;
+    }
+    return np;
+}
+
 int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
     if (!p || !out) PGB_FAIL("null argument");
     int ndev = 0;
@@ -503,6 +564,12 @@ int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
     const size_t npro = p->n_pro_levels ? (size_t)p->pro_level_ptr[p->n_pro_levels] : 0;
     CKR(h->pro_cells.upload(p->pro_cells, npro, st)); CKR(h->pro_nb.upload(p->pro_nb, npro * p->pro_nf, st));
     CKR(h->pro_w.upload(p->pro_w, npro * p->pro_nf, st));
+    h->n_panels = p->n_panels; h->max_halo = p->max_halo;
+    if (p->n_panels > 0) {
+        CKR(h->panel_ptr.upload(p->panel_ptr, (size_t)p->n_panels + 1, st)); CKR(h->halo_ptr.upload(p->halo_ptr, (size_t)p->n_panels + 1, st));
+        CKR(h->halo_cols.upload(p->halo_cols, (size_t)p->halo_ptr[p->n_panels], st));
+        CKR(h->lidx.upload(p->lidx, h->nnz, st)); CKR(h->self_idx.upload(p->self_idx, N, st));
+    }
     h->n_jac_cells = p->n_jac_cells;
     CKR(h->jac_cells.upload(p->jac_cells, p->n_jac_cells, st)); CKR(h->jac_col_ptr.upload(p->jac_col_ptr, (size_t)h->M + 1, st));
     CKR(h->abmn.upload(p->abmn, (size_t)h->D * 4, st)); CKR(h->kfac.upload(p->k_fac, h->D, st));
@@ -815,6 +882,7 @@ int pgb200_ert_reset_stats(pgb200_ert *h) {
     h->launches = 0; h->spmm_ms = 0.0; h->spmm_timed = 0; h->jac_ms = 0.0; h->n_pev = 0;
     return 0;
 }
+int pgb200_ert_set_spmm_variant(pgb200_ert *h, int panel_staged) { if (!h) PGB_FAIL("null handle"); h->use_panels = panel_staged; return 0; }
 int pgb200_ert_set_profile(pgb200_ert *h, int on) {
     if (!h) PGB_FAIL("null handle");
     CK(cudaSetDevice(h->device));

@@ -199,7 +199,7 @@ class CoreB200:
             if sch.k is None or np.min(np.abs(sch.k)) < TOLERANCE:
                 # response() computes missing k-factors analytically for flat earth (:1088-1093)
                 sch.k = geometric_factors(sch, self._mesh.dim)
-            self._plan = build_plan(self._mesh, sch, self._k, self._w, color_fn=_capi.color_cells)
+            self._plan = build_plan(self._mesh, sch, self._k, self._w, color_fn=_capi.color_cells, panel_fn=_capi.build_panels)
         return self._plan
 
     def _ensure_handle(self):
@@ -267,6 +267,12 @@ class CoreB200:
             r = _capi.lib().pgb200_ert_get(h, what.encode(), out.ctypes.data, int(n))
             if r < 0:
                 raise _capi.PGB200Error(_capi.last_error())
+        # back to the reference's numbering (the device works in the internal node order)
+        P = self._plan
+        if what in ("vals", "vals1") and n:
+            out = out.reshape(P.nK, P.nnz)[:, P.ref_slot].ravel()
+        elif what in ("prim", "pots", "rhs", "sec", "solutions") and n:
+            out = out.reshape(-1, P.N)[:, P.node_inv].ravel()
         return out
 
     def stats(self) -> dict:

@@ -380,14 +380,59 @@ def locate_point(mesh: MeshArrays, p: np.ndarray):
 
 
 # ---------------------------------------------------------------------------
+# internal node renumbering (locality for the staged SpMM; invisible at the boundary)
+# ---------------------------------------------------------------------------
+def _spread_bits(v: np.ndarray, dim: int, bits: int) -> np.ndarray:
+    out = np.zeros(v.shape, np.uint64)
+    for b in range(bits):
+        out |= ((v >> np.uint64(b)) & np.uint64(1)) << np.uint64(dim * b)
+    return out
+
+
+def node_ordering(mesh: MeshArrays) -> np.ndarray:
+    """Space-filling-curve (Morton) order of the nodes: perm[new] = old.  Coordinates are
+    rank-quantised per axis so graded meshes use the curve's resolution evenly."""
+    dim = mesh.dim
+    bits = 10 if dim == 3 else 15
+    code = np.zeros(mesh.node_count, np.uint64)
+    for ax in range(dim):
+        u, inv = np.unique(mesh.pos[:, ax], return_inverse=True)
+        q = (inv.astype(np.float64) * ((1 << bits) / max(1, u.size))).astype(np.uint64)
+        code |= _spread_bits(q, dim, bits) << np.uint64(ax)
+    return np.argsort(code, kind="stable").astype(np.int64)
+
+
+def renumber_nodes(mesh: MeshArrays, perm: np.ndarray) -> MeshArrays:
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)
+    return MeshArrays(mesh.dim, mesh.pos[perm], mesh.node_marker[perm], inv[mesh.cells].astype(np.int32),
+                      mesh.cell_marker.copy(), inv[mesh.bounds].astype(np.int32) if mesh.bounds.size else mesh.bounds.copy(),
+                      mesh.bound_marker.copy())
+
+
+# ---------------------------------------------------------------------------
 # the plan
 # ---------------------------------------------------------------------------
 class ERTPlan:
-    """All geometry-derived arrays of one (mesh, scheme) pair; see build_plan."""
+    """All geometry-derived arrays of one (mesh, scheme) pair; see build_plan.
+
+    Node-indexed arrays are in the INTERNAL numbering (``node_perm[new] = old``); the reference's
+    numbering is kept for everything that crosses the boundary: ``ref_rowptr/ref_colidx`` (the
+    pattern exactly as SparseMatrix::buildSparsityPattern produces it), ``ref_slot`` (reference CSR
+    slot -> internal slot) and ``node_inv`` (old -> new)."""
 
 
-def build_plan(mesh: MeshArrays, scheme, k_values=None, weights=None, color_fn=None) -> ERTPlan:
+def build_plan(mesh: MeshArrays, scheme, k_values=None, weights=None, color_fn=None, panel_fn=None,
+               reorder: bool = True) -> ERTPlan:
     P = ERTPlan()
+    P.mesh_ref = mesh
+    perm = node_ordering(mesh) if reorder else np.arange(mesh.node_count, dtype=np.int64)
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)
+    P.node_perm, P.node_inv = perm, inv
+    src_order_ref = np.nonzero(mesh.node_marker == MARKER_NODE_ELECTRODE)[0]      # reference visiting order
+    if reorder:
+        mesh = renumber_nodes(mesh, perm)
     dim, N, C, nloc = mesh.dim, mesh.node_count, mesh.cell_count, mesh.nloc
     P.dim, P.N, P.C, P.nloc = dim, N, C, nloc
     P.mesh, P.scheme = mesh, scheme
@@ -427,6 +472,14 @@ def build_plan(mesh: MeshArrays, scheme, k_values=None, weights=None, color_fn=N
     P.cells_col = np.ascontiguousarray(mesh.cells[order].T)        # (nloc, C) SoA, colour order
     P.pos_col = np.ascontiguousarray(pos[order].T)                 # (nloc^2, C)
     P.diag_pos = csr_positions(P.rowptr, P.colidx, np.arange(N), np.arange(N))
+    # the reference's pattern (original numbering) and the slot correspondence
+    rowof_i = np.repeat(np.arange(N, dtype=np.int64), np.diff(P.rowptr))
+    key_ref = perm[rowof_i] * N + perm[P.colidx]
+    o = np.argsort(key_ref, kind="stable")
+    P.ref_slot = o.astype(np.int64)
+    P.ref_colidx = perm[P.colidx][o].astype(np.int32)
+    P.ref_rowptr = np.concatenate([[0], np.cumsum(np.bincount(perm[rowof_i], minlength=N))]).astype(np.int32)
+    P.panels = panel_fn(P.rowptr, P.colidx) if panel_fn is not None else None
 
     # ---- electrodes (dcfemmodelling.cpp:845-940) ------------------------------------
     sens = np.array(scheme.sensors, float).reshape(-1, 3)
@@ -437,7 +490,7 @@ def build_plan(mesh: MeshArrays, scheme, k_values=None, weights=None, color_fn=N
             sens = sens[:, [0, 2, 1]].copy()
     nE = sens.shape[0]
     P.nE = nE
-    src_nodes = list(np.nonzero(mesh.node_marker == MARKER_NODE_ELECTRODE)[0])
+    src_nodes = [int(i) for i in inv[src_order_ref]]          # candidates in the reference's node order
     if np.any(mesh.node_marker == MARKER_NODE_REFERENCE):
         raise NotImplementedError("reference-electrode nodes (-999) are not supported on the B200 path")
     el_node = np.full(nE, -1, np.int64)          # mID: node id for node electrodes
@@ -473,6 +526,7 @@ def build_plan(mesh: MeshArrays, scheme, k_values=None, weights=None, color_fn=N
                 sing_node[i] = ids[near[-1]]
         pick_ptr.append(pick_ptr[-1] + len(pick_idx[-1]))
     P.el_node, P.el_pos, P.el_cell, P.sing_node = el_node, el_pos, el_cell, sing_node
+    P.el_node_ref = np.where(el_node >= 0, perm[np.maximum(el_node, 0)], -1)
     P.pick_ptr = np.asarray(pick_ptr, np.int32)
     P.pick_idx = np.concatenate(pick_idx).astype(np.int32)
     P.pick_w = np.concatenate(pick_w).astype(np.float64)
