@@ -87,6 +87,7 @@ typedef struct pgb200_plan {
 
     int n_panels;               /* row panels of the staged SpMM (0 = use the plain kernel)  */
     int max_halo;               /* largest halo (distinct columns) of a panel                */
+    int max_panel_nnz;          /* largest number of CSR entries of a panel                  */
     const int *panel_ptr;       /* [n_panels+1] row ranges                                   */
     const int *halo_ptr;        /* [n_panels+1] ranges into halo_cols                        */
     const int *halo_cols;       /* distinct columns touched by each panel                    */
@@ -174,7 +175,7 @@ long long pgb200_ert_get(pgb200_ert *h, const char *what, double *out_host, long
 int pgb200_ert_stats(pgb200_ert *h, double *stats, int n);
 int pgb200_ert_reset_stats(pgb200_ert *h);
 int pgb200_ert_set_profile(pgb200_ert *h, int on);
-/* 1 (default): panel-staged TMA SpMM inside PCG; 0: plain gather kernel (for A/B measurements) */
+/* 0: plain gather kernel; 1 / 2: panel-staged TMA SpMM with 1 / 2 (default) source columns per lane */
 int pgb200_ert_set_spmm_variant(pgb200_ert *h, int panel_staged);
 
 /* ---- single-kernel entry points (device pointers; unit tests and micro-benchmarks) --- */

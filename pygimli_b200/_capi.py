@@ -34,7 +34,7 @@ class Plan(C.Structure):
         ("pick_w", c_dbl_p), ("src_cell_ptr", c_int_p), ("src_cells", c_int_p),
         ("n_pro_levels", C.c_int), ("pro_nf", C.c_int), ("pro_level_ptr", c_int_p), ("pro_cells", c_int_p), ("pro_nb", c_int_p),
         ("pro_w", c_dbl_p),
-        ("n_panels", C.c_int), ("max_halo", C.c_int), ("panel_ptr", c_int_p), ("halo_ptr", c_int_p), ("halo_cols", c_int_p),
+        ("n_panels", C.c_int), ("max_halo", C.c_int), ("max_panel_nnz", C.c_int), ("panel_ptr", c_int_p), ("halo_ptr", c_int_p), ("halo_cols", c_int_p),
         ("lidx", C.POINTER(C.c_ushort)), ("self_idx", C.POINTER(C.c_ushort)),
         ("n_jac_cells", C.c_int), ("jac_cells", c_int_p), ("jac_col_ptr", c_int_p),
         ("abmn", c_int_p), ("k_fac", c_dbl_p),
@@ -126,7 +126,7 @@ def color_cells(cells: np.ndarray, n_nodes: int):
     return color, int(n)
 
 
-def build_panels(rowptr: np.ndarray, colidx: np.ndarray, rmax: int = 64, hmax: int = 320):
+def build_panels(rowptr: np.ndarray, colidx: np.ndarray, rmax: int = 64, hmax: int = 192):
     """row panels + halo lists + 16-bit local column indices for the staged SpMM (C++ host helper)"""
     rowptr = np.ascontiguousarray(rowptr, np.int32)
     colidx = np.ascontiguousarray(colidx, np.int32)
@@ -143,7 +143,8 @@ def build_panels(rowptr: np.ndarray, colidx: np.ndarray, rmax: int = 64, hmax: i
     panel_ptr = panel_ptr[: npan + 1].copy()
     halo_ptr = halo_ptr[: npan + 1].copy()
     return dict(n_panels=int(npan), panel_ptr=panel_ptr, halo_ptr=halo_ptr, halo_cols=halo_cols[: halo_ptr[-1]].copy(),
-                lidx=lidx, self_idx=self_idx, max_halo=int(np.diff(halo_ptr).max()))
+                lidx=lidx, self_idx=self_idx, max_halo=int(np.diff(halo_ptr).max()),
+                max_panel_nnz=int(np.diff(rowptr[panel_ptr]).max()))
 
 
 def _ip(a):
@@ -195,7 +196,7 @@ def make_plan_struct(P, sr: bool):
     s.pro_w = D(np.concatenate([w for _, _, w in lv]).ravel() if lv else np.zeros(0))
     pan = getattr(P, "panels", None)
     if pan:
-        s.n_panels, s.max_halo = pan["n_panels"], pan["max_halo"]
+        s.n_panels, s.max_halo, s.max_panel_nnz = pan["n_panels"], pan["max_halo"], pan["max_panel_nnz"]
         s.panel_ptr, s.halo_ptr, s.halo_cols = I(pan["panel_ptr"]), I(pan["halo_ptr"]), I(pan["halo_cols"])
         l16, s16 = np.ascontiguousarray(pan["lidx"], np.uint16), np.ascontiguousarray(pan["self_idx"], np.uint16)
         keep.extend([l16, s16])

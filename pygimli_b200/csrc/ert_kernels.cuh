@@ -305,21 +305,27 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <bool DOT>
+// NC = source columns per lane (tile width <= 32*NC).  Shared memory: X tile [halo][tw] doubles,
+// then the panel's CSR slice: values for the (at most two) wavenumber groups the tile touches and
+// the byte offset of every entry's X row inside the tile.
+template <int NC, bool DOT>
 __global__ void __launch_bounds__(PANEL_THREADS)
 k_spmm_panel(const int *__restrict__ rowptr, const unsigned short *__restrict__ lidx, const unsigned short *__restrict__ self_idx,
              const int *__restrict__ panel_ptr, const int *__restrict__ halo_ptr, const int *__restrict__ halo_cols,
              const double *__restrict__ vals, size_t nnz, const double *__restrict__ X, double *__restrict__ Y,
-             int nE, int c0, int c1, int tw, size_t ld, double *__restrict__ dots) {
+             int nE, int c0, int c1, int tw, int max_halo, int max_pnnz, size_t ld, double *__restrict__ dots) {
     extern __shared__ __align__(16) double sm[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ double red[PANEL_WARPS][32];
+    __shared__ double red[PANEL_WARPS][32 * NC];
     const int panel = blockIdx.x;
     const int tile0 = c0 + blockIdx.y * tw;                   // first column of this tile (even)
     const int w = min(tw, (int)ld - tile0);                    // copied width (even; may include zero padding)
     const int r0 = panel_ptr[panel], r1 = panel_ptr[panel + 1];
     const int h0 = halo_ptr[panel], hn = halo_ptr[panel + 1] - h0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *sA0 = sm + (size_t)max_halo * tw;                  // values, first wavenumber group of the tile
+    double *sA1 = sA0 + max_pnnz;                              // values, second group (if the tile straddles)
+    uint32_t *sOff = reinterpret_cast<uint32_t *>(sA1 + max_pnnz);
 
     if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncthreads();
@@ -328,33 +334,62 @@ k_spmm_panel(const int *__restrict__ rowptr, const unsigned short *__restrict__ 
     // the bulk copies are issued from all warps (the issue itself is serialised per warp)
     for (int i = threadIdx.x; i < hn; i += PANEL_THREADS)
         tma_bulk_g2s(sm + (size_t)i * tw, X + (size_t)halo_cols[h0 + i] * ld + tile0, (uint32_t)(w * 8), &bar);
-    const int col = tile0 + lane;
-    const bool ok = lane < w && col < c1;
-    const size_t voff = (size_t)((ok ? col : c0) / nE) * nnz;
+    // meanwhile: CSR slice of the panel -> shared memory (coalesced)
+    const int p0 = rowptr[r0], pn = rowptr[r1] - p0;
+    const int last = min(tile0 + w, c1) - 1;
+    const int kk0 = tile0 / nE, kk1 = last / nE;
+    for (int i = threadIdx.x; i < pn; i += PANEL_THREADS) {
+        sA0[i] = __ldg(vals + (size_t)kk0 * nnz + p0 + i);
+        if (kk1 != kk0) sA1[i] = __ldg(vals + (size_t)kk1 * nnz + p0 + i);
+        sOff[i] = (uint32_t)__ldg(lidx + p0 + i) * (uint32_t)tw;
+    }
+    int col[NC]; bool ok[NC]; const double *sA[NC];
+#pragma unroll
+    for (int m = 0; m < NC; m++) {
+        col[m] = tile0 + lane + 32 * m;
+        ok[m] = (lane + 32 * m) < w && col[m] < c1;
+        sA[m] = (ok[m] && col[m] / nE != kk0) ? sA1 : sA0;
+    }
+    __syncthreads();
     mbar_wait(&bar, 0);
 
-    double part = 0.0;
+    double part[NC];
+#pragma unroll
+    for (int m = 0; m < NC; m++) part[m] = 0.0;
     for (int row = r0 + warp; row < r1; row += PANEL_WARPS) {
-        const int pb = rowptr[row], pe = rowptr[row + 1];
-        double acc = 0.0;
-        if (lane < w) {
+        const int pb = rowptr[row] - p0, pe = rowptr[row + 1] - p0;
+        double acc[NC];
+#pragma unroll
+        for (int m = 0; m < NC; m++) acc[m] = 0.0;
 #pragma unroll 4
-            for (int p = pb; p < pe; p++)
-                acc = fma(__ldg(vals + voff + p), sm[(size_t)__ldg(lidx + p) * tw + lane], acc);
+        for (int p = pb; p < pe; p++) {
+            const double *xr = sm + sOff[p] + lane;
+#pragma unroll
+            for (int m = 0; m < NC; m++) if (ok[m]) acc[m] = fma(sA[m][p], xr[32 * m], acc[m]);
         }
-        if (ok) {
-            Y[(size_t)row * ld + col] = acc;
-            if (DOT) part = fma(acc, sm[(size_t)self_idx[row] * tw + lane], part);
+        const double *xs = sm + (size_t)self_idx[row] * tw + lane;
+#pragma unroll
+        for (int m = 0; m < NC; m++) {
+            if (ok[m]) {
+                Y[(size_t)row * ld + col[m]] = acc[m];
+                if (DOT) part[m] = fma(acc[m], xs[32 * m], part[m]);
+            }
         }
     }
     if (DOT) {
-        red[warp][lane] = part;
-        __syncthreads();
-        if (warp == 0 && ok) {
-            double s = 0.0;
 #pragma unroll
-            for (int y = 0; y < PANEL_WARPS; y++) s += red[y][lane];
-            atomicAdd(dots + col, s);
+        for (int m = 0; m < NC; m++) red[warp][lane + 32 * m] = part[m];
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int m = 0; m < NC; m++) {
+                if (ok[m]) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int y = 0; y < PANEL_WARPS; y++) s += red[y][lane + 32 * m];
+                    atomicAdd(dots + col[m], s);
+                }
+            }
         }
     }
 }

@@ -70,7 +70,7 @@ struct pgb200_ert {
         dir_zero, dir_diag, dir_nodes, sing_node, pick_ptr, pick_idx, src_cell_ptr, src_cells, pro_cells, pro_nb,
         jac_cells, jac_col_ptr, abmn;
     std::vector<int> color_ptr, pro_level_ptr;
-    DevBuf<int> panel_ptr, halo_ptr, halo_cols; DevBuf<unsigned short> lidx, self_idx; int n_panels = 0, max_halo = 0; int use_panels = 1;
+    DevBuf<int> panel_ptr, halo_ptr, halo_cols; DevBuf<unsigned short> lidx, self_idx; int n_panels = 0, max_halo = 0, max_pnnz = 0, panel_nc = 2; int use_panels = 1;
     std::vector<double> h_kvals;
     int n_colors = 0, n_bc_slots = 0, n_bc_entries = 0, n_dir_zero = 0, n_dir_nodes = 0, pro_nf = 0, n_jac_cells = 0;
     std::vector<int> h_abmn; std::vector<double> h_kfac;
@@ -163,27 +163,30 @@ int launch_spmm(pgb200_ert *h, const double *vals, const double *vals1, const do
 }
 
 // panel-staged SpMM (the PCG hot kernel): Y = A X on columns [c0,c1), fused p.Ap
-int launch_spmm_panel(pgb200_ert *h, const double *vals, const double *X, double *Y, int c0, int c1, double *dots) {
-    const int ncols = c1 - c0;
-    if (ncols <= 0) return 0;
-    const int c0e = c0;                                        // even by construction (16-byte aligned copies)
-    const int span = c1 - c0e;
-    const int ntile = cdiv(span, 32);
-    int tw = cdiv(span, ntile); tw += tw & 1;                  // even tile width <= 32
-    const size_t smem = (size_t)h->max_halo * tw * sizeof(double);
-    static size_t configured = 0;
-    if (smem > configured) {
-        CK(cudaFuncSetAttribute(k_spmm_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_spmm_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+template <int NC>
+int launch_spmm_panel_nc(pgb200_ert *h, const double *vals, const double *X, double *Y, int c0, int c1, double *dots) {
+    const int span = c1 - c0;
+    const int ntile = cdiv(span, 32 * NC);
+    int tw = cdiv(span, ntile); tw += tw & 1;                  // even tile width <= 32*NC (16-byte aligned bulk copies)
+    const size_t smem = sizeof(double) * ((size_t)h->max_halo * tw + 2 * (size_t)h->max_pnnz) + sizeof(uint32_t) * (size_t)h->max_pnnz + 16;
+    static size_t configured[3] = {0, 0, 0};
+    if (smem > configured[NC]) {
+        CK(cudaFuncSetAttribute(k_spmm_panel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_spmm_panel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[NC] = smem;
     }
     dim3 grid(h->n_panels, ntile);
-    if (dots) k_spmm_panel<true><<<grid, PANEL_THREADS, smem, h->st>>>(h->rowptr.p, h->lidx.p, h->self_idx.p, h->panel_ptr.p, h->halo_ptr.p,
-                                                                       h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0e, c1, tw, h->ld, dots);
-    else k_spmm_panel<false><<<grid, PANEL_THREADS, smem, h->st>>>(h->rowptr.p, h->lidx.p, h->self_idx.p, h->panel_ptr.p, h->halo_ptr.p,
-                                                                    h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0e, c1, tw, h->ld, nullptr);
+    if (dots) k_spmm_panel<NC, true><<<grid, PANEL_THREADS, smem, h->st>>>(h->rowptr.p, h->lidx.p, h->self_idx.p, h->panel_ptr.p, h->halo_ptr.p,
+                     h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0, c1, tw, h->max_halo, h->max_pnnz, h->ld, dots);
+    else k_spmm_panel<NC, false><<<grid, PANEL_THREADS, smem, h->st>>>(h->rowptr.p, h->lidx.p, h->self_idx.p, h->panel_ptr.p, h->halo_ptr.p,
+                     h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0, c1, tw, h->max_halo, h->max_pnnz, h->ld, nullptr);
     LAUNCH(h);
     return 0;
+}
+int launch_spmm_panel(pgb200_ert *h, const double *vals, const double *X, double *Y, int c0, int c1, double *dots) {
+    if (c1 <= c0) return 0;
+    if (h->panel_nc == 2) return launch_spmm_panel_nc<2>(h, vals, X, Y, c0, c1, dots);
+    return launch_spmm_panel_nc<1>(h, vals, X, Y, c0, c1, dots);
 }
 
 // scal layout: [0] rz_a [1] rz_b [2] rz_c [3] pAp [4] rr_a [5] rr_b [6] bb   (each ld doubles)
@@ -207,7 +210,7 @@ int pcg_solve(pgb200_ert *h) {
         const int rr_cur = 4 + (it % 2), rr_nxt = 4 + ((it + 1) % 2);
         const bool timed = h->prof && h->n_pev + 2 <= (int)h->pev.size();
         if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
-        if (h->use_panels && h->n_panels > 0 && !(c0 & 1)) CKR(launch_spmm_panel(h, h->vals.p, h->P.p, h->AP.p, c0, c1, sc(3)));
+        if (h->use_panels && h->n_panels > 0 && !(c0 & 1) && (h->nK == 1 || h->nE >= 32 * h->panel_nc)) CKR(launch_spmm_panel(h, h->vals.p, h->P.p, h->AP.p, c0, c1, sc(3)));
         else CKR((launch_spmm<0, true>(h, h->vals.p, nullptr, nullptr, h->P.p, h->AP.p, c0, c1, sc(3))));
         if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
         k_pcg_update_xr<<<vg, vb, 0, h->st>>>(h->P.p, h->AP.p, h->dinv.p, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
@@ -564,7 +567,7 @@ int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
     const size_t npro = p->n_pro_levels ? (size_t)p->pro_level_ptr[p->n_pro_levels] : 0;
     CKR(h->pro_cells.upload(p->pro_cells, npro, st)); CKR(h->pro_nb.upload(p->pro_nb, npro * p->pro_nf, st));
     CKR(h->pro_w.upload(p->pro_w, npro * p->pro_nf, st));
-    h->n_panels = p->n_panels; h->max_halo = p->max_halo;
+    h->n_panels = p->n_panels; h->max_halo = p->max_halo; h->max_pnnz = p->max_panel_nnz;
     if (p->n_panels > 0) {
         CKR(h->panel_ptr.upload(p->panel_ptr, (size_t)p->n_panels + 1, st)); CKR(h->halo_ptr.upload(p->halo_ptr, (size_t)p->n_panels + 1, st));
         CKR(h->halo_cols.upload(p->halo_cols, (size_t)p->halo_ptr[p->n_panels], st));
@@ -882,7 +885,11 @@ int pgb200_ert_reset_stats(pgb200_ert *h) {
     h->launches = 0; h->spmm_ms = 0.0; h->spmm_timed = 0; h->jac_ms = 0.0; h->n_pev = 0;
     return 0;
 }
-int pgb200_ert_set_spmm_variant(pgb200_ert *h, int panel_staged) { if (!h) PGB_FAIL("null handle"); h->use_panels = panel_staged; return 0; }
+int pgb200_ert_set_spmm_variant(pgb200_ert *h, int panel_staged) {
+    if (!h) PGB_FAIL("null handle");
+    h->use_panels = panel_staged != 0; if (panel_staged == 1 || panel_staged == 2) h->panel_nc = panel_staged;
+    return 0;
+}
 int pgb200_ert_set_profile(pgb200_ert *h, int on) {
     if (!h) PGB_FAIL("null handle");
     CK(cudaSetDevice(h->device));
