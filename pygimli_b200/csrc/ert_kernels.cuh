@@ -279,7 +279,7 @@ k_spmm(const int *__restrict__ rowptr, const int *__restrict__ colidx, const dou
 //        shared memory and leave the CTA as one atomicAdd per column.
 //   Each gathered X row is read from L2/HBM once per panel instead of once per touching row.
 // ---------------------------------------------------------------------------------
-constexpr int PANEL_THREADS = 256;
+constexpr int PANEL_THREADS = 512;
 constexpr int PANEL_WARPS = PANEL_THREADS / 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -306,76 +306,109 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 }
 
 // NC = source columns per lane (tile width <= 32*NC).  Shared memory: X tile [halo][tw] doubles,
-// then the panel's CSR slice: values for the (at most two) wavenumber groups the tile touches and
-// the byte offset of every entry's X row inside the tile.
+// then the panel's CSR slice: values for the (at most two) wavenumber groups the tile touches,
+// the offset of every entry's X row inside the tile, and the panel's row pointers.
+template <int NC, bool TWO_K>
+__device__ __forceinline__ void panel_rows(const double *sm, const double *sA0, const double *sA1, const uint32_t *sOff,
+                                           const int *sRow, const unsigned short *__restrict__ self_idx, int r0, int nrows, int warp,
+                                           const int (&loff)[NC], int tw, const bool (&ok)[NC], const bool (&second)[NC], const int (&col)[NC],
+                                           size_t ld, double *__restrict__ Y, double (&part)[NC], bool dot) {
+    for (int r = warp; r < nrows; r += PANEL_WARPS) {
+        const int pb = sRow[r], pe = sRow[r + 1];
+        double acc[NC];
+#pragma unroll
+        for (int m = 0; m < NC; m++) acc[m] = 0.0;
+#pragma unroll 4
+        for (int p = pb; p < pe; p++) {
+            const double *xr = sm + sOff[p];
+            const double a0 = sA0[p];
+            if (TWO_K) {
+                const double a1 = sA1[p];
+#pragma unroll
+                for (int m = 0; m < NC; m++) acc[m] = fma(second[m] ? a1 : a0, xr[loff[m]], acc[m]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < NC; m++) acc[m] = fma(a0, xr[loff[m]], acc[m]);
+            }
+        }
+        const int row = r0 + r;
+        const double *xs = sm + (size_t)self_idx[row] * tw;
+#pragma unroll
+        for (int m = 0; m < NC; m++) {
+            if (ok[m]) {
+                Y[(size_t)row * ld + col[m]] = acc[m];
+                if (dot) part[m] = fma(acc[m], xs[loff[m]], part[m]);
+            }
+        }
+    }
+}
+
 template <int NC, bool DOT>
 __global__ void __launch_bounds__(PANEL_THREADS)
 k_spmm_panel(const int *__restrict__ rowptr, const unsigned short *__restrict__ lidx, const unsigned short *__restrict__ self_idx,
              const int *__restrict__ panel_ptr, const int *__restrict__ halo_ptr, const int *__restrict__ halo_cols,
              const double *__restrict__ vals, size_t nnz, const double *__restrict__ X, double *__restrict__ Y,
-             int nE, int c0, int c1, int tw, int max_halo, int max_pnnz, size_t ld, double *__restrict__ dots) {
+             int nE, int c0, int c1, int tw, int max_halo, int max_pnnz, int max_rows, size_t ld, double *__restrict__ dots) {
     extern __shared__ __align__(16) double sm[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ double red[PANEL_WARPS][32 * NC];
     const int panel = blockIdx.x;
     const int tile0 = c0 + blockIdx.y * tw;                   // first column of this tile (even)
     const int w = min(tw, (int)ld - tile0);                    // copied width (even; may include zero padding)
-    const int r0 = panel_ptr[panel], r1 = panel_ptr[panel + 1];
+    const int r0 = panel_ptr[panel], nrows = panel_ptr[panel + 1] - r0;
     const int h0 = halo_ptr[panel], hn = halo_ptr[panel + 1] - h0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *sA0 = sm + (size_t)max_halo * tw;                  // values, first wavenumber group of the tile
     double *sA1 = sA0 + max_pnnz;                              // values, second group (if the tile straddles)
     uint32_t *sOff = reinterpret_cast<uint32_t *>(sA1 + max_pnnz);
+    int *sRow = reinterpret_cast<int *>(sOff + max_pnnz);
 
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&bar, (uint32_t)(hn * w * 8));
+    }
     __syncthreads();
-    if (threadIdx.x == 0) mbar_expect_tx(&bar, (uint32_t)(hn * w * 8));
-    __syncthreads();
-    // the bulk copies are issued from all warps (the issue itself is serialised per warp)
+    // one TMA bulk copy per halo row, issued from all warps (the issue is serialised per warp)
     for (int i = threadIdx.x; i < hn; i += PANEL_THREADS)
         tma_bulk_g2s(sm + (size_t)i * tw, X + (size_t)halo_cols[h0 + i] * ld + tile0, (uint32_t)(w * 8), &bar);
-    // meanwhile: CSR slice of the panel -> shared memory (coalesced)
-    const int p0 = rowptr[r0], pn = rowptr[r1] - p0;
+    // meanwhile: CSR slice of the panel -> shared memory (coalesced, loads batched before the stores)
+    const int p0 = rowptr[r0];
+    const int pn = rowptr[r0 + nrows] - p0;
     const int last = min(tile0 + w, c1) - 1;
     const int kk0 = tile0 / nE, kk1 = last / nE;
-    for (int i = threadIdx.x; i < pn; i += PANEL_THREADS) {
-        sA0[i] = __ldg(vals + (size_t)kk0 * nnz + p0 + i);
-        if (kk1 != kk0) sA1[i] = __ldg(vals + (size_t)kk1 * nnz + p0 + i);
-        sOff[i] = (uint32_t)__ldg(lidx + p0 + i) * (uint32_t)tw;
+    const bool two_k = kk1 != kk0;
+    const double *v0 = vals + (size_t)kk0 * nnz + p0, *v1 = vals + (size_t)kk1 * nnz + p0;
+    for (int i = threadIdx.x; i < pn; i += 2 * PANEL_THREADS) {
+        const int j = i + PANEL_THREADS;
+        const bool hj = j < pn;
+        const double a = __ldg(v0 + i), b = hj ? __ldg(v0 + j) : 0.0;
+        const unsigned short la = __ldg(lidx + p0 + i), lb = hj ? __ldg(lidx + p0 + j) : (unsigned short)0;
+        double c = 0.0, d = 0.0;
+        if (two_k) { c = __ldg(v1 + i); d = hj ? __ldg(v1 + j) : 0.0; }
+        sA0[i] = a; sOff[i] = (uint32_t)la * (uint32_t)tw;
+        if (two_k) sA1[i] = c;
+        if (hj) { sA0[j] = b; sOff[j] = (uint32_t)lb * (uint32_t)tw; if (two_k) sA1[j] = d; }
     }
-    int col[NC]; bool ok[NC]; const double *sA[NC];
+    for (int i = threadIdx.x; i <= nrows; i += PANEL_THREADS) sRow[i] = __ldg(rowptr + r0 + i) - p0;
+    int col[NC], loff[NC]; bool ok[NC], second[NC];
 #pragma unroll
     for (int m = 0; m < NC; m++) {
         col[m] = tile0 + lane + 32 * m;
         ok[m] = (lane + 32 * m) < w && col[m] < c1;
-        sA[m] = (ok[m] && col[m] / nE != kk0) ? sA1 : sA0;
+        second[m] = ok[m] && (col[m] / nE != kk0);
+        loff[m] = (lane + 32 * m) < w ? lane + 32 * m : 0;     // lanes beyond the tile read column 0 and never store
+        if (!ok[m]) col[m] = tile0;
     }
+    (void)max_rows;
     __syncthreads();
     mbar_wait(&bar, 0);
 
     double part[NC];
 #pragma unroll
     for (int m = 0; m < NC; m++) part[m] = 0.0;
-    for (int row = r0 + warp; row < r1; row += PANEL_WARPS) {
-        const int pb = rowptr[row] - p0, pe = rowptr[row + 1] - p0;
-        double acc[NC];
-#pragma unroll
-        for (int m = 0; m < NC; m++) acc[m] = 0.0;
-#pragma unroll 4
-        for (int p = pb; p < pe; p++) {
-            const double *xr = sm + sOff[p] + lane;
-#pragma unroll
-            for (int m = 0; m < NC; m++) if (ok[m]) acc[m] = fma(sA[m][p], xr[32 * m], acc[m]);
-        }
-        const double *xs = sm + (size_t)self_idx[row] * tw + lane;
-#pragma unroll
-        for (int m = 0; m < NC; m++) {
-            if (ok[m]) {
-                Y[(size_t)row * ld + col[m]] = acc[m];
-                if (DOT) part[m] = fma(acc[m], xs[32 * m], part[m]);
-            }
-        }
-    }
+    if (two_k) panel_rows<NC, true>(sm, sA0, sA1, sOff, sRow, self_idx, r0, nrows, warp, loff, tw, ok, second, col, ld, Y, part, DOT);
+    else panel_rows<NC, false>(sm, sA0, sA1, sOff, sRow, self_idx, r0, nrows, warp, loff, tw, ok, second, col, ld, Y, part, DOT);
     if (DOT) {
 #pragma unroll
         for (int m = 0; m < NC; m++) red[warp][lane + 32 * m] = part[m];

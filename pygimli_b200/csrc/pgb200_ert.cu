@@ -70,7 +70,7 @@ struct pgb200_ert {
         dir_zero, dir_diag, dir_nodes, sing_node, pick_ptr, pick_idx, src_cell_ptr, src_cells, pro_cells, pro_nb,
         jac_cells, jac_col_ptr, abmn;
     std::vector<int> color_ptr, pro_level_ptr;
-    DevBuf<int> panel_ptr, halo_ptr, halo_cols; DevBuf<unsigned short> lidx, self_idx; int n_panels = 0, max_halo = 0, max_pnnz = 0, panel_nc = 2; int use_panels = 1;
+    DevBuf<int> panel_ptr, halo_ptr, halo_cols; DevBuf<unsigned short> lidx, self_idx; int n_panels = 0, max_halo = 0, max_pnnz = 0, max_rows = 0, panel_nc = 2; int use_panels = 1;
     std::vector<double> h_kvals;
     int n_colors = 0, n_bc_slots = 0, n_bc_entries = 0, n_dir_zero = 0, n_dir_nodes = 0, pro_nf = 0, n_jac_cells = 0;
     std::vector<int> h_abmn; std::vector<double> h_kfac;
@@ -168,7 +168,8 @@ int launch_spmm_panel_nc(pgb200_ert *h, const double *vals, const double *X, dou
     const int span = c1 - c0;
     const int ntile = cdiv(span, 32 * NC);
     int tw = cdiv(span, ntile); tw += tw & 1;                  // even tile width <= 32*NC (16-byte aligned bulk copies)
-    const size_t smem = sizeof(double) * ((size_t)h->max_halo * tw + 2 * (size_t)h->max_pnnz) + sizeof(uint32_t) * (size_t)h->max_pnnz + 16;
+    const size_t smem = sizeof(double) * ((size_t)h->max_halo * tw + 2 * (size_t)h->max_pnnz) + sizeof(uint32_t) * (size_t)h->max_pnnz +
+                        sizeof(int) * ((size_t)h->max_rows + 2) + 16;
     static size_t configured[3] = {0, 0, 0};
     if (smem > configured[NC]) {
         CK(cudaFuncSetAttribute(k_spmm_panel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -177,9 +178,9 @@ int launch_spmm_panel_nc(pgb200_ert *h, const double *vals, const double *X, dou
     }
     dim3 grid(h->n_panels, ntile);
     if (dots) k_spmm_panel<NC, true><<<grid, PANEL_THREADS, smem, h->st>>>(h->rowptr.p, h->lidx.p, h->self_idx.p, h->panel_ptr.p, h->halo_ptr.p,
-                     h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0, c1, tw, h->max_halo, h->max_pnnz, h->ld, dots);
+                     h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0, c1, tw, h->max_halo, h->max_pnnz, h->max_rows, h->ld, dots);
     else k_spmm_panel<NC, false><<<grid, PANEL_THREADS, smem, h->st>>>(h->rowptr.p, h->lidx.p, h->self_idx.p, h->panel_ptr.p, h->halo_ptr.p,
-                     h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0, c1, tw, h->max_halo, h->max_pnnz, h->ld, nullptr);
+                     h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0, c1, tw, h->max_halo, h->max_pnnz, h->max_rows, h->ld, nullptr);
     LAUNCH(h);
     return 0;
 }
@@ -567,7 +568,8 @@ int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
     const size_t npro = p->n_pro_levels ? (size_t)p->pro_level_ptr[p->n_pro_levels] : 0;
     CKR(h->pro_cells.upload(p->pro_cells, npro, st)); CKR(h->pro_nb.upload(p->pro_nb, npro * p->pro_nf, st));
     CKR(h->pro_w.upload(p->pro_w, npro * p->pro_nf, st));
-    h->n_panels = p->n_panels; h->max_halo = p->max_halo; h->max_pnnz = p->max_panel_nnz;
+    h->n_panels = p->n_panels; h->max_halo = p->max_halo; h->max_pnnz = p->max_panel_nnz; h->max_rows = 0;
+    for (int i = 0; i < p->n_panels; i++) h->max_rows = std::max(h->max_rows, p->panel_ptr[i + 1] - p->panel_ptr[i]);
     if (p->n_panels > 0) {
         CKR(h->panel_ptr.upload(p->panel_ptr, (size_t)p->n_panels + 1, st)); CKR(h->halo_ptr.upload(p->halo_ptr, (size_t)p->n_panels + 1, st));
         CKR(h->halo_cols.upload(p->halo_cols, (size_t)p->halo_ptr[p->n_panels], st));
