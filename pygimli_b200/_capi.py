@@ -127,6 +127,8 @@ def color_cells(cells: np.ndarray, n_nodes: int):
 
 
 def build_panels(rowptr: np.ndarray, colidx: np.ndarray, rmax: int = 64, hmax: int = 192):
+    rmax = int(os.environ.get("PGB200_PANEL_ROWS", rmax))
+    hmax = int(os.environ.get("PGB200_PANEL_HALO", hmax))
     """row panels + halo lists + 16-bit local column indices for the staged SpMM (C++ host helper)"""
     rowptr = np.ascontiguousarray(rowptr, np.int32)
     colidx = np.ascontiguousarray(colidx, np.int32)

@@ -305,13 +305,16 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// NC = source columns per lane (tile width <= 32*NC).  Shared memory: X tile [halo][tw] doubles,
-// then the panel's CSR slice: values for the (at most two) wavenumber groups the tile touches,
-// the offset of every entry's X row inside the tile, and the panel's row pointers.
+// NC = source columns per lane (tile width <= 32*NC).  Shared memory: X tile [halo][tw] doubles
+// (+ one pad row so that lanes beyond the tile width read in-bounds garbage they never use),
+// then the panel's CSR slice as 16-byte entries {value, byte offset of the entry's X row}, the
+// values of a second wavenumber group (only if the tile straddles two), and the row pointers.
+struct __align__(16) PanelEntry { double a; uint32_t off; uint32_t pad; };
+
 template <int NC, bool TWO_K>
-__device__ __forceinline__ void panel_rows(const double *sm, const double *sA0, const double *sA1, const uint32_t *sOff,
-                                           const int *sRow, const unsigned short *__restrict__ self_idx, int r0, int nrows, int warp,
-                                           const int (&loff)[NC], int tw, const bool (&ok)[NC], const bool (&second)[NC], const int (&col)[NC],
+__device__ __forceinline__ void panel_rows(const char *sx_lane, const PanelEntry *sE, const double *sA1, const int *sRow,
+                                           const unsigned short *__restrict__ self_idx, int r0, int nrows, int warp, int tw,
+                                           const bool (&ok)[NC], const bool (&second)[NC], const int (&col)[NC],
                                            size_t ld, double *__restrict__ Y, double (&part)[NC], bool dot) {
     for (int r = warp; r < nrows; r += PANEL_WARPS) {
         const int pb = sRow[r], pe = sRow[r + 1];
@@ -320,24 +323,24 @@ __device__ __forceinline__ void panel_rows(const double *sm, const double *sA0, 
         for (int m = 0; m < NC; m++) acc[m] = 0.0;
 #pragma unroll 4
         for (int p = pb; p < pe; p++) {
-            const double *xr = sm + sOff[p];
-            const double a0 = sA0[p];
+            const PanelEntry e = sE[p];                               // one 128-bit broadcast load
+            const double *xr = reinterpret_cast<const double *>(sx_lane + e.off);
             if (TWO_K) {
                 const double a1 = sA1[p];
 #pragma unroll
-                for (int m = 0; m < NC; m++) acc[m] = fma(second[m] ? a1 : a0, xr[loff[m]], acc[m]);
+                for (int m = 0; m < NC; m++) acc[m] = fma(second[m] ? a1 : e.a, xr[32 * m], acc[m]);
             } else {
 #pragma unroll
-                for (int m = 0; m < NC; m++) acc[m] = fma(a0, xr[loff[m]], acc[m]);
+                for (int m = 0; m < NC; m++) acc[m] = fma(e.a, xr[32 * m], acc[m]);
             }
         }
         const int row = r0 + r;
-        const double *xs = sm + (size_t)self_idx[row] * tw;
+        const double *xs = reinterpret_cast<const double *>(sx_lane + (size_t)self_idx[row] * tw * 8);
 #pragma unroll
         for (int m = 0; m < NC; m++) {
             if (ok[m]) {
                 Y[(size_t)row * ld + col[m]] = acc[m];
-                if (dot) part[m] = fma(acc[m], xs[loff[m]], part[m]);
+                if (dot) part[m] = fma(acc[m], xs[32 * m], part[m]);
             }
         }
     }
@@ -358,10 +361,9 @@ k_spmm_panel(const int *__restrict__ rowptr, const unsigned short *__restrict__ 
     const int r0 = panel_ptr[panel], nrows = panel_ptr[panel + 1] - r0;
     const int h0 = halo_ptr[panel], hn = halo_ptr[panel + 1] - h0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *sA0 = sm + (size_t)max_halo * tw;                  // values, first wavenumber group of the tile
-    double *sA1 = sA0 + max_pnnz;                              // values, second group (if the tile straddles)
-    uint32_t *sOff = reinterpret_cast<uint32_t *>(sA1 + max_pnnz);
-    int *sRow = reinterpret_cast<int *>(sOff + max_pnnz);
+    PanelEntry *sE = reinterpret_cast<PanelEntry *>(sm + (size_t)max_halo * tw + 32 * NC);   // after the pad row
+    double *sA1 = reinterpret_cast<double *>(sE + max_pnnz);
+    int *sRow = reinterpret_cast<int *>(sA1 + max_pnnz);
 
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
@@ -386,18 +388,17 @@ k_spmm_panel(const int *__restrict__ rowptr, const unsigned short *__restrict__ 
         const unsigned short la = __ldg(lidx + p0 + i), lb = hj ? __ldg(lidx + p0 + j) : (unsigned short)0;
         double c = 0.0, d = 0.0;
         if (two_k) { c = __ldg(v1 + i); d = hj ? __ldg(v1 + j) : 0.0; }
-        sA0[i] = a; sOff[i] = (uint32_t)la * (uint32_t)tw;
+        sE[i].a = a; sE[i].off = (uint32_t)la * (uint32_t)(tw * 8);
         if (two_k) sA1[i] = c;
-        if (hj) { sA0[j] = b; sOff[j] = (uint32_t)lb * (uint32_t)tw; if (two_k) sA1[j] = d; }
+        if (hj) { sE[j].a = b; sE[j].off = (uint32_t)lb * (uint32_t)(tw * 8); if (two_k) sA1[j] = d; }
     }
     for (int i = threadIdx.x; i <= nrows; i += PANEL_THREADS) sRow[i] = __ldg(rowptr + r0 + i) - p0;
-    int col[NC], loff[NC]; bool ok[NC], second[NC];
+    int col[NC]; bool ok[NC], second[NC];
 #pragma unroll
     for (int m = 0; m < NC; m++) {
         col[m] = tile0 + lane + 32 * m;
         ok[m] = (lane + 32 * m) < w && col[m] < c1;
         second[m] = ok[m] && (col[m] / nE != kk0);
-        loff[m] = (lane + 32 * m) < w ? lane + 32 * m : 0;     // lanes beyond the tile read column 0 and never store
         if (!ok[m]) col[m] = tile0;
     }
     (void)max_rows;
@@ -407,8 +408,9 @@ k_spmm_panel(const int *__restrict__ rowptr, const unsigned short *__restrict__ 
     double part[NC];
 #pragma unroll
     for (int m = 0; m < NC; m++) part[m] = 0.0;
-    if (two_k) panel_rows<NC, true>(sm, sA0, sA1, sOff, sRow, self_idx, r0, nrows, warp, loff, tw, ok, second, col, ld, Y, part, DOT);
-    else panel_rows<NC, false>(sm, sA0, sA1, sOff, sRow, self_idx, r0, nrows, warp, loff, tw, ok, second, col, ld, Y, part, DOT);
+    const char *sx_lane = reinterpret_cast<const char *>(sm + lane);
+    if (two_k) panel_rows<NC, true>(sx_lane, sE, sA1, sRow, self_idx, r0, nrows, warp, tw, ok, second, col, ld, Y, part, DOT);
+    else panel_rows<NC, false>(sx_lane, sE, sA1, sRow, self_idx, r0, nrows, warp, tw, ok, second, col, ld, Y, part, DOT);
     if (DOT) {
 #pragma unroll
         for (int m = 0; m < NC; m++) red[warp][lane + 32 * m] = part[m];

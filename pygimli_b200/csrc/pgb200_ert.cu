@@ -168,7 +168,7 @@ int launch_spmm_panel_nc(pgb200_ert *h, const double *vals, const double *X, dou
     const int span = c1 - c0;
     const int ntile = cdiv(span, 32 * NC);
     int tw = cdiv(span, ntile); tw += tw & 1;                  // even tile width <= 32*NC (16-byte aligned bulk copies)
-    const size_t smem = sizeof(double) * ((size_t)h->max_halo * tw + 2 * (size_t)h->max_pnnz) + sizeof(uint32_t) * (size_t)h->max_pnnz +
+    const size_t smem = sizeof(double) * ((size_t)h->max_halo * tw + 32 * NC + 3 * (size_t)h->max_pnnz) +
                         sizeof(int) * ((size_t)h->max_rows + 2) + 16;
     static size_t configured[3] = {0, 0, 0};
     if (smem > configured[NC]) {
