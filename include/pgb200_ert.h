@@ -175,7 +175,8 @@ long long pgb200_ert_get(pgb200_ert *h, const char *what, double *out_host, long
 int pgb200_ert_stats(pgb200_ert *h, double *stats, int n);
 int pgb200_ert_reset_stats(pgb200_ert *h);
 int pgb200_ert_set_profile(pgb200_ert *h, int on);
-/* 0: plain gather kernel; 1 / 2: panel-staged TMA SpMM with 1 / 2 (default) source columns per lane */
+/* 0: plain gather kernel; 1 / 2: panel-staged SpMM (cp.async staging) with 1 / 2 (default) source
+ * columns per lane; 3: panel-staged with one TMA bulk copy per halo row (kept for A/B evidence)  */
 int pgb200_ert_set_spmm_variant(pgb200_ert *h, int panel_staged);
 
 /* ---- single-kernel entry points (device pointers; unit tests and micro-benchmarks) --- */

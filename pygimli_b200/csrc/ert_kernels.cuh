@@ -346,7 +346,13 @@ __device__ __forceinline__ void panel_rows(const char *sx_lane, const PanelEntry
     }
 }
 
-template <int NC, bool DOT>
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+// STAGE = 0: X rows arrive through cp.async (LDGSTS, 16 bytes per lane, one warp per halo row);
+// STAGE = 1: one TMA bulk copy (UBLKCP) per halo row, completion on an mbarrier.
+template <int NC, bool DOT, int STAGE>
 __global__ void __launch_bounds__(PANEL_THREADS)
 k_spmm_panel(const int *__restrict__ rowptr, const unsigned short *__restrict__ lidx, const unsigned short *__restrict__ self_idx,
              const int *__restrict__ panel_ptr, const int *__restrict__ halo_ptr, const int *__restrict__ halo_cols,
@@ -365,15 +371,30 @@ k_spmm_panel(const int *__restrict__ rowptr, const unsigned short *__restrict__ 
     double *sA1 = reinterpret_cast<double *>(sE + max_pnnz);
     int *sRow = reinterpret_cast<int *>(sA1 + max_pnnz);
 
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        mbar_expect_tx(&bar, (uint32_t)(hn * w * 8));
+    if (STAGE == 1) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(&bar, (uint32_t)(hn * w * 8));
+        }
+        __syncthreads();
+        // one TMA bulk copy per halo row, issued from all warps (the issue is serialised per warp)
+        for (int i = threadIdx.x; i < hn; i += PANEL_THREADS)
+            tma_bulk_g2s(sm + (size_t)i * tw, X + (size_t)halo_cols[h0 + i] * ld + tile0, (uint32_t)(w * 8), &bar);
+    } else {
+        // one warp per halo row, lane = 16-byte chunk (w <= 64 -> at most 32 chunks)
+        const int nchunk = w >> 1;
+        for (int i = warp; i < hn; i += 4 * PANEL_WARPS) {
+            int hc[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) hc[u] = (i + u * PANEL_WARPS < hn) ? __ldg(halo_cols + h0 + i + u * PANEL_WARPS) : -1;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (hc[u] >= 0 && lane < nchunk)
+                    cp_async16(sm + (size_t)(i + u * PANEL_WARPS) * tw + 2 * lane, X + (size_t)hc[u] * ld + tile0 + 2 * lane);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    __syncthreads();
-    // one TMA bulk copy per halo row, issued from all warps (the issue is serialised per warp)
-    for (int i = threadIdx.x; i < hn; i += PANEL_THREADS)
-        tma_bulk_g2s(sm + (size_t)i * tw, X + (size_t)halo_cols[h0 + i] * ld + tile0, (uint32_t)(w * 8), &bar);
     // meanwhile: CSR slice of the panel -> shared memory (coalesced, loads batched before the stores)
     const int p0 = rowptr[r0];
     const int pn = rowptr[r0 + nrows] - p0;
@@ -402,8 +423,9 @@ k_spmm_panel(const int *__restrict__ rowptr, const unsigned short *__restrict__ 
         if (!ok[m]) col[m] = tile0;
     }
     (void)max_rows;
+    if (STAGE == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    mbar_wait(&bar, 0);
+    if (STAGE == 1) mbar_wait(&bar, 0);
 
     double part[NC];
 #pragma unroll

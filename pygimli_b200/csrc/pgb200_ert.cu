@@ -70,7 +70,7 @@ struct pgb200_ert {
         dir_zero, dir_diag, dir_nodes, sing_node, pick_ptr, pick_idx, src_cell_ptr, src_cells, pro_cells, pro_nb,
         jac_cells, jac_col_ptr, abmn;
     std::vector<int> color_ptr, pro_level_ptr;
-    DevBuf<int> panel_ptr, halo_ptr, halo_cols; DevBuf<unsigned short> lidx, self_idx; int n_panels = 0, max_halo = 0, max_pnnz = 0, max_rows = 0, panel_nc = 2; int use_panels = 1;
+    DevBuf<int> panel_ptr, halo_ptr, halo_cols; DevBuf<unsigned short> lidx, self_idx; int n_panels = 0, max_halo = 0, max_pnnz = 0, max_rows = 0, panel_nc = 2, panel_tma = 0; int use_panels = 1;
     std::vector<double> h_kvals;
     int n_colors = 0, n_bc_slots = 0, n_bc_entries = 0, n_dir_zero = 0, n_dir_nodes = 0, pro_nf = 0, n_jac_cells = 0;
     std::vector<int> h_abmn; std::vector<double> h_kfac;
@@ -172,15 +172,18 @@ int launch_spmm_panel_nc(pgb200_ert *h, const double *vals, const double *X, dou
                         sizeof(int) * ((size_t)h->max_rows + 2) + 16;
     static size_t configured[3] = {0, 0, 0};
     if (smem > configured[NC]) {
-        CK(cudaFuncSetAttribute(k_spmm_panel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_spmm_panel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_spmm_panel<NC, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_spmm_panel<NC, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_spmm_panel<NC, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_spmm_panel<NC, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[NC] = smem;
     }
     dim3 grid(h->n_panels, ntile);
-    if (dots) k_spmm_panel<NC, true><<<grid, PANEL_THREADS, smem, h->st>>>(h->rowptr.p, h->lidx.p, h->self_idx.p, h->panel_ptr.p, h->halo_ptr.p,
-                     h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0, c1, tw, h->max_halo, h->max_pnnz, h->max_rows, h->ld, dots);
-    else k_spmm_panel<NC, false><<<grid, PANEL_THREADS, smem, h->st>>>(h->rowptr.p, h->lidx.p, h->self_idx.p, h->panel_ptr.p, h->halo_ptr.p,
-                     h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0, c1, tw, h->max_halo, h->max_pnnz, h->max_rows, h->ld, nullptr);
+#define PANEL_GO(D, S) k_spmm_panel<NC, D, S><<<grid, PANEL_THREADS, smem, h->st>>>(h->rowptr.p, h->lidx.p, h->self_idx.p, h->panel_ptr.p, \
+        h->halo_ptr.p, h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0, c1, tw, h->max_halo, h->max_pnnz, h->max_rows, h->ld, dots)
+    if (h->panel_tma) { if (dots) PANEL_GO(true, 1); else PANEL_GO(false, 1); }
+    else { if (dots) PANEL_GO(true, 0); else PANEL_GO(false, 0); }
+#undef PANEL_GO
     LAUNCH(h);
     return 0;
 }
@@ -889,7 +892,8 @@ int pgb200_ert_reset_stats(pgb200_ert *h) {
 }
 int pgb200_ert_set_spmm_variant(pgb200_ert *h, int panel_staged) {
     if (!h) PGB_FAIL("null handle");
-    h->use_panels = panel_staged != 0; if (panel_staged == 1 || panel_staged == 2) h->panel_nc = panel_staged;
+    h->use_panels = panel_staged != 0; h->panel_tma = (panel_staged == 3);
+    if (panel_staged == 1 || panel_staged == 2) h->panel_nc = panel_staged; else if (panel_staged == 3) h->panel_nc = 2;
     return 0;
 }
 int pgb200_ert_set_profile(pgb200_ert *h, int on) {
