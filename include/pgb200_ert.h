@@ -170,13 +170,14 @@ int pgb200_ert_pack_potentials(pgb200_ert *h, int c0, int c1, double *buf_dev, i
  * "rel_res" [nS].  Returns the number of doubles written (or needed when out == NULL), < 0 on error. */
 long long pgb200_ert_get(pgb200_ert *h, const char *what, double *out_host, long long capacity);
 /* stats[0]=PCG iterations of the last solve, [1]=max relative residual, [2]=kernel launches
- * since create/reset, [3..8] = ms of the last call: map, assemble, rhs, solve, epilogue, jacobian,
- * [9]=SpMM launches timed, [10]=their total ms, [11]=Jacobian kernel ms                     */
+ * since create/reset, [3..8] = accumulated ms since reset: map, assemble, rhs, solve, epilogue,
+ * jacobian, [9]=SpMM launches timed, [10]=their total ms, [11]=Jacobian kernel ms (total),
+ * [12]=Jacobian passes timed, [13]=PCG iterations since reset, [14]=solves since reset       */
 int pgb200_ert_stats(pgb200_ert *h, double *stats, int n);
 int pgb200_ert_reset_stats(pgb200_ert *h);
 int pgb200_ert_set_profile(pgb200_ert *h, int on);
-/* 0: plain gather kernel; 1 / 2: panel-staged SpMM (cp.async staging) with 1 / 2 (default) source
- * columns per lane; 3: panel-staged with one TMA bulk copy per halo row (kept for A/B evidence)  */
+/* 0: plain gather kernel; 1 / 2: panel-staged SpMM, one TMA bulk copy per halo row, with 1 / 2
+ * (default) source columns per lane; 3: same as 2 but cp.async (LDGSTS) staging (A/B evidence)   */
 int pgb200_ert_set_spmm_variant(pgb200_ert *h, int panel_staged);
 
 /* ---- single-kernel entry points (device pointers; unit tests and micro-benchmarks) --- */

@@ -126,7 +126,7 @@ def color_cells(cells: np.ndarray, n_nodes: int):
     return color, int(n)
 
 
-def build_panels(rowptr: np.ndarray, colidx: np.ndarray, rmax: int = 64, hmax: int = 192):
+def build_panels(rowptr: np.ndarray, colidx: np.ndarray, rmax: int = 64, hmax: int = 208):
     rmax = int(os.environ.get("PGB200_PANEL_ROWS", rmax))
     hmax = int(os.environ.get("PGB200_PANEL_HALO", hmax))
     """row panels + halo lists + 16-bit local column indices for the staged SpMM (C++ host helper)"""

@@ -70,7 +70,7 @@ struct pgb200_ert {
         dir_zero, dir_diag, dir_nodes, sing_node, pick_ptr, pick_idx, src_cell_ptr, src_cells, pro_cells, pro_nb,
         jac_cells, jac_col_ptr, abmn;
     std::vector<int> color_ptr, pro_level_ptr;
-    DevBuf<int> panel_ptr, halo_ptr, halo_cols; DevBuf<unsigned short> lidx, self_idx; int n_panels = 0, max_halo = 0, max_pnnz = 0, max_rows = 0, panel_nc = 2, panel_tma = 0; int use_panels = 1;
+    DevBuf<int> panel_ptr, halo_ptr, halo_cols; DevBuf<unsigned short> lidx, self_idx; int n_panels = 0, max_halo = 0, max_pnnz = 0, max_rows = 0, panel_nc = 2, panel_tma = 1; int use_panels = 1;
     std::vector<double> h_kvals;
     int n_colors = 0, n_bc_slots = 0, n_bc_entries = 0, n_dir_zero = 0, n_dir_nodes = 0, pro_nf = 0, n_jac_cells = 0;
     std::vector<int> h_abmn; std::vector<double> h_kfac;
@@ -90,7 +90,7 @@ struct pgb200_ert {
     cudaEvent_t ev[PH_COUNT + 1]; bool ev_ok = false; float ph_ms[PH_COUNT] = {0};
     bool ph_rec[PH_COUNT + 1] = {false};
     int prof = 0; std::vector<cudaEvent_t> pev; int n_pev = 0; double spmm_ms = 0.0; int spmm_timed = 0; double jac_ms = 0.0;
-    cudaEvent_t jev[2];
+    cudaEvent_t jev[2]; bool jac_timed = false; int jac_launches = 0; long long total_iters = 0; int solves = 0;
     double *h_pinned = nullptr; size_t h_pinned_n = 0;
     int num_sms = 148;
 };
@@ -241,7 +241,7 @@ int pcg_solve(pgb200_ert *h) {
         }
     }
     CK(cudaGetLastError());
-    h->last_iters = it;
+    h->last_iters = it; h->total_iters += it; h->solves++;
     if (!converged) {
         char buf[256];
         snprintf(buf, sizeof buf, "block-PCG did not reach rel. residual %.1e in %d iterations (worst column %.3e)", h->tol, it, h->last_relres);
@@ -436,7 +436,7 @@ int jacobian(pgb200_ert *h, const double *rho_col) {
         case TET10: CKR(launch_jacobian<TET10>(h, rho_col)); break;
         default: PGB_FAIL("unknown element type");
     }
-    if (h->prof) CK(cudaEventRecord(h->jev[1], h->st));
+    if (h->prof) { CK(cudaEventRecord(h->jev[1], h->st)); h->jac_timed = true; }
     h->jac_valid = true;
     return 0;
 }
@@ -445,14 +445,14 @@ int finish_timing(pgb200_ert *h) {
     CK(cudaEventRecord(h->ev[PH_COUNT], h->st));
     CK(cudaStreamSynchronize(h->st));
     int order[PH_COUNT + 1], n = 0;
-    for (int p = 0; p < PH_COUNT; p++) { h->ph_ms[p] = 0.f; if (h->ph_rec[p]) order[n++] = p; }
+    for (int p = 0; p < PH_COUNT; p++) { if (h->ph_rec[p]) order[n++] = p; }
     order[n] = PH_COUNT;
-    for (int i = 0; i < n; i++) { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev[order[i]], h->ev[order[i + 1]]); h->ph_ms[order[i]] = ms; }
+    for (int i = 0; i < n; i++) { float ms = 0.f; cudaEventElapsedTime(&ms, h->ev[order[i]], h->ev[order[i + 1]]); h->ph_ms[order[i]] += ms; }
     for (int p = 0; p <= PH_COUNT; p++) h->ph_rec[p] = false;
     if (h->prof) {
         for (int i = 0; i + 1 < h->n_pev; i += 2) { float ms = 0.f; cudaEventElapsedTime(&ms, h->pev[i], h->pev[i + 1]); h->spmm_ms += ms; h->spmm_timed++; }
         h->n_pev = 0;
-        if (h->jac_valid && h->ph_ms[PH_JAC] > 0.f) { float ms = 0.f; if (cudaEventElapsedTime(&ms, h->jev[0], h->jev[1]) == cudaSuccess) h->jac_ms = ms; }
+        if (h->jac_timed) { float ms = 0.f; if (cudaEventElapsedTime(&ms, h->jev[0], h->jev[1]) == cudaSuccess) { h->jac_ms += ms; h->jac_launches++; } h->jac_timed = false; }
     }
     return 0;
 }
@@ -880,20 +880,22 @@ long long pgb200_ert_get(pgb200_ert *h, const char *what, double *out, long long
 
 int pgb200_ert_stats(pgb200_ert *h, double *s, int n) {
     if (!h || !s) PGB_FAIL("null argument");
-    double v[12] = {(double)h->last_iters, h->last_relres, (double)h->launches, h->ph_ms[PH_MAP], h->ph_ms[PH_ASM], h->ph_ms[PH_RHS],
-                    h->ph_ms[PH_SOLVE], h->ph_ms[PH_EPI], h->ph_ms[PH_JAC], (double)h->spmm_timed, h->spmm_ms, h->jac_ms};
-    for (int i = 0; i < n && i < 12; i++) s[i] = v[i];
+    double v[15] = {(double)h->last_iters, h->last_relres, (double)h->launches, h->ph_ms[PH_MAP], h->ph_ms[PH_ASM], h->ph_ms[PH_RHS],
+                    h->ph_ms[PH_SOLVE], h->ph_ms[PH_EPI], h->ph_ms[PH_JAC], (double)h->spmm_timed, h->spmm_ms, h->jac_ms,
+                    (double)h->jac_launches, (double)h->total_iters, (double)h->solves};
+    for (int i = 0; i < n && i < 15; i++) s[i] = v[i];
     return 0;
 }
 int pgb200_ert_reset_stats(pgb200_ert *h) {
     if (!h) PGB_FAIL("null handle");
-    h->launches = 0; h->spmm_ms = 0.0; h->spmm_timed = 0; h->jac_ms = 0.0; h->n_pev = 0;
+    h->launches = 0; h->spmm_ms = 0.0; h->spmm_timed = 0; h->jac_ms = 0.0; h->n_pev = 0; h->jac_launches = 0; h->total_iters = 0; h->solves = 0;
+    for (int p = 0; p < PH_COUNT; p++) h->ph_ms[p] = 0.f;
     return 0;
 }
 int pgb200_ert_set_spmm_variant(pgb200_ert *h, int panel_staged) {
     if (!h) PGB_FAIL("null handle");
-    h->use_panels = panel_staged != 0; h->panel_tma = (panel_staged == 3);
-    if (panel_staged == 1 || panel_staged == 2) h->panel_nc = panel_staged; else if (panel_staged == 3) h->panel_nc = 2;
+    h->use_panels = panel_staged != 0; h->panel_tma = (panel_staged == 1 || panel_staged == 2);
+    h->panel_nc = (panel_staged == 1) ? 1 : 2;
     return 0;
 }
 int pgb200_ert_set_profile(pgb200_ert *h, int on) {

@@ -276,10 +276,11 @@ class CoreB200:
         return out
 
     def stats(self) -> dict:
-        s = np.zeros(12)
-        _capi.check(_capi.lib().pgb200_ert_stats(self._ensure_handle(), s.ctypes.data, 12))
+        s = np.zeros(15)
+        _capi.check(_capi.lib().pgb200_ert_stats(self._ensure_handle(), s.ctypes.data, 15))
         keys = ["pcg_iterations", "max_rel_residual", "launches", "ms_map", "ms_assemble", "ms_rhs", "ms_solve",
-                "ms_epilogue", "ms_jacobian", "spmm_timed", "spmm_ms_total", "jacobian_kernel_ms"]
+                "ms_epilogue", "ms_jacobian", "spmm_timed", "spmm_ms_total", "jacobian_kernel_ms", "jacobian_timed",
+                "pcg_iterations_total", "solves"]
         return dict(zip(keys, s.tolist()))
 
     def resetStats(self):
