@@ -113,6 +113,10 @@ int pgb200_color_cells(int n_cells, int nloc, const int *cells, int n_nodes, int
 int pgb200_build_panels(int n_rows, const int *rowptr, const int *colidx, int rmax, int hmax,
                         int *panel_ptr, int *halo_ptr, int *halo_cols, unsigned short *lidx, unsigned short *self_idx);
 
+/* Greedy pairwise aggregation along the strongest negative coupling (multilevel preconditioner
+ * set-up); agg[n] receives the aggregate id per node; returns the number of aggregates.        */
+int pgb200_pairwise_aggregate(int n, const int *rowptr, const int *colidx, const double *vals, int *agg);
+
 /* ---- life cycle ------------------------------------------------------------------- */
 int pgb200_ert_create(const pgb200_plan *plan, int device, pgb200_ert **out);
 int pgb200_ert_destroy(pgb200_ert *h);

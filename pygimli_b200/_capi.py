@@ -43,7 +43,7 @@ class Plan(C.Structure):
 
 # every symbol include/pgb200_ert.h declares (checked by tests/test_capi_symbols.py)
 EXPORTS = [
-    "pgb200_last_error", "pgb200_version", "pgb200_color_cells", "pgb200_build_panels", "pgb200_ert_set_spmm_variant",
+    "pgb200_last_error", "pgb200_version", "pgb200_color_cells", "pgb200_build_panels", "pgb200_ert_set_spmm_variant", "pgb200_pairwise_aggregate",
     "pgb200_ert_create", "pgb200_ert_destroy", "pgb200_ert_set_stream", "pgb200_ert_set_solver", "pgb200_ert_set_shard",
     "pgb200_ert_set_kfac", "pgb200_ert_response", "pgb200_ert_create_jacobian", "pgb200_ert_jacobian_copy",
     "pgb200_ert_jacobian_mult", "pgb200_ert_jacobian_tmult", "pgb200_ert_response_dev", "pgb200_ert_create_jacobian_dev",
@@ -97,6 +97,7 @@ def lib():
         L.pgb200_color_cells.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.pgb200_build_panels.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
         L.pgb200_ert_set_spmm_variant.argtypes = [C.c_void_p, C.c_int]
+        L.pgb200_pairwise_aggregate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pgb200_spmm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p]
         _lib = L
@@ -124,6 +125,15 @@ def color_cells(cells: np.ndarray, n_nodes: int):
     if n <= 0:
         raise PGB200Error(last_error())
     return color, int(n)
+
+
+def pairwise_aggregate(rowptr, colidx, vals):
+    rowptr = np.ascontiguousarray(rowptr, np.int32)
+    colidx = np.ascontiguousarray(colidx, np.int32)
+    vals = np.ascontiguousarray(vals, np.float64)
+    agg = np.zeros(rowptr.size - 1, np.int32)
+    na = lib().pgb200_pairwise_aggregate(rowptr.size - 1, rowptr.ctypes.data, colidx.ctypes.data, vals.ctypes.data, agg.ctypes.data)
+    return agg, int(na)
 
 
 def build_panels(rowptr: np.ndarray, colidx: np.ndarray, rmax: int = 64, hmax: int = 208):

@@ -633,8 +633,10 @@ __global__ void k_transpose_out(const double *__restrict__ U, size_t ld, int N, 
 //       G[a][m] - G[a][n] - G[b][m] + G[b][n],
 //   scaled and stored to the column-major J with consecutive threads writing consecutive rows.
 // ---------------------------------------------------------------------------------
-constexpr int JAC_THREADS = 256;
-constexpr int JAC_MAX_TILES = 4;     // micro-tiles per thread
+constexpr int JAC_THREADS = 512;
+constexpr int JAC_MAX_TILES = 2;     // 4x4 micro-tiles per thread
+
+struct __align__(8) JacDatum { unsigned short a, b, m, n; };   // indices into plist / qlist, 0xFFFF = unused electrode
 
 struct JacArgs {
     const double *pos; const int *cells; int nloc;
@@ -642,8 +644,9 @@ struct JacArgs {
     const double *U; size_t ld; int nE; int nK; const double *kvals; const double *kw;
     const int *plist; int nP, nPp;            // current-side electrodes, padded to a multiple of 4
     const int *qlist; int nQ, nQp;
-    const int *ia, *ib, *im, *in;             // [nd] indices into plist / qlist (-1 unused)
+    const JacDatum *idx;                      // [nd]
     const int *out_row; const double *kfac; int nd;
+    int idx_in_smem;                          // stage idx[] in shared memory (it is reused by every column)
     const double *rho_col;                    // [M] model value per column or nullptr (no scaling)
     double *Jt; size_t ldJ;
 };
@@ -659,10 +662,16 @@ k_jacobian(const JacArgs A) {
     double *sK  = sV + NL * A.nQp;                  // [NL*NL] stiffness
     double *sM  = sK + NL * NL;                     // [NL*NL] mass
     double *sG  = sM + NL * NL;                     // [nPp][nQp + 1]
+    const int gstride = A.nQp + 1;
+    JacDatum *sIdx = reinterpret_cast<JacDatum *>(sG + (size_t)A.nPp * gstride);
     __shared__ int snode[NL];
     const int tid = threadIdx.x;
     const int tilesQ = A.nQp / 4, tilesP = A.nPp / 4, ntiles = tilesP * tilesQ;
-    const int gstride = A.nQp + 1;
+    const JacDatum *idx = A.idx;
+    if (A.idx_in_smem) {
+        for (int d = tid; d < A.nd; d += JAC_THREADS) sIdx[d] = A.idx[d];
+        idx = sIdx;
+    }
 
     for (int col = A.col_begin + blockIdx.x; col < A.col_end; col += gridDim.x) {
         double acc[JAC_MAX_TILES][16];
@@ -674,7 +683,7 @@ k_jacobian(const JacArgs A) {
         const int cb = A.jac_col_ptr[col], ce = A.jac_col_ptr[col + 1];
         for (int ci = cb; ci < ce; ci++) {
             const int cell = A.jac_cells[ci];
-            __syncthreads();                         // previous cell fully consumed
+            __syncthreads();                         // previous cell / previous column's epilogue fully consumed
             if (tid < NL) snode[tid] = A.cells[(size_t)cell * NL + tid];
             if (tid < NL * NL) {
                 double X[NV][3];
@@ -735,7 +744,8 @@ k_jacobian(const JacArgs A) {
                 }
             }
         }
-        // drop G to shared memory
+        // drop G to shared memory (the previous column's epilogue has passed the barrier above,
+        // or this is an empty column)
         __syncthreads();
 #pragma unroll
         for (int t = 0; t < JAC_MAX_TILES; t++) {
@@ -750,16 +760,21 @@ k_jacobian(const JacArgs A) {
         }
         __syncthreads();
         double scale = 1.0;
-        if (A.rho_col) { const double r = A.rho_col[col]; scale = 1.0 / (r * r); }
+        const bool scaled = A.rho_col != nullptr;
+        if (scaled) { const double r = A.rho_col[col]; scale = 1.0 / (r * r); }
         double *out = A.Jt + (size_t)col * A.ldJ;
+#pragma unroll 4
         for (int d = tid; d < A.nd; d += JAC_THREADS) {
-            const int a = A.ia[d], b = A.ib[d], m = A.im[d], n = A.in[d];
+            const JacDatum e = idx[d];
+            const double kf = scaled ? __ldg(A.kfac + d) * scale : 1.0;   // k_i / rho_j^2 only if len(model) == cols (:1377)
+            const int orow = __ldg(A.out_row + d);
             double v = 0.0;
-            if (a >= 0 && m >= 0) v += sG[a * gstride + m];
-            if (a >= 0 && n >= 0) v -= sG[a * gstride + n];
-            if (b >= 0 && m >= 0) v -= sG[b * gstride + m];
-            if (b >= 0 && n >= 0) v += sG[b * gstride + n];
-            out[A.out_row[d]] = A.rho_col ? v * scale * A.kfac[d] : v;   // k_i / rho_j^2 only if len(model) == cols (:1377)
+            const bool ha = e.a != 0xFFFF, hb = e.b != 0xFFFF, hm = e.m != 0xFFFF, hn = e.n != 0xFFFF;
+            if (ha && hm) v += sG[e.a * gstride + e.m];
+            if (ha && hn) v -= sG[e.a * gstride + e.n];
+            if (hb && hm) v -= sG[e.b * gstride + e.m];
+            if (hb && hn) v += sG[e.b * gstride + e.n];
+            out[orow] = v * kf;
         }
     }
 }

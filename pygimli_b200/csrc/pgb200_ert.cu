@@ -44,7 +44,7 @@ template <class T> struct DevBuf {
 };
 
 struct JacChunk {
-    int nP, nPp, nd;
+    int nP, nPp, nd, idx_in_smem;
     size_t plist_off, data_off;   // offsets into the concatenated device arrays
     size_t smem;
 };
@@ -81,7 +81,7 @@ struct pgb200_ert {
     int model_len = 0;
     std::vector<double> h_model;
     // jacobian plan
-    DevBuf<int> j_plist, j_qlist, j_ia, j_ib, j_im, j_in, j_out;
+    DevBuf<int> j_plist, j_qlist, j_out; DevBuf<JacDatum> j_idx;
     DevBuf<double> j_kfac;
     std::vector<JacChunk> chunks; int nQ = 0, nQp = 0;
     size_t ldJ = 0; int j_rows = 0; bool jac_valid = false;
@@ -357,13 +357,13 @@ int build_jac_plan(pgb200_ert *h) {
     });
     int dev_smem = 0;
     CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    const size_t smem_cap = std::min<size_t>((size_t)dev_smem, 200 * 1024) - 64;
+    const size_t smem_cap = std::min<size_t>((size_t)dev_smem, 220 * 1024) - 256;
     const int max_tiles = JAC_MAX_TILES * JAC_THREADS;
-    std::vector<int> plist_all, ia, ib, im, in, outr; std::vector<double> kf;
+    std::vector<int> plist_all, outr; std::vector<JacDatum> idx; std::vector<double> kf;
     size_t i = 0;
     while (i < (size_t)nd) {
         std::vector<int> pmap(h->nE, -1), plist;
-        JacChunk ch; ch.plist_off = plist_all.size(); ch.data_off = ia.size(); ch.nd = 0;
+        JacChunk ch; ch.plist_off = plist_all.size(); ch.data_off = idx.size(); ch.nd = 0; ch.idx_in_smem = 0;
         while (i < (size_t)nd) {
             const int d = order[i];
             const int a = h->h_abmn[4 * d], b = h->h_abmn[4 * d + 1];
@@ -379,20 +379,22 @@ int build_jac_plan(pgb200_ert *h) {
             if (a >= 0 && pmap[a] < 0) { pmap[a] = (int)plist.size(); plist.push_back(a); }
             if (b >= 0 && pmap[b] < 0) { pmap[b] = (int)plist.size(); plist.push_back(b); }
             const int m = h->h_abmn[4 * d + 2], n = h->h_abmn[4 * d + 3];
-            ia.push_back(a >= 0 ? pmap[a] : -1); ib.push_back(b >= 0 ? pmap[b] : -1);
-            im.push_back(m >= 0 ? qmap[m] : -1); in.push_back(n >= 0 ? qmap[n] : -1);
+            JacDatum jd;
+            jd.a = (unsigned short)(a >= 0 ? pmap[a] : 0xFFFF); jd.b = (unsigned short)(b >= 0 ? pmap[b] : 0xFFFF);
+            jd.m = (unsigned short)(m >= 0 ? qmap[m] : 0xFFFF); jd.n = (unsigned short)(n >= 0 ? qmap[n] : 0xFFFF);
+            idx.push_back(jd);
             outr.push_back(d - r0); kf.push_back(h->h_kfac[d]);
             ch.nd++; i++;
         }
         ch.nP = (int)plist.size(); ch.nPp = std::max(4, (ch.nP + 3) / 4 * 4);
         ch.smem = jac_smem(NL, ch.nPp, h->nQp);
+        if (ch.smem + (size_t)ch.nd * sizeof(JacDatum) <= smem_cap) { ch.idx_in_smem = 1; ch.smem += (size_t)ch.nd * sizeof(JacDatum); }
         plist_all.insert(plist_all.end(), plist.begin(), plist.end());
         h->chunks.push_back(ch);
     }
     CKR(h->j_plist.upload(plist_all.data(), plist_all.size(), h->st));
     CKR(h->j_qlist.upload(qlist.data(), qlist.size(), h->st));
-    CKR(h->j_ia.upload(ia.data(), ia.size(), h->st)); CKR(h->j_ib.upload(ib.data(), ib.size(), h->st));
-    CKR(h->j_im.upload(im.data(), im.size(), h->st)); CKR(h->j_in.upload(in.data(), in.size(), h->st));
+    CKR(h->j_idx.upload(idx.data(), idx.size(), h->st));
     CKR(h->j_out.upload(outr.data(), outr.size(), h->st));
     CKR(h->j_kfac.upload(kf.data(), kf.size(), h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -412,7 +414,7 @@ int launch_jacobian(pgb200_ert *h, const double *rho_col) {
         A.U = h->U.p; A.ld = h->ld; A.nE = h->nE; A.nK = h->nK; A.kvals = h->kvals.p; A.kw = h->kw.p;
         A.plist = h->j_plist.p + c.plist_off; A.nP = c.nP; A.nPp = c.nPp;
         A.qlist = h->j_qlist.p; A.nQ = h->nQ; A.nQp = h->nQp;
-        A.ia = h->j_ia.p + c.data_off; A.ib = h->j_ib.p + c.data_off; A.im = h->j_im.p + c.data_off; A.in = h->j_in.p + c.data_off;
+        A.idx = h->j_idx.p + c.data_off; A.idx_in_smem = c.idx_in_smem;
         A.out_row = h->j_out.p + c.data_off; A.kfac = h->j_kfac.p + c.data_off; A.nd = c.nd;
         A.rho_col = rho_col; A.Jt = h->Jt.p; A.ldJ = h->ldJ;
         int occ = 1;
@@ -522,6 +524,37 @@ int pgb200_build_panels(int n_rows, const int *rowptr, const int *colidx, int rm
         panel_ptr[np] = row; halo_ptr[np] = hcount;
     }
     return np;
+}
+
+// Pairwise aggregation for the multilevel preconditioner: nodes are visited in order; an unaggregated
+// node is matched with the unaggregated neighbour it is most strongly coupled to (most negative
+// off-diagonal); nodes left alone join the aggregate of their strongest neighbour.
+int pgb200_pairwise_aggregate(int n, const int *rowptr, const int *colidx, const double *vals, int *agg) {
+    for (int i = 0; i < n; i++) agg[i] = -1;
+    int na = 0;
+    for (int i = 0; i < n; i++) {
+        if (agg[i] >= 0) continue;
+        int best = -1; double bs = 0.0;
+        for (int p = rowptr[i]; p < rowptr[i + 1]; p++) {
+            const int j = colidx[p];
+            if (j == i || agg[j] >= 0) continue;
+            const double sgn = -vals[p];
+            if (sgn > bs) { bs = sgn; best = j; }
+        }
+        if (best >= 0) { agg[i] = na; agg[best] = na; na++; }
+    }
+    for (int i = 0; i < n; i++) {
+        if (agg[i] >= 0) continue;
+        int best = -1; double bs = 0.0;
+        for (int p = rowptr[i]; p < rowptr[i + 1]; p++) {
+            const int j = colidx[p];
+            if (j == i || agg[j] < 0) continue;
+            const double sgn = -vals[p];
+            if (sgn > bs) { bs = sgn; best = j; }
+        }
+        agg[i] = (best >= 0) ? agg[best] : na++;
+    }
+    return na;
 }
 
 int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {

@@ -139,3 +139,119 @@ def test_against_compiled_reference_live(case):
     assert np.all(np.abs(rhoa - r_ref) <= TOL * np.abs(r_ref) + 2e-10 * kf)
     assert _relmax(J, J_ref) < TOL
     R.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# variants of the path checked against the reference run live (oracle/_ref travels with the repo)
+# ---------------------------------------------------------------------------------------------
+def _live(mesh, scheme, model, sr=True, k=None, w=None):
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    R = ref.RefERT(mesh, scheme, sr=sr)
+    if k is not None:
+        R.set_kw(k, w)
+    r_ref = R.response(model)
+    pots = R.subpotentials()
+    J_ref = R.create_jacobian(model)
+    R.close()
+    return r_ref, pots, J_ref
+
+
+def _ours(mesh, scheme, model, sr=True, k=None, w=None):
+    fop = _fop(mesh, scheme, sr=sr)
+    if k is not None:
+        fop._core.setkValues(k)
+        fop._core.setWeights(w)
+    rhoa = fop.response(model)
+    P = fop._core._plan
+    pots = fop._core.get("pots").reshape(P.nS, P.N)
+    fop.createJacobian(model)
+    J = fop.jacobian().numpy()
+    fop._core.close()
+    return rhoa, pots, J
+
+
+def _check(ours, refv, scheme):
+    rhoa, pots, J = ours
+    r_ref, p_ref, J_ref = refv
+    kf = np.abs(scheme.k)
+    assert np.all(np.abs(rhoa - r_ref) <= TOL * np.abs(r_ref) + 2e-10 * kf)
+    for s in range(0, pots.shape[0], max(1, pots.shape[0] // 7)):
+        assert _relmax(pots[s], p_ref[s]) < TOL
+    assert _relmax(J, J_ref) < TOL
+
+
+@pytest.mark.parametrize("name", ["2d_p1", "3d_p1"])
+def test_total_field_variant_sr_false(name):
+    """DCMultiElectrodeModelling (no singularity removal, dcfemmodelling.cpp:1755-1928)"""
+    mesh, scheme, model = make_case(name)
+    _check(_ours(mesh, scheme, model, sr=False), _live(mesh, scheme, model, sr=False), scheme)
+
+
+@pytest.mark.parametrize("name", ["2d_p1", "2d_p2", "3d_p1"])
+def test_free_electrodes(name):
+    """sensors that do not coincide with mesh nodes -> ElectrodeShapeEntity (electrode.cpp:199-287)"""
+    mesh, scheme, model = make_case(name)
+    mesh.node_marker[:] = 0                       # no electrode nodes: every sensor is located in a cell
+    sch = scheme.subset(np.arange(scheme.size))
+    sch.sensors = scheme.sensors.copy()
+    sch.sensors[:, 0] += 0.13                     # off the nodes, still on the surface
+    from pygimli_b200.scheme import geometric_factors
+    sch.k = geometric_factors(sch, mesh.dim)
+    _check(_ours(mesh, sch, model), _live(mesh, sch, model), sch)
+
+
+def test_user_wavenumbers():
+    """setkValues / setWeights override the default list (dcfemmodelling.h:239-243)"""
+    mesh, scheme, model = make_case("2d_p1")
+    k = np.array([0.01, 0.05, 0.2, 0.8, 2.5])
+    w = np.array([0.02, 0.05, 0.2, 0.6, 1.1])
+    _check(_ours(mesh, scheme, model, k=k, w=w), _live(mesh, scheme, model, k=k, w=w), scheme)
+
+
+def test_dirichlet_boundary_marker():
+    """faces with marker -3 become homogeneous Dirichlet rows/columns (dcfemmodelling.cpp:141-161)"""
+    mesh, scheme, model = make_case("3d_p1")
+    zb = mesh.pos[mesh.bounds].mean(1)[:, 2]
+    mesh.bound_marker[np.isclose(zb, mesh.pos[:, 2].min())] = -3        # bottom of the box
+    _check(_ours(mesh, scheme, model), _live(mesh, scheme, model), scheme)
+
+
+def test_error_behaviour():
+    from pygimli_b200 import _capi
+    mesh, scheme, model = make_case("2d_p1")
+    fop = _fop(mesh, scheme)
+    bad = model.copy()
+    bad[3] = -1.0
+    with pytest.raises(_capi.PGB200Error, match="negative or zero resistivity"):
+        fop.response(bad)
+    with pytest.raises(_capi.PGB200Error, match="model length"):
+        fop.response(model[:-1])
+    fop._core.close()
+
+
+def test_linearity_of_jacobian_rows_sum_rule():
+    """size-independent property: sum_j J_ij rho_j == rhoa_i when every cell is a model cell and the
+    model is homogeneous (Euler relation for the degree-1 homogeneous map rho -> rhoa)."""
+    from pygimli_b200.mesh import graded_axis, grid_mesh_2d, mark_electrode_nodes
+    from pygimli_b200.scheme import create_dd, geometric_factors
+    ne = 9
+    xs = graded_axis(0.0, 8.0, 0.5, 1.4, 40.0)
+    ys = -graded_axis(0.0, 3.0, 0.5, 1.4, 40.0, both=False)
+    mesh = grid_mesh_2d(xs, ys)                  # every quad is a model cell
+    sens = np.zeros((ne, 3)); sens[:, 0] = np.arange(ne)
+    mark_electrode_nodes(mesh, sens)
+    sch = create_dd(sens); sch.k = geometric_factors(sch, 2)
+    M = int(mesh.cell_marker.max()) + 1
+    rng = np.random.default_rng(2)
+    model = 10.0 ** (2 + 0.3 * rng.standard_normal(M))
+    fop = _fop(mesh, sch)
+    rhoa = fop.response(model)
+    fop.createJacobian(model)
+    Jop = fop.jacobian()
+    assert np.max(np.abs(Jop.mult(model) - rhoa) / rhoa) < 2e-2     # FE consistency, not round-off
+    # scaling property: response(c * model) == c * response(model) to solver accuracy
+    r2 = fop.response(3.0 * model)
+    assert np.max(np.abs(r2 - 3.0 * rhoa) / rhoa) < 1e-7
+    fop._core.close()
