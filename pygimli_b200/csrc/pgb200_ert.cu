@@ -286,9 +286,8 @@ int forward_solve(pgb200_ert *h) {
         CK(cudaMemsetAsync(h->B.p, 0, sizeof(double) * h->N * h->ld, h->st));
         if (c1 > c0) { k_delta_rhs<<<cdiv(c1 - c0, 128), 128, 0, h->st>>>(h->pick_ptr.p, h->pick_idx.p, h->pick_w.p, h->nE, c0, c1, h->ld, h->B.p); LAUNCH(h); }
     }
-    if (h->n_dir_nodes && c1 > c0) {
-        k_zero_rows<<<dim3(h->n_dir_nodes, cdiv(c1 - c0, 128)), 128, 0, h->st>>>(h->dir_nodes.p, h->n_dir_nodes, c0, c1, h->ld, h->B.p); LAUNCH(h);
-    }
+    // NB: the reference zeroes right-hand-side rows only for calibration nodes (:2281-2283), which never exist on
+    // the non-Neumann domains handled here; rows of -3 Dirichlet faces keep S1*p/rho_s - S*p = p (1 - rho_s).
     CK(cudaGetLastError());
     // model / matrix sanity before iterating
     int hf[4];
