@@ -167,7 +167,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     t_setup = time.perf_counter()
     mesh, scheme, model, desc = build_workload(args.workload, args.scale)
-    fop = ShardedERT(mesh, scheme, device=local, rank=rank, world=world, sr=True)
+    fop = ShardedERT(mesh, scheme, device=local, rank=rank, world=world, sr=True, preconditioner=args.precond)
     fop.set_solver(args.tol, 100000, 25)
     stream = torch.cuda.current_stream()
     fop.set_stream(stream.cuda_stream)
@@ -240,14 +240,15 @@ def run_b200(args):
         spmm_bytes = 12.0 * P.nnz * (P.nK if ncols >= P.nS else max(1, ncols // P.nE)) + 4.0 * (P.N + 1) + 16.0 * P.N * ncols
         spmm_ms = st["spmm_ms_total"] / max(1.0, st["spmm_timed"])
         ach = spmm_bytes / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0
-        jac_bytes = 8.0 * D * M + 8.0 * P.nS * P.N + P.C * (4.0 * P.nloc + 4.0) + 24.0 * P.N + 16.0 * D
+        d_local = fop.rows[1] - fop.rows[0]
+        jac_bytes = 8.0 * d_local * M + 8.0 * P.nS * P.N + P.C * (4.0 * P.nloc + 4.0) + 24.0 * P.N + 16.0 * D
         jac_ms = st["jacobian_kernel_ms"] / max(1.0, st["jacobian_timed"])
         line = {
             "metric": "ert_forward_jacobian_s_per_iter", "value": sec, "unit": "s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload + ": " + desc, "cells": P.C, "nodes": P.N, "nnz": P.nnz, "electrodes": P.nE,
-                       "wavenumbers": P.nK, "sources": P.nS, "data": D, "model_cells": M, "pcg_rel_tol": args.tol,
+                       "wavenumbers": P.nK, "sources": P.nS, "data": D, "model_cells": M, "pcg_rel_tol": args.tol, "preconditioner": args.precond,
                        "l2": "working set (PCG block vectors) larger than L2", "parallelism": f"sources+rows sharded x{world}",
                        "setup_s": t_setup},
             "pcg_iterations": st["pcg_iterations"], "pcg_max_rel_residual": st["max_rel_residual"],
@@ -293,6 +294,7 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=24, help="data rows in the CPU sensitivity sample")
     ap.add_argument("--ref-sources", type=int, default=1, help="sources in the CPU solve sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precond", default="multilevel", choices=["multilevel", "jacobi"], help="block-PCG preconditioner")
     ap.add_argument("--spmm", default="panel", choices=["panel", "panel1", "panel_cpasync", "plain"], help="SpMM kernel inside PCG (A/B measurement)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -102,6 +102,21 @@ typedef struct pgb200_plan {
     const double *k_fac;        /* [D] geometric factors                                     */
 } pgb200_plan;
 
+/* One coarse level of the aggregation hierarchy of the multilevel preconditioner (host pointers, copied).
+ * Geometry only: built once per mesh by pygimli_b200/amg_setup.py.                                         */
+typedef struct pgb200_amg_level {
+    int n;                  /* nodes of this level                                                       */
+    int nnz;                /* CSR entries of this level                                                 */
+    const int *rowptr;      /* [n+1]                                                                     */
+    const int *colidx;      /* [nnz]                                                                     */
+    const int *diag_pos;    /* [n]                                                                       */
+    const int *gal_ptr;     /* [nnz+1] entry s of this level = sum of finer entries gal_idx[gal_ptr[s]..) */
+    const int *gal_idx;     /* [nnz of the finer level]                                                  */
+    const int *agg;         /* [n of the finer level] finer node -> node of this level                   */
+    const int *mem_ptr;     /* [n+1] members of every aggregate ...                                      */
+    const int *mem_idx;     /* [n of the finer level] ... as finer-level node ids                        */
+} pgb200_amg_level;
+
 /* ---- host-only helpers (no GPU needed) -------------------------------------------- */
 const char *pgb200_last_error(void);
 int pgb200_version(void);
@@ -120,6 +135,11 @@ int pgb200_pairwise_aggregate(int n, const int *rowptr, const int *colidx, const
 /* ---- life cycle ------------------------------------------------------------------- */
 int pgb200_ert_create(const pgb200_plan *plan, int device, pgb200_ert **out);
 int pgb200_ert_destroy(pgb200_ert *h);
+/* Install (n_levels > 0) or remove the aggregation hierarchy of the multilevel preconditioner.  */
+int pgb200_ert_set_hierarchy(pgb200_ert *h, int n_levels, const pgb200_amg_level *levels);
+/* multilevel = 0: Jacobi-PCG, 1: V(1,1) aggregation multigrid preconditioner (default when a hierarchy is
+ * installed); coarse_sweeps: damped-Jacobi sweeps on the coarsest level (default 8).              */
+int pgb200_ert_set_preconditioner(pgb200_ert *h, int multilevel, int coarse_sweeps);
 /* CUDA stream (cudaStream_t) all work is enqueued on; 0/NULL = legacy default stream.   */
 int pgb200_ert_set_stream(pgb200_ert *h, void *stream);
 /* Block-PCG controls: relative residual tolerance ||r||/||b|| per source column,

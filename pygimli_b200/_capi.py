@@ -41,9 +41,14 @@ class Plan(C.Structure):
     ]
 
 
+class AmgLevel(C.Structure):
+    _fields_ = [("n", C.c_int), ("nnz", C.c_int), ("rowptr", c_int_p), ("colidx", c_int_p), ("diag_pos", c_int_p),
+                ("gal_ptr", c_int_p), ("gal_idx", c_int_p), ("agg", c_int_p), ("mem_ptr", c_int_p), ("mem_idx", c_int_p)]
+
+
 # every symbol include/pgb200_ert.h declares (checked by tests/test_capi_symbols.py)
 EXPORTS = [
-    "pgb200_last_error", "pgb200_version", "pgb200_color_cells", "pgb200_build_panels", "pgb200_ert_set_spmm_variant", "pgb200_pairwise_aggregate",
+    "pgb200_last_error", "pgb200_version", "pgb200_color_cells", "pgb200_build_panels", "pgb200_ert_set_spmm_variant", "pgb200_pairwise_aggregate", "pgb200_ert_set_hierarchy", "pgb200_ert_set_preconditioner",
     "pgb200_ert_create", "pgb200_ert_destroy", "pgb200_ert_set_stream", "pgb200_ert_set_solver", "pgb200_ert_set_shard",
     "pgb200_ert_set_kfac", "pgb200_ert_response", "pgb200_ert_create_jacobian", "pgb200_ert_jacobian_copy",
     "pgb200_ert_jacobian_mult", "pgb200_ert_jacobian_tmult", "pgb200_ert_response_dev", "pgb200_ert_create_jacobian_dev",
@@ -97,6 +102,8 @@ def lib():
         L.pgb200_color_cells.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.pgb200_build_panels.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
         L.pgb200_ert_set_spmm_variant.argtypes = [C.c_void_p, C.c_int]
+        L.pgb200_ert_set_hierarchy.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.pgb200_ert_set_preconditioner.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.pgb200_pairwise_aggregate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pgb200_spmm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p]
@@ -157,6 +164,21 @@ def build_panels(rowptr: np.ndarray, colidx: np.ndarray, rmax: int = 64, hmax: i
     return dict(n_panels=int(npan), panel_ptr=panel_ptr, halo_ptr=halo_ptr, halo_cols=halo_cols[: halo_ptr[-1]].copy(),
                 lidx=lidx, self_idx=self_idx, max_halo=int(np.diff(halo_ptr).max()),
                 max_panel_nnz=int(np.diff(rowptr[panel_ptr]).max()))
+
+
+def set_hierarchy(handle, levels):
+    """levels: output of amg_setup.build_hierarchy"""
+    keep = []
+    arr = (AmgLevel * max(1, len(levels)))()
+    for i, L in enumerate(levels):
+        a = arr[i]
+        a.n, a.nnz = int(L["n"]), int(L["nnz"])
+        for name in ("rowptr", "colidx", "diag_pos", "gal_ptr", "gal_idx", "agg", "mem_ptr", "mem_idx"):
+            v = np.ascontiguousarray(L[name], np.int32)
+            keep.append(v)
+            setattr(a, name, v.ctypes.data_as(c_int_p))
+    check(lib().pgb200_ert_set_hierarchy(handle, len(levels), C.cast(arr, C.c_void_p)))
+    return keep
 
 
 def _ip(a):

@@ -493,6 +493,7 @@ k_pcg_init(const double *__restrict__ B, const double *__restrict__ dinv, double
     block_col_reduce(s0, s1, rz, bb, col, ok);
 }
 // alpha = rz/pAp;  x += alpha p;  r -= alpha Ap;  rz_new = r.Dinv r;  rr = r.r
+template <bool JACOBI>
 __global__ void __launch_bounds__(VEC_TX * VEC_TY)
 k_pcg_update_xr(const double *__restrict__ P, const double *__restrict__ AP, const double *__restrict__ dinv,
                 double *__restrict__ Xv, double *__restrict__ R, int N, int nE, int c0, int c1, size_t ld,
@@ -511,13 +512,16 @@ k_pcg_update_xr(const double *__restrict__ P, const double *__restrict__ AP, con
             const double rn = fma(-alpha, AP[o], R[o]);
             Xv[o] = fma(alpha, P[o], Xv[o]);
             R[o] = rn;
-            s0 = fma(rn * dk[row], rn, s0); s1 = fma(rn, rn, s1);
+            if (JACOBI) s0 = fma(rn * dk[row], rn, s0);
+            s1 = fma(rn, rn, s1);
         }
     }
-    block_col_reduce(s0, s1, rz_new, rr, col, ok);
+    block_col_reduce(s0, s1, JACOBI ? rz_new : nullptr, rr, col, ok);
 }
 // beta = rz_new/rz;  p = Dinv r + beta p   (p = 0 once the column has converged: it freezes)
 // also clears the accumulators of the next iteration (buffers nobody reads in this launch)
+// JACOBI: z = Dinv r on the fly; otherwise R points at the preconditioned residual Z and dinv is unused
+template <bool JACOBI>
 __global__ void __launch_bounds__(VEC_TX * VEC_TY)
 k_pcg_update_p(const double *__restrict__ R, const double *__restrict__ dinv, double *__restrict__ P, int N, int nE,
                int c0, int c1, size_t ld, const double *__restrict__ rz, const double *__restrict__ rz_new,
@@ -534,8 +538,165 @@ k_pcg_update_p(const double *__restrict__ R, const double *__restrict__ dinv, do
     for (int r = threadIdx.y; r < VEC_ROWS; r += VEC_TY) {
         const int row = row0 + r; if (row >= N) break;
         const size_t o = (size_t)row * ld + col;
-        P[o] = done ? 0.0 : fma(beta, P[o], dk[row] * R[o]);
+        P[o] = done ? 0.0 : fma(beta, P[o], JACOBI ? dk[row] * R[o] : R[o]);
     }
+}
+
+// ---------------------------------------------------------------------------------
+// multilevel preconditioner (unsmoothed aggregation, V(1,1), damped Jacobi) -- see amg_setup.py
+// All kernels work on node-major block vectors of one level and the column window [c0,c1).
+// ---------------------------------------------------------------------------------
+// coarse matrix values: plain sums of finer-level entries (Galerkin product with piecewise-constant P)
+__global__ void k_galerkin(const int *__restrict__ gal_ptr, const int *__restrict__ gal_idx, int n_slots, int nK,
+                           size_t nnz_f, size_t nnz_c, const double *__restrict__ vals_f, double *__restrict__ vals_c) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    const int b = gal_ptr[s], e = gal_ptr[s + 1];
+    for (int kk = 0; kk < nK; kk++) {
+        double acc = 0.0;
+        for (int p = b; p < e; p++) acc += vals_f[(size_t)kk * nnz_f + gal_idx[p]];
+        vals_c[(size_t)kk * nnz_c + s] = acc;
+    }
+}
+// Gershgorin bound of lambda_max(D^-1 A) per wavenumber: max_i sum_j |a_ij| / a_ii  (positive doubles order like integers)
+__global__ void k_row_ratio(const int *__restrict__ rowptr, const int *__restrict__ diag_pos, int n, int nK, size_t nnz,
+                            const double *__restrict__ vals, unsigned long long *gmax) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int kk = 0; kk < nK; kk++) {
+        const double *v = vals + (size_t)kk * nnz;
+        double s = 0.0;
+        for (int p = rowptr[i]; p < rowptr[i + 1]; p++) s += fabs(v[p]);
+        const double g = s / v[diag_pos[i]];
+        if (g > 0.0) atomicMax(gmax + kk, (unsigned long long)__double_as_longlong(g));
+    }
+}
+// dinvw = omega / a_ii with omega = 1.6 / max(2, Gershgorin bound): damped Jacobi that stays convergent
+__global__ void k_inv_diag_w(const int *__restrict__ diag_pos, int n, int nK, size_t nnz, const double *__restrict__ vals,
+                             const unsigned long long *__restrict__ gmax, double *__restrict__ dinvw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int kk = 0; kk < nK; kk++) {
+        const double g = __longlong_as_double((long long)gmax[kk]);
+        const double omega = 1.6 / fmax(2.0, g);
+        dinvw[(size_t)kk * n + i] = omega / vals[(size_t)kk * nnz + diag_pos[i]];
+    }
+}
+
+constexpr int AMG_TX = 16, AMG_TY = 8, AMG_ROWS = 32;
+
+// Z = X + dw .* (R - A X)   (post-smoothing / Jacobi sweep); optional fused dot  sum_i R_i Z_i
+template <int CPT, bool DOT>
+__global__ void __launch_bounds__(AMG_TX * AMG_TY)
+k_amg_post(const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals, size_t nnz,
+           const double *__restrict__ dinvw, int n, const double *__restrict__ X, const double *__restrict__ R,
+           double *__restrict__ Z, int nE, int c0, int c1, size_t ld, double *__restrict__ dots) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int cbase = c0 + blockIdx.y * (AMG_TX * CPT) + tx;
+    int col[CPT]; size_t voff[CPT]; const double *dw[CPT]; bool ok[CPT];
+#pragma unroll
+    for (int m = 0; m < CPT; m++) {
+        const int c = cbase + m * AMG_TX;
+        ok[m] = c < c1;
+        col[m] = ok[m] ? c : c0;
+        const int kk = col[m] / nE;
+        voff[m] = (size_t)kk * nnz; dw[m] = dinvw + (size_t)kk * n;
+    }
+    double part[CPT];
+#pragma unroll
+    for (int m = 0; m < CPT; m++) part[m] = 0.0;
+    const int row0 = blockIdx.x * AMG_ROWS;
+    for (int r = ty; r < AMG_ROWS; r += AMG_TY) {
+        const int row = row0 + r;
+        if (row >= n) break;
+        double acc[CPT];
+#pragma unroll
+        for (int m = 0; m < CPT; m++) acc[m] = 0.0;
+        for (int p = rowptr[row]; p < rowptr[row + 1]; p++) {
+            const size_t xo = (size_t)colidx[p] * ld;
+#pragma unroll
+            for (int m = 0; m < CPT; m++) acc[m] = fma(__ldg(vals + voff[m] + p), __ldg(X + xo + col[m]), acc[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < CPT; m++) {
+            if (ok[m]) {
+                const size_t o = (size_t)row * ld + col[m];
+                const double rr = R[o];
+                const double z = fma(dw[m][row], rr - acc[m], X[o]);
+                Z[o] = z;
+                if (DOT) part[m] = fma(rr, z, part[m]);
+            }
+        }
+    }
+    if (DOT) {
+        __shared__ double red[AMG_TY][AMG_TX * CPT];
+#pragma unroll
+        for (int m = 0; m < CPT; m++) red[ty][m * AMG_TX + tx] = part[m];
+        __syncthreads();
+        if (ty == 0) {
+#pragma unroll
+            for (int m = 0; m < CPT; m++) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int y = 0; y < AMG_TY; y++) sacc += red[y][m * AMG_TX + tx];
+                if (ok[m]) atomicAdd(dots + col[m], sacc);
+            }
+        }
+    }
+}
+
+// pre-smoothing from a zero guess + residual + restriction, fused:
+//   RC[I] = sum_{i in aggregate I} ( R_i - sum_j a_ij * dw_j * R_j )
+template <int CPT>
+__global__ void __launch_bounds__(AMG_TX * AMG_TY)
+k_amg_restrict(const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals, size_t nnz,
+               const double *__restrict__ dinvw, int n_f, const int *__restrict__ mem_ptr, const int *__restrict__ mem_idx, int n_c,
+               const double *__restrict__ R, double *__restrict__ RC, int nE, int c0, int c1, size_t ld) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int cbase = c0 + blockIdx.y * (AMG_TX * CPT) + tx;
+    int col[CPT]; size_t voff[CPT]; const double *dw[CPT]; bool ok[CPT];
+#pragma unroll
+    for (int m = 0; m < CPT; m++) {
+        const int c = cbase + m * AMG_TX;
+        ok[m] = c < c1;
+        col[m] = ok[m] ? c : c0;
+        const int kk = col[m] / nE;
+        voff[m] = (size_t)kk * nnz; dw[m] = dinvw + (size_t)kk * n_f;
+    }
+    const int row0 = blockIdx.x * AMG_ROWS;
+    for (int r = ty; r < AMG_ROWS; r += AMG_TY) {
+        const int I = row0 + r;
+        if (I >= n_c) break;
+        double acc[CPT];
+#pragma unroll
+        for (int m = 0; m < CPT; m++) acc[m] = 0.0;
+        for (int q = mem_ptr[I]; q < mem_ptr[I + 1]; q++) {
+            const int i = mem_idx[q];
+#pragma unroll
+            for (int m = 0; m < CPT; m++) acc[m] += __ldg(R + (size_t)i * ld + col[m]);
+            for (int p = rowptr[i]; p < rowptr[i + 1]; p++) {
+                const int j = colidx[p];
+                const size_t xo = (size_t)j * ld;
+#pragma unroll
+                for (int m = 0; m < CPT; m++)
+                    acc[m] = fma(-__ldg(vals + voff[m] + p) * __ldg(dw[m] + j), __ldg(R + xo + col[m]), acc[m]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < CPT; m++) if (ok[m]) RC[(size_t)I * ld + col[m]] = acc[m];
+    }
+}
+
+// X = dw .* R + EC[agg]   (pre-smoothed iterate plus prolongated coarse correction); EC == nullptr -> X = dw .* R
+__global__ void k_amg_prolong(const double *__restrict__ dinvw, int n, const int *__restrict__ agg, const double *__restrict__ R,
+                              const double *__restrict__ EC, double *__restrict__ X, int nE, int c0, int c1, size_t ld) {
+    const int col = c0 + blockIdx.y * blockDim.x + threadIdx.x;
+    const int row = blockIdx.x * blockDim.y + threadIdx.y;
+    if (col >= c1 || row >= n) return;
+    const size_t o = (size_t)row * ld + col;
+    double x = dinvw[(size_t)(col / nE) * n + row] * R[o];
+    if (EC) x += EC[(size_t)agg[row] * ld + col];
+    X[o] = x;
 }
 
 // total field  U = X + rho_src * prim   (:2287)  /  analytic branch  U = scale * prim (:1295-1300)

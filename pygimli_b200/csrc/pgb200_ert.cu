@@ -53,6 +53,12 @@ enum Phase { PH_MAP = 0, PH_ASM, PH_RHS, PH_SOLVE, PH_EPI, PH_JAC, PH_COUNT };
 
 } // namespace
 
+struct AmgLevel {      // one coarse level of the aggregation hierarchy (device arrays)
+    int n = 0; size_t nnz = 0; int n_finer = 0;
+    DevBuf<int> rowptr, colidx, diag_pos, gal_ptr, gal_idx, agg, mem_ptr, mem_idx;
+    DevBuf<double> vals, dinvw, R, X, Z;
+};
+
 struct pgb200_ert {
     // sizes
     int dim = 0, nloc = 0, elem = 0, N = 0, C = 0, nE = 0, nK = 0, nS = 0, M = 0, D = 0, sr = 1, fullspace = 0;
@@ -85,6 +91,8 @@ struct pgb200_ert {
     DevBuf<double> j_kfac;
     std::vector<JacChunk> chunks; int nQ = 0, nQp = 0;
     size_t ldJ = 0; int j_rows = 0; bool jac_valid = false;
+    // multilevel preconditioner
+    std::vector<AmgLevel *> amg; int use_amg = 1, coarse_sweeps = 8; DevBuf<double> Z0, X0, dinvw0; DevBuf<unsigned long long> gmax;
     // stats
     int last_iters = 0; double last_relres = 0.0; long long launches = 0;
     cudaEvent_t ev[PH_COUNT + 1]; bool ev_ok = false; float ph_ms[PH_COUNT] = {0};
@@ -193,6 +201,101 @@ int launch_spmm_panel(pgb200_ert *h, const double *vals, const double *X, double
     return launch_spmm_panel_nc<1>(h, vals, X, Y, c0, c1, dots);
 }
 
+template <int CPT>
+int amg_post_cpt(pgb200_ert *h, const int *rowptr, const int *colidx, const double *vals, size_t nnz, const double *dinvw, int n,
+                 const double *X, const double *R, double *Z, int c0, int c1, double *dots) {
+    dim3 block(AMG_TX, AMG_TY), grid(cdiv(n, AMG_ROWS), cdiv(c1 - c0, AMG_TX * CPT));
+    if (dots) k_amg_post<CPT, true><<<grid, block, 0, h->st>>>(rowptr, colidx, vals, nnz, dinvw, n, X, R, Z, h->nE, c0, c1, h->ld, dots);
+    else k_amg_post<CPT, false><<<grid, block, 0, h->st>>>(rowptr, colidx, vals, nnz, dinvw, n, X, R, Z, h->nE, c0, c1, h->ld, nullptr);
+    LAUNCH(h);
+    return 0;
+}
+int pick_cpt(int ncols) {
+    int best = 1; double beste = 0.0;
+    for (int cpt : {4, 2, 1}) {
+        const int w = AMG_TX * cpt; const double eff = (double)ncols / (double)(cdiv(ncols, w) * w);
+        if (eff > beste + 0.05) { beste = eff; best = cpt; }
+    }
+    return best;
+}
+int amg_post(pgb200_ert *h, const int *rowptr, const int *colidx, const double *vals, size_t nnz, const double *dinvw, int n,
+             const double *X, const double *R, double *Z, int c0, int c1, double *dots) {
+    switch (pick_cpt(c1 - c0)) {
+        case 4: return amg_post_cpt<4>(h, rowptr, colidx, vals, nnz, dinvw, n, X, R, Z, c0, c1, dots);
+        case 2: return amg_post_cpt<2>(h, rowptr, colidx, vals, nnz, dinvw, n, X, R, Z, c0, c1, dots);
+        default: return amg_post_cpt<1>(h, rowptr, colidx, vals, nnz, dinvw, n, X, R, Z, c0, c1, dots);
+    }
+}
+int amg_restrict(pgb200_ert *h, const int *rowptr, const int *colidx, const double *vals, size_t nnz, const double *dinvw, int n_f,
+                 const AmgLevel *L, const double *R, int c0, int c1) {
+    const int cpt = pick_cpt(c1 - c0);
+    dim3 block(AMG_TX, AMG_TY), grid(cdiv(L->n, AMG_ROWS), cdiv(c1 - c0, AMG_TX * cpt));
+#define RGO(C) k_amg_restrict<C><<<grid, block, 0, h->st>>>(rowptr, colidx, vals, nnz, dinvw, n_f, L->mem_ptr.p, L->mem_idx.p, L->n, R, L->R.p, h->nE, c0, c1, h->ld)
+    if (cpt == 4) RGO(4); else if (cpt == 2) RGO(2); else RGO(1);
+#undef RGO
+    LAUNCH(h);
+    return 0;
+}
+
+// recompute the coarse matrices and smoother weights for the current vals (once per assembled model)
+int amg_setup_values(pgb200_ert *h) {
+    if (h->amg.empty()) return 0;
+    const int nK = h->nK;
+    auto smoother = [&](const int *rowptr, const int *diag_pos, int n, size_t nnz, const double *vals, double *dinvw) -> int {
+        CK(cudaMemsetAsync(h->gmax.p, 0, sizeof(unsigned long long) * nK, h->st));
+        k_row_ratio<<<cdiv(n, 128), 128, 0, h->st>>>(rowptr, diag_pos, n, nK, nnz, vals, h->gmax.p); LAUNCH(h);
+        k_inv_diag_w<<<cdiv(n, 128), 128, 0, h->st>>>(diag_pos, n, nK, nnz, vals, h->gmax.p, dinvw); LAUNCH(h);
+        return 0;
+    };
+    CKR(smoother(h->rowptr.p, h->diag_pos.p, h->N, h->nnz, h->vals.p, h->dinvw0.p));
+    const double *vf = h->vals.p; size_t nnz_f = h->nnz;
+    for (AmgLevel *L : h->amg) {
+        k_galerkin<<<cdiv((long long)L->nnz, 128), 128, 0, h->st>>>(L->gal_ptr.p, L->gal_idx.p, (int)L->nnz, nK, nnz_f, L->nnz, vf, L->vals.p); LAUNCH(h);
+        CKR(smoother(L->rowptr.p, L->diag_pos.p, L->n, L->nnz, L->vals.p, L->dinvw.p));
+        vf = L->vals.p; nnz_f = L->nnz;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// one V(1,1) cycle: Z0 = M^-1 R (level 0 residual = h->R); optionally accumulates dots[c] += R.Z
+int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
+    const int nl = (int)h->amg.size();
+    struct Lv { const int *rowptr, *colidx; const double *vals; size_t nnz; const double *dinvw; int n; const double *R; double *X, *Z; };
+    std::vector<Lv> lv(nl + 1);
+    lv[0] = {h->rowptr.p, h->colidx.p, h->vals.p, h->nnz, h->dinvw0.p, h->N, h->R.p, h->X0.p, h->Z0.p};
+    for (int l = 0; l < nl; l++) { AmgLevel *L = h->amg[l]; lv[l + 1] = {L->rowptr.p, L->colidx.p, L->vals.p, L->nnz, L->dinvw.p, L->n, L->R.p, L->X.p, L->Z.p}; }
+    dim3 pb(32, 8);
+    // downward: residual after one damped-Jacobi sweep from zero, restricted
+    for (int l = 0; l < nl; l++)
+        CKR(amg_restrict(h, lv[l].rowptr, lv[l].colidx, lv[l].vals, lv[l].nnz, lv[l].dinvw, lv[l].n, h->amg[l], lv[l].R, c0, c1));
+    // coarsest level: fixed number of Jacobi sweeps
+    const double *E;
+    {
+        Lv &c = lv[nl];
+        dim3 pg(cdiv(c.n, 8), cdiv(c1 - c0, 32));
+        k_amg_prolong<<<pg, pb, 0, h->st>>>(c.dinvw, c.n, nullptr, c.R, nullptr, c.X, h->nE, c0, c1, h->ld); LAUNCH(h);
+        double *a = c.X, *b = c.Z;
+        const int sweeps = (nl == 0) ? 1 : h->coarse_sweeps;
+        for (int s = 0; s + 1 < sweeps; s++) {
+            CKR(amg_post(h, c.rowptr, c.colidx, c.vals, c.nnz, c.dinvw, c.n, a, c.R, b, c0, c1, nullptr));
+            std::swap(a, b);
+        }
+        if (nl == 0) { CKR(amg_post(h, c.rowptr, c.colidx, c.vals, c.nnz, c.dinvw, c.n, a, c.R, b, c0, c1, dots)); a = b; }
+        E = a;
+    }
+    // upward: prolongate, post-smooth
+    for (int l = nl - 1; l >= 0; l--) {
+        Lv &f = lv[l];
+        dim3 pg(cdiv(f.n, 8), cdiv(c1 - c0, 32));
+        k_amg_prolong<<<pg, pb, 0, h->st>>>(f.dinvw, f.n, h->amg[l]->agg.p, f.R, E, f.X, h->nE, c0, c1, h->ld); LAUNCH(h);
+        CKR(amg_post(h, f.rowptr, f.colidx, f.vals, f.nnz, f.dinvw, f.n, f.X, f.R, f.Z, c0, c1, l == 0 ? dots : nullptr));
+        E = f.Z;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // scal layout: [0] rz_a [1] rz_b [2] rz_c [3] pAp [4] rr_a [5] rr_b [6] bb   (each ld doubles)
 int pcg_solve(pgb200_ert *h) {
     const int c0 = h->c0, c1 = h->c1, ncols = c1 - c0;
@@ -203,7 +306,12 @@ int pcg_solve(pgb200_ert *h) {
     auto sc = [&](int i) { return S + (size_t)i * ld; };
     CK(cudaMemsetAsync(S, 0, sizeof(double) * 7 * ld, h->st));
     dim3 vb(VEC_TX, VEC_TY), vg(cdiv(h->N, VEC_ROWS), cdiv(ncols, VEC_TX));
-    k_pcg_init<<<vg, vb, 0, h->st>>>(h->B.p, h->dinv.p, h->X.p, h->R.p, h->P.p, h->N, h->nE, c0, c1, ld, sc(0), sc(6)); LAUNCH(h);
+    const bool amg = h->use_amg && !h->amg.empty();
+    k_pcg_init<<<vg, vb, 0, h->st>>>(h->B.p, h->dinv.p, h->X.p, h->R.p, h->P.p, h->N, h->nE, c0, c1, ld, amg ? nullptr : sc(0), sc(6)); LAUNCH(h);
+    if (amg) {
+        CKR(amg_vcycle(h, c0, c1, sc(0)));
+        CK(cudaMemcpyAsync(h->P.p, h->Z0.p, sizeof(double) * (size_t)h->N * ld, cudaMemcpyDeviceToDevice, h->st));
+    }
     CK(cudaGetLastError());
     CKR(ensure_pinned(h, 2 * ld));
     const double tol2 = h->tol * h->tol;
@@ -217,16 +325,27 @@ int pcg_solve(pgb200_ert *h) {
         if (h->use_panels && h->n_panels > 0 && !(c0 & 1) && (h->nK == 1 || h->nE >= 32 * h->panel_nc)) CKR(launch_spmm_panel(h, h->vals.p, h->P.p, h->AP.p, c0, c1, sc(3)));
         else CKR((launch_spmm<0, true>(h, h->vals.p, nullptr, nullptr, h->P.p, h->AP.p, c0, c1, sc(3))));
         if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
-        k_pcg_update_xr<<<vg, vb, 0, h->st>>>(h->P.p, h->AP.p, h->dinv.p, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
-                                             sc(rz_old), sc(3), sc(rz_new), sc(rr_cur)); LAUNCH(h);
+        if (amg) {
+            k_pcg_update_xr<false><<<vg, vb, 0, h->st>>>(h->P.p, h->AP.p, nullptr, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
+                                                        sc(rz_old), sc(3), sc(rz_new), sc(rr_cur)); LAUNCH(h);
+        } else {
+            k_pcg_update_xr<true><<<vg, vb, 0, h->st>>>(h->P.p, h->AP.p, h->dinv.p, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
+                                                       sc(rz_old), sc(3), sc(rz_new), sc(rr_cur)); LAUNCH(h);
+        }
         it++;
         const bool check = (it % h->check_every == 0) || it >= h->max_iter;
         if (check) {
             CK(cudaMemcpyAsync(h->h_pinned, sc(rr_cur), sizeof(double) * ld, cudaMemcpyDeviceToHost, h->st));
             CK(cudaMemcpyAsync(h->h_pinned + ld, sc(6), sizeof(double) * ld, cudaMemcpyDeviceToHost, h->st));
         }
-        k_pcg_update_p<<<vg, vb, 0, h->st>>>(h->R.p, h->dinv.p, h->P.p, h->N, h->nE, c0, c1, ld, sc(rz_old), sc(rz_new),
-                                            sc(rr_cur), sc(6), tol2, sc(3), sc(rr_nxt), sc(rz_nxt)); LAUNCH(h);
+        if (amg) {
+            CKR(amg_vcycle(h, c0, c1, sc(rz_new)));
+            k_pcg_update_p<false><<<vg, vb, 0, h->st>>>(h->Z0.p, nullptr, h->P.p, h->N, h->nE, c0, c1, ld, sc(rz_old), sc(rz_new),
+                                                       sc(rr_cur), sc(6), tol2, sc(3), sc(rr_nxt), sc(rz_nxt)); LAUNCH(h);
+        } else {
+            k_pcg_update_p<true><<<vg, vb, 0, h->st>>>(h->R.p, h->dinv.p, h->P.p, h->N, h->nE, c0, c1, ld, sc(rz_old), sc(rz_new),
+                                                      sc(rr_cur), sc(6), tol2, sc(3), sc(rr_nxt), sc(rz_nxt)); LAUNCH(h);
+        }
         if (check) {
             CK(cudaStreamSynchronize(h->st));
             double worst = 0.0;
@@ -277,6 +396,7 @@ int forward_solve(pgb200_ert *h) {
     k_count_singular<<<cdiv(h->N, 256), 256, 0, h->st>>>(h->diag_pos.p, h->N, h->nK, h->nnz, h->vals.p, h->flags.p + 1); LAUNCH(h);
     k_inv_diag<<<cdiv(h->N, 256), 256, 0, h->st>>>(h->diag_pos.p, h->N, h->nK, h->nnz, h->vals.p, h->dinv.p); LAUNCH(h);
     h->have_vals = true;
+    if (h->use_amg) CKR(amg_setup_values(h));
     phase_begin(h, PH_RHS);
     const int c0 = h->c0, c1 = h->c1;
     if (h->sr) {
@@ -637,7 +757,9 @@ int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
                                   h->fullspace, h->prim.p, h->ld); LAUNCH(h);
         CK(cudaGetLastError());
     }
-    if (h->sr) { CKR(h->vals1.alloc(h->nnz * nK)); CKR(assemble(h, nullptr, h->vals1.p)); }
+    // rho = 1 matrices: the S1 of the singularity-removal right-hand side, and the (geometry-only) strength
+    // information the multilevel hierarchy is built from
+    CKR(h->vals1.alloc(h->nnz * nK)); CKR(assemble(h, nullptr, h->vals1.p));
     CKR(build_jac_plan(h));
     CK(cudaStreamSynchronize(st));
     return 0;
@@ -650,7 +772,47 @@ int pgb200_ert_destroy(pgb200_ert *h) {
     if (h->ev_ok) { for (int i = 0; i <= PH_COUNT; i++) cudaEventDestroy(h->ev[i]); cudaEventDestroy(h->jev[0]); cudaEventDestroy(h->jev[1]); }
     for (auto e : h->pev) cudaEventDestroy(e);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    for (AmgLevel *L : h->amg) delete L;
     delete h;
+    return 0;
+}
+
+int pgb200_ert_set_hierarchy(pgb200_ert *h, int n_levels, const pgb200_amg_level *lv) {
+    if (!h) PGB_FAIL("null handle");
+    CK(cudaSetDevice(h->device));
+    for (AmgLevel *L : h->amg) delete L;
+    h->amg.clear();
+    if (n_levels <= 0) return 0;
+    if (!lv) PGB_FAIL("null level array");
+    cudaStream_t st = h->st;
+    int n_finer = h->N; size_t nnz_finer = h->nnz;
+    for (int l = 0; l < n_levels; l++) {
+        const pgb200_amg_level &s = lv[l];
+        AmgLevel *L = new AmgLevel();
+        h->amg.push_back(L);
+        L->n = s.n; L->nnz = (size_t)s.nnz; L->n_finer = n_finer;
+        CKR(L->rowptr.upload(s.rowptr, (size_t)s.n + 1, st)); CKR(L->colidx.upload(s.colidx, L->nnz, st));
+        CKR(L->diag_pos.upload(s.diag_pos, s.n, st));
+        CKR(L->gal_ptr.upload(s.gal_ptr, L->nnz + 1, st)); CKR(L->gal_idx.upload(s.gal_idx, nnz_finer, st));
+        CKR(L->agg.upload(s.agg, n_finer, st)); CKR(L->mem_ptr.upload(s.mem_ptr, (size_t)s.n + 1, st)); CKR(L->mem_idx.upload(s.mem_idx, n_finer, st));
+        CKR(L->vals.alloc(L->nnz * h->nK)); CKR(L->dinvw.alloc((size_t)s.n * h->nK));
+        const size_t blk = (size_t)s.n * h->ld;
+        CKR(L->R.alloc(blk)); CKR(L->X.alloc(blk)); CKR(L->Z.alloc(blk));
+        CK(cudaMemsetAsync(L->R.p, 0, blk * sizeof(double), st)); CK(cudaMemsetAsync(L->X.p, 0, blk * sizeof(double), st));
+        CK(cudaMemsetAsync(L->Z.p, 0, blk * sizeof(double), st));
+        n_finer = s.n; nnz_finer = L->nnz;
+    }
+    const size_t blk0 = (size_t)h->N * h->ld;
+    if (!h->Z0.p) { CKR(h->Z0.alloc(blk0)); CKR(h->X0.alloc(blk0)); CKR(h->dinvw0.alloc((size_t)h->N * h->nK)); CKR(h->gmax.alloc(h->nK));
+        CK(cudaMemsetAsync(h->Z0.p, 0, blk0 * sizeof(double), st)); CK(cudaMemsetAsync(h->X0.p, 0, blk0 * sizeof(double), st)); }
+    CK(cudaStreamSynchronize(st));
+    h->have_vals = false;
+    return 0;
+}
+/* 0: Jacobi-PCG; 1: multilevel V-cycle preconditioner (needs a hierarchy); sweeps: Jacobi sweeps on the coarsest level */
+int pgb200_ert_set_preconditioner(pgb200_ert *h, int multilevel, int coarse_sweeps) {
+    if (!h) PGB_FAIL("null handle");
+    h->use_amg = multilevel != 0; if (coarse_sweeps > 0) h->coarse_sweeps = coarse_sweeps;
     return 0;
 }
 

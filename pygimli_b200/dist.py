@@ -56,12 +56,12 @@ class _DevView:
 
 
 class ShardedERT:
-    def __init__(self, mesh, scheme: SchemeArrays, device=0, rank=0, world=1, sr=True):
+    def __init__(self, mesh, scheme: SchemeArrays, device=0, rank=0, world=1, sr=True, preconditioner="multilevel"):
         self.rank, self.world, self.device = int(rank), int(world), int(device)
         self.perm = row_order(scheme) if world > 1 else np.arange(scheme.size)
         self.inv_perm = np.argsort(self.perm)
         self.scheme = scheme.subset(self.perm) if world > 1 else scheme
-        self.core = CoreB200(sr=sr, device=device)
+        self.core = CoreB200(sr=sr, device=device, preconditioner=preconditioner)
         self.core.setMesh(mesh)
         self.core.setData(self.scheme)
         P = self.core._ensure_plan()

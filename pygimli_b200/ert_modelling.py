@@ -22,6 +22,7 @@ import ctypes as C
 import numpy as np
 
 from . import _capi
+from .amg_setup import build_hierarchy
 from .host_setup import build_plan, TOLERANCE
 from .mesh import MeshArrays, from_pg_mesh
 from .scheme import SchemeArrays, geometric_factors
@@ -103,7 +104,11 @@ class CoreB200:
     """Replacement for ``pg.core.DCSRMultiElectrodeModelling`` (sr=True) /
     ``DCMultiElectrodeModelling`` (sr=False) on one B200."""
 
-    def __init__(self, sr: bool = True, verbose: bool = False, device: int = 0):
+    def __init__(self, sr: bool = True, verbose: bool = False, device: int = 0, preconditioner: str = "multilevel"):
+        if preconditioner not in ("multilevel", "jacobi"):
+            raise ValueError("preconditioner must be 'multilevel' or 'jacobi'")
+        self.preconditioner = preconditioner
+        self.hierarchy = None
         self.sr = bool(sr)
         self.verbose = bool(verbose)
         self.device = int(device)
@@ -219,6 +224,14 @@ class CoreB200:
                 _capi.check(_capi.lib().pgb200_ert_set_stream(h, C.c_void_p(self._stream)))
             if self._shard:
                 _capi.check(_capi.lib().pgb200_ert_set_shard(h, *self._shard))
+            if self.preconditioner == "multilevel":
+                # aggregation hierarchy from the rho = 1 matrix of the smallest wavenumber (geometry only)
+                v1 = self.get("vals1", raw=True).reshape(P.nK, P.nnz)[0]
+                self.hierarchy = build_hierarchy(P.rowptr, P.colidx, v1, _capi.pairwise_aggregate)
+                self._keep_amg = _capi.set_hierarchy(h, self.hierarchy)
+                _capi.check(_capi.lib().pgb200_ert_set_preconditioner(h, 1 if self.hierarchy else 0, 8))
+            else:
+                _capi.check(_capi.lib().pgb200_ert_set_preconditioner(h, 0, 8))
         return self._h
 
     # ---- the path ---------------------------------------------------------------------
@@ -257,8 +270,8 @@ class CoreB200:
         raise NotImplementedError("use get('rho') after response(); the mapping runs on the GPU")
 
     # ---- introspection ------------------------------------------------------------------
-    def get(self, what: str) -> np.ndarray:
-        h = self._ensure_handle()
+    def get(self, what: str, raw: bool = False) -> np.ndarray:
+        h = self._h if (raw and self._h) else self._ensure_handle()
         n = _capi.lib().pgb200_ert_get(h, what.encode(), None, 0)
         if n < 0:
             raise _capi.PGB200Error(_capi.last_error())
@@ -267,6 +280,8 @@ class CoreB200:
             r = _capi.lib().pgb200_ert_get(h, what.encode(), out.ctypes.data, int(n))
             if r < 0:
                 raise _capi.PGB200Error(_capi.last_error())
+        if raw:
+            return out
         # back to the reference's numbering (the device works in the internal node order)
         P = self._plan
         if what in ("vals", "vals1") and n:
