@@ -583,6 +583,15 @@ __global__ void k_inv_diag_w(const int *__restrict__ diag_pos, int n, int nK, si
     }
 }
 
+// vals_dw[k][p] = vals[k][p] * dinvw[k][col(p)]
+__global__ void k_scale_cols(const int *__restrict__ colidx, size_t nnz, int n, int nK, const double *__restrict__ vals,
+                             const double *__restrict__ dinvw, double *__restrict__ vals_dw) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    const int j = colidx[p];
+    for (int kk = 0; kk < nK; kk++) vals_dw[(size_t)kk * nnz + p] = vals[(size_t)kk * nnz + p] * dinvw[(size_t)kk * n + j];
+}
+
 constexpr int AMG_TX = 16, AMG_TY = 8, AMG_ROWS = 32;
 
 // Z = X + dw .* (R - A X)   (post-smoothing / Jacobi sweep); optional fused dot  sum_i R_i Z_i
@@ -646,23 +655,23 @@ k_amg_post(const int *__restrict__ rowptr, const int *__restrict__ colidx, const
 }
 
 // pre-smoothing from a zero guess + residual + restriction, fused:
-//   RC[I] = sum_{i in aggregate I} ( R_i - sum_j a_ij * dw_j * R_j )
+//   RC[I] = sum_{i in aggregate I} ( R_i - sum_j a_ij * dw_j * R_j )      (vals_dw[p] = a_ij * dw_j, see k_scale_cols)
 template <int CPT>
 __global__ void __launch_bounds__(AMG_TX * AMG_TY)
-k_amg_restrict(const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals, size_t nnz,
-               const double *__restrict__ dinvw, int n_f, const int *__restrict__ mem_ptr, const int *__restrict__ mem_idx, int n_c,
+k_amg_restrict(const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals_dw, size_t nnz,
+               int n_f, const int *__restrict__ mem_ptr, const int *__restrict__ mem_idx, int n_c,
                const double *__restrict__ R, double *__restrict__ RC, int nE, int c0, int c1, size_t ld) {
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int cbase = c0 + blockIdx.y * (AMG_TX * CPT) + tx;
-    int col[CPT]; size_t voff[CPT]; const double *dw[CPT]; bool ok[CPT];
+    int col[CPT]; size_t voff[CPT]; bool ok[CPT];
 #pragma unroll
     for (int m = 0; m < CPT; m++) {
         const int c = cbase + m * AMG_TX;
         ok[m] = c < c1;
         col[m] = ok[m] ? c : c0;
-        const int kk = col[m] / nE;
-        voff[m] = (size_t)kk * nnz; dw[m] = dinvw + (size_t)kk * n_f;
+        voff[m] = (size_t)(col[m] / nE) * nnz;
     }
+    (void)n_f;
     const int row0 = blockIdx.x * AMG_ROWS;
     for (int r = ty; r < AMG_ROWS; r += AMG_TY) {
         const int I = row0 + r;
@@ -675,11 +684,9 @@ k_amg_restrict(const int *__restrict__ rowptr, const int *__restrict__ colidx, c
 #pragma unroll
             for (int m = 0; m < CPT; m++) acc[m] += __ldg(R + (size_t)i * ld + col[m]);
             for (int p = rowptr[i]; p < rowptr[i + 1]; p++) {
-                const int j = colidx[p];
-                const size_t xo = (size_t)j * ld;
+                const size_t xo = (size_t)colidx[p] * ld;
 #pragma unroll
-                for (int m = 0; m < CPT; m++)
-                    acc[m] = fma(-__ldg(vals + voff[m] + p) * __ldg(dw[m] + j), __ldg(R + xo + col[m]), acc[m]);
+                for (int m = 0; m < CPT; m++) acc[m] = fma(-__ldg(vals_dw + voff[m] + p), __ldg(R + xo + col[m]), acc[m]);
             }
         }
 #pragma unroll

@@ -56,7 +56,7 @@ enum Phase { PH_MAP = 0, PH_ASM, PH_RHS, PH_SOLVE, PH_EPI, PH_JAC, PH_COUNT };
 struct AmgLevel {      // one coarse level of the aggregation hierarchy (device arrays)
     int n = 0; size_t nnz = 0; int n_finer = 0;
     DevBuf<int> rowptr, colidx, diag_pos, gal_ptr, gal_idx, agg, mem_ptr, mem_idx;
-    DevBuf<double> vals, dinvw, R, X, Z;
+    DevBuf<double> vals, vals_dw, dinvw, R, X, Z;
 };
 
 struct pgb200_ert {
@@ -92,7 +92,7 @@ struct pgb200_ert {
     std::vector<JacChunk> chunks; int nQ = 0, nQp = 0;
     size_t ldJ = 0; int j_rows = 0; bool jac_valid = false;
     // multilevel preconditioner
-    std::vector<AmgLevel *> amg; int use_amg = 1, coarse_sweeps = 8; DevBuf<double> Z0, X0, dinvw0; DevBuf<unsigned long long> gmax;
+    std::vector<AmgLevel *> amg; int use_amg = 1, coarse_sweeps = 8; DevBuf<double> Z0, X0, dinvw0, vals_dw0; DevBuf<unsigned long long> gmax;
     // stats
     int last_iters = 0; double last_relres = 0.0; long long launches = 0;
     cudaEvent_t ev[PH_COUNT + 1]; bool ev_ok = false; float ph_ms[PH_COUNT] = {0};
@@ -211,12 +211,10 @@ int amg_post_cpt(pgb200_ert *h, const int *rowptr, const int *colidx, const doub
     return 0;
 }
 int pick_cpt(int ncols) {
-    int best = 1; double beste = 0.0;
-    for (int cpt : {4, 2, 1}) {
-        const int w = AMG_TX * cpt; const double eff = (double)ncols / (double)(cdiv(ncols, w) * w);
-        if (eff > beste + 0.05) { beste = eff; best = cpt; }
-    }
-    return best;
+    // wide column blocks amortise the index/value loads over 4 accumulators; only narrow shards use fewer
+    if (ncols >= 48) return 4;
+    if (ncols >= 24) return 2;
+    return 1;
 }
 int amg_post(pgb200_ert *h, const int *rowptr, const int *colidx, const double *vals, size_t nnz, const double *dinvw, int n,
              const double *X, const double *R, double *Z, int c0, int c1, double *dots) {
@@ -226,11 +224,11 @@ int amg_post(pgb200_ert *h, const int *rowptr, const int *colidx, const double *
         default: return amg_post_cpt<1>(h, rowptr, colidx, vals, nnz, dinvw, n, X, R, Z, c0, c1, dots);
     }
 }
-int amg_restrict(pgb200_ert *h, const int *rowptr, const int *colidx, const double *vals, size_t nnz, const double *dinvw, int n_f,
+int amg_restrict(pgb200_ert *h, const int *rowptr, const int *colidx, const double *vals_dw, size_t nnz, int n_f,
                  const AmgLevel *L, const double *R, int c0, int c1) {
     const int cpt = pick_cpt(c1 - c0);
     dim3 block(AMG_TX, AMG_TY), grid(cdiv(L->n, AMG_ROWS), cdiv(c1 - c0, AMG_TX * cpt));
-#define RGO(C) k_amg_restrict<C><<<grid, block, 0, h->st>>>(rowptr, colidx, vals, nnz, dinvw, n_f, L->mem_ptr.p, L->mem_idx.p, L->n, R, L->R.p, h->nE, c0, c1, h->ld)
+#define RGO(C) k_amg_restrict<C><<<grid, block, 0, h->st>>>(rowptr, colidx, vals_dw, nnz, n_f, L->mem_ptr.p, L->mem_idx.p, L->n, R, L->R.p, h->nE, c0, c1, h->ld)
     if (cpt == 4) RGO(4); else if (cpt == 2) RGO(2); else RGO(1);
 #undef RGO
     LAUNCH(h);
@@ -241,17 +239,19 @@ int amg_restrict(pgb200_ert *h, const int *rowptr, const int *colidx, const doub
 int amg_setup_values(pgb200_ert *h) {
     if (h->amg.empty()) return 0;
     const int nK = h->nK;
-    auto smoother = [&](const int *rowptr, const int *diag_pos, int n, size_t nnz, const double *vals, double *dinvw) -> int {
+    auto smoother = [&](const int *rowptr, const int *colidx, const int *diag_pos, int n, size_t nnz, const double *vals, double *dinvw,
+                        double *vals_dw) -> int {
         CK(cudaMemsetAsync(h->gmax.p, 0, sizeof(unsigned long long) * nK, h->st));
         k_row_ratio<<<cdiv(n, 128), 128, 0, h->st>>>(rowptr, diag_pos, n, nK, nnz, vals, h->gmax.p); LAUNCH(h);
         k_inv_diag_w<<<cdiv(n, 128), 128, 0, h->st>>>(diag_pos, n, nK, nnz, vals, h->gmax.p, dinvw); LAUNCH(h);
+        if (vals_dw) { k_scale_cols<<<cdiv((long long)nnz, 256), 256, 0, h->st>>>(colidx, nnz, n, nK, vals, dinvw, vals_dw); LAUNCH(h); }
         return 0;
     };
-    CKR(smoother(h->rowptr.p, h->diag_pos.p, h->N, h->nnz, h->vals.p, h->dinvw0.p));
+    CKR(smoother(h->rowptr.p, h->colidx.p, h->diag_pos.p, h->N, h->nnz, h->vals.p, h->dinvw0.p, h->vals_dw0.p));
     const double *vf = h->vals.p; size_t nnz_f = h->nnz;
     for (AmgLevel *L : h->amg) {
         k_galerkin<<<cdiv((long long)L->nnz, 128), 128, 0, h->st>>>(L->gal_ptr.p, L->gal_idx.p, (int)L->nnz, nK, nnz_f, L->nnz, vf, L->vals.p); LAUNCH(h);
-        CKR(smoother(L->rowptr.p, L->diag_pos.p, L->n, L->nnz, L->vals.p, L->dinvw.p));
+        CKR(smoother(L->rowptr.p, L->colidx.p, L->diag_pos.p, L->n, L->nnz, L->vals.p, L->dinvw.p, L->vals_dw.p));
         vf = L->vals.p; nnz_f = L->nnz;
     }
     CK(cudaGetLastError());
@@ -261,14 +261,14 @@ int amg_setup_values(pgb200_ert *h) {
 // one V(1,1) cycle: Z0 = M^-1 R (level 0 residual = h->R); optionally accumulates dots[c] += R.Z
 int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
     const int nl = (int)h->amg.size();
-    struct Lv { const int *rowptr, *colidx; const double *vals; size_t nnz; const double *dinvw; int n; const double *R; double *X, *Z; };
+    struct Lv { const int *rowptr, *colidx; const double *vals, *vals_dw; size_t nnz; const double *dinvw; int n; const double *R; double *X, *Z; };
     std::vector<Lv> lv(nl + 1);
-    lv[0] = {h->rowptr.p, h->colidx.p, h->vals.p, h->nnz, h->dinvw0.p, h->N, h->R.p, h->X0.p, h->Z0.p};
-    for (int l = 0; l < nl; l++) { AmgLevel *L = h->amg[l]; lv[l + 1] = {L->rowptr.p, L->colidx.p, L->vals.p, L->nnz, L->dinvw.p, L->n, L->R.p, L->X.p, L->Z.p}; }
+    lv[0] = {h->rowptr.p, h->colidx.p, h->vals.p, h->vals_dw0.p, h->nnz, h->dinvw0.p, h->N, h->R.p, h->X0.p, h->Z0.p};
+    for (int l = 0; l < nl; l++) { AmgLevel *L = h->amg[l]; lv[l + 1] = {L->rowptr.p, L->colidx.p, L->vals.p, L->vals_dw.p, L->nnz, L->dinvw.p, L->n, L->R.p, L->X.p, L->Z.p}; }
     dim3 pb(32, 8);
     // downward: residual after one damped-Jacobi sweep from zero, restricted
     for (int l = 0; l < nl; l++)
-        CKR(amg_restrict(h, lv[l].rowptr, lv[l].colidx, lv[l].vals, lv[l].nnz, lv[l].dinvw, lv[l].n, h->amg[l], lv[l].R, c0, c1));
+        CKR(amg_restrict(h, lv[l].rowptr, lv[l].colidx, lv[l].vals_dw, lv[l].nnz, lv[l].n, h->amg[l], lv[l].R, c0, c1));
     // coarsest level: fixed number of Jacobi sweeps
     const double *E;
     {
@@ -795,7 +795,7 @@ int pgb200_ert_set_hierarchy(pgb200_ert *h, int n_levels, const pgb200_amg_level
         CKR(L->diag_pos.upload(s.diag_pos, s.n, st));
         CKR(L->gal_ptr.upload(s.gal_ptr, L->nnz + 1, st)); CKR(L->gal_idx.upload(s.gal_idx, nnz_finer, st));
         CKR(L->agg.upload(s.agg, n_finer, st)); CKR(L->mem_ptr.upload(s.mem_ptr, (size_t)s.n + 1, st)); CKR(L->mem_idx.upload(s.mem_idx, n_finer, st));
-        CKR(L->vals.alloc(L->nnz * h->nK)); CKR(L->dinvw.alloc((size_t)s.n * h->nK));
+        CKR(L->vals.alloc(L->nnz * h->nK)); CKR(L->vals_dw.alloc(L->nnz * h->nK)); CKR(L->dinvw.alloc((size_t)s.n * h->nK));
         const size_t blk = (size_t)s.n * h->ld;
         CKR(L->R.alloc(blk)); CKR(L->X.alloc(blk)); CKR(L->Z.alloc(blk));
         CK(cudaMemsetAsync(L->R.p, 0, blk * sizeof(double), st)); CK(cudaMemsetAsync(L->X.p, 0, blk * sizeof(double), st));
@@ -803,7 +803,7 @@ int pgb200_ert_set_hierarchy(pgb200_ert *h, int n_levels, const pgb200_amg_level
         n_finer = s.n; nnz_finer = L->nnz;
     }
     const size_t blk0 = (size_t)h->N * h->ld;
-    if (!h->Z0.p) { CKR(h->Z0.alloc(blk0)); CKR(h->X0.alloc(blk0)); CKR(h->dinvw0.alloc((size_t)h->N * h->nK)); CKR(h->gmax.alloc(h->nK));
+    if (!h->Z0.p) { CKR(h->Z0.alloc(blk0)); CKR(h->X0.alloc(blk0)); CKR(h->dinvw0.alloc((size_t)h->N * h->nK)); CKR(h->vals_dw0.alloc(h->nnz * h->nK)); CKR(h->gmax.alloc(h->nK));
         CK(cudaMemsetAsync(h->Z0.p, 0, blk0 * sizeof(double), st)); CK(cudaMemsetAsync(h->X0.p, 0, blk0 * sizeof(double), st)); }
     CK(cudaStreamSynchronize(st));
     h->have_vals = false;
