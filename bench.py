@@ -72,12 +72,14 @@ class ClockSampler:
 
 def build_workload(name, scale):
     from pygimli_b200.workloads import WORKLOADS, model_for
-    mesh, scheme, desc = WORKLOADS[name](scale)
+    out = WORKLOADS[name](scale)
+    mesh, scheme, desc = out[:3]
+    kw = out[3] if len(out) > 3 else None          # explicit wavenumbers (setkValues / setWeights)
     ok = np.isfinite(scheme.k) & (np.abs(scheme.k) < 1e9)
     if not ok.all():
         scheme = scheme.subset(np.nonzero(ok)[0])
     M = int(mesh.cell_marker.max()) + 1
-    return mesh, scheme, model_for(M), desc
+    return mesh, scheme, model_for(M), desc, kw
 
 
 # ----------------------------------------------------------------------------------------
@@ -91,13 +93,13 @@ def run_reference(args):
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libgimli_ref.so not built"}))
         return
-    mesh, scheme, model, desc = build_workload(args.workload, args.scale)
+    mesh, scheme, model, desc, kw = build_workload(args.workload, args.scale)
     cores = os.cpu_count() or 1
     threads = max(1, min(8, cores - 2))          # reference default (modellingbase.cpp:77)
     samples = []
     info = {}
     for step in range(args.warmup + args.steps):
-        t, info = reference_sample(ref, mesh, scheme, model, threads, args)
+        t, info = reference_sample(ref, mesh, scheme, model, threads, args, kw)
         if step >= args.warmup:
             samples.append(t)
     val = float(np.mean(samples))
@@ -112,7 +114,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def reference_sample(ref, mesh, scheme, model, threads, args):
+def reference_sample(ref, mesh, scheme, model, threads, args, kw=None):
     """One bounded sample of the reference path, extrapolated to the whole workload:
       (i)  pattern + assembly of S(rho) and S(1) for every wavenumber: full, unmodified reference code
            (dcfemmodelling.cpp:2175-2192)
@@ -127,6 +129,8 @@ def reference_sample(ref, mesh, scheme, model, threads, args):
     R = ref.RefERT(mesh, sub, sr=True, solver="pcg")
     R.set_threads(threads)
     R.set_pcg_tol(args.tol)
+    if kw is not None:
+        R.set_kw(kw[0], kw[1])
     k, _ = R.kw()
     nK = k.size
     t0 = time.perf_counter()
@@ -166,8 +170,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     t_setup = time.perf_counter()
-    mesh, scheme, model, desc = build_workload(args.workload, args.scale)
-    fop = ShardedERT(mesh, scheme, device=local, rank=rank, world=world, sr=True, preconditioner=args.precond)
+    mesh, scheme, model, desc, kw = build_workload(args.workload, args.scale)
+    fop = ShardedERT(mesh, scheme, device=local, rank=rank, world=world, sr=True, preconditioner=args.precond, kw=kw)
     fop.set_solver(args.tol, 100000, 25)
     stream = torch.cuda.current_stream()
     fop.set_stream(stream.cuda_stream)
@@ -270,7 +274,7 @@ def run_b200(args):
                 if ref.available():
                     cores = os.cpu_count() or 1
                     threads = max(1, min(8, cores - 2))
-                    tv, info = reference_sample(ref, mesh, scheme, model, threads, args)
+                    tv, info = reference_sample(ref, mesh, scheme, model, threads, args, kw)
                     line["cpu_baseline"] = {"value": tv, "unit": "s", "cores": threads, "kind": "reference",
                                             "sample": info["sample"], "stages_s": info["stages"]}
                 else:

@@ -56,7 +56,7 @@ class _DevView:
 
 
 class ShardedERT:
-    def __init__(self, mesh, scheme: SchemeArrays, device=0, rank=0, world=1, sr=True, preconditioner="multilevel"):
+    def __init__(self, mesh, scheme: SchemeArrays, device=0, rank=0, world=1, sr=True, preconditioner="multilevel", kw=None):
         self.rank, self.world, self.device = int(rank), int(world), int(device)
         self.perm = row_order(scheme) if world > 1 else np.arange(scheme.size)
         self.inv_perm = np.argsort(self.perm)
@@ -64,6 +64,9 @@ class ShardedERT:
         self.core = CoreB200(sr=sr, device=device, preconditioner=preconditioner)
         self.core.setMesh(mesh)
         self.core.setData(self.scheme)
+        if kw is not None:
+            self.core.setkValues(kw[0])
+            self.core.setWeights(kw[1])
         P = self.core._ensure_plan()
         self.nS, self.N, self.nE, self.D, self.M = P.nS, P.N, P.nE, self.scheme.size, P.M
         self.src = padded_range(self.nS, world, rank) if world > 1 else (0, self.nS)

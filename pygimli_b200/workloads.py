@@ -6,6 +6,7 @@ from __future__ import annotations
 import numpy as np
 
 from .mesh import graded_axis, grid_mesh_2d, grid_mesh_3d, create_p2, mark_electrode_nodes
+from .host_setup import kwave_from_range
 from .scheme import create_dd, create_slm, create_dd_complete, create_grid_dd, geometric_factors
 
 
@@ -43,7 +44,9 @@ def c2_2d_slm_p2(scale: float = 1.0):
     mesh = create_p2(mesh)
     scheme = create_slm(sens)
     scheme.k = geometric_factors(scheme, 2)
-    return mesh, scheme, "2.5D slm, 96 electrodes, P2 triangles, 11 wavenumbers"
+    # 11 wavenumbers set explicitly (setkValues/setWeights): 7 Legendre + 4 Laguerre nodes
+    kw = kwave_from_range(sp / 2.0, (ne - 1) * sp * 2.0, 7, 4)
+    return mesh, scheme, "2.5D slm, 96 electrodes, P2 triangles, 11 wavenumbers", kw
 
 
 def c3_3d_grid(scale: float = 1.0, complete: bool = True, marker_per: str = "cell"):

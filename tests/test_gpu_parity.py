@@ -231,9 +231,9 @@ def test_error_behaviour():
     fop._core.close()
 
 
-def test_linearity_of_jacobian_rows_sum_rule():
-    """size-independent property: sum_j J_ij rho_j == rhoa_i when every cell is a model cell and the
-    model is homogeneous (Euler relation for the degree-1 homogeneous map rho -> rhoa)."""
+def test_response_is_homogeneous_of_degree_one():
+    """size-independent property: response(c * model) == c * response(model) (S scales with 1/c, the
+    secondary-field right-hand side with it), and J(c * model) == J(model) for the same reason."""
     from pygimli_b200.mesh import graded_axis, grid_mesh_2d, mark_electrode_nodes
     from pygimli_b200.scheme import create_dd, geometric_factors
     ne = 9
@@ -248,10 +248,12 @@ def test_linearity_of_jacobian_rows_sum_rule():
     model = 10.0 ** (2 + 0.3 * rng.standard_normal(M))
     fop = _fop(mesh, sch)
     rhoa = fop.response(model)
-    fop.createJacobian(model)
-    Jop = fop.jacobian()
-    assert np.max(np.abs(Jop.mult(model) - rhoa) / rhoa) < 0.15     # discretisation-level consistency (the reference reports 0.97-1.0)
     # scaling property: response(c * model) == c * response(model) to solver accuracy
+    fop.createJacobian(model)
+    J1 = fop.jacobian().numpy()
     r2 = fop.response(3.0 * model)
     assert np.max(np.abs(r2 - 3.0 * rhoa) / rhoa) < 1e-7
+    fop.createJacobian(3.0 * model)
+    J2 = fop.jacobian().numpy()
+    assert np.max(np.abs(J2 - J1)) / np.max(np.abs(J1)) < 1e-7
     fop._core.close()
