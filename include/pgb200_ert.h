@@ -115,6 +115,8 @@ typedef struct pgb200_amg_level {
     const int *agg;         /* [n of the finer level] finer node -> node of this level                   */
     const int *mem_ptr;     /* [n+1] members of every aggregate ...                                      */
     const int *mem_idx;     /* [n of the finer level] ... as finer-level node ids                        */
+    const int *panel_agg_ptr; /* first coarse level only, optional: [n_panels+1] aggregates of every SpMM row
+                             * panel (aggregates never straddle panels and are numbered panel by panel)  */
 } pgb200_amg_level;
 
 /* ---- host-only helpers (no GPU needed) -------------------------------------------- */
@@ -129,8 +131,9 @@ int pgb200_build_panels(int n_rows, const int *rowptr, const int *colidx, int rm
                         int *panel_ptr, int *halo_ptr, int *halo_cols, unsigned short *lidx, unsigned short *self_idx);
 
 /* Greedy pairwise aggregation along the strongest negative coupling (multilevel preconditioner
- * set-up); agg[n] receives the aggregate id per node; returns the number of aggregates.        */
-int pgb200_pairwise_aggregate(int n, const int *rowptr, const int *colidx, const double *vals, int *agg);
+ * set-up); agg[n] receives the aggregate id per node; returns the number of aggregates.  With
+ * group != NULL only nodes of the same group are matched (aggregates stay inside SpMM row panels). */
+int pgb200_pairwise_aggregate(int n, const int *rowptr, const int *colidx, const double *vals, const int *group, int *agg);
 
 /* ---- life cycle ------------------------------------------------------------------- */
 int pgb200_ert_create(const pgb200_plan *plan, int device, pgb200_ert **out);

@@ -43,7 +43,8 @@ class Plan(C.Structure):
 
 class AmgLevel(C.Structure):
     _fields_ = [("n", C.c_int), ("nnz", C.c_int), ("rowptr", c_int_p), ("colidx", c_int_p), ("diag_pos", c_int_p),
-                ("gal_ptr", c_int_p), ("gal_idx", c_int_p), ("agg", c_int_p), ("mem_ptr", c_int_p), ("mem_idx", c_int_p)]
+                ("gal_ptr", c_int_p), ("gal_idx", c_int_p), ("agg", c_int_p), ("mem_ptr", c_int_p), ("mem_idx", c_int_p),
+                ("panel_agg_ptr", c_int_p)]
 
 
 # every symbol include/pgb200_ert.h declares (checked by tests/test_capi_symbols.py)
@@ -104,7 +105,7 @@ def lib():
         L.pgb200_ert_set_spmm_variant.argtypes = [C.c_void_p, C.c_int]
         L.pgb200_ert_set_hierarchy.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.pgb200_ert_set_preconditioner.argtypes = [C.c_void_p, C.c_int, C.c_int]
-        L.pgb200_pairwise_aggregate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pgb200_pairwise_aggregate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pgb200_spmm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p]
         _lib = L
@@ -134,12 +135,14 @@ def color_cells(cells: np.ndarray, n_nodes: int):
     return color, int(n)
 
 
-def pairwise_aggregate(rowptr, colidx, vals):
+def pairwise_aggregate(rowptr, colidx, vals, group=None):
     rowptr = np.ascontiguousarray(rowptr, np.int32)
     colidx = np.ascontiguousarray(colidx, np.int32)
     vals = np.ascontiguousarray(vals, np.float64)
     agg = np.zeros(rowptr.size - 1, np.int32)
-    na = lib().pgb200_pairwise_aggregate(rowptr.size - 1, rowptr.ctypes.data, colidx.ctypes.data, vals.ctypes.data, agg.ctypes.data)
+    g = None if group is None else np.ascontiguousarray(group, np.int32)
+    na = lib().pgb200_pairwise_aggregate(rowptr.size - 1, rowptr.ctypes.data, colidx.ctypes.data, vals.ctypes.data,
+                                         None if g is None else g.ctypes.data, agg.ctypes.data)
     return agg, int(na)
 
 
@@ -177,6 +180,10 @@ def set_hierarchy(handle, levels):
             v = np.ascontiguousarray(L[name], np.int32)
             keep.append(v)
             setattr(a, name, v.ctypes.data_as(c_int_p))
+        if L.get("panel_agg_ptr") is not None:
+            v = np.ascontiguousarray(L["panel_agg_ptr"], np.int32)
+            keep.append(v)
+            a.panel_agg_ptr = v.ctypes.data_as(c_int_p)
     check(lib().pgb200_ert_set_hierarchy(handle, len(levels), C.cast(arr, C.c_void_p)))
     return keep
 

@@ -50,10 +50,13 @@ def _diag_pos(rowptr, colidx):
     return d.astype(np.int32)
 
 
-def build_hierarchy(rowptr, colidx, vals, aggregate_fn, passes: int = 2, min_size: int = 256, max_levels: int = 12):
+def build_hierarchy(rowptr, colidx, vals, aggregate_fn, passes: int = 2, min_size: int = 256, max_levels: int = 12,
+                    panel_ptr=None):
     """-> list of coarse levels (finest first).  Each level dict describes the transfer from the
     next finer level: n, nnz, rowptr, colidx, diag_pos, gal_ptr, gal_idx, agg (finer node -> node),
-    mem_ptr/mem_idx (members of every aggregate)."""
+    mem_ptr/mem_idx (members of every aggregate).  With ``panel_ptr`` (row panels of the staged SpMM) the first
+    level's aggregates never straddle a panel and are numbered panel by panel (``panel_agg_ptr``), so the
+    fine-level restriction can run inside the panel kernel without atomics."""
     levels = []
     rp, ci, v = np.asarray(rowptr, np.int32), np.asarray(colidx, np.int32), np.asarray(vals, np.float64)
     while len(levels) < max_levels:
@@ -62,8 +65,14 @@ def build_hierarchy(rowptr, colidx, vals, aggregate_fn, passes: int = 2, min_siz
             break
         agg = np.arange(n, dtype=np.int32)
         rp_p, ci_p, v_p, nc = rp, ci, v, n
+        first = not levels and panel_ptr is not None
+        group = np.repeat(np.arange(len(panel_ptr) - 1, dtype=np.int32), np.diff(panel_ptr)) if first else None
         for _ in range(passes):
-            a, na = aggregate_fn(rp_p, ci_p, v_p)
+            a, na = aggregate_fn(rp_p, ci_p, v_p, group) if first else aggregate_fn(rp_p, ci_p, v_p)
+            if first:
+                g2 = np.zeros(na, np.int32)
+                g2[a] = group
+                group = g2
             crp, cci, gp, gi = _coarsen(rp_p, ci_p, a, na)
             v_p = _sum_values(v_p, gp, gi)
             rp_p, ci_p = crp, cci
@@ -71,12 +80,21 @@ def build_hierarchy(rowptr, colidx, vals, aggregate_fn, passes: int = 2, min_siz
             nc = na
         if nc > 0.7 * n:
             break
+        panel_agg_ptr = None
+        if first:
+            # number the aggregates panel by panel (fine rows are consecutive inside a panel)
+            order_a = np.argsort(group, kind="stable")
+            newid = np.empty(nc, np.int32)
+            newid[order_a] = np.arange(nc, dtype=np.int32)
+            agg = newid[agg]
+            panel_agg_ptr = np.concatenate([[0], np.cumsum(np.bincount(group, minlength=len(panel_ptr) - 1))]).astype(np.int32)
         crp, cci, gp, gi = _coarsen(rp, ci, agg, nc)
         order = np.argsort(agg, kind="stable").astype(np.int32)
         mem_ptr = np.zeros(nc + 1, np.int32)
         np.cumsum(np.bincount(agg, minlength=nc), out=mem_ptr[1:])
         levels.append(dict(n=int(nc), nnz=int(cci.size), rowptr=crp, colidx=cci, diag_pos=_diag_pos(crp, cci),
-                           gal_ptr=gp, gal_idx=gi, agg=agg.astype(np.int32), mem_ptr=mem_ptr, mem_idx=order))
+                           gal_ptr=gp, gal_idx=gi, agg=agg.astype(np.int32), mem_ptr=mem_ptr, mem_idx=order,
+                           panel_agg_ptr=panel_agg_ptr))
         v = _sum_values(v, gp, gi)
         rp, ci = crp, cci
     return levels

@@ -311,36 +311,90 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 // values of a second wavenumber group (only if the tile straddles two), and the row pointers.
 struct __align__(16) PanelEntry { double a; uint32_t off; uint32_t pad; };
 
+// accumulate one matrix row of the panel against the staged X tile: acc[m] = sum_p a_p * X[col_p][lane + 32 m]
 template <int NC, bool TWO_K>
-__device__ __forceinline__ void panel_rows(const char *sx_lane, const PanelEntry *sE, const double *sA1, const int *sRow,
-                                           const unsigned short *__restrict__ self_idx, int r0, int nrows, int warp, int tw,
-                                           const bool (&ok)[NC], const bool (&second)[NC], const int (&col)[NC],
-                                           size_t ld, double *__restrict__ Y, double (&part)[NC], bool dot) {
-    for (int r = warp; r < nrows; r += PANEL_WARPS) {
-        const int pb = sRow[r], pe = sRow[r + 1];
-        double acc[NC];
+__device__ __forceinline__ void panel_row_acc(const char *sx_lane, const PanelEntry *sE, const double *sA1, int pb, int pe,
+                                              const bool (&second)[NC], double (&acc)[NC]) {
 #pragma unroll
-        for (int m = 0; m < NC; m++) acc[m] = 0.0;
+    for (int m = 0; m < NC; m++) acc[m] = 0.0;
 #pragma unroll 4
-        for (int p = pb; p < pe; p++) {
-            const PanelEntry e = sE[p];                               // one 128-bit broadcast load
-            const double *xr = reinterpret_cast<const double *>(sx_lane + e.off);
-            if (TWO_K) {
-                const double a1 = sA1[p];
+    for (int p = pb; p < pe; p++) {
+        const PanelEntry e = sE[p];                               // one 128-bit broadcast load
+        const double *xr = reinterpret_cast<const double *>(sx_lane + e.off);
+        if (TWO_K) {
+            const double a1 = sA1[p];
 #pragma unroll
-                for (int m = 0; m < NC; m++) acc[m] = fma(second[m] ? a1 : e.a, xr[32 * m], acc[m]);
-            } else {
+            for (int m = 0; m < NC; m++) acc[m] = fma(second[m] ? a1 : e.a, xr[32 * m], acc[m]);
+        } else {
 #pragma unroll
-                for (int m = 0; m < NC; m++) acc[m] = fma(e.a, xr[32 * m], acc[m]);
-            }
+            for (int m = 0; m < NC; m++) acc[m] = fma(e.a, xr[32 * m], acc[m]);
         }
+    }
+}
+
+// what a panel CTA does with the row sums  acc = (A X)[row]:
+//   EPI_SPMM     Y = acc                         (+ optional dot  X_row . Y_row : p.Ap of PCG)
+//   EPI_POST     Y = X_row + dw_row (R_row - acc) (+ dot R_row . Y_row): damped-Jacobi post-smoothing, r.z of PCG
+//   EPI_RESTRICT Y[aggregate] = sum over the aggregate's rows of (X_row - acc): residual after the pre-smoothing
+//                sweep from a zero guess (values pre-scaled by dw), restricted with piecewise-constant P
+enum PanelEpi : int { EPI_SPMM = 0, EPI_POST = 1, EPI_RESTRICT = 2 };
+
+struct PanelExtra {
+    const double *R;          // EPI_POST: residual block
+    const double *dinvw;      // EPI_POST: [nK][N] damped inverse diagonal
+    int n;                    // rows of the level (stride of dinvw per wavenumber)
+    const int *agg_panel_ptr; // EPI_RESTRICT: [n_panels+1] aggregates of every panel (coarse rows are numbered panel by panel)
+    const int *mem_ptr;       // EPI_RESTRICT: [n_coarse+1] members of every aggregate ...
+    const int *mem_idx;       //               ... as fine row ids (all inside the aggregate's panel)
+};
+
+template <int NC, bool TWO_K, int EPI>
+__device__ __forceinline__ void panel_rows(const char *sx_lane, const PanelEntry *sE, const double *sA1, const int *sRow,
+                                           const unsigned short *__restrict__ self_idx, int panel, int r0, int nrows, int warp, int tw,
+                                           const bool (&ok)[NC], const bool (&second)[NC], const int (&col)[NC], int nE,
+                                           size_t ld, double *__restrict__ Y, double (&part)[NC], bool dot, const PanelExtra &ex) {
+    if (EPI == EPI_RESTRICT) {
+        const int a0 = ex.agg_panel_ptr[panel], a1 = ex.agg_panel_ptr[panel + 1];
+        for (int a = a0 + warp; a < a1; a += PANEL_WARPS) {
+            double sum[NC];
+#pragma unroll
+            for (int m = 0; m < NC; m++) sum[m] = 0.0;
+            for (int q = ex.mem_ptr[a]; q < ex.mem_ptr[a + 1]; q++) {
+                const int row = ex.mem_idx[q], r = row - r0;
+                double acc[NC];
+                panel_row_acc<NC, TWO_K>(sx_lane, sE, sA1, sRow[r], sRow[r + 1], second, acc);
+                const double *xs = reinterpret_cast<const double *>(sx_lane + (size_t)self_idx[row] * tw * 8);
+#pragma unroll
+                for (int m = 0; m < NC; m++) sum[m] += xs[32 * m] - acc[m];
+            }
+#pragma unroll
+            for (int m = 0; m < NC; m++) if (ok[m]) Y[(size_t)a * ld + col[m]] = sum[m];
+        }
+        return;
+    }
+    const double *dw[NC];
+    if (EPI == EPI_POST) {
+#pragma unroll
+        for (int m = 0; m < NC; m++) dw[m] = ex.dinvw + (size_t)(col[m] / nE) * ex.n;
+    }
+    for (int r = warp; r < nrows; r += PANEL_WARPS) {
+        double acc[NC];
+        panel_row_acc<NC, TWO_K>(sx_lane, sE, sA1, sRow[r], sRow[r + 1], second, acc);
         const int row = r0 + r;
         const double *xs = reinterpret_cast<const double *>(sx_lane + (size_t)self_idx[row] * tw * 8);
 #pragma unroll
         for (int m = 0; m < NC; m++) {
             if (ok[m]) {
-                Y[(size_t)row * ld + col[m]] = acc[m];
-                if (dot) part[m] = fma(acc[m], xs[32 * m], part[m]);
+                const size_t o = (size_t)row * ld + col[m];
+                if (EPI == EPI_POST) {
+                    const double rr = __ldg(ex.R + o);
+                    const double z = fma(dw[m][row], rr - acc[m], xs[32 * m]);
+                    Y[o] = z;
+                    if (dot) part[m] = fma(rr, z, part[m]);
+                } else {
+                    Y[o] = acc[m];
+                    if (dot) part[m] = fma(acc[m], xs[32 * m], part[m]);
+                }
             }
         }
     }
@@ -352,12 +406,13 @@ __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
 
 // STAGE = 0: X rows arrive through cp.async (LDGSTS, 16 bytes per lane, one warp per halo row);
 // STAGE = 1: one TMA bulk copy (UBLKCP) per halo row, completion on an mbarrier.
-template <int NC, bool DOT, int STAGE>
+template <int NC, bool DOT, int STAGE, int EPI>
 __global__ void __launch_bounds__(PANEL_THREADS)
 k_spmm_panel(const int *__restrict__ rowptr, const unsigned short *__restrict__ lidx, const unsigned short *__restrict__ self_idx,
              const int *__restrict__ panel_ptr, const int *__restrict__ halo_ptr, const int *__restrict__ halo_cols,
              const double *__restrict__ vals, size_t nnz, const double *__restrict__ X, double *__restrict__ Y,
-             int nE, int c0, int c1, int tw, int max_halo, int max_pnnz, int max_rows, size_t ld, double *__restrict__ dots) {
+             int nE, int c0, int c1, int tw, int max_halo, int max_pnnz, int max_rows, size_t ld, double *__restrict__ dots,
+             const PanelExtra ex) {
     extern __shared__ __align__(16) double sm[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ double red[PANEL_WARPS][32 * NC];
@@ -431,8 +486,8 @@ k_spmm_panel(const int *__restrict__ rowptr, const unsigned short *__restrict__ 
 #pragma unroll
     for (int m = 0; m < NC; m++) part[m] = 0.0;
     const char *sx_lane = reinterpret_cast<const char *>(sm + lane);
-    if (two_k) panel_rows<NC, true>(sx_lane, sE, sA1, sRow, self_idx, r0, nrows, warp, tw, ok, second, col, ld, Y, part, DOT);
-    else panel_rows<NC, false>(sx_lane, sE, sA1, sRow, self_idx, r0, nrows, warp, tw, ok, second, col, ld, Y, part, DOT);
+    if (two_k) panel_rows<NC, true, EPI>(sx_lane, sE, sA1, sRow, self_idx, panel, r0, nrows, warp, tw, ok, second, col, nE, ld, Y, part, DOT, ex);
+    else panel_rows<NC, false, EPI>(sx_lane, sE, sA1, sRow, self_idx, panel, r0, nrows, warp, tw, ok, second, col, nE, ld, Y, part, DOT, ex);
     if (DOT) {
 #pragma unroll
         for (int m = 0; m < NC; m++) red[warp][lane + 32 * m] = part[m];

@@ -92,7 +92,7 @@ struct pgb200_ert {
     std::vector<JacChunk> chunks; int nQ = 0, nQp = 0;
     size_t ldJ = 0; int j_rows = 0; bool jac_valid = false;
     // multilevel preconditioner
-    std::vector<AmgLevel *> amg; int use_amg = 1, coarse_sweeps = 8; DevBuf<double> Z0, X0, dinvw0, vals_dw0; DevBuf<unsigned long long> gmax;
+    std::vector<AmgLevel *> amg; int use_amg = 1, coarse_sweeps = 8; DevBuf<double> Z0, X0, dinvw0, vals_dw0; DevBuf<int> amg_panel_ptr; DevBuf<unsigned long long> gmax;
     // stats
     int last_iters = 0; double last_relres = 0.0; long long launches = 0;
     cudaEvent_t ev[PH_COUNT + 1]; bool ev_ok = false; float ph_ms[PH_COUNT] = {0};
@@ -170,35 +170,44 @@ int launch_spmm(pgb200_ert *h, const double *vals, const double *vals1, const do
     return 0;
 }
 
-// panel-staged SpMM (the PCG hot kernel): Y = A X on columns [c0,c1), fused p.Ap
-template <int NC>
-int launch_spmm_panel_nc(pgb200_ert *h, const double *vals, const double *X, double *Y, int c0, int c1, double *dots) {
+// panel-staged SpMM (the PCG hot kernel): Y = A X on columns [c0,c1), fused p.Ap; the same kernel with other
+// epilogues is the fine-level smoother / residual-restriction of the multilevel preconditioner
+template <int NC, int EPI>
+int launch_spmm_panel_nc(pgb200_ert *h, const double *vals, const double *X, double *Y, int c0, int c1, double *dots, const PanelExtra &ex) {
     const int span = c1 - c0;
     const int ntile = cdiv(span, 32 * NC);
     int tw = cdiv(span, ntile); tw += tw & 1;                  // even tile width <= 32*NC (16-byte aligned bulk copies)
     const size_t smem = sizeof(double) * ((size_t)h->max_halo * tw + 32 * NC + 3 * (size_t)h->max_pnnz) +
                         sizeof(int) * ((size_t)h->max_rows + 2) + 16;
-    static size_t configured[3] = {0, 0, 0};
-    if (smem > configured[NC]) {
-        CK(cudaFuncSetAttribute(k_spmm_panel<NC, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_spmm_panel<NC, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_spmm_panel<NC, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_spmm_panel<NC, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[NC] = smem;
+    static size_t configured[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    if (smem > configured[NC][EPI]) {
+        CK(cudaFuncSetAttribute(k_spmm_panel<NC, true, 0, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_spmm_panel<NC, false, 0, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_spmm_panel<NC, true, 1, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_spmm_panel<NC, false, 1, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[NC][EPI] = smem;
     }
     dim3 grid(h->n_panels, ntile);
-#define PANEL_GO(D, S) k_spmm_panel<NC, D, S><<<grid, PANEL_THREADS, smem, h->st>>>(h->rowptr.p, h->lidx.p, h->self_idx.p, h->panel_ptr.p, \
-        h->halo_ptr.p, h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0, c1, tw, h->max_halo, h->max_pnnz, h->max_rows, h->ld, dots)
+#define PANEL_GO(D, S) k_spmm_panel<NC, D, S, EPI><<<grid, PANEL_THREADS, smem, h->st>>>(h->rowptr.p, h->lidx.p, h->self_idx.p, h->panel_ptr.p, \
+        h->halo_ptr.p, h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0, c1, tw, h->max_halo, h->max_pnnz, h->max_rows, h->ld, dots, ex)
     if (h->panel_tma) { if (dots) PANEL_GO(true, 1); else PANEL_GO(false, 1); }
     else { if (dots) PANEL_GO(true, 0); else PANEL_GO(false, 0); }
 #undef PANEL_GO
     LAUNCH(h);
     return 0;
 }
-int launch_spmm_panel(pgb200_ert *h, const double *vals, const double *X, double *Y, int c0, int c1, double *dots) {
+template <int EPI>
+int launch_panel(pgb200_ert *h, const double *vals, const double *X, double *Y, int c0, int c1, double *dots, const PanelExtra &ex) {
     if (c1 <= c0) return 0;
-    if (h->panel_nc == 2) return launch_spmm_panel_nc<2>(h, vals, X, Y, c0, c1, dots);
-    return launch_spmm_panel_nc<1>(h, vals, X, Y, c0, c1, dots);
+    if (h->panel_nc == 2) return launch_spmm_panel_nc<2, EPI>(h, vals, X, Y, c0, c1, dots, ex);
+    return launch_spmm_panel_nc<1, EPI>(h, vals, X, Y, c0, c1, dots, ex);
+}
+int launch_spmm_panel(pgb200_ert *h, const double *vals, const double *X, double *Y, int c0, int c1, double *dots) {
+    PanelExtra ex{}; 
+    return launch_panel<EPI_SPMM>(h, vals, X, Y, c0, c1, dots, ex);
+}
+bool panel_path_ok(const pgb200_ert *h, int c0) {
+    return h->use_panels && h->n_panels > 0 && !(c0 & 1) && (h->nK == 1 || h->nE >= 32 * h->panel_nc);
 }
 
 template <int CPT>
@@ -267,8 +276,15 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
     for (int l = 0; l < nl; l++) { AmgLevel *L = h->amg[l]; lv[l + 1] = {L->rowptr.p, L->colidx.p, L->vals.p, L->vals_dw.p, L->nnz, L->dinvw.p, L->n, L->R.p, L->X.p, L->Z.p}; }
     dim3 pb(32, 8);
     // downward: residual after one damped-Jacobi sweep from zero, restricted
-    for (int l = 0; l < nl; l++)
-        CKR(amg_restrict(h, lv[l].rowptr, lv[l].colidx, lv[l].vals_dw, lv[l].nnz, lv[l].n, h->amg[l], lv[l].R, c0, c1));
+    const bool fine_panels = nl > 0 && panel_path_ok(h, c0) && h->amg_panel_ptr.p != nullptr;
+    for (int l = 0; l < nl; l++) {
+        if (l == 0 && fine_panels) {
+            PanelExtra ex{}; ex.agg_panel_ptr = h->amg_panel_ptr.p; ex.mem_ptr = h->amg[0]->mem_ptr.p; ex.mem_idx = h->amg[0]->mem_idx.p;
+            CKR(launch_panel<EPI_RESTRICT>(h, h->vals_dw0.p, h->R.p, h->amg[0]->R.p, c0, c1, nullptr, ex));
+        } else {
+            CKR(amg_restrict(h, lv[l].rowptr, lv[l].colidx, lv[l].vals_dw, lv[l].nnz, lv[l].n, h->amg[l], lv[l].R, c0, c1));
+        }
+    }
     // coarsest level: fixed number of Jacobi sweeps
     const double *E;
     {
@@ -289,7 +305,12 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
         Lv &f = lv[l];
         dim3 pg(cdiv(f.n, 8), cdiv(c1 - c0, 32));
         k_amg_prolong<<<pg, pb, 0, h->st>>>(f.dinvw, f.n, h->amg[l]->agg.p, f.R, E, f.X, h->nE, c0, c1, h->ld); LAUNCH(h);
-        CKR(amg_post(h, f.rowptr, f.colidx, f.vals, f.nnz, f.dinvw, f.n, f.X, f.R, f.Z, c0, c1, l == 0 ? dots : nullptr));
+        if (l == 0 && fine_panels) {
+            PanelExtra ex{}; ex.R = f.R; ex.dinvw = f.dinvw; ex.n = f.n;
+            CKR(launch_panel<EPI_POST>(h, f.vals, f.X, f.Z, c0, c1, dots, ex));
+        } else {
+            CKR(amg_post(h, f.rowptr, f.colidx, f.vals, f.nnz, f.dinvw, f.n, f.X, f.R, f.Z, c0, c1, l == 0 ? dots : nullptr));
+        }
         E = f.Z;
     }
     CK(cudaGetLastError());
@@ -322,7 +343,7 @@ int pcg_solve(pgb200_ert *h) {
         const int rr_cur = 4 + (it % 2), rr_nxt = 4 + ((it + 1) % 2);
         const bool timed = h->prof && h->n_pev + 2 <= (int)h->pev.size();
         if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
-        if (h->use_panels && h->n_panels > 0 && !(c0 & 1) && (h->nK == 1 || h->nE >= 32 * h->panel_nc)) CKR(launch_spmm_panel(h, h->vals.p, h->P.p, h->AP.p, c0, c1, sc(3)));
+        if (panel_path_ok(h, c0)) CKR(launch_spmm_panel(h, h->vals.p, h->P.p, h->AP.p, c0, c1, sc(3)));
         else CKR((launch_spmm<0, true>(h, h->vals.p, nullptr, nullptr, h->P.p, h->AP.p, c0, c1, sc(3))));
         if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
         if (amg) {
@@ -648,7 +669,7 @@ int pgb200_build_panels(int n_rows, const int *rowptr, const int *colidx, int rm
 // Pairwise aggregation for the multilevel preconditioner: nodes are visited in order; an unaggregated
 // node is matched with the unaggregated neighbour it is most strongly coupled to (most negative
 // off-diagonal); nodes left alone join the aggregate of their strongest neighbour.
-int pgb200_pairwise_aggregate(int n, const int *rowptr, const int *colidx, const double *vals, int *agg) {
+int pgb200_pairwise_aggregate(int n, const int *rowptr, const int *colidx, const double *vals, const int *group, int *agg) {
     for (int i = 0; i < n; i++) agg[i] = -1;
     int na = 0;
     for (int i = 0; i < n; i++) {
@@ -657,6 +678,7 @@ int pgb200_pairwise_aggregate(int n, const int *rowptr, const int *colidx, const
         for (int p = rowptr[i]; p < rowptr[i + 1]; p++) {
             const int j = colidx[p];
             if (j == i || agg[j] >= 0) continue;
+            if (group && group[j] != group[i]) continue;
             const double sgn = -vals[p];
             if (sgn > bs) { bs = sgn; best = j; }
         }
@@ -668,6 +690,7 @@ int pgb200_pairwise_aggregate(int n, const int *rowptr, const int *colidx, const
         for (int p = rowptr[i]; p < rowptr[i + 1]; p++) {
             const int j = colidx[p];
             if (j == i || agg[j] < 0) continue;
+            if (group && group[j] != group[i]) continue;
             const double sgn = -vals[p];
             if (sgn > bs) { bs = sgn; best = j; }
         }
@@ -800,6 +823,10 @@ int pgb200_ert_set_hierarchy(pgb200_ert *h, int n_levels, const pgb200_amg_level
         CKR(L->R.alloc(blk)); CKR(L->X.alloc(blk)); CKR(L->Z.alloc(blk));
         CK(cudaMemsetAsync(L->R.p, 0, blk * sizeof(double), st)); CK(cudaMemsetAsync(L->X.p, 0, blk * sizeof(double), st));
         CK(cudaMemsetAsync(L->Z.p, 0, blk * sizeof(double), st));
+        if (l == 0) {
+            if (s.panel_agg_ptr && h->n_panels > 0) CKR(h->amg_panel_ptr.upload(s.panel_agg_ptr, (size_t)h->n_panels + 1, st));
+            else h->amg_panel_ptr.release();
+        }
         n_finer = s.n; nnz_finer = L->nnz;
     }
     const size_t blk0 = (size_t)h->N * h->ld;
