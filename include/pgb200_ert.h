@@ -115,8 +115,6 @@ typedef struct pgb200_amg_level {
     const int *agg;         /* [n of the finer level] finer node -> node of this level                   */
     const int *mem_ptr;     /* [n+1] members of every aggregate ...                                      */
     const int *mem_idx;     /* [n of the finer level] ... as finer-level node ids                        */
-    const int *panel_agg_ptr; /* first coarse level only, optional: [n_panels+1] aggregates of every SpMM row
-                             * panel (aggregates never straddle panels and are numbered panel by panel)  */
 } pgb200_amg_level;
 
 /* ---- host-only helpers (no GPU needed) -------------------------------------------- */

@@ -43,8 +43,7 @@ class Plan(C.Structure):
 
 class AmgLevel(C.Structure):
     _fields_ = [("n", C.c_int), ("nnz", C.c_int), ("rowptr", c_int_p), ("colidx", c_int_p), ("diag_pos", c_int_p),
-                ("gal_ptr", c_int_p), ("gal_idx", c_int_p), ("agg", c_int_p), ("mem_ptr", c_int_p), ("mem_idx", c_int_p),
-                ("panel_agg_ptr", c_int_p)]
+                ("gal_ptr", c_int_p), ("gal_idx", c_int_p), ("agg", c_int_p), ("mem_ptr", c_int_p), ("mem_idx", c_int_p)]
 
 
 # every symbol include/pgb200_ert.h declares (checked by tests/test_capi_symbols.py)
@@ -180,10 +179,6 @@ def set_hierarchy(handle, levels):
             v = np.ascontiguousarray(L[name], np.int32)
             keep.append(v)
             setattr(a, name, v.ctypes.data_as(c_int_p))
-        if L.get("panel_agg_ptr") is not None:
-            v = np.ascontiguousarray(L["panel_agg_ptr"], np.int32)
-            keep.append(v)
-            a.panel_agg_ptr = v.ctypes.data_as(c_int_p)
     check(lib().pgb200_ert_set_hierarchy(handle, len(levels), C.cast(arr, C.c_void_p)))
     return keep
 

@@ -335,17 +335,14 @@ __device__ __forceinline__ void panel_row_acc(const char *sx_lane, const PanelEn
 // what a panel CTA does with the row sums  acc = (A X)[row]:
 //   EPI_SPMM     Y = acc                         (+ optional dot  X_row . Y_row : p.Ap of PCG)
 //   EPI_POST     Y = X_row + dw_row (R_row - acc) (+ dot R_row . Y_row): damped-Jacobi post-smoothing, r.z of PCG
-//   EPI_RESTRICT Y[aggregate] = sum over the aggregate's rows of (X_row - acc): residual after the pre-smoothing
-//                sweep from a zero guess (values pre-scaled by dw), restricted with piecewise-constant P
-enum PanelEpi : int { EPI_SPMM = 0, EPI_POST = 1, EPI_RESTRICT = 2 };
+//   EPI_RESIDUAL Y = X_row - acc: with values pre-scaled by dw this is the residual after the pre-smoothing sweep
+//                from a zero guess, R - A (dw .* R); k_amg_sum_members then restricts it (piecewise-constant P)
+enum PanelEpi : int { EPI_SPMM = 0, EPI_POST = 1, EPI_RESIDUAL = 2 };
 
 struct PanelExtra {
     const double *R;          // EPI_POST: residual block
     const double *dinvw;      // EPI_POST: [nK][N] damped inverse diagonal
     int n;                    // rows of the level (stride of dinvw per wavenumber)
-    const int *agg_panel_ptr; // EPI_RESTRICT: [n_panels+1] aggregates of every panel (coarse rows are numbered panel by panel)
-    const int *mem_ptr;       // EPI_RESTRICT: [n_coarse+1] members of every aggregate ...
-    const int *mem_idx;       //               ... as fine row ids (all inside the aggregate's panel)
 };
 
 template <int NC, bool TWO_K, int EPI>
@@ -353,25 +350,6 @@ __device__ __forceinline__ void panel_rows(const char *sx_lane, const PanelEntry
                                            const unsigned short *__restrict__ self_idx, int panel, int r0, int nrows, int warp, int tw,
                                            const bool (&ok)[NC], const bool (&second)[NC], const int (&col)[NC], int nE,
                                            size_t ld, double *__restrict__ Y, double (&part)[NC], bool dot, const PanelExtra &ex) {
-    if (EPI == EPI_RESTRICT) {
-        const int a0 = ex.agg_panel_ptr[panel], a1 = ex.agg_panel_ptr[panel + 1];
-        for (int a = a0 + warp; a < a1; a += PANEL_WARPS) {
-            double sum[NC];
-#pragma unroll
-            for (int m = 0; m < NC; m++) sum[m] = 0.0;
-            for (int q = ex.mem_ptr[a]; q < ex.mem_ptr[a + 1]; q++) {
-                const int row = ex.mem_idx[q], r = row - r0;
-                double acc[NC];
-                panel_row_acc<NC, TWO_K>(sx_lane, sE, sA1, sRow[r], sRow[r + 1], second, acc);
-                const double *xs = reinterpret_cast<const double *>(sx_lane + (size_t)self_idx[row] * tw * 8);
-#pragma unroll
-                for (int m = 0; m < NC; m++) sum[m] += xs[32 * m] - acc[m];
-            }
-#pragma unroll
-            for (int m = 0; m < NC; m++) if (ok[m]) Y[(size_t)a * ld + col[m]] = sum[m];
-        }
-        return;
-    }
     const double *dw[NC];
     if (EPI == EPI_POST) {
 #pragma unroll
@@ -391,6 +369,8 @@ __device__ __forceinline__ void panel_rows(const char *sx_lane, const PanelEntry
                     const double z = fma(dw[m][row], rr - acc[m], xs[32 * m]);
                     Y[o] = z;
                     if (dot) part[m] = fma(rr, z, part[m]);
+                } else if (EPI == EPI_RESIDUAL) {
+                    Y[o] = xs[32 * m] - acc[m];
                 } else {
                     Y[o] = acc[m];
                     if (dot) part[m] = fma(acc[m], xs[32 * m], part[m]);
@@ -747,6 +727,17 @@ k_amg_restrict(const int *__restrict__ rowptr, const int *__restrict__ colidx, c
 #pragma unroll
         for (int m = 0; m < CPT; m++) if (ok[m]) RC[(size_t)I * ld + col[m]] = acc[m];
     }
+}
+
+// RC[I] = sum of RES over the members of aggregate I (deterministic restriction of a fine residual block)
+__global__ void k_amg_sum_members(const int *__restrict__ mem_ptr, const int *__restrict__ mem_idx, int n_c, const double *__restrict__ RES,
+                                  double *__restrict__ RC, int c0, int c1, size_t ld) {
+    const int col = c0 + blockIdx.y * blockDim.x + threadIdx.x;
+    const int I = blockIdx.x * blockDim.y + threadIdx.y;
+    if (col >= c1 || I >= n_c) return;
+    double acc = 0.0;
+    for (int q = mem_ptr[I]; q < mem_ptr[I + 1]; q++) acc += RES[(size_t)mem_idx[q] * ld + col];
+    RC[(size_t)I * ld + col] = acc;
 }
 
 // X = dw .* R + EC[agg]   (pre-smoothed iterate plus prolongated coarse correction); EC == nullptr -> X = dw .* R

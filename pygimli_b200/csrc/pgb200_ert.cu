@@ -92,7 +92,7 @@ struct pgb200_ert {
     std::vector<JacChunk> chunks; int nQ = 0, nQp = 0;
     size_t ldJ = 0; int j_rows = 0; bool jac_valid = false;
     // multilevel preconditioner
-    std::vector<AmgLevel *> amg; int use_amg = 1, coarse_sweeps = 8; DevBuf<double> Z0, X0, dinvw0, vals_dw0; DevBuf<int> amg_panel_ptr; DevBuf<unsigned long long> gmax;
+    std::vector<AmgLevel *> amg; int use_amg = 1, coarse_sweeps = 8; DevBuf<double> Z0, X0, dinvw0, vals_dw0; DevBuf<unsigned long long> gmax;
     // stats
     int last_iters = 0; double last_relres = 0.0; long long launches = 0;
     cudaEvent_t ev[PH_COUNT + 1]; bool ev_ok = false; float ph_ms[PH_COUNT] = {0};
@@ -276,11 +276,15 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
     for (int l = 0; l < nl; l++) { AmgLevel *L = h->amg[l]; lv[l + 1] = {L->rowptr.p, L->colidx.p, L->vals.p, L->vals_dw.p, L->nnz, L->dinvw.p, L->n, L->R.p, L->X.p, L->Z.p}; }
     dim3 pb(32, 8);
     // downward: residual after one damped-Jacobi sweep from zero, restricted
-    const bool fine_panels = nl > 0 && panel_path_ok(h, c0) && h->amg_panel_ptr.p != nullptr;
+    const bool fine_panels = nl > 0 && panel_path_ok(h, c0);
     for (int l = 0; l < nl; l++) {
         if (l == 0 && fine_panels) {
-            PanelExtra ex{}; ex.agg_panel_ptr = h->amg_panel_ptr.p; ex.mem_ptr = h->amg[0]->mem_ptr.p; ex.mem_idx = h->amg[0]->mem_idx.p;
-            CKR(launch_panel<EPI_RESTRICT>(h, h->vals_dw0.p, h->R.p, h->amg[0]->R.p, c0, c1, nullptr, ex));
+            // fine level: residual through the panel-staged kernel (into X0, free until the prolongation), then a
+            // deterministic member sum
+            PanelExtra ex{};
+            CKR(launch_panel<EPI_RESIDUAL>(h, h->vals_dw0.p, h->R.p, h->X0.p, c0, c1, nullptr, ex));
+            AmgLevel *L = h->amg[0];
+            k_amg_sum_members<<<dim3(cdiv(L->n, 8), cdiv(c1 - c0, 32)), dim3(32, 8), 0, h->st>>>(L->mem_ptr.p, L->mem_idx.p, L->n, h->X0.p, L->R.p, c0, c1, h->ld); LAUNCH(h);
         } else {
             CKR(amg_restrict(h, lv[l].rowptr, lv[l].colidx, lv[l].vals_dw, lv[l].nnz, lv[l].n, h->amg[l], lv[l].R, c0, c1));
         }
@@ -823,10 +827,6 @@ int pgb200_ert_set_hierarchy(pgb200_ert *h, int n_levels, const pgb200_amg_level
         CKR(L->R.alloc(blk)); CKR(L->X.alloc(blk)); CKR(L->Z.alloc(blk));
         CK(cudaMemsetAsync(L->R.p, 0, blk * sizeof(double), st)); CK(cudaMemsetAsync(L->X.p, 0, blk * sizeof(double), st));
         CK(cudaMemsetAsync(L->Z.p, 0, blk * sizeof(double), st));
-        if (l == 0) {
-            if (s.panel_agg_ptr && h->n_panels > 0) CKR(h->amg_panel_ptr.upload(s.panel_agg_ptr, (size_t)h->n_panels + 1, st));
-            else h->amg_panel_ptr.release();
-        }
         n_finer = s.n; nnz_finer = L->nnz;
     }
     const size_t blk0 = (size_t)h->N * h->ld;

@@ -227,8 +227,7 @@ class CoreB200:
             if self.preconditioner == "multilevel":
                 # aggregation hierarchy from the rho = 1 matrix of the smallest wavenumber (geometry only)
                 v1 = self.get("vals1", raw=True).reshape(P.nK, P.nnz)[0]
-                pp = P.panels["panel_ptr"] if P.panels else None
-                self.hierarchy = build_hierarchy(P.rowptr, P.colidx, v1, _capi.pairwise_aggregate, panel_ptr=pp)
+                self.hierarchy = build_hierarchy(P.rowptr, P.colidx, v1, _capi.pairwise_aggregate)
                 self._keep_amg = _capi.set_hierarchy(h, self.hierarchy)
                 _capi.check(_capi.lib().pgb200_ert_set_preconditioner(h, 1 if self.hierarchy else 0, 8))
             else:
