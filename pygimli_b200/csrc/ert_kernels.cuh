@@ -847,8 +847,7 @@ __global__ void k_transpose_out(const double *__restrict__ U, size_t ld, int N, 
 //       G[a][m] - G[a][n] - G[b][m] + G[b][n],
 //   scaled and stored to the column-major J with consecutive threads writing consecutive rows.
 // ---------------------------------------------------------------------------------
-constexpr int JAC_THREADS = 512;
-constexpr int JAC_MAX_TILES = 2;     // 4x4 micro-tiles per thread
+constexpr int JAC_MAX_THREADS = 640;   // MT = 1: one 4x4 micro-tile per thread (<= 640 tiles); MT = 2: two (<= 1024 tiles, 512 threads)
 
 struct __align__(8) JacDatum { unsigned short a, b, m, n; };   // indices into plist / qlist, 0xFFFF = unused electrode
 
@@ -858,16 +857,21 @@ struct JacArgs {
     const double *U; size_t ld; int nE; int nK; const double *kvals; const double *kw;
     const int *plist; int nP, nPp;            // current-side electrodes, padded to a multiple of 4
     const int *qlist; int nQ, nQp;
-    const JacDatum *idx;                      // [nd]
+    const JacDatum *idx;                      // [nd] 16-bit indices ...
+    const uchar4 *idx8;                       // ... or 8-bit ones (x=a y=b z=m w=n, 0xFF = unused) when both lists are < 255 long
     const int *out_row; const double *kfac; int nd;
-    int idx_in_smem;                          // stage idx[] in shared memory (it is reused by every column)
+    int idx_in_smem;                          // stage the index records in shared memory (reused by every column)
+    int kfac_in_smem;                         // stage the geometric factors too
+    int out_identity;                         // out_row[d] == out_base + d: no indirection on the store
+    int out_base;
     const double *rho_col;                    // [M] model value per column or nullptr (no scaling)
     double *Jt; size_t ldJ;
 };
 
-template <int E>
-__global__ void __launch_bounds__(JAC_THREADS)
+template <int E, int JAC_MAX_TILES>
+__global__ void __launch_bounds__(JAC_MAX_TILES == 1 ? JAC_MAX_THREADS : 512)
 k_jacobian(const JacArgs A) {
+    const int JAC_THREADS = blockDim.x;
     constexpr int NV = ElemTraits<E>::NV, NL = ElemTraits<E>::NL, DIM = ElemTraits<E>::DIM;
     extern __shared__ __align__(16) double sm[];
     double *sUp = sm;                               // [NL][nPp]
@@ -877,14 +881,18 @@ k_jacobian(const JacArgs A) {
     double *sM  = sK + NL * NL;                     // [NL*NL] mass
     double *sG  = sM + NL * NL;                     // [nPp][nQp + 1]
     const int gstride = A.nQp + 1;
-    JacDatum *sIdx = reinterpret_cast<JacDatum *>(sG + (size_t)A.nPp * gstride);
+    double *sKf = sG + (size_t)A.nPp * gstride;                       // [nd] geometric factors (optional)
+    void *sIdxRaw = A.kfac_in_smem ? (void *)(sKf + A.nd) : (void *)sKf;
     __shared__ int snode[NL];
     const int tid = threadIdx.x;
     const int tilesQ = A.nQp / 4, tilesP = A.nPp / 4, ntiles = tilesP * tilesQ;
     const JacDatum *idx = A.idx;
+    const uchar4 *idx8 = A.idx8;
+    const double *kfp = A.kfac;
+    if (A.kfac_in_smem) { for (int d = tid; d < A.nd; d += JAC_THREADS) sKf[d] = A.kfac[d]; kfp = sKf; }
     if (A.idx_in_smem) {
-        for (int d = tid; d < A.nd; d += JAC_THREADS) sIdx[d] = A.idx[d];
-        idx = sIdx;
+        if (idx8) { uchar4 *s8 = reinterpret_cast<uchar4 *>(sIdxRaw); for (int d = tid; d < A.nd; d += JAC_THREADS) s8[d] = A.idx8[d]; idx8 = s8; }
+        else { JacDatum *s16 = reinterpret_cast<JacDatum *>(sIdxRaw); for (int d = tid; d < A.nd; d += JAC_THREADS) s16[d] = A.idx[d]; idx = s16; }
     }
 
     for (int col = A.col_begin + blockIdx.x; col < A.col_end; col += gridDim.x) {
@@ -977,18 +985,18 @@ k_jacobian(const JacArgs A) {
         const bool scaled = A.rho_col != nullptr;
         if (scaled) { const double r = A.rho_col[col]; scale = 1.0 / (r * r); }
         double *out = A.Jt + (size_t)col * A.ldJ;
-#pragma unroll 4
+#pragma unroll 2
         for (int d = tid; d < A.nd; d += JAC_THREADS) {
-            const JacDatum e = idx[d];
-            const double kf = scaled ? __ldg(A.kfac + d) * scale : 1.0;   // k_i / rho_j^2 only if len(model) == cols (:1377)
-            const int orow = __ldg(A.out_row + d);
+            int ea, eb, em, en;
+            if (idx8) { const uchar4 e = idx8[d]; ea = e.x == 0xFF ? -1 : e.x; eb = e.y == 0xFF ? -1 : e.y; em = e.z == 0xFF ? -1 : e.z; en = e.w == 0xFF ? -1 : e.w; }
+            else { const JacDatum e = idx[d]; ea = e.a == 0xFFFF ? -1 : e.a; eb = e.b == 0xFFFF ? -1 : e.b; em = e.m == 0xFFFF ? -1 : e.m; en = e.n == 0xFFFF ? -1 : e.n; }
+            const double kf = scaled ? kfp[d] * scale : 1.0;          // k_i / rho_j^2 only if len(model) == cols (:1377)
             double v = 0.0;
-            const bool ha = e.a != 0xFFFF, hb = e.b != 0xFFFF, hm = e.m != 0xFFFF, hn = e.n != 0xFFFF;
-            if (ha && hm) v += sG[e.a * gstride + e.m];
-            if (ha && hn) v -= sG[e.a * gstride + e.n];
-            if (hb && hm) v -= sG[e.b * gstride + e.m];
-            if (hb && hn) v += sG[e.b * gstride + e.n];
-            out[orow] = v * kf;
+            if (ea >= 0 && em >= 0) v += sG[ea * gstride + em];
+            if (ea >= 0 && en >= 0) v -= sG[ea * gstride + en];
+            if (eb >= 0 && em >= 0) v -= sG[eb * gstride + em];
+            if (eb >= 0 && en >= 0) v += sG[eb * gstride + en];
+            out[A.out_identity ? A.out_base + d : __ldg(A.out_row + d)] = v * kf;
         }
     }
 }
