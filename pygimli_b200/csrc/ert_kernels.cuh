@@ -868,22 +868,53 @@ struct JacArgs {
     double *Jt; size_t ldJ;
 };
 
+// cursor over the work items (column, cell, wavenumber) of one CTA; columns are dealt round-robin to the CTAs
+struct JacCursor {
+    int col, ci, ce, kk, cell;
+    __device__ __forceinline__ bool valid(const JacArgs &A) const { return col < A.col_end; }
+    __device__ __forceinline__ void seek(const JacArgs &A, int stride) {      // first column >= col that has cells
+        while (col < A.col_end) {
+            ci = A.jac_col_ptr[col]; ce = A.jac_col_ptr[col + 1];
+            if (ci < ce) { cell = A.jac_cells[ci]; kk = 0; return; }
+            col += stride;
+        }
+    }
+    __device__ __forceinline__ void advance(const JacArgs &A, int stride) {
+        if (++kk < A.nK) return;
+        kk = 0;
+        if (++ci < ce) { cell = A.jac_cells[ci]; return; }
+        col += stride;
+        seek(A, stride);
+    }
+};
+
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+// Software-pipelined over the work items: while item t is contracted (and its column written), the node ids of
+// item t+2 and the coordinates + nodal potentials of item t+1 are already in flight (cp.async, one group per item).
 template <int E, int JAC_MAX_TILES>
 __global__ void __launch_bounds__(JAC_MAX_TILES == 1 ? JAC_MAX_THREADS : 512)
 k_jacobian(const JacArgs A) {
-    const int JAC_THREADS = blockDim.x;
     constexpr int NV = ElemTraits<E>::NV, NL = ElemTraits<E>::NL, DIM = ElemTraits<E>::DIM;
+    const int JAC_THREADS = blockDim.x;
     extern __shared__ __align__(16) double sm[];
-    double *sUp = sm;                               // [NL][nPp]
-    double *sUq = sUp + NL * A.nPp;                 // [NL][nQp]
-    double *sV  = sUq + NL * A.nQp;                 // [NL][nQp]
-    double *sK  = sV + NL * A.nQp;                  // [NL*NL] stiffness
+    const int szP = NL * A.nPp, szQ = NL * A.nQp;
+    double *sUp = sm;                               // [2][NL][nPp]
+    double *sUq = sUp + 2 * szP;                    // [2][NL][nQp]
+    double *sV  = sUq + 2 * szQ;                    // [NL][nQp]
+    double *sK  = sV + szQ;                         // [NL*NL] stiffness
     double *sM  = sK + NL * NL;                     // [NL*NL] mass
-    double *sG  = sM + NL * NL;                     // [nPp][nQp + 1]
+    double *sXYZ = sM + NL * NL;                    // [2][NV][3] corner coordinates
+    double *sG  = sXYZ + 2 * NV * 3;                // [nPp][nQp + 1]
     const int gstride = A.nQp + 1;
-    double *sKf = sG + (size_t)A.nPp * gstride;                       // [nd] geometric factors (optional)
+    double *sKf = sG + (size_t)A.nPp * gstride;     // [nd] geometric factors (optional)
     void *sIdxRaw = A.kfac_in_smem ? (void *)(sKf + A.nd) : (void *)sKf;
-    __shared__ int snode[NL];
+    __shared__ int snode[3][NL];
     const int tid = threadIdx.x;
     const int tilesQ = A.nQp / 4, tilesP = A.nPp / 4, ntiles = tilesP * tilesQ;
     const JacDatum *idx = A.idx;
@@ -894,111 +925,144 @@ k_jacobian(const JacArgs A) {
         if (idx8) { uchar4 *s8 = reinterpret_cast<uchar4 *>(sIdxRaw); for (int d = tid; d < A.nd; d += JAC_THREADS) s8[d] = A.idx8[d]; idx8 = s8; }
         else { JacDatum *s16 = reinterpret_cast<JacDatum *>(sIdxRaw); for (int d = tid; d < A.nd; d += JAC_THREADS) s16[d] = A.idx[d]; idx = s16; }
     }
+    const int stride = gridDim.x;
+    const bool scaled = A.rho_col != nullptr;
 
-    for (int col = A.col_begin + blockIdx.x; col < A.col_end; col += gridDim.x) {
-        double acc[JAC_MAX_TILES][16];
-#pragma unroll
-        for (int t = 0; t < JAC_MAX_TILES; t++)
-#pragma unroll
-            for (int x = 0; x < 16; x++) acc[t][x] = 0.0;
+    // zero-fill the padding of the gather buffers once (the async copies only touch the used part)
+    for (int x = tid; x < 2 * szP; x += JAC_THREADS) sUp[x] = 0.0;
+    for (int x = tid; x < 2 * szQ; x += JAC_THREADS) sUq[x] = 0.0;
 
-        const int cb = A.jac_col_ptr[col], ce = A.jac_col_ptr[col + 1];
-        for (int ci = cb; ci < ce; ci++) {
-            const int cell = A.jac_cells[ci];
-            __syncthreads();                         // previous cell / previous column's epilogue fully consumed
-            if (tid < NL) snode[tid] = A.cells[(size_t)cell * NL + tid];
-            if (tid < NL * NL) {
-                double X[NV][3];
+    auto load_ids = [&](const JacCursor &c, int slot) {            // node ids of an item -> snode[slot]
+        if (c.valid(A) && tid < NL) cp_async4(&snode[slot][tid], A.cells + (size_t)c.cell * NL + tid);
+    };
+    auto load_item = [&](const JacCursor &c, int slot, int buf) {  // coordinates + nodal potentials; ids must be visible
+        if (!c.valid(A)) return;
+        if (tid < NV * 3) { const int v = tid / 3, d = tid - 3 * v; cp_async8(sXYZ + buf * NV * 3 + tid, A.pos + 3 * (size_t)snode[slot][v] + d); }
+        double *up = sUp + buf * szP, *uq = sUq + buf * szQ;
+        for (int x = tid; x < szP; x += JAC_THREADS) {
+            const int i = x / A.nPp, p = x - i * A.nPp;
+            if (p < A.nP) cp_async8(up + x, A.U + (size_t)snode[slot][i] * A.ld + A.plist[p] + A.nE * c.kk);
+        }
+        for (int x = tid; x < szQ; x += JAC_THREADS) {
+            const int i = x / A.nQp, q = x - i * A.nQp;
+            if (q < A.nQ) cp_async8(uq + x, A.U + (size_t)snode[slot][i] * A.ld + A.qlist[q] + A.nE * c.kk);
+        }
+    };
+
+    JacCursor cur; cur.col = A.col_begin + blockIdx.x; cur.ci = cur.ce = cur.kk = cur.cell = 0; cur.seek(A, stride);
+    JacCursor nxt = cur; if (nxt.valid(A)) nxt.advance(A, stride);
+    JacCursor nn = nxt;  if (nn.valid(A)) nn.advance(A, stride);
+    // columns before the first non-empty one are all-zero
+    for (int cz = A.col_begin + blockIdx.x; cz < min(cur.col, A.col_end); cz += stride)
+        for (int d = tid; d < A.nd; d += JAC_THREADS) A.Jt[(size_t)cz * A.ldJ + (A.out_identity ? A.out_base + d : A.out_row[d])] = 0.0;
+
+    // prologue: ids(0), ids(1) -> then coordinates + potentials of item 0
+    load_ids(cur, 0); load_ids(nxt, 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    load_item(cur, 0, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    double acc[JAC_MAX_TILES][16];
 #pragma unroll
-                for (int v = 0; v < NV; v++) {
-                    const int n = A.cells[(size_t)cell * NL + v];
-                    X[v][0] = A.pos[3 * (size_t)n]; X[v][1] = A.pos[3 * (size_t)n + 1]; X[v][2] = A.pos[3 * (size_t)n + 2];
-                }
-                double size, G[NV][NV];
-                simplex_gram<DIM>(X, size, G);
-                const int i = tid / NL, j = tid - i * NL;
-                sK[tid] = stiff_entry<E>(i, j, size, G);
-                sM[tid] = size * mass_unit<E>(i, j);
-            }
-            __syncthreads();
-            for (int kk = 0; kk < A.nK; kk++) {
-                const double k = A.kvals[kk], wk = A.kw[kk];
-                const double k2 = k * k;
-                if (kk > 0) __syncthreads();         // tiles of the previous k consumed
-                // gather nodal potentials (coalesced along the electrode index)
-                for (int x = tid; x < NL * A.nPp; x += JAC_THREADS) {
-                    const int i = x / A.nPp, p = x - i * A.nPp;
-                    sUp[x] = (p < A.nP) ? A.U[(size_t)snode[i] * A.ld + A.plist[p] + A.nE * kk] : 0.0;
-                }
-                for (int x = tid; x < NL * A.nQp; x += JAC_THREADS) {
-                    const int i = x / A.nQp, q = x - i * A.nQp;
-                    sUq[x] = (q < A.nQ) ? A.U[(size_t)snode[i] * A.ld + A.qlist[q] + A.nE * kk] : 0.0;
-                }
-                __syncthreads();
-                // V = w_k (K + k^2 M) U_Q
-                for (int x = tid; x < NL * A.nQp; x += JAC_THREADS) {
-                    const int i = x / A.nQp, q = x - i * A.nQp;
-                    double v = 0.0;
+    for (int t = 0; t < JAC_MAX_TILES; t++)
 #pragma unroll
-                    for (int j = 0; j < NL; j++) v = fma(fma(k2, sM[i * NL + j], sK[i * NL + j]), sUq[j * A.nQp + q], v);
-                    sV[x] = v * wk;
-                }
-                __syncthreads();
+        for (int x = 0; x < 16; x++) acc[t][x] = 0.0;
+
+    for (int t = 0; cur.valid(A); t++) {
+        const int buf = t & 1, slot1 = (t + 1) % 3, slot2 = (t + 2) % 3;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                             // item t landed; everybody is done with item t-1
+        // next items in flight while this one is processed
+        load_ids(nn, slot2);
+        load_item(nxt, slot1, buf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (tid < NL * NL) {
+            double X[NV][3];
 #pragma unroll
-                for (int t = 0; t < JAC_MAX_TILES; t++) {
-                    const int tile = tid + t * JAC_THREADS;
-                    if (tile < ntiles) {
-                        const int tp = tile / tilesQ, tq = tile - tp * tilesQ;
+            for (int v = 0; v < NV; v++) { X[v][0] = sXYZ[buf * NV * 3 + 3 * v]; X[v][1] = sXYZ[buf * NV * 3 + 3 * v + 1]; X[v][2] = sXYZ[buf * NV * 3 + 3 * v + 2]; }
+            double size, G[NV][NV];
+            simplex_gram<DIM>(X, size, G);
+            const int i = tid / NL, j = tid - i * NL;
+            sK[tid] = stiff_entry<E>(i, j, size, G);
+            sM[tid] = size * mass_unit<E>(i, j);
+        }
+        __syncthreads();
+        const double *up = sUp + buf * szP, *uq = sUq + buf * szQ;
+        {
+            const double k = A.kvals[cur.kk], wk = A.kw[cur.kk];
+            const double k2 = k * k;
+            for (int x = tid; x < szQ; x += JAC_THREADS) {     // V = w_k (K + k^2 M) U_Q
+                const int i = x / A.nQp, q = x - i * A.nQp;
+                double v = 0.0;
 #pragma unroll
-                        for (int i = 0; i < NL; i++) {
-                            const double2 u01 = *reinterpret_cast<const double2 *>(sUp + i * A.nPp + 4 * tp);
-                            const double2 u23 = *reinterpret_cast<const double2 *>(sUp + i * A.nPp + 4 * tp + 2);
-                            const double2 v01 = *reinterpret_cast<const double2 *>(sV + i * A.nQp + 4 * tq);
-                            const double2 v23 = *reinterpret_cast<const double2 *>(sV + i * A.nQp + 4 * tq + 2);
-                            const double u[4] = {u01.x, u01.y, u23.x, u23.y};
-                            const double v[4] = {v01.x, v01.y, v23.x, v23.y};
-#pragma unroll
-                            for (int a = 0; a < 4; a++)
-#pragma unroll
-                                for (int b = 0; b < 4; b++) acc[t][a * 4 + b] = fma(u[a], v[b], acc[t][a * 4 + b]);
-                        }
-                    }
-                }
+                for (int j = 0; j < NL; j++) v = fma(fma(k2, sM[i * NL + j], sK[i * NL + j]), uq[j * A.nQp + q], v);
+                sV[x] = v * wk;
             }
         }
-        // drop G to shared memory (the previous column's epilogue has passed the barrier above,
-        // or this is an empty column)
         __syncthreads();
 #pragma unroll
-        for (int t = 0; t < JAC_MAX_TILES; t++) {
-            const int tile = tid + t * JAC_THREADS;
+        for (int tt = 0; tt < JAC_MAX_TILES; tt++) {
+            const int tile = tid + tt * JAC_THREADS;
             if (tile < ntiles) {
                 const int tp = tile / tilesQ, tq = tile - tp * tilesQ;
 #pragma unroll
-                for (int a = 0; a < 4; a++)
+                for (int i = 0; i < NL; i++) {
+                    const double2 u01 = *reinterpret_cast<const double2 *>(up + i * A.nPp + 4 * tp);
+                    const double2 u23 = *reinterpret_cast<const double2 *>(up + i * A.nPp + 4 * tp + 2);
+                    const double2 v01 = *reinterpret_cast<const double2 *>(sV + i * A.nQp + 4 * tq);
+                    const double2 v23 = *reinterpret_cast<const double2 *>(sV + i * A.nQp + 4 * tq + 2);
+                    const double u[4] = {u01.x, u01.y, u23.x, u23.y};
+                    const double v[4] = {v01.x, v01.y, v23.x, v23.y};
 #pragma unroll
-                    for (int b = 0; b < 4; b++) sG[(4 * tp + a) * gstride + 4 * tq + b] = acc[t][a * 4 + b];
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int b = 0; b < 4; b++) acc[tt][a * 4 + b] = fma(u[a], v[b], acc[tt][a * 4 + b]);
+                }
             }
         }
-        __syncthreads();
-        double scale = 1.0;
-        const bool scaled = A.rho_col != nullptr;
-        if (scaled) { const double r = A.rho_col[col]; scale = 1.0 / (r * r); }
-        double *out = A.Jt + (size_t)col * A.ldJ;
+        const bool last_of_col = !nxt.valid(A) || nxt.col != cur.col;
+        if (last_of_col) {
+            const int col = cur.col;
+            // drop G to shared memory (every thread passed the V barrier, so the previous epilogue is over)
+#pragma unroll
+            for (int tt = 0; tt < JAC_MAX_TILES; tt++) {
+                const int tile = tid + tt * JAC_THREADS;
+                if (tile < ntiles) {
+                    const int tp = tile / tilesQ, tq = tile - tp * tilesQ;
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int b = 0; b < 4; b++) { sG[(4 * tp + a) * gstride + 4 * tq + b] = acc[tt][a * 4 + b]; acc[tt][a * 4 + b] = 0.0; }
+                }
+            }
+            __syncthreads();
+            double scale = 1.0;
+            if (scaled) { const double r = A.rho_col[col]; scale = 1.0 / (r * r); }
+            double *out = A.Jt + (size_t)col * A.ldJ;
 #pragma unroll 2
-        for (int d = tid; d < A.nd; d += JAC_THREADS) {
-            int ea, eb, em, en;
-            if (idx8) { const uchar4 e = idx8[d]; ea = e.x == 0xFF ? -1 : e.x; eb = e.y == 0xFF ? -1 : e.y; em = e.z == 0xFF ? -1 : e.z; en = e.w == 0xFF ? -1 : e.w; }
-            else { const JacDatum e = idx[d]; ea = e.a == 0xFFFF ? -1 : e.a; eb = e.b == 0xFFFF ? -1 : e.b; em = e.m == 0xFFFF ? -1 : e.m; en = e.n == 0xFFFF ? -1 : e.n; }
-            const double kf = scaled ? kfp[d] * scale : 1.0;          // k_i / rho_j^2 only if len(model) == cols (:1377)
-            double v = 0.0;
-            if (ea >= 0 && em >= 0) v += sG[ea * gstride + em];
-            if (ea >= 0 && en >= 0) v -= sG[ea * gstride + en];
-            if (eb >= 0 && em >= 0) v -= sG[eb * gstride + em];
-            if (eb >= 0 && en >= 0) v += sG[eb * gstride + en];
-            out[A.out_identity ? A.out_base + d : __ldg(A.out_row + d)] = v * kf;
+            for (int d = tid; d < A.nd; d += JAC_THREADS) {
+                int ea, eb, em, en;
+                if (idx8) { const uchar4 e = idx8[d]; ea = e.x == 0xFF ? -1 : e.x; eb = e.y == 0xFF ? -1 : e.y; em = e.z == 0xFF ? -1 : e.z; en = e.w == 0xFF ? -1 : e.w; }
+                else { const JacDatum e = idx[d]; ea = e.a == 0xFFFF ? -1 : e.a; eb = e.b == 0xFFFF ? -1 : e.b; em = e.m == 0xFFFF ? -1 : e.m; en = e.n == 0xFFFF ? -1 : e.n; }
+                const double kf = scaled ? kfp[d] * scale : 1.0;      // k_i / rho_j^2 only if len(model) == cols (:1377)
+                double v = 0.0;
+                if (ea >= 0 && em >= 0) v += sG[ea * gstride + em];
+                if (ea >= 0 && en >= 0) v -= sG[ea * gstride + en];
+                if (eb >= 0 && em >= 0) v -= sG[eb * gstride + em];
+                if (eb >= 0 && en >= 0) v += sG[eb * gstride + en];
+                out[A.out_identity ? A.out_base + d : __ldg(A.out_row + d)] = v * kf;
+            }
+            // columns of this CTA without any model cell between this one and the next item are all-zero
+            const int stop = nxt.valid(A) ? nxt.col : A.col_end;
+            for (int cz = col + stride; cz < stop; cz += stride)
+                for (int d = tid; d < A.nd; d += JAC_THREADS) A.Jt[(size_t)cz * A.ldJ + (A.out_identity ? A.out_base + d : A.out_row[d])] = 0.0;
         }
+        cur = nxt; nxt = nn;
+        if (nn.valid(A)) nn.advance(A, stride);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // y = J x  (J column-major [cols][ld]):  y[d] = sum_j Jt[j][d] x[j]

@@ -479,7 +479,8 @@ int finish_response(pgb200_ert *h, double *rhoa_dev) {
 }
 
 size_t jac_smem(int NL, int nPp, int nQp) {
-    return sizeof(double) * ((size_t)NL * nPp + 2 * (size_t)NL * nQp + 2 * (size_t)NL * NL + (size_t)nPp * (nQp + 1));
+    // double-buffered gathers, V, K, M, corner coordinates (2 x 4 x 3), G
+    return sizeof(double) * (2 * (size_t)NL * nPp + 3 * (size_t)NL * nQp + 2 * (size_t)NL * NL + 24 + (size_t)nPp * (nQp + 1));
 }
 
 // Build the chunked electrode-pair plan of the Jacobian for data rows [row0,row1)
