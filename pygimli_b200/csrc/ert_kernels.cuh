@@ -627,14 +627,14 @@ __global__ void k_scale_cols(const int *__restrict__ colidx, size_t nnz, int n, 
     for (int kk = 0; kk < nK; kk++) vals_dw[(size_t)kk * nnz + p] = vals[(size_t)kk * nnz + p] * dinvw[(size_t)kk * n + j];
 }
 
-constexpr int AMG_TX = 16, AMG_TY = 8, AMG_ROWS = 32;
+constexpr int AMG_TX = 16, AMG_TY = 8;   // rows per CTA are a launch parameter: small (coarse) levels use fewer rows for more CTAs
 
 // Z = X + dw .* (R - A X)   (post-smoothing / Jacobi sweep); optional fused dot  sum_i R_i Z_i
 template <int CPT, bool DOT>
 __global__ void __launch_bounds__(AMG_TX * AMG_TY)
 k_amg_post(const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals, size_t nnz,
            const double *__restrict__ dinvw, int n, const double *__restrict__ X, const double *__restrict__ R,
-           double *__restrict__ Z, int nE, int c0, int c1, size_t ld, double *__restrict__ dots) {
+           double *__restrict__ Z, int nE, int c0, int c1, size_t ld, double *__restrict__ dots, int AMG_ROWS) {
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int cbase = c0 + blockIdx.y * (AMG_TX * CPT) + tx;
     int col[CPT]; size_t voff[CPT]; const double *dw[CPT]; bool ok[CPT];
@@ -695,7 +695,7 @@ template <int CPT>
 __global__ void __launch_bounds__(AMG_TX * AMG_TY)
 k_amg_restrict(const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals_dw, size_t nnz,
                int n_f, const int *__restrict__ mem_ptr, const int *__restrict__ mem_idx, int n_c,
-               const double *__restrict__ R, double *__restrict__ RC, int nE, int c0, int c1, size_t ld) {
+               const double *__restrict__ R, double *__restrict__ RC, int nE, int c0, int c1, size_t ld, int AMG_ROWS) {
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int cbase = c0 + blockIdx.y * (AMG_TX * CPT) + tx;
     int col[CPT]; size_t voff[CPT]; bool ok[CPT];

@@ -210,12 +210,16 @@ bool panel_path_ok(const pgb200_ert *h, int c0) {
     return h->use_panels && h->n_panels > 0 && !(c0 & 1) && (h->nK == 1 || h->nE >= 32 * h->panel_nc);
 }
 
+// rows per CTA of the plain multilevel kernels: 32 on big levels, 8 on small ones so that they still fill the GPU
+inline int amg_rows_per_cta(int n) { return n >= 60000 ? 32 : 8; }
+
 template <int CPT>
 int amg_post_cpt(pgb200_ert *h, const int *rowptr, const int *colidx, const double *vals, size_t nnz, const double *dinvw, int n,
                  const double *X, const double *R, double *Z, int c0, int c1, double *dots) {
-    dim3 block(AMG_TX, AMG_TY), grid(cdiv(n, AMG_ROWS), cdiv(c1 - c0, AMG_TX * CPT));
-    if (dots) k_amg_post<CPT, true><<<grid, block, 0, h->st>>>(rowptr, colidx, vals, nnz, dinvw, n, X, R, Z, h->nE, c0, c1, h->ld, dots);
-    else k_amg_post<CPT, false><<<grid, block, 0, h->st>>>(rowptr, colidx, vals, nnz, dinvw, n, X, R, Z, h->nE, c0, c1, h->ld, nullptr);
+    const int rows = amg_rows_per_cta(n);
+    dim3 block(AMG_TX, AMG_TY), grid(cdiv(n, rows), cdiv(c1 - c0, AMG_TX * CPT));
+    if (dots) k_amg_post<CPT, true><<<grid, block, 0, h->st>>>(rowptr, colidx, vals, nnz, dinvw, n, X, R, Z, h->nE, c0, c1, h->ld, dots, rows);
+    else k_amg_post<CPT, false><<<grid, block, 0, h->st>>>(rowptr, colidx, vals, nnz, dinvw, n, X, R, Z, h->nE, c0, c1, h->ld, nullptr, rows);
     LAUNCH(h);
     return 0;
 }
@@ -236,8 +240,9 @@ int amg_post(pgb200_ert *h, const int *rowptr, const int *colidx, const double *
 int amg_restrict(pgb200_ert *h, const int *rowptr, const int *colidx, const double *vals_dw, size_t nnz, int n_f,
                  const AmgLevel *L, const double *R, int c0, int c1) {
     const int cpt = pick_cpt(c1 - c0);
-    dim3 block(AMG_TX, AMG_TY), grid(cdiv(L->n, AMG_ROWS), cdiv(c1 - c0, AMG_TX * cpt));
-#define RGO(C) k_amg_restrict<C><<<grid, block, 0, h->st>>>(rowptr, colidx, vals_dw, nnz, n_f, L->mem_ptr.p, L->mem_idx.p, L->n, R, L->R.p, h->nE, c0, c1, h->ld)
+    const int rows = amg_rows_per_cta(L->n);
+    dim3 block(AMG_TX, AMG_TY), grid(cdiv(L->n, rows), cdiv(c1 - c0, AMG_TX * cpt));
+#define RGO(C) k_amg_restrict<C><<<grid, block, 0, h->st>>>(rowptr, colidx, vals_dw, nnz, n_f, L->mem_ptr.p, L->mem_idx.p, L->n, R, L->R.p, h->nE, c0, c1, h->ld, rows)
     if (cpt == 4) RGO(4); else if (cpt == 2) RGO(2); else RGO(1);
 #undef RGO
     LAUNCH(h);
