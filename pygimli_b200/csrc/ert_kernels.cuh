@@ -857,8 +857,9 @@ struct JacArgs {
     const double *U; size_t ld; int nE; int nK; const double *kvals; const double *kw;
     const int *plist; int nP, nPp;            // current-side electrodes, padded to a multiple of 4
     const int *qlist; int nQ, nQp;
-    const JacDatum *idx;                      // [nd] 16-bit indices ...
-    const uchar4 *idx8;                       // ... or 8-bit ones (x=a y=b z=m w=n, 0xFF = unused) when both lists are < 255 long
+    const JacDatum *idx;                      // [nd] 16-bit indices (a, b, m, n) into plist / qlist ...
+    int resolved;                             // ... or, if the Gram block has < 65536 entries, the four shared-memory
+                                              // offsets of G[a][m], G[a][n], G[b][m], G[b][n] (unused -> a zero slot)
     const int *out_row; const double *kfac; int nd;
     int idx_in_smem;                          // stage the index records in shared memory (reused by every column)
     int kfac_in_smem;                         // stage the geometric factors too
@@ -918,13 +919,14 @@ k_jacobian(const JacArgs A) {
     const int tid = threadIdx.x;
     const int tilesQ = A.nQp / 4, tilesP = A.nPp / 4, ntiles = tilesP * tilesQ;
     const JacDatum *idx = A.idx;
-    const uchar4 *idx8 = A.idx8;
     const double *kfp = A.kfac;
     if (A.kfac_in_smem) { for (int d = tid; d < A.nd; d += JAC_THREADS) sKf[d] = A.kfac[d]; kfp = sKf; }
     if (A.idx_in_smem) {
-        if (idx8) { uchar4 *s8 = reinterpret_cast<uchar4 *>(sIdxRaw); for (int d = tid; d < A.nd; d += JAC_THREADS) s8[d] = A.idx8[d]; idx8 = s8; }
-        else { JacDatum *s16 = reinterpret_cast<JacDatum *>(sIdxRaw); for (int d = tid; d < A.nd; d += JAC_THREADS) s16[d] = A.idx[d]; idx = s16; }
+        JacDatum *s16 = reinterpret_cast<JacDatum *>(sIdxRaw);
+        for (int d = tid; d < A.nd; d += JAC_THREADS) s16[d] = A.idx[d];
+        idx = s16;
     }
+    if (tid == 0) sG[A.nQp] = 0.0;                  // the zero slot unused electrodes point at (padding column of row 0)
     const int stride = gridDim.x;
     const bool scaled = A.rho_col != nullptr;
 
@@ -1041,18 +1043,27 @@ k_jacobian(const JacArgs A) {
             double scale = 1.0;
             if (scaled) { const double r = A.rho_col[col]; scale = 1.0 / (r * r); }
             double *out = A.Jt + (size_t)col * A.ldJ;
+            if (A.resolved) {
+#pragma unroll 4
+                for (int d = tid; d < A.nd; d += JAC_THREADS) {
+                    const JacDatum e = idx[d];                        // four pre-resolved offsets into G
+                    const double v = (sG[e.a] - sG[e.b]) - (sG[e.m] - sG[e.n]);
+                    const double kf = scaled ? kfp[d] * scale : 1.0;  // k_i / rho_j^2 only if len(model) == cols (:1377)
+                    out[A.out_identity ? A.out_base + d : __ldg(A.out_row + d)] = v * kf;
+                }
+            } else {
 #pragma unroll 2
-            for (int d = tid; d < A.nd; d += JAC_THREADS) {
-                int ea, eb, em, en;
-                if (idx8) { const uchar4 e = idx8[d]; ea = e.x == 0xFF ? -1 : e.x; eb = e.y == 0xFF ? -1 : e.y; em = e.z == 0xFF ? -1 : e.z; en = e.w == 0xFF ? -1 : e.w; }
-                else { const JacDatum e = idx[d]; ea = e.a == 0xFFFF ? -1 : e.a; eb = e.b == 0xFFFF ? -1 : e.b; em = e.m == 0xFFFF ? -1 : e.m; en = e.n == 0xFFFF ? -1 : e.n; }
-                const double kf = scaled ? kfp[d] * scale : 1.0;      // k_i / rho_j^2 only if len(model) == cols (:1377)
-                double v = 0.0;
-                if (ea >= 0 && em >= 0) v += sG[ea * gstride + em];
-                if (ea >= 0 && en >= 0) v -= sG[ea * gstride + en];
-                if (eb >= 0 && em >= 0) v -= sG[eb * gstride + em];
-                if (eb >= 0 && en >= 0) v += sG[eb * gstride + en];
-                out[A.out_identity ? A.out_base + d : __ldg(A.out_row + d)] = v * kf;
+                for (int d = tid; d < A.nd; d += JAC_THREADS) {
+                    const JacDatum e = idx[d];
+                    const int ea = e.a == 0xFFFF ? -1 : e.a, eb = e.b == 0xFFFF ? -1 : e.b, em = e.m == 0xFFFF ? -1 : e.m, en = e.n == 0xFFFF ? -1 : e.n;
+                    const double kf = scaled ? kfp[d] * scale : 1.0;
+                    double v = 0.0;
+                    if (ea >= 0 && em >= 0) v += sG[ea * gstride + em];
+                    if (ea >= 0 && en >= 0) v -= sG[ea * gstride + en];
+                    if (eb >= 0 && em >= 0) v -= sG[eb * gstride + em];
+                    if (eb >= 0 && en >= 0) v += sG[eb * gstride + en];
+                    out[A.out_identity ? A.out_base + d : __ldg(A.out_row + d)] = v * kf;
+                }
             }
             // columns of this CTA without any model cell between this one and the next item are all-zero
             const int stop = nxt.valid(A) ? nxt.col : A.col_end;

@@ -44,7 +44,7 @@ template <class T> struct DevBuf {
 };
 
 struct JacChunk {
-    int nP, nPp, nd, idx_in_smem, kfac_in_smem, out_identity, idx8, mt, threads;
+    int nP, nPp, nd, idx_in_smem, kfac_in_smem, out_identity, resolved, mt, threads;
     size_t plist_off, data_off;   // offsets into the concatenated device arrays
     size_t smem;
 };
@@ -87,7 +87,7 @@ struct pgb200_ert {
     int model_len = 0;
     std::vector<double> h_model;
     // jacobian plan
-    DevBuf<int> j_plist, j_qlist, j_out; DevBuf<JacDatum> j_idx; DevBuf<uchar4> j_idx8;
+    DevBuf<int> j_plist, j_qlist, j_out; DevBuf<JacDatum> j_idx;
     DevBuf<double> j_kfac;
     std::vector<JacChunk> chunks; int nQ = 0, nQp = 0;
     size_t ldJ = 0; int j_rows = 0; bool jac_valid = false;
@@ -509,7 +509,7 @@ int build_jac_plan(pgb200_ert *h) {
     CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     const size_t smem_cap = std::min<size_t>((size_t)dev_smem, 220 * 1024) - 256;
     const int max_tiles = 1024;
-    std::vector<int> plist_all, outr; std::vector<JacDatum> idx; std::vector<uchar4> idx8; std::vector<double> kf;
+    std::vector<int> plist_all, outr; std::vector<JacDatum> idx; std::vector<double> kf;
     size_t i = 0;
     while (i < (size_t)nd) {
         std::vector<int> pmap(h->nE, -1), plist;
@@ -533,18 +533,27 @@ int build_jac_plan(pgb200_ert *h) {
             jd.a = (unsigned short)(a >= 0 ? pmap[a] : 0xFFFF); jd.b = (unsigned short)(b >= 0 ? pmap[b] : 0xFFFF);
             jd.m = (unsigned short)(m >= 0 ? qmap[m] : 0xFFFF); jd.n = (unsigned short)(n >= 0 ? qmap[n] : 0xFFFF);
             idx.push_back(jd);
-            uchar4 j8; j8.x = (unsigned char)std::min<int>(jd.a, 0xFF); j8.y = (unsigned char)std::min<int>(jd.b, 0xFF);
-            j8.z = (unsigned char)std::min<int>(jd.m, 0xFF); j8.w = (unsigned char)std::min<int>(jd.n, 0xFF);
-            idx8.push_back(j8);
             outr.push_back(d - r0); kf.push_back(h->h_kfac[d]);
             ch.nd++; i++;
         }
         ch.nP = (int)plist.size(); ch.nPp = std::max(4, (ch.nP + 3) / 4 * 4);
         ch.smem = jac_smem(NL, ch.nPp, h->nQp);
-        ch.idx8 = (ch.nPp < 255 && h->nQp < 255) ? 1 : 0;
-        const size_t isz = ch.idx8 ? sizeof(uchar4) : sizeof(JacDatum);
-        if (ch.smem + (size_t)ch.nd * sizeof(double) <= smem_cap) { ch.kfac_in_smem = 1; ch.smem += (size_t)ch.nd * sizeof(double); }
+        // resolved form: the record holds the offsets of G[a][m], G[a][n], G[b][m], G[b][n] inside the Gram block
+        // (unused electrode -> the zero slot at offset nQp, the padding column of row 0)
+        const int gstride = h->nQp + 1;
+        ch.resolved = ((size_t)ch.nPp * gstride <= 65535) ? 1 : 0;
+        if (ch.resolved) {
+            for (int q = 0; q < ch.nd; q++) {
+                JacDatum &jd = idx[ch.data_off + q];
+                const int a = jd.a, b = jd.b, m = jd.m, n = jd.n;
+                auto off = [&](int p, int qq) { return (unsigned short)((p == 0xFFFF || qq == 0xFFFF) ? h->nQp : p * gstride + qq); };
+                // v = (G[a][m] - G[a][n]) - (G[b][m] - G[b][n])  ->  record order {am, an, bm, bn}
+                jd.a = off(a, m); jd.b = off(a, n); jd.m = off(b, m); jd.n = off(b, n);
+            }
+        }
+        const size_t isz = sizeof(JacDatum);
         if (ch.smem + (size_t)ch.nd * isz <= smem_cap) { ch.idx_in_smem = 1; ch.smem += (size_t)ch.nd * isz; }
+        if (ch.smem + (size_t)ch.nd * sizeof(double) <= smem_cap) { ch.kfac_in_smem = 1; ch.smem += (size_t)ch.nd * sizeof(double); }
         ch.out_identity = 1;
         for (int q = 0; q < ch.nd; q++) if (outr[ch.data_off + q] != (int)ch.data_off + q) { ch.out_identity = 0; break; }
         const int ntiles = (ch.nPp / 4) * (h->nQp / 4);
@@ -555,7 +564,7 @@ int build_jac_plan(pgb200_ert *h) {
     }
     CKR(h->j_plist.upload(plist_all.data(), plist_all.size(), h->st));
     CKR(h->j_qlist.upload(qlist.data(), qlist.size(), h->st));
-    CKR(h->j_idx.upload(idx.data(), idx.size(), h->st)); CKR(h->j_idx8.upload(idx8.data(), idx8.size(), h->st));
+    CKR(h->j_idx.upload(idx.data(), idx.size(), h->st));
     CKR(h->j_out.upload(outr.data(), outr.size(), h->st));
     CKR(h->j_kfac.upload(kf.data(), kf.size(), h->st));
     CK(cudaStreamSynchronize(h->st));
@@ -576,7 +585,7 @@ int launch_jacobian(pgb200_ert *h, const double *rho_col) {
         A.U = h->U.p; A.ld = h->ld; A.nE = h->nE; A.nK = h->nK; A.kvals = h->kvals.p; A.kw = h->kw.p;
         A.plist = h->j_plist.p + c.plist_off; A.nP = c.nP; A.nPp = c.nPp;
         A.qlist = h->j_qlist.p; A.nQ = h->nQ; A.nQp = h->nQp;
-        A.idx = h->j_idx.p + c.data_off; A.idx8 = c.idx8 ? h->j_idx8.p + c.data_off : nullptr;
+        A.idx = h->j_idx.p + c.data_off; A.resolved = c.resolved;
         A.idx_in_smem = c.idx_in_smem; A.kfac_in_smem = c.kfac_in_smem; A.out_identity = c.out_identity; A.out_base = (int)c.data_off;
         A.out_row = h->j_out.p + c.data_off; A.kfac = h->j_kfac.p + c.data_off; A.nd = c.nd;
         A.rho_col = rho_col; A.Jt = h->Jt.p; A.ldJ = h->ldJ;
