@@ -854,6 +854,7 @@ struct __align__(8) JacDatum { unsigned short a, b, m, n; };   // indices into p
 struct JacArgs {
     const double *pos; const int *cells; int nloc;
     const int *jac_cells; const int *jac_col_ptr; int col_begin, col_end;
+    const int *cta_col_ptr;                   // [gridDim.x + 1] contiguous column range of every CTA
     const double *U; size_t ld; int nE; int nK; const double *kvals; const double *kw;
     const int *plist; int nP, nPp;            // current-side electrodes, padded to a multiple of 4
     const int *qlist; int nQ, nQp;
@@ -869,23 +870,25 @@ struct JacArgs {
     double *Jt; size_t ldJ;
 };
 
-// cursor over the work items (column, cell, wavenumber) of one CTA; columns are dealt round-robin to the CTAs
+// cursor over the work items (column, cell, wavenumber) of one CTA.  Every CTA owns a contiguous range of
+// columns (balanced by cell count on the host): the column pointers and cell lists are then read sequentially
+// (L1 hits), neighbouring cells share nodes, and adjacent columns of J are adjacent in memory.
 struct JacCursor {
-    int col, ci, ce, kk, cell;
-    __device__ __forceinline__ bool valid(const JacArgs &A) const { return col < A.col_end; }
-    __device__ __forceinline__ void seek(const JacArgs &A, int stride) {      // first column >= col that has cells
-        while (col < A.col_end) {
+    int col, end, ci, ce, kk, cell;
+    __device__ __forceinline__ bool valid() const { return col < end; }
+    __device__ __forceinline__ void seek(const JacArgs &A) {                   // first column >= col that has cells
+        while (col < end) {
             ci = A.jac_col_ptr[col]; ce = A.jac_col_ptr[col + 1];
             if (ci < ce) { cell = A.jac_cells[ci]; kk = 0; return; }
-            col += stride;
+            col++;
         }
     }
-    __device__ __forceinline__ void advance(const JacArgs &A, int stride) {
+    __device__ __forceinline__ void advance(const JacArgs &A) {
         if (++kk < A.nK) return;
         kk = 0;
         if (++ci < ce) { cell = A.jac_cells[ci]; return; }
-        col += stride;
-        seek(A, stride);
+        col++;
+        seek(A);
     }
 };
 
@@ -927,7 +930,7 @@ k_jacobian(const JacArgs A) {
         idx = s16;
     }
     if (tid == 0) sG[A.nQp] = 0.0;                  // the zero slot unused electrodes point at (padding column of row 0)
-    const int stride = gridDim.x;
+    const int my_lo = A.cta_col_ptr[blockIdx.x], my_hi = A.cta_col_ptr[blockIdx.x + 1];
     const bool scaled = A.rho_col != nullptr;
 
     // zero-fill the padding of the gather buffers once (the async copies only touch the used part)
@@ -935,10 +938,10 @@ k_jacobian(const JacArgs A) {
     for (int x = tid; x < 2 * szQ; x += JAC_THREADS) sUq[x] = 0.0;
 
     auto load_ids = [&](const JacCursor &c, int slot) {            // node ids of an item -> snode[slot]
-        if (c.valid(A) && tid < NL) cp_async4(&snode[slot][tid], A.cells + (size_t)c.cell * NL + tid);
+        if (c.valid() && tid < NL) cp_async4(&snode[slot][tid], A.cells + (size_t)c.cell * NL + tid);
     };
     auto load_item = [&](const JacCursor &c, int slot, int buf) {  // coordinates + nodal potentials; ids must be visible
-        if (!c.valid(A)) return;
+        if (!c.valid()) return;
         if (tid < NV * 3) { const int v = tid / 3, d = tid - 3 * v; cp_async8(sXYZ + buf * NV * 3 + tid, A.pos + 3 * (size_t)snode[slot][v] + d); }
         double *up = sUp + buf * szP, *uq = sUq + buf * szQ;
         for (int x = tid; x < szP; x += JAC_THREADS) {
@@ -951,11 +954,11 @@ k_jacobian(const JacArgs A) {
         }
     };
 
-    JacCursor cur; cur.col = A.col_begin + blockIdx.x; cur.ci = cur.ce = cur.kk = cur.cell = 0; cur.seek(A, stride);
-    JacCursor nxt = cur; if (nxt.valid(A)) nxt.advance(A, stride);
-    JacCursor nn = nxt;  if (nn.valid(A)) nn.advance(A, stride);
+    JacCursor cur; cur.col = my_lo; cur.end = my_hi; cur.ci = cur.ce = cur.kk = cur.cell = 0; cur.seek(A);
+    JacCursor nxt = cur; if (nxt.valid()) nxt.advance(A);
+    JacCursor nn = nxt;  if (nn.valid()) nn.advance(A);
     // columns before the first non-empty one are all-zero
-    for (int cz = A.col_begin + blockIdx.x; cz < min(cur.col, A.col_end); cz += stride)
+    for (int cz = my_lo; cz < min(cur.col, my_hi); cz++)
         for (int d = tid; d < A.nd; d += JAC_THREADS) A.Jt[(size_t)cz * A.ldJ + (A.out_identity ? A.out_base + d : A.out_row[d])] = 0.0;
 
     // prologue: ids(0), ids(1) -> then coordinates + potentials of item 0
@@ -972,7 +975,7 @@ k_jacobian(const JacArgs A) {
 #pragma unroll
         for (int x = 0; x < 16; x++) acc[t][x] = 0.0;
 
-    for (int t = 0; cur.valid(A); t++) {
+    for (int t = 0; cur.valid(); t++) {
         const int buf = t & 1, slot1 = (t + 1) % 3, slot2 = (t + 2) % 3;
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();                             // item t landed; everybody is done with item t-1
@@ -1024,7 +1027,7 @@ k_jacobian(const JacArgs A) {
                 }
             }
         }
-        const bool last_of_col = !nxt.valid(A) || nxt.col != cur.col;
+        const bool last_of_col = !nxt.valid() || nxt.col != cur.col;
         if (last_of_col) {
             const int col = cur.col;
             // drop G to shared memory (every thread passed the V barrier, so the previous epilogue is over)
@@ -1043,10 +1046,23 @@ k_jacobian(const JacArgs A) {
             double scale = 1.0;
             if (scaled) { const double r = A.rho_col[col]; scale = 1.0 / (r * r); }
             double *out = A.Jt + (size_t)col * A.ldJ;
-            if (A.resolved) {
+            if (A.resolved && A.out_identity && scaled) {
+                // the common case, kept lean: pre-resolved offsets, k_i / rho_j^2 scaling, rows in place
+                const JacDatum *ip = idx + tid;
+                const double *kp = kfp + tid;
+                double *op = out + A.out_base + tid;
+                const int n_it = (A.nd - tid + JAC_THREADS - 1) / JAC_THREADS;
+#pragma unroll 4
+                for (int it = 0; it < n_it; it++) {
+                    const JacDatum e = *ip;                           // four pre-resolved offsets into G
+                    const double v = (sG[e.a] - sG[e.b]) - (sG[e.m] - sG[e.n]);
+                    *op = v * (*kp * scale);
+                    ip += JAC_THREADS; kp += JAC_THREADS; op += JAC_THREADS;
+                }
+            } else if (A.resolved) {
 #pragma unroll 4
                 for (int d = tid; d < A.nd; d += JAC_THREADS) {
-                    const JacDatum e = idx[d];                        // four pre-resolved offsets into G
+                    const JacDatum e = idx[d];
                     const double v = (sG[e.a] - sG[e.b]) - (sG[e.m] - sG[e.n]);
                     const double kf = scaled ? kfp[d] * scale : 1.0;  // k_i / rho_j^2 only if len(model) == cols (:1377)
                     out[A.out_identity ? A.out_base + d : __ldg(A.out_row + d)] = v * kf;
@@ -1066,12 +1082,12 @@ k_jacobian(const JacArgs A) {
                 }
             }
             // columns of this CTA without any model cell between this one and the next item are all-zero
-            const int stop = nxt.valid(A) ? nxt.col : A.col_end;
-            for (int cz = col + stride; cz < stop; cz += stride)
+            const int stop = nxt.valid() ? nxt.col : my_hi;
+            for (int cz = col + 1; cz < stop; cz++)
                 for (int d = tid; d < A.nd; d += JAC_THREADS) A.Jt[(size_t)cz * A.ldJ + (A.out_identity ? A.out_base + d : A.out_row[d])] = 0.0;
         }
         cur = nxt; nxt = nn;
-        if (nn.valid(A)) nn.advance(A, stride);
+        if (nn.valid()) nn.advance(A);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }

@@ -87,7 +87,7 @@ struct pgb200_ert {
     int model_len = 0;
     std::vector<double> h_model;
     // jacobian plan
-    DevBuf<int> j_plist, j_qlist, j_out; DevBuf<JacDatum> j_idx;
+    DevBuf<int> j_plist, j_qlist, j_out, j_cta_ptr; DevBuf<JacDatum> j_idx; std::vector<int> h_jac_col_ptr; int j_grid = 0;
     DevBuf<double> j_kfac;
     std::vector<JacChunk> chunks; int nQ = 0, nQp = 0;
     size_t ldJ = 0; int j_rows = 0; bool jac_valid = false;
@@ -593,6 +593,20 @@ int launch_jacobian(pgb200_ert *h, const double *rho_col) {
         if (c.mt == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_jacobian<E, 1>, c.threads, c.smem));
         else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_jacobian<E, 2>, c.threads, c.smem));
         const int grid = std::max(1, std::min(h->M, h->num_sms * std::max(1, occ)));
+        if (grid != h->j_grid) {
+            // contiguous column ranges per CTA, balanced by the number of cells (+1 per column for the epilogue)
+            std::vector<int> ptr(grid + 1, h->M);
+            const long long total = (long long)h->h_jac_col_ptr[h->M] + h->M;
+            int col = 0; ptr[0] = 0;
+            for (int b = 1; b < grid; b++) {
+                const long long target = total * b / grid;
+                while (col < h->M && (long long)h->h_jac_col_ptr[col] + col < target) col++;
+                ptr[b] = col;
+            }
+            CKR(h->j_cta_ptr.upload(ptr.data(), ptr.size(), h->st));
+            h->j_grid = grid;
+        }
+        A.cta_col_ptr = h->j_cta_ptr.p;
         if (c.mt == 1) k_jacobian<E, 1><<<grid, c.threads, c.smem, h->st>>>(A);
         else k_jacobian<E, 2><<<grid, c.threads, c.smem, h->st>>>(A);
         LAUNCH(h);
@@ -790,6 +804,7 @@ int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
     }
     h->n_jac_cells = p->n_jac_cells;
     CKR(h->jac_cells.upload(p->jac_cells, p->n_jac_cells, st)); CKR(h->jac_col_ptr.upload(p->jac_col_ptr, (size_t)h->M + 1, st));
+    h->h_jac_col_ptr.assign(p->jac_col_ptr, p->jac_col_ptr + h->M + 1);
     CKR(h->abmn.upload(p->abmn, (size_t)h->D * 4, st)); CKR(h->kfac.upload(p->k_fac, h->D, st));
     h->h_abmn.assign(p->abmn, p->abmn + (size_t)h->D * 4); h->h_kfac.assign(p->k_fac, p->k_fac + h->D);
     for (int d = 0; d < h->D * 4; d++) if (h->h_abmn[d] >= nE || h->h_abmn[d] < -1) PGB_FAIL("Collect matrix too small: electrode index out of range in the data (datamap.cpp:184-194)");
