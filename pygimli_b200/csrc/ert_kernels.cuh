@@ -858,6 +858,7 @@ struct JacArgs {
     const double *U; size_t ld; int nE; int nK; const double *kvals; const double *kw;
     const int *plist; int nP, nPp;            // current-side electrodes, padded to a multiple of 4
     const int *qlist; int nQ, nQp;
+    int gplane;                               // plane stride of the Gram block in shared memory
     const JacDatum *idx;                      // [nd] 16-bit indices (a, b, m, n) into plist / qlist ...
     int resolved;                             // ... or, if the Gram block has < 65536 entries, the four shared-memory
                                               // offsets of G[a][m], G[a][n], G[b][m], G[b][n] (unused -> a zero slot)
@@ -914,9 +915,9 @@ k_jacobian(const JacArgs A) {
     double *sK  = sV + szQ;                         // [NL*NL] stiffness
     double *sM  = sK + NL * NL;                     // [NL*NL] mass
     double *sXYZ = sM + NL * NL;                    // [2][NV][3] corner coordinates
-    double *sG  = sXYZ + 2 * NV * 3;                // [nPp][nQp + 1]
-    const int gstride = A.nQp + 1;
-    double *sKf = sG + (size_t)A.nPp * gstride;     // [nd] geometric factors (optional)
+    double *sG  = sXYZ + 2 * NV * 3;                // Gram block, element-major: 16 planes [a][b] of one value per 4x4 tile
+    const int PL = A.gplane;                        // plane stride (>= number of tiles, = 1 mod 16: conflict-free both ways)
+    double *sKf = sG + 16 * (size_t)PL + 1;         // [nd] geometric factors (optional); sG[16 PL] is the zero slot
     void *sIdxRaw = A.kfac_in_smem ? (void *)(sKf + A.nd) : (void *)sKf;
     __shared__ int snode[3][NL];
     const int tid = threadIdx.x;
@@ -929,7 +930,7 @@ k_jacobian(const JacArgs A) {
         for (int d = tid; d < A.nd; d += JAC_THREADS) s16[d] = A.idx[d];
         idx = s16;
     }
-    if (tid == 0) sG[A.nQp] = 0.0;                  // the zero slot unused electrodes point at (padding column of row 0)
+    if (tid == 0) sG[16 * PL] = 0.0;                // the zero slot unused electrodes point at
     const int my_lo = A.cta_col_ptr[blockIdx.x], my_hi = A.cta_col_ptr[blockIdx.x + 1];
     const bool scaled = A.rho_col != nullptr;
 
@@ -1039,7 +1040,8 @@ k_jacobian(const JacArgs A) {
 #pragma unroll
                     for (int a = 0; a < 4; a++)
 #pragma unroll
-                        for (int b = 0; b < 4; b++) { sG[(4 * tp + a) * gstride + 4 * tq + b] = acc[tt][a * 4 + b]; acc[tt][a * 4 + b] = 0.0; }
+                        for (int b = 0; b < 4; b++) { sG[(a * 4 + b) * PL + tile] = acc[tt][a * 4 + b]; acc[tt][a * 4 + b] = 0.0; }
+                    (void)tp; (void)tq;
                 }
             }
             __syncthreads();
@@ -1073,11 +1075,12 @@ k_jacobian(const JacArgs A) {
                     const JacDatum e = idx[d];
                     const int ea = e.a == 0xFFFF ? -1 : e.a, eb = e.b == 0xFFFF ? -1 : e.b, em = e.m == 0xFFFF ? -1 : e.m, en = e.n == 0xFFFF ? -1 : e.n;
                     const double kf = scaled ? kfp[d] * scale : 1.0;
+                    auto goff = [&](int p, int q) { return ((p & 3) * 4 + (q & 3)) * PL + (p >> 2) * tilesQ + (q >> 2); };
                     double v = 0.0;
-                    if (ea >= 0 && em >= 0) v += sG[ea * gstride + em];
-                    if (ea >= 0 && en >= 0) v -= sG[ea * gstride + en];
-                    if (eb >= 0 && em >= 0) v -= sG[eb * gstride + em];
-                    if (eb >= 0 && en >= 0) v += sG[eb * gstride + en];
+                    if (ea >= 0 && em >= 0) v += sG[goff(ea, em)];
+                    if (ea >= 0 && en >= 0) v -= sG[goff(ea, en)];
+                    if (eb >= 0 && em >= 0) v -= sG[goff(eb, em)];
+                    if (eb >= 0 && en >= 0) v += sG[goff(eb, en)];
                     out[A.out_identity ? A.out_base + d : __ldg(A.out_row + d)] = v * kf;
                 }
             }

@@ -483,9 +483,13 @@ int finish_response(pgb200_ert *h, double *rhoa_dev) {
     return 0;
 }
 
+int jac_plane(int nPp, int nQp) {               // plane stride of the element-major Gram block: >= #tiles and = 1 (mod 16)
+    const int nt = (nPp / 4) * (nQp / 4);
+    return (nt + 14) / 16 * 16 + 1;
+}
 size_t jac_smem(int NL, int nPp, int nQp) {
-    // double-buffered gathers, V, K, M, corner coordinates (2 x 4 x 3), G
-    return sizeof(double) * (2 * (size_t)NL * nPp + 3 * (size_t)NL * nQp + 2 * (size_t)NL * NL + 24 + (size_t)nPp * (nQp + 1));
+    // double-buffered gathers, V, K, M, corner coordinates (2 x 4 x 3), G (16 planes + zero slot)
+    return sizeof(double) * (2 * (size_t)NL * nPp + 3 * (size_t)NL * nQp + 2 * (size_t)NL * NL + 24 + 16 * (size_t)jac_plane(nPp, nQp) + 1);
 }
 
 // Build the chunked electrode-pair plan of the Jacobian for data rows [row0,row1)
@@ -540,13 +544,13 @@ int build_jac_plan(pgb200_ert *h) {
         ch.smem = jac_smem(NL, ch.nPp, h->nQp);
         // resolved form: the record holds the offsets of G[a][m], G[a][n], G[b][m], G[b][n] inside the Gram block
         // (unused electrode -> the zero slot at offset nQp, the padding column of row 0)
-        const int gstride = h->nQp + 1;
-        ch.resolved = ((size_t)ch.nPp * gstride <= 65535) ? 1 : 0;
+        const int PL = jac_plane(ch.nPp, h->nQp), tilesQ = h->nQp / 4;
+        ch.resolved = (16 * (size_t)PL + 1 <= 65535) ? 1 : 0;
         if (ch.resolved) {
             for (int q = 0; q < ch.nd; q++) {
                 JacDatum &jd = idx[ch.data_off + q];
                 const int a = jd.a, b = jd.b, m = jd.m, n = jd.n;
-                auto off = [&](int p, int qq) { return (unsigned short)((p == 0xFFFF || qq == 0xFFFF) ? h->nQp : p * gstride + qq); };
+                auto off = [&](int p, int qq) { return (unsigned short)((p == 0xFFFF || qq == 0xFFFF) ? 16 * PL : ((p & 3) * 4 + (qq & 3)) * PL + (p >> 2) * tilesQ + (qq >> 2)); };
                 // v = (G[a][m] - G[a][n]) - (G[b][m] - G[b][n])  ->  record order {am, an, bm, bn}
                 jd.a = off(a, m); jd.b = off(a, n); jd.m = off(b, m); jd.n = off(b, n);
             }
@@ -584,7 +588,7 @@ int launch_jacobian(pgb200_ert *h, const double *rho_col) {
         A.jac_cells = h->jac_cells.p; A.jac_col_ptr = h->jac_col_ptr.p; A.col_begin = 0; A.col_end = h->M;
         A.U = h->U.p; A.ld = h->ld; A.nE = h->nE; A.nK = h->nK; A.kvals = h->kvals.p; A.kw = h->kw.p;
         A.plist = h->j_plist.p + c.plist_off; A.nP = c.nP; A.nPp = c.nPp;
-        A.qlist = h->j_qlist.p; A.nQ = h->nQ; A.nQp = h->nQp;
+        A.qlist = h->j_qlist.p; A.nQ = h->nQ; A.nQp = h->nQp; A.gplane = jac_plane(c.nPp, h->nQp);
         A.idx = h->j_idx.p + c.data_off; A.resolved = c.resolved;
         A.idx_in_smem = c.idx_in_smem; A.kfac_in_smem = c.kfac_in_smem; A.out_identity = c.out_identity; A.out_base = (int)c.data_off;
         A.out_row = h->j_out.p + c.data_off; A.kfac = h->j_kfac.p + c.data_off; A.nd = c.nd;
