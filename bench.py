@@ -27,6 +27,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+def _traffic(workload, kernel):
+    """DRAM bytes per launch from the committed ncu capture (profiles/r01_traffic.json), or None"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)[workload][kernel]
+        return float(t["dram_read_bytes"] + t["dram_write_bytes"])
+    except Exception:
+        return None
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -258,10 +268,13 @@ def run_b200(args):
             "pcg_iterations": st["pcg_iterations"], "pcg_max_rel_residual": st["max_rel_residual"],
             "phase_ms_per_step": {k: st[k] / args.steps for k in ("ms_map", "ms_assemble", "ms_rhs", "ms_solve", "ms_epilogue", "ms_jacobian")},
             "roofline": {"kernel": ("k_spmm_panel (%s-staged row panels" % ("cp.async" if args.spmm == "panel_cpasync" else "TMA") if args.spmm != "plain" else "k_spmm (plain gather") + ", CSR x dense block, inside block-PCG)", "bound": "hbm", "achieved": ach, "peak": peak,
-                         "unit": "GB/s", "frac": ach / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": ach / peak if peak else None,
+                         "traffic": _traffic(args.workload, "k_spmm_panel") if (world == 1 and args.scale == 1.0 and args.spmm == "panel") else None, "peak_source": peak_src,
                          "launches_timed": st["spmm_timed"], "avg_launch_ms": spmm_ms, "algorithmic_bytes_per_launch": spmm_bytes},
             "roofline_jacobian": {"kernel": "k_jacobian", "bound": "hbm", "achieved": jac_bytes / (jac_ms * 1e-3) / 1e9 if jac_ms > 0 else None,
-                                  "peak": peak, "unit": "GB/s", "launch_ms": jac_ms, "algorithmic_bytes_per_launch": jac_bytes},
+                                  "peak": peak, "unit": "GB/s", "frac": (jac_bytes / (jac_ms * 1e-3) / 1e9 / peak) if jac_ms > 0 else None,
+                                  "traffic": _traffic(args.workload, "k_jacobian") if (world == 1 and args.scale == 1.0) else None,
+                                  "launch_ms": jac_ms, "algorithmic_bytes_per_launch": jac_bytes},
             "e2e": {"value": ms_e2e / 1e3 / args.steps, "unit": "s", "h2d_bytes_per_step": 8 * (2 * M + M + D),
                     "d2h_bytes_per_step": 8 * (D + D + M),
                     "note": "host-buffer C ABI: response + createJacobian + one J.x and one J^T.y; J stays in HBM"},

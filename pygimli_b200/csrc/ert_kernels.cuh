@@ -916,7 +916,7 @@ k_jacobian(const JacArgs A) {
     double *sM  = sK + NL * NL;                     // [NL*NL] mass
     double *sXYZ = sM + NL * NL;                    // [2][NV][3] corner coordinates
     double *sG  = sXYZ + 2 * NV * 3;                // Gram block, element-major: 16 planes [a][b] of one value per 4x4 tile
-    const int PL = A.gplane;                        // plane stride (>= number of tiles, = 1 mod 16: conflict-free both ways)
+    const int PL = A.gplane;                        // plane stride (>= number of tiles, = 4 mod 16: conflict-free tile stores and row reads)
     double *sKf = sG + 16 * (size_t)PL + 1;         // [nd] geometric factors (optional); sG[16 PL] is the zero slot
     void *sIdxRaw = A.kfac_in_smem ? (void *)(sKf + A.nd) : (void *)sKf;
     __shared__ int snode[3][NL];

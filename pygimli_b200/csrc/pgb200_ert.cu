@@ -483,9 +483,9 @@ int finish_response(pgb200_ert *h, double *rhoa_dev) {
     return 0;
 }
 
-int jac_plane(int nPp, int nQp) {               // plane stride of the element-major Gram block: >= #tiles and = 1 (mod 16)
-    const int nt = (nPp / 4) * (nQp / 4);
-    return (nt + 14) / 16 * 16 + 1;
+int jac_plane(int nPp, int nQp) {               // plane stride of the element-major Gram block: >= #tiles and = 4 (mod 16), so that
+    const int nt = (nPp / 4) * (nQp / 4);       // 16 consecutive q of one p hit 16 different 8-byte banks: (q & 3) * 4 + (q >> 2)
+    return (nt + 11) / 16 * 16 + 4;
 }
 size_t jac_smem(int NL, int nPp, int nQp) {
     // double-buffered gathers, V, K, M, corner coordinates (2 x 4 x 3), G (16 planes + zero slot)
