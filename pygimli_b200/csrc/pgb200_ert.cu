@@ -199,7 +199,7 @@ int launch_spmm_panel_nc(pgb200_ert *h, const double *vals, const double *X, dou
 template <int EPI>
 int launch_panel(pgb200_ert *h, const double *vals, const double *X, double *Y, int c0, int c1, double *dots, const PanelExtra &ex) {
     if (c1 <= c0) return 0;
-    if (h->panel_nc == 2) return launch_spmm_panel_nc<2, EPI>(h, vals, X, Y, c0, c1, dots, ex);
+    if (h->panel_nc == 2 && c1 - c0 > 32) return launch_spmm_panel_nc<2, EPI>(h, vals, X, Y, c0, c1, dots, ex);   // narrow shards: 1 column per lane
     return launch_spmm_panel_nc<1, EPI>(h, vals, X, Y, c0, c1, dots, ex);
 }
 int launch_spmm_panel(pgb200_ert *h, const double *vals, const double *X, double *Y, int c0, int c1, double *dots) {

@@ -36,10 +36,15 @@ def chunk_width(n: int, world: int) -> int:
 
 
 def padded_range(n: int, world: int, rank: int):
-    """equal-width chunks (last ones may be short/empty): the unit of the all-gather"""
-    w = chunk_width(n, world)
-    lo = min(n, rank * w)
-    return lo, min(n, lo + w)
+    """balanced contiguous chunks whose boundaries are EVEN (the panel-staged SpMM needs 16-byte aligned
+    column tiles); the all-gather uses slots of the largest chunk width"""
+    def bound(r):
+        return n if r >= world else min(n, 2 * int(round(r * n / (2.0 * world))))
+    return bound(rank), bound(rank + 1)
+
+
+def max_chunk(n: int, world: int) -> int:
+    return max(padded_range(n, world, r)[1] - padded_range(n, world, r)[0] for r in range(world))
 
 
 def row_order(scheme: SchemeArrays) -> np.ndarray:
@@ -101,7 +106,7 @@ class ShardedERT:
 
     def _allgather_potentials(self):
         torch, dist = self._torch()
-        w = chunk_width(self.nS, self.world)
+        w = max_chunk(self.nS, self.world)
         if self._bufs is None:
             self._bufs = (torch.zeros(self.N * w, dtype=torch.float64, device=f"cuda:{self.device}"),
                           torch.zeros(self.world * self.N * w, dtype=torch.float64, device=f"cuda:{self.device}"))

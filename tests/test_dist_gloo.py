@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from pygimli_b200.dist import split_range, padded_range, chunk_width, row_order
+from pygimli_b200.dist import split_range, padded_range, chunk_width, max_chunk, row_order
 from pygimli_b200.scheme import create_dd
 
 
@@ -22,10 +22,10 @@ def test_partitions_cover_everything():
                 seen[a:b] += 1
             assert np.all(seen == 1)
             seen[:] = 0
-            w = chunk_width(n, world)
+            w = max_chunk(n, world)
             for r in range(world):
                 a, b = padded_range(n, world, r)
-                assert b - a <= w
+                assert b - a <= w and a % 2 == 0
                 seen[a:b] += 1
             assert np.all(seen == 1)
 
@@ -47,7 +47,7 @@ def _worker(rank, world, port, n_nodes, n_src, out):
     # every rank owns the source columns padded_range(rank) of a global [n_nodes x n_src] block
     rng = np.random.default_rng(0)
     U = rng.standard_normal((n_nodes, n_src))
-    w = chunk_width(n_src, world)
+    w = max_chunk(n_src, world)
     a, b = padded_range(n_src, world, rank)
     send = torch.zeros(n_nodes * w, dtype=torch.float64)
     send[: n_nodes * (b - a)] = torch.from_numpy(np.ascontiguousarray(U[:, a:b]).ravel())     # pack
