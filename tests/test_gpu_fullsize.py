@@ -1,0 +1,87 @@
+"""Size-independent properties at BASELINE.json's full sizes (the reference cannot run these in seconds,
+so parity is checked through invariants of the path instead of element-wise comparison):
+
+  * homogeneous half-space: with singularity removal the secondary field vanishes and the 3-D response is
+    the analytic one, rhoa == rho (dcfemmodelling.cpp:2252-2254 with S == S1 / rho);
+  * degree-one homogeneity of the forward map: response(c m) == c response(m);
+  * every source column of the block solve meets the stated relative residual;
+  * the Jacobian operator is consistent: (J x) . y == x . (J^T y), and J(c m) == J(m);
+  * sharded 2.5-D wavenumber integration (C1): reciprocity of the k-summed electrode matrix.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(name):
+    import bench
+    from pygimli_b200 import ERTModellingB200
+    mesh, scheme, model, desc, kw = bench.build_workload(name, 1.0)
+    fop = ERTModellingB200(sr=True)
+    fop.setMesh(mesh)
+    fop.setData(scheme)
+    if kw is not None:
+        fop._core.setkValues(kw[0])
+        fop._core.setWeights(kw[1])
+    return mesh, scheme, model, fop
+
+
+@pytest.fixture(scope="module")
+def c3():
+    out = _build("c3")
+    yield out
+    out[3]._core.close()
+
+
+def test_c3_sizes(c3):
+    mesh, scheme, model, fop = c3
+    assert 0.9e6 < mesh.cell_count < 1.2e6 and scheme.sensor_count == 100 and scheme.size == 9700
+
+
+def test_c3_homogeneous_halfspace_is_exact(c3):
+    mesh, scheme, model, fop = c3
+    rhoa = fop.response(np.full(model.size, 100.0))
+    assert np.max(np.abs(rhoa - 100.0)) < 1e-5          # round(u, 1e-10) * |k| quantum + rounding
+
+
+def test_c3_homogeneity_residuals_and_operator(c3):
+    mesh, scheme, model, fop = c3
+    r1 = fop.response(model)
+    res = fop._core.get("rel_res")
+    assert res.size == 100 and np.max(res) <= 1.0e-12 * 1.0001
+    fop.createJacobian(model)
+    Jop = fop.jacobian()
+    assert (Jop.rows(), Jop.cols()) == (9700, model.size)
+    rng = np.random.default_rng(0)
+    x, y = rng.standard_normal(Jop.cols()), rng.standard_normal(Jop.rows())
+    lhs, rhs = float(Jop.mult(x) @ y), float(x @ Jop.transMult(y))
+    assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs))
+    jx1 = Jop.mult(x)
+    r2 = fop.response(2.5 * model)
+    assert np.max(np.abs(r2 - 2.5 * r1) / np.abs(r1)) < 1e-7
+    fop.createJacobian(2.5 * model)
+    jx2 = fop.jacobian().mult(x)
+    assert np.max(np.abs(jx2 - jx1)) <= 1e-7 * np.max(np.abs(jx1))
+    # all finite, and the response is positive for this dipole-dipole layout
+    assert np.all(np.isfinite(r1)) and np.all(r1 > 0)
+
+
+def test_c1_full_size_properties():
+    mesh, scheme, model, fop = _build("c1")
+    assert scheme.size == 741 and scheme.sensor_count == 41
+    core = fop._core
+    r1 = fop.response(model)
+    P = core._plan
+    assert P.nK == P.k.size and P.nS == 41 * P.nK
+    assert np.max(core.get("rel_res")) <= 1.0e-12 * 1.0001
+    pm = core.get("pm").reshape(41, 41)
+    off = ~np.eye(41, dtype=bool)
+    # reciprocity of the electrode-potential matrix (symmetric operator, symmetric pick-up): to solver accuracy
+    assert np.max(np.abs(pm - pm.T)[off]) <= 1e-8 * np.max(np.abs(pm[off]))
+    r2 = fop.response(0.4 * model)
+    assert np.max(np.abs(r2 - 0.4 * r1) / np.abs(r1)) < 1e-7
+    fop.createJacobian(model)
+    J = fop.jacobian().numpy()
+    assert J.shape == (741, model.size) and np.all(np.isfinite(J))
+    fop._core.close()
