@@ -60,7 +60,7 @@ def test_c3_homogeneity_residuals_and_operator(c3):
     assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs))
     jx1 = Jop.mult(x)
     r2 = fop.response(2.5 * model)
-    assert np.max(np.abs(r2 - 2.5 * r1) / np.abs(r1)) < 1e-7
+    assert np.all(np.abs(r2 - 2.5 * r1) <= 1e-7 * np.abs(r1) + 1e-9 * np.abs(scheme.k))    # solver accuracy + round(u, 1e-10) quanta
     fop.createJacobian(2.5 * model)
     jx2 = fop.jacobian().mult(x)
     assert np.max(np.abs(jx2 - jx1)) <= 1e-7 * np.max(np.abs(jx1))
@@ -81,7 +81,7 @@ def test_c1_full_size_properties():
     # reciprocity of the electrode-potential matrix (symmetric operator, symmetric pick-up): to solver accuracy
     assert np.max(np.abs(pm - pm.T)[off]) <= 1e-8 * np.max(np.abs(pm[off]))
     r2 = fop.response(0.4 * model)
-    assert np.max(np.abs(r2 - 0.4 * r1) / np.abs(r1)) < 1e-7
+    assert np.all(np.abs(r2 - 0.4 * r1) <= 1e-7 * np.abs(r1) + 1e-9 * np.abs(scheme.k))
     fop.createJacobian(model)
     J = fop.jacobian().numpy()
     assert J.shape == (741, model.size) and np.all(np.isfinite(J))
