@@ -78,8 +78,10 @@ def test_c1_full_size_properties():
     assert np.max(core.get("rel_res")) <= 1.0e-12 * 1.0001
     pm = core.get("pm").reshape(41, 41)
     off = ~np.eye(41, dtype=bool)
-    # reciprocity of the electrode-potential matrix (symmetric operator, symmetric pick-up): to solver accuracy
-    assert np.max(np.abs(pm - pm.T)[off]) <= 1e-8 * np.max(np.abs(pm[off]))
+    # reciprocity of the electrode-potential matrix: exact only for the continuous problem (the secondary-field
+    # scheme solves S u = S1 u_p, not S u = delta), so it holds to discretisation accuracy -- which is why the
+    # reference returns the geometric mean of the forward and the reciprocal response (dcfemmodelling.cpp:1196)
+    assert np.max(np.abs(pm - pm.T)[off]) <= 5e-2 * np.max(np.abs(pm[off]))
     r2 = fop.response(0.4 * model)
     assert np.all(np.abs(r2 - 0.4 * r1) <= 1e-7 * np.abs(r1) + 1e-9 * np.abs(scheme.k))
     fop.createJacobian(model)
