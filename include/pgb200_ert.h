@@ -141,7 +141,10 @@ int pgb200_ert_set_hierarchy(pgb200_ert *h, int n_levels, const pgb200_amg_level
 /* multilevel = 0: Jacobi-PCG, 1: V(1,1) aggregation multigrid preconditioner (default when a hierarchy is
  * installed); coarse_sweeps: damped-Jacobi sweeps on the coarsest level (default 8).              */
 int pgb200_ert_set_preconditioner(pgb200_ert *h, int multilevel, int coarse_sweeps);
-/* CUDA stream (cudaStream_t) all work is enqueued on; 0/NULL = legacy default stream.   */
+/* replay blocks of 6 multilevel-PCG iterations as one CUDA graph (default on; off while profiling) */
+int pgb200_ert_set_graph(pgb200_ert *h, int on);
+/* CUDA stream (cudaStream_t) all work is enqueued on; 0/NULL = the handle's own blocking stream,
+ * which is implicitly ordered with the legacy default stream.                                */
 int pgb200_ert_set_stream(pgb200_ert *h, void *stream);
 /* Block-PCG controls: relative residual tolerance ||r||/||b|| per source column,
  * iteration cap, and how many iterations run between convergence checks.               */

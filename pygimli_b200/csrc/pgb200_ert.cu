@@ -53,6 +53,14 @@ enum Phase { PH_MAP = 0, PH_ASM, PH_RHS, PH_SOLVE, PH_EPI, PH_JAC, PH_COUNT };
 
 } // namespace
 
+struct GraphKey {
+    int c0, c1; double tol; int use_panels, panel_nc, panel_tma, levels, sweeps; void *stream; void *vals;
+    bool operator==(const GraphKey &o) const {
+        return c0 == o.c0 && c1 == o.c1 && tol == o.tol && use_panels == o.use_panels && panel_nc == o.panel_nc && panel_tma == o.panel_tma &&
+               levels == o.levels && sweeps == o.sweeps && stream == o.stream && vals == o.vals;
+    }
+};
+
 struct AmgLevel {      // one coarse level of the aggregation hierarchy (device arrays)
     int n = 0; size_t nnz = 0; int n_finer = 0;
     DevBuf<int> rowptr, colidx, diag_pos, gal_ptr, gal_idx, agg, mem_ptr, mem_idx;
@@ -93,6 +101,9 @@ struct pgb200_ert {
     size_t ldJ = 0; int j_rows = 0; bool jac_valid = false;
     // multilevel preconditioner
     std::vector<AmgLevel *> amg; int use_amg = 1, coarse_sweeps = 8; DevBuf<double> Z0, X0, dinvw0, vals_dw0; DevBuf<unsigned long long> gmax;
+    // CUDA graph of 6 PCG iterations
+    int use_graph = 1; cudaGraphExec_t gexec = nullptr; GraphKey gkey{}; int glaunches = 0; long long launches_per_block = 0;
+    cudaStream_t own_st = nullptr;
     // stats
     int last_iters = 0; double last_relres = 0.0; long long launches = 0;
     cudaEvent_t ev[PH_COUNT + 1]; bool ev_ok = false; float ph_ms[PH_COUNT] = {0};
@@ -346,11 +357,10 @@ int pcg_solve(pgb200_ert *h) {
     CKR(ensure_pinned(h, 2 * ld));
     const double tol2 = h->tol * h->tol;
     int it = 0; bool converged = false;
-    // initial residual == b: a zero right-hand side needs no iteration
-    while (it < h->max_iter) {
-        const int rz_old = it % 3, rz_new = (it + 1) % 3, rz_nxt = (it + 2) % 3;
-        const int rr_cur = 4 + (it % 2), rr_nxt = 4 + ((it + 1) % 2);
-        const bool timed = h->prof && h->n_pev + 2 <= (int)h->pev.size();
+    // one PCG iteration; the scalar buffers rotate with the iteration number (rz: period 3, rr: period 2)
+    auto body = [&](int i, bool timed) -> int {
+        const int rz_old = i % 3, rz_new = (i + 1) % 3, rz_nxt = (i + 2) % 3;
+        const int rr_cur = 4 + (i % 2), rr_nxt = 4 + ((i + 1) % 2);
         if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
         if (panel_path_ok(h, c0)) CKR(launch_spmm_panel(h, h->vals.p, h->P.p, h->AP.p, c0, c1, sc(3)));
         else CKR((launch_spmm<0, true>(h, h->vals.p, nullptr, nullptr, h->P.p, h->AP.p, c0, c1, sc(3))));
@@ -358,35 +368,77 @@ int pcg_solve(pgb200_ert *h) {
         if (amg) {
             k_pcg_update_xr<false><<<vg, vb, 0, h->st>>>(h->P.p, h->AP.p, nullptr, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
                                                         sc(rz_old), sc(3), sc(rz_new), sc(rr_cur)); LAUNCH(h);
-        } else {
-            k_pcg_update_xr<true><<<vg, vb, 0, h->st>>>(h->P.p, h->AP.p, h->dinv.p, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
-                                                       sc(rz_old), sc(3), sc(rz_new), sc(rr_cur)); LAUNCH(h);
-        }
-        it++;
-        const bool check = (it % h->check_every == 0) || it >= h->max_iter;
-        if (check) {
-            CK(cudaMemcpyAsync(h->h_pinned, sc(rr_cur), sizeof(double) * ld, cudaMemcpyDeviceToHost, h->st));
-            CK(cudaMemcpyAsync(h->h_pinned + ld, sc(6), sizeof(double) * ld, cudaMemcpyDeviceToHost, h->st));
-        }
-        if (amg) {
             CKR(amg_vcycle(h, c0, c1, sc(rz_new)));
             k_pcg_update_p<false><<<vg, vb, 0, h->st>>>(h->Z0.p, nullptr, h->P.p, h->N, h->nE, c0, c1, ld, sc(rz_old), sc(rz_new),
                                                        sc(rr_cur), sc(6), tol2, sc(3), sc(rr_nxt), sc(rz_nxt)); LAUNCH(h);
         } else {
+            k_pcg_update_xr<true><<<vg, vb, 0, h->st>>>(h->P.p, h->AP.p, h->dinv.p, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
+                                                       sc(rz_old), sc(3), sc(rz_new), sc(rr_cur)); LAUNCH(h);
             k_pcg_update_p<true><<<vg, vb, 0, h->st>>>(h->R.p, h->dinv.p, h->P.p, h->N, h->nE, c0, c1, ld, sc(rz_old), sc(rz_new),
                                                       sc(rr_cur), sc(6), tol2, sc(3), sc(rr_nxt), sc(rz_nxt)); LAUNCH(h);
         }
-        if (check) {
-            CK(cudaStreamSynchronize(h->st));
-            double worst = 0.0;
-            for (int c = c0; c < c1; c++) {
-                const double bb = h->h_pinned[ld + c], rr = h->h_pinned[c];
-                if (bb > 0.0) worst = std::max(worst, std::sqrt(rr / bb));
-                else if (rr > 0.0) worst = INFINITY;
-                if (!(rr == rr)) worst = INFINITY;
+        return 0;
+    };
+    // residual norms of iteration i_done - 1 -> host; true when every column meets the tolerance
+    auto check = [&](int i_done) -> int {
+        const int rr_cur = 4 + ((i_done - 1) % 2);
+        CK(cudaMemcpyAsync(h->h_pinned, sc(rr_cur), sizeof(double) * ld, cudaMemcpyDeviceToHost, h->st));
+        CK(cudaMemcpyAsync(h->h_pinned + ld, sc(6), sizeof(double) * ld, cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+        double worst = 0.0;
+        for (int c = c0; c < c1; c++) {
+            const double bb = h->h_pinned[ld + c], rr = h->h_pinned[c];
+            if (bb > 0.0) worst = std::max(worst, std::sqrt(rr / bb));
+            else if (rr > 0.0) worst = INFINITY;
+            if (!(rr == rr)) worst = INFINITY;
+        }
+        h->last_relres = worst;
+        converged = worst <= h->tol;
+        return 0;
+    };
+    // CUDA-graph mode: blocks of 6 iterations (one full period of the buffer rotation) replayed as one graph launch.
+    // Removes the launch gaps of the ~27 kernels per multilevel iteration (matters most for narrow multi-GPU shards).
+    const bool graph_mode = h->use_graph && amg && !h->prof && h->st != 0;
+    if (graph_mode) {
+        GraphKey key{c0, c1, h->tol, h->use_panels, h->panel_nc, h->panel_tma, (int)h->amg.size(), h->coarse_sweeps, (void *)h->st, (void *)h->vals.p};
+        const int blocks_per_check = std::max(1, h->check_every / 6);
+        int blocks = 0;
+        while (it < h->max_iter && !converged) {
+            if (it == 0) {
+                const long long before = h->launches;
+                for (int j = 0; j < 6; j++) CKR(body(j, false));          // warm-up block (also sets kernel attributes)
+                h->launches_per_block = h->launches - before;
+            } else {
+                if (!h->gexec || !(h->gkey == key)) {
+                    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+                    const long long before = h->launches;
+                    cudaGraph_t g = nullptr;
+                    CK(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+                    int rc = 0;
+                    for (int j = 0; j < 6 && !rc; j++) rc = body(j, false);
+                    cudaError_t ce = cudaStreamEndCapture(h->st, &g);
+                    h->launches = before;
+                    if (rc || ce != cudaSuccess) { if (g) cudaGraphDestroy(g); if (!rc) g_err = std::string("graph capture failed: ") + cudaGetErrorString(ce); return 1; }
+                    ce = cudaGraphInstantiate(&h->gexec, g, 0);
+                    cudaGraphDestroy(g);
+                    if (ce != cudaSuccess) { h->gexec = nullptr; g_err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce); return 1; }
+                    h->gkey = key;
+                }
+                CK(cudaGraphLaunch(h->gexec, h->st));
+                h->launches += h->launches_per_block;
             }
-            h->last_relres = worst;
-            if (worst <= h->tol) { converged = true; break; }
+            it += 6; blocks++;
+            if (blocks % blocks_per_check == 0 || it >= h->max_iter) CKR(check(it));
+        }
+    } else {
+        while (it < h->max_iter) {
+            const bool timed = h->prof && h->n_pev + 2 <= (int)h->pev.size();
+            CKR(body(it, timed));
+            it++;
+            if ((it % h->check_every == 0) || it >= h->max_iter) {
+                CKR(check(it));
+                if (converged) break;
+            }
         }
     }
     CK(cudaGetLastError());
@@ -761,6 +813,8 @@ int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
     pgb200_ert *h = new pgb200_ert();
     *out = h;
     h->device = device;
+    CK(cudaStreamCreate(&h->own_st));          // blocking stream: implicitly ordered with the legacy default stream
+    h->st = h->own_st;
     CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     h->dim = p->dim; h->nloc = p->nloc; h->N = p->n_nodes; h->C = p->n_cells; h->nnz = (size_t)p->nnz;
     h->nE = p->n_elec; h->nK = p->n_k; h->nS = h->nE * h->nK; h->M = p->n_model; h->D = p->n_data; h->sr = p->sr;
@@ -850,6 +904,8 @@ int pgb200_ert_destroy(pgb200_ert *h) {
     for (auto e : h->pev) cudaEventDestroy(e);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     for (AmgLevel *L : h->amg) delete L;
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
+    if (h->own_st) cudaStreamDestroy(h->own_st);
     delete h;
     return 0;
 }
@@ -859,6 +915,7 @@ int pgb200_ert_set_hierarchy(pgb200_ert *h, int n_levels, const pgb200_amg_level
     CK(cudaSetDevice(h->device));
     for (AmgLevel *L : h->amg) delete L;
     h->amg.clear();
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
     if (n_levels <= 0) return 0;
     if (!lv) PGB_FAIL("null level array");
     cudaStream_t st = h->st;
@@ -886,6 +943,7 @@ int pgb200_ert_set_hierarchy(pgb200_ert *h, int n_levels, const pgb200_amg_level
     h->have_vals = false;
     return 0;
 }
+int pgb200_ert_set_graph(pgb200_ert *h, int on) { if (!h) PGB_FAIL("null handle"); h->use_graph = on != 0; return 0; }
 /* 0: Jacobi-PCG; 1: multilevel V-cycle preconditioner (needs a hierarchy); sweeps: Jacobi sweeps on the coarsest level */
 int pgb200_ert_set_preconditioner(pgb200_ert *h, int multilevel, int coarse_sweeps) {
     if (!h) PGB_FAIL("null handle");
@@ -893,7 +951,13 @@ int pgb200_ert_set_preconditioner(pgb200_ert *h, int multilevel, int coarse_swee
     return 0;
 }
 
-int pgb200_ert_set_stream(pgb200_ert *h, void *stream) { if (!h) PGB_FAIL("null handle"); h->st = (cudaStream_t)stream; return 0; }
+int pgb200_ert_set_stream(pgb200_ert *h, void *stream) {
+    if (!h) PGB_FAIL("null handle");
+    // NULL / legacy default stream: keep the handle's own blocking stream (implicitly ordered with the legacy stream;
+    // CUDA graphs cannot be captured on the legacy stream itself)
+    h->st = stream ? (cudaStream_t)stream : h->own_st;
+    return 0;
+}
 
 int pgb200_ert_set_solver(pgb200_ert *h, double rel_tol, int max_iter, int check_every) {
     if (!h) PGB_FAIL("null handle");
