@@ -179,7 +179,9 @@ def reference_sample(ref, mesh, scheme, model, threads, args, kw=None, cache=Non
     total = t_map + t_asm + t_solve + t_sens
     return total, {"sample": f"assembly: {min(nK, 2)} of {nK} wavenumbers x2 matrices (full mesh); solves: {n_src} of {nE} sources x "
                              f"{nK} k with " + ("scipy SuperLU (direct, factorisation counted in full)" if direct else "a Jacobi-PCG") + f" standing in for CHOLMOD; sensitivity: {d_sub} of {D} rows on {threads} threads; "
-                             "each stage scaled linearly to the full workload",
+                             "each stage scaled linearly to the full workload"
+                             + ("" if direct else "; off-line on the c3 matrix a direct stand-in (SuperLU, 1 thread) needs 223 s to factorise "
+                                "+ 0.49 s per source (DESIGN.md section 6), so the Jacobi-PCG solve stage is an upper bound"),
                    "stages": {"map_model": t_map, "assembly": t_asm, "solve_substitute": t_solve, "sensitivity": t_sens}}
 
 
