@@ -162,6 +162,8 @@ int pgb200_ert_response(pgb200_ert *h, const double *model_host, int n_model_in,
 /* createJacobian: uses the potentials of the last response() if present (:1262), else
  * solves (analytic branch for homogeneous models, :1272-1301).  J stays in HBM.          */
 int pgb200_ert_create_jacobian(pgb200_ert *h, const double *model_host, int n_model_in);
+/* mapERTModel (dcfemmodelling.cpp:1211-1218): model vector -> cell resistivities rho_cells_host[C]      */
+int pgb200_ert_map_model(pgb200_ert *h, const double *model_host, int n_model_in, double *rho_cells_host);
 /* copy J to the host, row-major [D_local x M].                                           */
 int pgb200_ert_jacobian_copy(pgb200_ert *h, double *j_host);
 /* y = J x  and  y = J^T x  with host vectors (jacobian().mult / transMult).              */

@@ -48,7 +48,7 @@ class AmgLevel(C.Structure):
 
 # every symbol include/pgb200_ert.h declares (checked by tests/test_capi_symbols.py)
 EXPORTS = [
-    "pgb200_last_error", "pgb200_version", "pgb200_color_cells", "pgb200_build_panels", "pgb200_ert_set_spmm_variant", "pgb200_pairwise_aggregate", "pgb200_ert_set_hierarchy", "pgb200_ert_set_preconditioner", "pgb200_ert_set_graph",
+    "pgb200_last_error", "pgb200_version", "pgb200_color_cells", "pgb200_build_panels", "pgb200_ert_set_spmm_variant", "pgb200_pairwise_aggregate", "pgb200_ert_set_hierarchy", "pgb200_ert_set_preconditioner", "pgb200_ert_set_graph", "pgb200_ert_map_model",
     "pgb200_ert_create", "pgb200_ert_destroy", "pgb200_ert_set_stream", "pgb200_ert_set_solver", "pgb200_ert_set_shard",
     "pgb200_ert_set_kfac", "pgb200_ert_response", "pgb200_ert_create_jacobian", "pgb200_ert_jacobian_copy",
     "pgb200_ert_jacobian_mult", "pgb200_ert_jacobian_tmult", "pgb200_ert_response_dev", "pgb200_ert_create_jacobian_dev",
@@ -105,6 +105,7 @@ def lib():
         L.pgb200_ert_set_hierarchy.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.pgb200_ert_set_preconditioner.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.pgb200_ert_set_graph.argtypes = [C.c_void_p, C.c_int]
+        L.pgb200_ert_map_model.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.pgb200_pairwise_aggregate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pgb200_spmm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p]

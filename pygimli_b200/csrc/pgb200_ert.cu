@@ -1021,6 +1021,20 @@ int pgb200_ert_response(pgb200_ert *h, const double *model_host, int n_in, doubl
     return 0;
 }
 
+// mapERTModel (dcfemmodelling.cpp:1211-1218): cell resistivities for a model vector (per marker or per cell),
+// including the prolongation into background cells; rho_cells_host[C]
+int pgb200_ert_map_model(pgb200_ert *h, const double *model_host, int n_in, double *rho_cells_host) {
+    if (!h || !model_host || !rho_cells_host) PGB_FAIL("null argument");
+    CK(cudaSetDevice(h->device));
+    if (n_in != h->M && n_in != h->C) PGB_FAIL("model length must equal the number of model cells (max marker + 1) or the cell count");
+    CK(cudaMemcpyAsync(h->model.p, model_host, sizeof(double) * n_in, cudaMemcpyHostToDevice, h->st));
+    CKR(map_model(h, h->model.p, n_in));
+    CK(cudaMemcpyAsync(rho_cells_host, h->rho.p, sizeof(double) * h->C, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->pots_valid = h->pots_valid;   // potentials of the last response stay valid, as in the reference
+    return 0;
+}
+
 // multi-GPU staging: solve this shard's sources and leave the partial electrode matrix in HBM
 int pgb200_ert_forward_dev(pgb200_ert *h, const double *model_dev, int n_in) {
     if (!h || !model_dev) PGB_FAIL("null argument");

@@ -267,7 +267,15 @@ class CoreB200:
         return self.get("solutions").reshape(P.nE, P.N)
 
     def mapERTModel(self, model, background=-9e99):
-        raise NotImplementedError("use get('rho') after response(); the mapping runs on the GPU")
+        """cell resistivities for a model vector (dcfemmodelling.cpp:1211-1218); only the prolongating
+        background (-9e99, the value response() uses) is supported"""
+        if background > -9e99:
+            raise NotImplementedError("explicit background values are not supported on the B200 path")
+        h = self._ensure_handle()
+        m = np.ascontiguousarray(model, np.float64)
+        out = np.zeros(self._plan.C)
+        _capi.check(_capi.lib().pgb200_ert_map_model(h, m.ctypes.data, int(m.size), out.ctypes.data))
+        return out
 
     # ---- introspection ------------------------------------------------------------------
     def get(self, what: str, raw: bool = False) -> np.ndarray:

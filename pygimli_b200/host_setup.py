@@ -534,18 +534,21 @@ def build_plan(mesh: MeshArrays, scheme, k_values=None, weights=None, color_fn=N
 
     # node -> cells incidence for the electrodes (rho at the source, electrode.cpp:102-120, :252-268)
     flat = mesh.cells.ravel()
-    cell_of = np.repeat(np.arange(C), nloc)
+    order_nc = np.argsort(flat, kind="stable")
+    nc_ptr = np.concatenate([[0], np.cumsum(np.bincount(flat, minlength=N))])
+    nc_cells = (order_nc // nloc)
+
+    def cells_of(node):
+        return np.unique(nc_cells[nc_ptr[node]:nc_ptr[node + 1]])
+
     inc_ptr, inc_cells = [0], []
     min_radius = np.zeros(nE)
     for i in range(nE):
-        if el_node[i] >= 0:
-            cs = np.unique(cell_of[flat == el_node[i]])
-        else:
-            cs = np.array([el_cell[i]])
+        cs = cells_of(el_node[i]) if el_node[i] >= 0 else np.array([el_cell[i]])
         inc_cells.append(cs)
         inc_ptr.append(inc_ptr[-1] + cs.size)
         if sing_node[i] >= 0:
-            cs2 = np.unique(cell_of[flat == sing_node[i]])
+            cs2 = cells_of(sing_node[i])
             nbn = np.unique(mesh.cells[cs2].ravel())
             nbn = nbn[nbn != sing_node[i]]
             min_radius[i] = np.sqrt(((mesh.pos[nbn] - mesh.pos[sing_node[i]]) ** 2).sum(1)).min()

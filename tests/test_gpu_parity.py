@@ -59,6 +59,7 @@ def test_wavenumbers(case):
 def test_model_mapping(case):
     rho = case["fop"]._core.get("rho")
     assert _relmax(rho, case["g"]["rho"]) < 1e-13
+    assert _relmax(case["fop"].mapERTModel(case["model"]), case["g"]["rho"]) < 1e-13
 
 
 def test_matrix_values(case):
