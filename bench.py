@@ -46,6 +46,22 @@ def _peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+class stdout_to_stderr:
+    """The reference C++ prints diagnostics with std::cout; keep stdout clean for the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -109,10 +125,11 @@ def run_reference(args):
     samples = []
     info = {}
     cache = {}
-    for step in range(args.warmup + args.steps):
-        t, info = reference_sample(ref, mesh, scheme, model, threads, args, kw, cache)
-        if step >= args.warmup:
-            samples.append(t)
+    with stdout_to_stderr():
+        for step in range(args.warmup + args.steps):
+            t, info = reference_sample(ref, mesh, scheme, model, threads, args, kw, cache)
+            if step >= args.warmup:
+                samples.append(t)
     val = float(np.mean(samples))
     line = {"metric": "ert_forward_jacobian_s_per_iter", "value": val, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": val * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
@@ -313,7 +330,8 @@ def run_b200(args):
                 if ref.available():
                     cores = os.cpu_count() or 1
                     threads = max(1, min(8, cores - 2))
-                    tv, info = reference_sample(ref, mesh, scheme, model, threads, args, kw)
+                    with stdout_to_stderr():
+                        tv, info = reference_sample(ref, mesh, scheme, model, threads, args, kw)
                     line["cpu_baseline"] = {"value": tv, "unit": "s", "cores": threads, "kind": "reference",
                                             "sample": info["sample"], "stages_s": info["stages"]}
                 else:
