@@ -349,7 +349,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="mesh refinement factor (1.0 = the named size)")
     ap.add_argument("--tol", type=float, default=1e-12, help="block-PCG relative residual tolerance")
     ap.add_argument("--ref-rows", type=int, default=24, help="data rows in the CPU sensitivity sample")

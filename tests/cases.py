@@ -6,6 +6,7 @@ from pygimli_b200.mesh import (graded_axis, grid_mesh_2d, grid_mesh_3d, create_p
 from pygimli_b200.scheme import create_dd, create_slm, create_grid_dd, geometric_factors
 
 CASES = ("2d_p1", "2d_p2", "3d_p1", "3d_p2", "2d_p1_h2", "3d_p1_cellmodel")
+EXTRA_CASES = ("3d_crosshole",)      # checked against the reference run live (no committed vectors)
 
 
 def _model(M, seed=1234):
@@ -29,6 +30,24 @@ def make_case(name: str):
             mesh = create_p2(mesh)
         scheme = create_dd(sens) if name != "2d_p2" else create_slm(sens)
         scheme.k = geometric_factors(scheme, 2)
+    elif name == "3d_crosshole":
+        # two short boreholes with buried electrodes (mirror sources with z < 0, SURVEY §8 C4 in miniature)
+        h = 1.0
+        xs = graded_axis(-2.0, 8.0, h, 1.6, 60.0)
+        zs = -graded_axis(0.0, 8.0, h, 1.6, 60.0, both=False)
+        mesh = grid_mesh_3d(xs, xs, zs, para_box=(-2.5, 8.5, -2.5, 8.5, -8.5), marker_per="cube")
+        sens = np.array([[bx, 3.0, -1.0 - i] for bx in (1.0, 5.0) for i in range(5)], float)
+        ids = mark_electrode_nodes(mesh, sens)
+        assert np.all(ids >= 0)
+        rows = []
+        for i in range(4):
+            for j in range(4):
+                rows.append((i, i + 1, 5 + j, 5 + j + 1))                 # cross-hole dipoles
+        rows += [(0, 1, 3, 4), (5, 6, 8, 9), (0, 4, 5, 9)]                   # in-hole and long dipoles
+        r = np.asarray(rows, np.int32)
+        from pygimli_b200.scheme import SchemeArrays
+        scheme = SchemeArrays(sens, r[:, 0], r[:, 1], r[:, 2], r[:, 3])
+        scheme.k = geometric_factors(scheme, 3)
     else:
         nx = 5
         sp = 2.0

@@ -203,6 +203,12 @@ def test_free_electrodes(name):
     _check(_ours(mesh, sch, model), _live(mesh, sch, model), sch)
 
 
+def test_buried_electrodes_crosshole():
+    """electrodes below the surface: analytic primary potentials with a real mirror source (bertMisc.cpp:196-214)"""
+    mesh, scheme, model = make_case("3d_crosshole")
+    _check(_ours(mesh, scheme, model), _live(mesh, scheme, model), scheme)
+
+
 def test_user_wavenumbers():
     """setkValues / setWeights override the default list (dcfemmodelling.h:239-243)"""
     mesh, scheme, model = make_case("2d_p1")
