@@ -101,6 +101,7 @@ struct pgb200_ert {
     size_t ldJ = 0; int j_rows = 0; bool jac_valid = false;
     // multilevel preconditioner
     std::vector<AmgLevel *> amg; int use_amg = 1, coarse_sweeps = 8; DevBuf<double> Z0, X0, dinvw0, vals_dw0; DevBuf<unsigned long long> gmax;
+    std::vector<double> col_relres; int shrink_window = 1;
     // CUDA graph of 6 PCG iterations
     int use_graph = 1; cudaGraphExec_t gexec = nullptr; GraphKey gkey{}; int glaunches = 0; long long launches_per_block = 0;
     cudaStream_t own_st = nullptr;
@@ -339,14 +340,17 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
 
 // scal layout: [0] rz_a [1] rz_b [2] rz_c [3] pAp [4] rr_a [5] rr_b [6] bb   (each ld doubles)
 int pcg_solve(pgb200_ert *h) {
-    const int c0 = h->c0, c1 = h->c1, ncols = c1 - c0;
+    const int s0 = h->c0, s1 = h->c1, ncols = s1 - s0;      // this shard's source columns
+    int c0 = s0, c1 = s1;                                    // ACTIVE window: shrinks as wavenumber groups converge
     h->last_iters = 0; h->last_relres = 0.0;
     if (ncols <= 0) return 0;
+    h->col_relres.assign(h->ld, 0.0);
     const size_t ld = h->ld;
     double *S = h->scal.p;
     auto sc = [&](int i) { return S + (size_t)i * ld; };
     CK(cudaMemsetAsync(S, 0, sizeof(double) * 7 * ld, h->st));
     dim3 vb(VEC_TX, VEC_TY), vg(cdiv(h->N, VEC_ROWS), cdiv(ncols, VEC_TX));
+    auto regrid = [&]() { vg = dim3(cdiv(h->N, VEC_ROWS), cdiv(c1 - c0, VEC_TX)); };
     const bool amg = h->use_amg && !h->amg.empty();
     k_pcg_init<<<vg, vb, 0, h->st>>>(h->B.p, h->dinv.p, h->X.p, h->R.p, h->P.p, h->N, h->nE, c0, c1, ld, amg ? nullptr : sc(0), sc(6)); LAUNCH(h);
     if (amg) {
@@ -385,25 +389,36 @@ int pcg_solve(pgb200_ert *h) {
         CK(cudaMemcpyAsync(h->h_pinned, sc(rr_cur), sizeof(double) * ld, cudaMemcpyDeviceToHost, h->st));
         CK(cudaMemcpyAsync(h->h_pinned + ld, sc(6), sizeof(double) * ld, cudaMemcpyDeviceToHost, h->st));
         CK(cudaStreamSynchronize(h->st));
-        double worst = 0.0;
+        int lo = c1, hi = c0;                                  // unconverged columns of the active window
         for (int c = c0; c < c1; c++) {
             const double bb = h->h_pinned[ld + c], rr = h->h_pinned[c];
-            if (bb > 0.0) worst = std::max(worst, std::sqrt(rr / bb));
-            else if (rr > 0.0) worst = INFINITY;
-            if (!(rr == rr)) worst = INFINITY;
+            double rel = 0.0;
+            if (bb > 0.0) rel = std::sqrt(rr / bb);
+            else if (rr > 0.0) rel = INFINITY;
+            if (!(rr == rr)) rel = INFINITY;
+            h->col_relres[c] = rel;
+            if (!(rel <= h->tol)) { lo = std::min(lo, c); hi = std::max(hi, c + 1); }
         }
+        double worst = 0.0;
+        for (int c = s0; c < s1; c++) worst = std::max(worst, h->col_relres[c]);
         h->last_relres = worst;
-        converged = worst <= h->tol;
+        converged = lo >= hi;
+        if (!converged && h->shrink_window) {
+            // columns are ordered by wavenumber, and whole wavenumber groups converge together (large k first):
+            // drop the converged ends of the window.  Frozen columns keep their final X; all kernels take [c0,c1).
+            lo &= ~1;                                            // even start: 16-byte aligned column tiles
+            if (lo > c0 || hi < c1) { c0 = lo; c1 = hi; regrid(); }
+        }
         return 0;
     };
     // CUDA-graph mode: blocks of 6 iterations (one full period of the buffer rotation) replayed as one graph launch.
     // Removes the launch gaps of the ~27 kernels per multilevel iteration (matters most for narrow multi-GPU shards).
     const bool graph_mode = h->use_graph && amg && !h->prof && h->st != 0;
     if (graph_mode) {
-        GraphKey key{c0, c1, h->tol, h->use_panels, h->panel_nc, h->panel_tma, (int)h->amg.size(), h->coarse_sweeps, (void *)h->st, (void *)h->vals.p};
         const int blocks_per_check = std::max(1, h->check_every / 6);
         int blocks = 0;
         while (it < h->max_iter && !converged) {
+            GraphKey key{c0, c1, h->tol, h->use_panels, h->panel_nc, h->panel_tma, (int)h->amg.size(), h->coarse_sweeps, (void *)h->st, (void *)h->vals.p};
             if (it == 0) {
                 const long long before = h->launches;
                 for (int j = 0; j < 6; j++) CKR(body(j, false));          // warm-up block (also sets kernel attributes)
@@ -1199,14 +1214,8 @@ long long pgb200_ert_get(pgb200_ert *h, const char *what, double *out, long long
     if (n == 0) return 0;
     cudaError_t e = cudaSuccess;
     if (w == "rel_res") {
-        std::vector<double> rr(h->ld), bb(h->ld);
-        // the buffer holding the last residual norms alternates; take the larger (the other one is zeroed)
-        std::vector<double> ra(h->ld), rb(h->ld);
-        cudaStreamSynchronize(h->st);
-        cudaMemcpy(ra.data(), h->scal.p + 4 * h->ld, sizeof(double) * h->ld, cudaMemcpyDeviceToHost);
-        cudaMemcpy(rb.data(), h->scal.p + 5 * h->ld, sizeof(double) * h->ld, cudaMemcpyDeviceToHost);
-        e = cudaMemcpy(bb.data(), h->scal.p + 6 * h->ld, sizeof(double) * h->ld, cudaMemcpyDeviceToHost);
-        for (int c = 0; c < h->nS; c++) { const double r = std::max(ra[c], rb[c]); out[c] = bb[c] > 0 ? std::sqrt(r / bb[c]) : 0.0; }
+        // per-column relative residuals recorded by the convergence checks of the last solve
+        for (int c = 0; c < h->nS; c++) out[c] = c < (int)h->col_relres.size() ? h->col_relres[c] : 0.0;
     } else if (transposed || w == "solutions") {
         if (h->tmp.n < (size_t)n) { if (h->tmp.alloc((size_t)n)) return -1; }
         if (w == "solutions") {
