@@ -443,7 +443,8 @@ int pcg_solve(pgb200_ert *h) {
                 h->launches += h->launches_per_block;
             }
             it += 6; blocks++;
-            if (blocks % blocks_per_check == 0 || it >= h->max_iter) CKR(check(it));
+            // close to the tolerance the check runs after every block, so that at most 5 iterations are wasted
+            if (blocks % blocks_per_check == 0 || it >= h->max_iter || (h->last_relres > 0.0 && h->last_relres <= 50.0 * h->tol)) CKR(check(it));
         }
     } else {
         while (it < h->max_iter) {
