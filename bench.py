@@ -283,6 +283,23 @@ def run_b200(args):
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3
 
+    # inversion-side operators on the HBM-resident J: weighted J.x, J^T.y and the coverage, each one
+    # pass over this rank's rows of J; wall clock around the synchronous C-ABI call (includes the small vector copies)
+    jops = None
+    if world == 1:
+        Jop = fop.core.jacobian()
+        lw, rw = np.full(Jop.rows(), 0.5), np.full(Jop.cols(), 2.0)
+        jops = {}
+        for name, fn in (("mult_lr", lambda: Jop.mult_lr(x_host, lw, rw)), ("tmult_lr", lambda: Jop.transMult_lr(y_host, lw, rw)),
+                         ("coverage_trans", lambda: Jop.coverageDCtrans(lw, rw))):
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                fn()
+            jops[name + "_ms"] = (time.perf_counter() - t0) * 1e3 / 5
+        jops["bytes_per_pass"] = 8.0 * Jop.rows() * Jop.cols()
+        jops["GBps"] = {k[:-3]: jops["bytes_per_pass"] / (v * 1e-3) / 1e9 for k, v in jops.items() if k.endswith("_ms")}
+
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -324,6 +341,8 @@ def run_b200(args):
             "gpu_launches": int(st["launches"]),
             "clocks": clocks,
         }
+        if jops:
+            line["jacobian_ops"] = jops
         if world == 1 and not args.no_cpu_baseline:
             try:
                 from oracle import ref

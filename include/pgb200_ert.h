@@ -169,6 +169,15 @@ int pgb200_ert_jacobian_copy(pgb200_ert *h, double *j_host);
 /* y = J x  and  y = J^T x  with host vectors (jacobian().mult / transMult).              */
 int pgb200_ert_jacobian_mult(pgb200_ert *h, const double *x_host, double *y_host);
 int pgb200_ert_jacobian_tmult(pgb200_ert *h, const double *x_host, double *y_host);
+/* Error-/transform-weighted Jacobian of the inversion (MultLeftRightMatrix, pygimli/frameworks/inversion.py:705-708):
+ *   mult_lr   y[D_local] = left .* (J (right .* x)),    tmult_lr   y[M] = right .* (J^T (left .* x)).
+ * left has D_local entries, right has M; either may be NULL (= ones).  J never leaves HBM.   */
+int pgb200_ert_jacobian_mult_lr(pgb200_ert *h, const double *left_host, const double *right_host, const double *x_host, double *y_host);
+int pgb200_ert_jacobian_tmult_lr(pgb200_ert *h, const double *left_host, const double *right_host, const double *x_host, double *y_host);
+/* coverageDCtrans (core/src/bert/bertJacobian.cpp:569-598, RMatrix branch): cov[j] = sum_i |J_ij dd_i| / |mm_j|.
+ * dd has D_local entries, mm has M; mm == NULL returns the undivided column sums (the partial result of a row shard,
+ * to be summed over the ranks and divided afterwards).                                        */
+int pgb200_ert_coverage_trans(pgb200_ert *h, const double *dd_host, const double *mm_host, double *cov_host);
 
 /* ---- the path: DEVICE buffers (inputs already resident in HBM) ---------------------- */
 int pgb200_ert_response_dev(pgb200_ert *h, const double *model_dev, int n_model_in, double *rhoa_dev);

@@ -284,3 +284,28 @@ def refine(mesh, kind):
     L.ref_mesh_export(h, _d(out["pos"]), _i(out["node_marker"]), _i(out["cells"]), _i(out["cell_marker"]),
                       _i(out["bounds"]), _i(out["bound_marker"]))
     return out
+
+
+def coverage_trans(J, dd, mm):
+    """the reference's coverageDCtrans (core/src/bert/bertJacobian.cpp:569) on a dense matrix"""
+    J = np.ascontiguousarray(J, np.float64)
+    dd = np.ascontiguousarray(dd, np.float64)
+    mm = np.ascontiguousarray(mm, np.float64)
+    out = np.zeros(J.shape[1])
+    lib().ref_coverage_trans(C.c_int(J.shape[0]), C.c_int(J.shape[1]), _d(J), _d(dd), _d(mm), _d(out))
+    return out
+
+
+def create_coverage(J, mesh, response=None, model=None):
+    """the reference's createCoverage (core/src/bert/bertJacobian.cpp:600-628); ``mesh`` is the parameter mesh"""
+    J = np.ascontiguousarray(J, np.float64)
+    pos = np.ascontiguousarray(mesh.pos, np.float64)
+    cells = np.ascontiguousarray(mesh.cells, np.int32)
+    cm = np.ascontiguousarray(mesh.cell_marker, np.int32)
+    out = np.zeros(cells.shape[0])
+    r = None if response is None else np.ascontiguousarray(response, np.float64)
+    m = None if model is None else np.ascontiguousarray(model, np.float64)
+    lib().ref_create_coverage(C.c_int(J.shape[0]), C.c_int(J.shape[1]), _d(J), C.c_int(mesh.dim), C.c_int(pos.shape[0]), _d(pos),
+                              C.c_int(cells.shape[0]), C.c_int(cells.shape[1]), _i(cells), _i(cm),
+                              _d(r) if r is not None else None, _d(m) if m is not None else None, _d(out))
+    return out

@@ -269,6 +269,41 @@ void ref_sensitivity_only(void * vh, int nThreads, int nRowsPots, const double *
     if (outJ) for (Index i = 0; i < J.rows(); i++) std::memcpy(outJ + i*J.cols(), &J[i][0], J.cols()*sizeof(double));
 }
 
+// coverageDCtrans (bertJacobian.cpp:569-598) on a dense row-major matrix handed in by the caller
+void ref_coverage_trans(int rows, int cols, const double * J, const double * dd, const double * mm, double * out){
+    RMatrix S(rows, cols);
+    for (int i = 0; i < rows; i++) std::memcpy(&S[i][0], J + (size_t)i*cols, cols*sizeof(double));
+    RVector d(rows), m(cols);
+    for (int i = 0; i < rows; i++) d[i] = dd[i];
+    for (int j = 0; j < cols; j++) m[j] = mm[j];
+    RVector cov(coverageDCtrans(S, d, m));
+    for (int j = 0; j < cols; j++) out[j] = cov[j];
+}
+// createCoverage (bertJacobian.cpp:600-628) with the parameter mesh given as flat arrays; out has nCells entries
+void ref_create_coverage(int rows, int cols, const double * J, int dim, int nNodes, const double * xyz,
+                         int nCells, int nloc, const int * cells, const int * cellMarker,
+                         const double * response, const double * model, double * out){
+    RMatrix S(rows, cols);
+    for (int i = 0; i < rows; i++) std::memcpy(&S[i][0], J + (size_t)i*cols, cols*sizeof(double));
+    Mesh mesh(dim);
+    for (int i = 0; i < nNodes; i++) mesh.createNode(xyz[3*i], xyz[3*i+1], xyz[3*i+2], 0);
+    for (int c = 0; c < nCells; c++){
+        IndexArray ids(nloc);
+        for (int j = 0; j < nloc; j++) ids[j] = cells[c*nloc + j];
+        mesh.createCell(ids, cellMarker[c]);
+    }
+    RVector cov;
+    if (response && model){
+        RVector r(rows), m(cols);
+        for (int i = 0; i < rows; i++) r[i] = response[i];
+        for (int j = 0; j < cols; j++) m[j] = model[j];
+        cov = createCoverage(S, mesh, r, m);
+    } else {
+        cov = createCoverage(S, mesh);
+    }
+    for (int c = 0; c < nCells; c++) out[c] = cov[c];
+}
+
 int ref_subpot_rows(void * vh){ return (int)((RefHandle *)vh)->subPots->rows(); }
 // k-resolved potentials, row = electrode + nE*kIdx (dcfemmodelling.cpp:1681)
 void ref_get_subpotentials(void * vh, double * out){

@@ -1095,25 +1095,58 @@ k_jacobian(const JacArgs A) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
-// y = J x  (J column-major [cols][ld]):  y[d] = sum_j Jt[j][d] x[j]
-__global__ void k_jac_mult(const double *__restrict__ Jt, size_t ld, int rows, int cols, const double *__restrict__ x, double *__restrict__ y) {
+// y = l .* (J (r .* x))  (J column-major [cols][ld]):  y[d] = l[d] * sum_j Jt[j][d] r[j] x[j];  l, r optional
+// (MultLeftRightMatrix of the inversion, pygimli/frameworks/inversion.py:705-708)
+__global__ void k_jac_mult(const double *__restrict__ Jt, size_t ld, int rows, int cols, const double *__restrict__ x,
+                           const double *__restrict__ left, const double *__restrict__ right, double *__restrict__ y) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= rows) return;
     const int j0 = blockIdx.y * 256, j1 = min(cols, j0 + 256);
-    double acc = 0.0;
-    for (int j = j0; j < j1; j++) acc = fma(Jt[(size_t)j * ld + d], x[j], acc);
-    atomicAdd(y + d, acc);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int j = j0;
+    for (; j + 4 <= j1; j += 4) {
+        const double *c = Jt + (size_t)j * ld + d;
+        const double v0 = c[0], v1 = c[ld], v2 = c[2 * ld], v3 = c[3 * ld];
+        a0 = fma(v0, right ? x[j] * right[j] : x[j], a0);
+        a1 = fma(v1, right ? x[j + 1] * right[j + 1] : x[j + 1], a1);
+        a2 = fma(v2, right ? x[j + 2] * right[j + 2] : x[j + 2], a2);
+        a3 = fma(v3, right ? x[j + 3] * right[j + 3] : x[j + 3], a3);
+    }
+    for (; j < j1; j++) a0 = fma(Jt[(size_t)j * ld + d], right ? x[j] * right[j] : x[j], a0);
+    const double acc = (a0 + a1) + (a2 + a3);
+    atomicAdd(y + d, left ? left[d] * acc : acc);
 }
-// y = J^T x:  y[j] = sum_d Jt[j][d] x[d]   (one warp per column)
-__global__ void k_jac_tmult(const double *__restrict__ Jt, size_t ld, int rows, int cols, const double *__restrict__ x, double *__restrict__ y) {
+// one warp per column j of J^T:
+//   MODE 0  y[j] = r[j] * sum_d Jt[j][d] l[d] x[d]            (transMult; l, r optional)
+//   MODE 1  y[j] = sum_d |Jt[j][d] x[d]| / |r[j]|             (coverageDCtrans, bertJacobian.cpp:569-598; x = dd, r = mm)
+//   MODE 2  y[j] = sum_d |Jt[j][d] x[d]|                      (partial coverage of a row shard; divided after the all-reduce)
+template <int MODE>
+__global__ void k_jac_tmult(const double *__restrict__ Jt, size_t ld, int rows, int cols, const double *__restrict__ x,
+                            const double *__restrict__ left, const double *__restrict__ right, double *__restrict__ y) {
     const int j = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     if (j >= cols) return;
     const int lane = threadIdx.x & 31;
-    double acc = 0.0;
-    for (int d = lane; d < rows; d += 32) acc = fma(Jt[(size_t)j * ld + d], x[d], acc);
+    const double *c = Jt + (size_t)j * ld;
+    double a0 = 0.0, a1 = 0.0;
+    int d = lane;
+    for (; d + 32 < rows; d += 64) {
+        const double v0 = c[d], v1 = c[d + 32];
+        const double x0 = (MODE == 0 && left) ? left[d] * x[d] : x[d], x1 = (MODE == 0 && left) ? left[d + 32] * x[d + 32] : x[d + 32];
+        if (MODE == 0) { a0 = fma(v0, x0, a0); a1 = fma(v1, x1, a1); }
+        else { a0 += fabs(v0 * x0); a1 += fabs(v1 * x1); }
+    }
+    if (d < rows) {
+        const double x0 = (MODE == 0 && left) ? left[d] * x[d] : x[d];
+        if (MODE == 0) a0 = fma(c[d], x0, a0); else a0 += fabs(c[d] * x0);
+    }
+    double acc = a0 + a1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) y[j] = acc;
+    if (lane == 0) {
+        if (MODE == 0) y[j] = right ? right[j] * acc : acc;
+        else if (MODE == 1) y[j] = acc / fabs(right[j]);
+        else y[j] = acc;
+    }
 }
 // row-major copy of the column-major J: out[d][j] = Jt[j][d]
 __global__ void k_jac_to_rowmajor(const double *__restrict__ Jt, size_t ld, int rows, int cols, double *__restrict__ out) {

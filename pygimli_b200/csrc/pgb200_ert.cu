@@ -891,7 +891,7 @@ int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
     CK(cudaMemsetAsync(h->U.p, 0, blk * sizeof(double), st));
     CK(cudaMemsetAsync(h->P.p, 0, blk * sizeof(double), st)); CK(cudaMemsetAsync(h->AP.p, 0, blk * sizeof(double), st));
     CKR(h->scal.alloc(7 * h->ld)); CKR(h->pM.alloc((size_t)nE * nE)); CKR(h->resp.alloc(h->D)); CKR(h->resp_rez.alloc(h->D)); CKR(h->rhoa.alloc(h->D));
-    CKR(h->flags.alloc(4)); CKR(h->xin.alloc(std::max(h->M, h->D))); CKR(h->yout.alloc(std::max(h->M, h->D)));
+    CKR(h->flags.alloc(4)); CKR(h->xin.alloc(3 * (size_t)std::max(h->M, h->D))); CKR(h->yout.alloc(std::max(h->M, h->D)));
     for (int i = 0; i <= PH_COUNT; i++) CK(cudaEventCreate(&h->ev[i]));
     CK(cudaEventCreate(&h->jev[0])); CK(cudaEventCreate(&h->jev[1]));
     h->ev_ok = true;
@@ -1159,27 +1159,60 @@ int pgb200_ert_jacobian_copy(pgb200_ert *h, double *j_host) {
     return 0;
 }
 
-int pgb200_ert_jacobian_mult(pgb200_ert *h, const double *x_host, double *y_host) {
+// stage optional host scaling vectors next to x: xin = [x | left | right] (each max(M, D) doubles)
+static int jac_stage(pgb200_ert *h, const double *x, int nx, const double *left, const double *right, const double **dl, const double **dr) {
+    const size_t blk = (size_t)std::max(h->M, h->D);
+    if (nx > 0) CK(cudaMemcpyAsync(h->xin.p, x, sizeof(double) * nx, cudaMemcpyHostToDevice, h->st));
+    *dl = nullptr; *dr = nullptr;
+    if (left && h->j_rows) { CK(cudaMemcpyAsync(h->xin.p + blk, left, sizeof(double) * h->j_rows, cudaMemcpyHostToDevice, h->st)); *dl = h->xin.p + blk; }
+    if (right) { CK(cudaMemcpyAsync(h->xin.p + 2 * blk, right, sizeof(double) * h->M, cudaMemcpyHostToDevice, h->st)); *dr = h->xin.p + 2 * blk; }
+    return 0;
+}
+
+int pgb200_ert_jacobian_mult_lr(pgb200_ert *h, const double *left_host, const double *right_host, const double *x_host, double *y_host) {
     if (!h || !x_host || !y_host) PGB_FAIL("null argument");
     if (!h->jac_valid) PGB_FAIL("no Jacobian: call createJacobian first");
     CK(cudaSetDevice(h->device));
-    CK(cudaMemcpyAsync(h->xin.p, x_host, sizeof(double) * h->M, cudaMemcpyHostToDevice, h->st));
+    const double *dl, *dr;
+    CKR(jac_stage(h, x_host, h->M, left_host, right_host, &dl, &dr));
     CK(cudaMemsetAsync(h->yout.p, 0, sizeof(double) * std::max(1, h->j_rows), h->st));
-    if (h->j_rows) { k_jac_mult<<<dim3(cdiv(h->j_rows, 128), cdiv(h->M, 256)), 128, 0, h->st>>>(h->Jt.p, h->ldJ, h->j_rows, h->M, h->xin.p, h->yout.p); LAUNCH(h); }
+    if (h->j_rows) { k_jac_mult<<<dim3(cdiv(h->j_rows, 128), cdiv(h->M, 256)), 128, 0, h->st>>>(h->Jt.p, h->ldJ, h->j_rows, h->M, h->xin.p, dl, dr, h->yout.p); LAUNCH(h); }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(y_host, h->yout.p, sizeof(double) * h->j_rows, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     return 0;
 }
+int pgb200_ert_jacobian_mult(pgb200_ert *h, const double *x_host, double *y_host) {
+    return pgb200_ert_jacobian_mult_lr(h, nullptr, nullptr, x_host, y_host);
+}
 
-int pgb200_ert_jacobian_tmult(pgb200_ert *h, const double *x_host, double *y_host) {
+int pgb200_ert_jacobian_tmult_lr(pgb200_ert *h, const double *left_host, const double *right_host, const double *x_host, double *y_host) {
     if (!h || !x_host || !y_host) PGB_FAIL("null argument");
     if (!h->jac_valid) PGB_FAIL("no Jacobian: call createJacobian first");
     CK(cudaSetDevice(h->device));
-    CK(cudaMemcpyAsync(h->xin.p, x_host, sizeof(double) * std::max(1, h->j_rows), cudaMemcpyHostToDevice, h->st));
-    k_jac_tmult<<<cdiv(h->M, 8), 256, 0, h->st>>>(h->Jt.p, h->ldJ, h->j_rows, h->M, h->xin.p, h->yout.p); LAUNCH(h);
+    const double *dl, *dr;
+    CKR(jac_stage(h, x_host, h->j_rows, left_host, right_host, &dl, &dr));
+    k_jac_tmult<0><<<cdiv(h->M, 8), 256, 0, h->st>>>(h->Jt.p, h->ldJ, h->j_rows, h->M, h->xin.p, dl, dr, h->yout.p); LAUNCH(h);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(y_host, h->yout.p, sizeof(double) * h->M, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+int pgb200_ert_jacobian_tmult(pgb200_ert *h, const double *x_host, double *y_host) {
+    return pgb200_ert_jacobian_tmult_lr(h, nullptr, nullptr, x_host, y_host);
+}
+
+int pgb200_ert_coverage_trans(pgb200_ert *h, const double *dd_host, const double *mm_host, double *cov_host) {
+    if (!h || !dd_host || !cov_host) PGB_FAIL("null argument");
+    if (!h->jac_valid) PGB_FAIL("no Jacobian: call createJacobian first");
+    CK(cudaSetDevice(h->device));
+    const double *dl, *dr;
+    CKR(jac_stage(h, dd_host, h->j_rows, nullptr, mm_host, &dl, &dr));
+    if (mm_host) k_jac_tmult<1><<<cdiv(h->M, 8), 256, 0, h->st>>>(h->Jt.p, h->ldJ, h->j_rows, h->M, h->xin.p, nullptr, dr, h->yout.p);
+    else k_jac_tmult<2><<<cdiv(h->M, 8), 256, 0, h->st>>>(h->Jt.p, h->ldJ, h->j_rows, h->M, h->xin.p, nullptr, nullptr, h->yout.p);
+    LAUNCH(h);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(cov_host, h->yout.p, sizeof(double) * h->M, cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     return 0;
 }

@@ -10,7 +10,7 @@ What shards, and what is exchanged:
     by current dipole so a shard touches few current electrodes).  A row needs the potentials
     of a, b, m and n, so the k-resolved potentials are exchanged ONCE per iteration with an
     NCCL all-gather (N x nS doubles in total); everything else stays local.
-  * J.x needs an all-gather of D doubles, J^T.y an all-reduce of M doubles.
+  * J.x needs an all-gather of D doubles, J^T.y and the coverage (column sums of |J|) an all-reduce of M doubles.
 torch.distributed is plumbing only; all arithmetic is in libpgb200_ert.so.
 """
 from __future__ import annotations
@@ -187,6 +187,18 @@ class ShardedERT:
         t = torch.from_numpy(x_loc).to(f"cuda:{self.device}")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t.cpu().numpy()
+
+    def coverage_trans(self, dd: np.ndarray, mm: np.ndarray) -> np.ndarray:
+        """coverageDCtrans (bertJacobian.cpp:569) over the row-sharded J: local column sums of |J_ij dd_i|, one
+        all-reduce of M doubles, then the division by |mm|"""
+        if self.world == 1:
+            return self.core.jacobian().coverageDCtrans(dd, mm)
+        torch, dist = self._torch()
+        ddp = np.asarray(dd, float)[self.perm][self.rows[0]: self.rows[1]]
+        part = self.core.jacobian().coverageDCtrans(ddp) if ddp.size else np.zeros(self.M)
+        t = torch.from_numpy(part).to(f"cuda:{self.device}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy() / np.abs(np.asarray(mm, float))
 
     def jacobian_rows(self) -> np.ndarray:
         """this rank's rows of J (row-major), and their ORIGINAL data indices"""

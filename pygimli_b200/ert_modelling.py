@@ -81,6 +81,44 @@ class JacobianB200:
         _capi.check(_capi.lib().pgb200_ert_jacobian_tmult(self._core._h, y.ctypes.data, x.ctypes.data))
         return x
 
+    # ---- weighted products and coverage: J stays in HBM -------------------
+    def _vec(self, v, n, what):
+        if v is None:
+            return None
+        v = np.ascontiguousarray(v, np.float64)
+        if v.size != n:
+            raise ValueError(f"{what}: vector length {v.size} does not fit ({n})")
+        return v
+
+    def mult_lr(self, x, left=None, right=None):
+        """left .* (J (right .* x)) -- MultLeftRightMatrix.mult (pygimli/frameworks/inversion.py:705-708)"""
+        x = self._vec(x, self.cols(), "mult")
+        left, right = self._vec(left, self.rows(), "left"), self._vec(right, self.cols(), "right")
+        y = np.zeros(self.rows())
+        _capi.check(_capi.lib().pgb200_ert_jacobian_mult_lr(
+            self._core._h, left.ctypes.data if left is not None else None, right.ctypes.data if right is not None else None,
+            x.ctypes.data, y.ctypes.data))
+        return y
+
+    def transMult_lr(self, y, left=None, right=None):
+        """right .* (J^T (left .* y)) -- MultLeftRightMatrix.transMult"""
+        y = self._vec(y, self.rows(), "transMult")
+        left, right = self._vec(left, self.rows(), "left"), self._vec(right, self.cols(), "right")
+        x = np.zeros(self.cols())
+        _capi.check(_capi.lib().pgb200_ert_jacobian_tmult_lr(
+            self._core._h, left.ctypes.data if left is not None else None, right.ctypes.data if right is not None else None,
+            y.ctypes.data, x.ctypes.data))
+        return x
+
+    def coverageDCtrans(self, dd, mm=None):
+        """cov[j] = sum_i |J_ij dd_i| / |mm_j|  (core/src/bert/bertJacobian.cpp:569-598); mm=None -> undivided sums"""
+        dd = self._vec(dd, self.rows(), "dd")
+        mm = self._vec(mm, self.cols(), "mm")
+        cov = np.zeros(self.cols())
+        _capi.check(_capi.lib().pgb200_ert_coverage_trans(self._core._h, dd.ctypes.data, mm.ctypes.data if mm is not None else None,
+                                                          cov.ctypes.data))
+        return cov
+
     def numpy(self) -> np.ndarray:
         r, c = self.shape
         out = np.zeros((r, c))
@@ -98,6 +136,54 @@ class JacobianB200:
             __cuda_array_interface__ = dict(shape=(cols, ld), typestr="<f8", data=(ptr, False), version=3, strides=None)
         t = torch.as_tensor(_Iface(), device=f"cuda:{self._core.device}")
         return t[:, :rows].t()
+
+
+class MultLeftRightMatrixB200:
+    """``pg.matrix.MultLeftRightMatrix(J, left, right)`` over the HBM-resident Jacobian: the error-/transform-weighted
+    Jacobian the Gauss-Newton inversion hands to its LSQR/CG solver (pygimli/frameworks/inversion.py:705-708, 776-779)."""
+
+    def __init__(self, A: JacobianB200, left, right):
+        if A.cols() != len(right):
+            raise Exception("Matrix columns do not fit right vector length!")
+        if A.rows() != len(left):
+            raise Exception("Matrix rows do not fit left vector length!")
+        self.A = A
+        self.l = np.ascontiguousarray(left, np.float64)
+        self.r = np.ascontiguousarray(right, np.float64)
+
+    def rows(self):
+        return self.A.rows()
+
+    def cols(self):
+        return self.A.cols()
+
+    def mult(self, x):
+        return self.A.mult_lr(x, self.l, self.r)
+
+    def transMult(self, y):
+        return self.A.transMult_lr(y, self.l, self.r)
+
+
+def coverageDCtrans(S: JacobianB200, dd, mm):
+    """drop-in for ``pg.core.coverageDCtrans(S, dd, mm)`` (core/src/bert/bertJacobian.cpp:569)"""
+    return S.coverageDCtrans(dd, mm)
+
+
+def createCoverage(S: JacobianB200, mesh, response=None, model=None):
+    """drop-in for ``pg.core.createCoverage(S, mesh[, response, model])`` (core/src/bert/bertJacobian.cpp:600-628):
+    coverageDCtrans(S, 1/response, 1/model) looked up per cell of ``mesh`` (the parameter domain, markers 0..M-1) and
+    divided by the cell sizes.  The reference's branch for cellCount != len(model) cannot succeed (it sizes the
+    per-marker accumulator by cells and then requires every entry to be positive), so that case raises here."""
+    mesh = _as_mesh(mesh)
+    response = np.ones(S.rows()) if response is None else np.asarray(response, float)
+    model = np.ones(S.cols()) if model is None else np.asarray(model, float)
+    cov_model = S.coverageDCtrans(1.0 / response, 1.0 / model)
+    marker = np.asarray(mesh.cell_marker)
+    if marker.min() < 0 or marker.max() >= cov_model.size:
+        raise IndexError("createCoverage: cell markers of the mesh must index the model vector")
+    if mesh.cell_count != model.size:
+        raise RuntimeError(f"Coverage fails:{mesh.cell_count} {model.size}")
+    return cov_model[marker] / mesh.cell_sizes()
 
 
 class CoreB200:

@@ -66,3 +66,23 @@ def make_case(name: str):
     M = int(mesh.cell_marker.max()) + 1
     model = _model(mesh.cell_count if name.endswith("cellmodel") else M)
     return mesh, scheme, model
+
+
+def coverage_case(dim: int, seed: int = 77):
+    """-> (parameter mesh with one cell per model entry and shuffled markers, dense J, dd, mm, response, model):
+    seeded inputs of the coverage tests (coverageDCtrans / createCoverage, bertJacobian.cpp:569-628)"""
+    rng = np.random.default_rng(seed + dim)
+    if dim == 2:
+        mesh = grid_mesh_2d(graded_axis(0.0, 6.0, 1.0, 1.3, 0.0), -graded_axis(0.0, 3.0, 0.5, 1.3, 0.0, both=False))
+    else:
+        ax = graded_axis(0.0, 3.0, 1.0, 1.3, 0.0)
+        mesh = grid_mesh_3d(ax, ax, -graded_axis(0.0, 2.0, 1.0, 1.3, 0.0, both=False))
+    M = mesh.cell_count
+    mesh.cell_marker = rng.permutation(M).astype(np.int32)
+    D = 37
+    J = rng.standard_normal((D, M)) * 10.0 ** rng.uniform(-6, 0, size=(D, 1))
+    dd = rng.standard_normal(D)
+    mm = rng.standard_normal(M) + 3.0
+    resp = 10.0 ** rng.uniform(1, 3, D)
+    model = 10.0 ** rng.uniform(1, 3, M)
+    return mesh, J, dd, mm, resp, model

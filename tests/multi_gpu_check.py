@@ -38,9 +38,12 @@ def main():
         e_J = np.max(np.abs(Jloc - J1[rows])) / np.max(np.abs(J1)) if rows.size else 0.0
         e_x = np.max(np.abs(sh.jac_mult(x) - J1 @ x)) / np.max(np.abs(J1 @ x))
         e_y = np.max(np.abs(sh.jac_tmult(y) - J1.T @ y)) / np.max(np.abs(J1.T @ y))
-        good = e_r < 1e-9 and e_J < 1e-9 and e_x < 1e-9 and e_y < 1e-9
+        dd, mm = 1.0 / r1, 1.0 / model
+        cov1 = np.abs(J1 * dd[:, None]).sum(0) / np.abs(mm)
+        e_c = np.max(np.abs(sh.coverage_trans(dd, mm) - cov1)) / np.max(cov1)
+        good = e_r < 1e-9 and e_J < 1e-9 and e_x < 1e-9 and e_y < 1e-9 and e_c < 1e-9
         ok = ok and good
-        print(f"rank {rank} {name}: rows {rows.size} sources {sh.n_local_sources}  rhoa {e_r:.2e}  J {e_J:.2e}  Jx {e_x:.2e}  JTy {e_y:.2e}  {'OK' if good else 'FAIL'}", flush=True)
+        print(f"rank {rank} {name}: rows {rows.size} sources {sh.n_local_sources}  rhoa {e_r:.2e}  J {e_J:.2e}  Jx {e_x:.2e}  JTy {e_y:.2e}  cov {e_c:.2e}  {'OK' if good else 'FAIL'}", flush=True)
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

@@ -73,3 +73,31 @@ def test_potential_exchange_layout_gloo():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, 37, 11, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world))
+
+
+def _coverage_worker(rank, world, port, out):
+    """row-sharded coverageDCtrans: local column sums of |J_ij dd_i| over this rank's (a,b)-ordered rows, one
+    all-reduce, division by |mm| afterwards -- the exchange ShardedERT.coverage_trans performs with NCCL"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle.ert_oracle import coverage_dc_trans
+    rng = np.random.default_rng(3)
+    D, M = 23, 17
+    J, dd, mm = rng.standard_normal((D, M)), rng.standard_normal(D), rng.standard_normal(M) + 2.0
+    perm = rng.permutation(D)                                           # stands in for row_order(scheme)
+    lo, hi = split_range(D, world, rank)
+    rows = perm[lo:hi]
+    part = torch.from_numpy(np.abs(J[rows] * dd[rows, None]).sum(0))
+    dist.all_reduce(part)
+    got = part.numpy() / np.abs(mm)
+    out[rank] = bool(np.allclose(got, coverage_dc_trans(J, dd, mm), rtol=1e-13, atol=0.0))
+    dist.destroy_process_group()
+
+
+def test_sharded_coverage_gloo():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_coverage_worker, args=(world, port, out), nprocs=world, join=True)
+    assert all(out[r] for r in range(world))
