@@ -100,6 +100,10 @@ typedef struct pgb200_plan {
 
     const int *abmn;            /* [D*4] electrode indices, -1 = unused                      */
     const double *k_fac;        /* [D] geometric factors                                     */
+
+    int topography;             /* 1: non-flat surface or pure-Neumann domain (dcfemmodelling.cpp:718-754): no analytic
+                                 * primary potentials / analytic branches; with sr = 1 the primary potentials must be
+                                 * supplied through pgb200_ert_set_primary_dev before the first solve (:2009-2056)  */
 } pgb200_plan;
 
 /* One coarse level of the aggregation hierarchy of the multilevel preconditioner (host pointers, copied).
@@ -178,6 +182,12 @@ int pgb200_ert_jacobian_tmult_lr(pgb200_ert *h, const double *left_host, const d
  * dd has D_local entries, mm has M; mm == NULL returns the undivided column sums (the partial result of a row shard,
  * to be summed over the ranks and divided afterwards).                                        */
 int pgb200_ert_coverage_trans(pgb200_ert *h, const double *dd_host, const double *mm_host, double *cov_host);
+
+/* Numeric primary potentials for the singularity-removal path with topography (checkPrimpotentials_,
+ * dcfemmodelling.cpp:2009-2056: total-field solve for rho = 1 on the P2-refined mesh, taken at the nodes of this mesh).
+ * src_dev: node-major potentials of the primary handle ([n_src_nodes][src_ld], column = electrode + nE * k, see
+ * pgb200_ert_potentials_info); row_map_host[i] = row of src_dev holding node i of THIS handle (plan numbering).  */
+int pgb200_ert_set_primary_dev(pgb200_ert *h, const double *src_dev, long long src_ld, const int *row_map_host);
 
 /* ---- the path: DEVICE buffers (inputs already resident in HBM) ---------------------- */
 int pgb200_ert_response_dev(pgb200_ert *h, const double *model_dev, int n_model_in, double *rhoa_dev);

@@ -137,6 +137,10 @@ class RefERT:
         w = np.ascontiguousarray(w, np.float64)
         lib().ref_set_kw(self.h, C.c_int(k.size), _d(k), _d(w))
 
+    def set_primary_from(self, p2_handle: "RefERT"):
+        """numeric primary potentials from a total-field run on the P2 mesh (see ref_driver.cpp ref_set_primary_from)"""
+        return int(lib().ref_set_primary_from(self.h, p2_handle.h))
+
     def topography(self):
         return bool(lib().ref_topography(self.h))
 

@@ -23,6 +23,7 @@
 #include <sparsematrix.h>
 #include <solverWrapper.h>
 #include <matrix.h>
+#include <interpolate.h>
 #include <stopwatch.h>
 #include <bert/bert.h>
 #include <bert/dcfemmodelling.h>
@@ -113,6 +114,7 @@ struct RefHandle {
     InjectedSolver * solver;
     RMatrix * subPots;
     bool sr;
+    RMatrix * prim;      // numeric primary potentials handed to the SR fop (topography), owned here
 };
 
 } // namespace
@@ -164,7 +166,7 @@ void * ref_create(int dim, int nNodes, const double * xyz, const int * nodeMarke
 
 void ref_destroy(void * vh){
     RefHandle * h = (RefHandle *)vh;
-    delete h->fop; delete h->solver; delete h->subPots; delete h->data; delete h->mesh; delete h;
+    delete h->fop; delete h->solver; delete h->subPots; delete h->data; delete h->mesh; if (h->prim) delete h->prim; delete h;
 }
 
 void ref_set_solver_callbacks(void * vh, set_matrix_cb a, solve_cb b){
@@ -324,6 +326,20 @@ int ref_get_primary(void * vh, double * out){
     return (int)U.rows();
 }
 
+// Numeric primary potentials the way checkPrimpotentials_ builds them with topography (dcfemmodelling.cpp:2009-2056):
+// k-resolved potentials of a total-field run (rho = 1) on the P2 mesh of handle vp -- collected by its response() --
+// interpolated to the node positions of the SR handle vs (interpolate.h:75) and handed over with setPrimaryPotential.
+// (The reference's own temporary fop inside checkPrimpotentials_ cannot take the injected solver, and no CHOLMOD is
+// installed here; this performs the same three steps from the outside.)
+int ref_set_primary_from(void * vs, void * vp){
+    RefHandle * s = (RefHandle *)vs; RefHandle * p = (RefHandle *)vp;
+    if (!s->sr || p->subPots->rows() == 0) return 0;
+    if (s->prim) delete s->prim;
+    s->prim = new RMatrix();
+    interpolate(*p->mesh, *p->subPots, s->mesh->positions(), *s->prim, false);
+    dynamic_cast< DCSRMultiElectrodeModelling * >(s->fop)->setPrimaryPotential(*s->prim);
+    return (int)s->prim->rows();
+}
 // CSR pattern exactly as SparseMatrix::buildSparsityPattern (sparsematrix.h:966)
 int ref_pattern(void * vh, int * rowptr, int * colidx){
     RefHandle * h = (RefHandle *)vh;

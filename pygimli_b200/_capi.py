@@ -38,6 +38,7 @@ class Plan(C.Structure):
         ("lidx", C.POINTER(C.c_ushort)), ("self_idx", C.POINTER(C.c_ushort)),
         ("n_jac_cells", C.c_int), ("jac_cells", c_int_p), ("jac_col_ptr", c_int_p),
         ("abmn", c_int_p), ("k_fac", c_dbl_p),
+        ("topography", C.c_int),
     ]
 
 
@@ -55,7 +56,7 @@ EXPORTS = [
     "pgb200_ert_jacobian_info", "pgb200_ert_clear_potentials", "pgb200_ert_potentials_info",
     "pgb200_ert_mark_potentials_valid", "pgb200_ert_forward_dev", "pgb200_ert_pm_info", "pgb200_ert_finish_response_dev",
     "pgb200_ert_pack_potentials", "pgb200_ert_get", "pgb200_ert_stats", "pgb200_ert_reset_stats", "pgb200_ert_set_profile",
-    "pgb200_spmm", "pgb200_ert_jacobian_mult_lr", "pgb200_ert_jacobian_tmult_lr", "pgb200_ert_coverage_trans",
+    "pgb200_spmm", "pgb200_ert_set_primary_dev", "pgb200_ert_jacobian_mult_lr", "pgb200_ert_jacobian_tmult_lr", "pgb200_ert_coverage_trans",
 ]
 
 _lib = None
@@ -94,6 +95,7 @@ def lib():
         L.pgb200_ert_jacobian_mult_lr.argtypes = [C.c_void_p] * 5
         L.pgb200_ert_jacobian_tmult_lr.argtypes = [C.c_void_p] * 5
         L.pgb200_ert_coverage_trans.argtypes = [C.c_void_p] * 4
+        L.pgb200_ert_set_primary_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
         L.pgb200_ert_jacobian_info.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), c_int_p, c_int_p, C.POINTER(C.c_longlong)]
         L.pgb200_ert_potentials_info.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), c_int_p, c_int_p, C.POINTER(C.c_longlong)]
         L.pgb200_ert_forward_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -215,6 +217,7 @@ def make_plan_struct(P, sr: bool):
     s.n_elec, s.n_k, s.n_model, s.n_data, s.sr = P.nE, P.nK, P.M, P.scheme.size, 1 if sr else 0
     s.fullspace = 1 if P.surface_z <= -1e300 else 0
     s.surface_z = 0.0 if s.fullspace else P.surface_z
+    s.topography = 1 if getattr(P, "topography", False) else 0
     s.pos, s.cells, s.cell_marker = D(P.mesh.pos), I(P.mesh.cells), I(P.cell_marker)
     s.rowptr, s.colidx, s.diag_pos = I(P.rowptr), I(P.colidx), I(P.diag_pos)
     s.n_colors, s.color_ptr, s.color_order = P.n_colors, I(P.color_ptr), I(P.color_order)

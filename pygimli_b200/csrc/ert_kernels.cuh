@@ -752,6 +752,15 @@ __global__ void k_amg_prolong(const double *__restrict__ dinvw, int n, const int
     X[o] = x;
 }
 
+// numeric primary potentials: prim[i][c] = SRC[map[i]][c]  (rows of the P2 primary solve at this mesh's nodes)
+__global__ void k_gather_rows(const double *__restrict__ SRC, size_t ld_src, const int *__restrict__ map, int n, int ncols,
+                              size_t ld, double *__restrict__ OUT) {
+    const int col = blockIdx.y * blockDim.x + threadIdx.x;
+    const int row = blockIdx.x * blockDim.y + threadIdx.y;
+    if (col >= ncols || row >= n) return;
+    OUT[(size_t)row * ld + col] = SRC[(size_t)map[row] * ld_src + col];
+}
+
 // total field  U = X + rho_src * prim   (:2287)  /  analytic branch  U = scale * prim (:1295-1300)
 __global__ void k_finalize_pots(const double *__restrict__ Xv, const double *__restrict__ prim, const double *__restrict__ rho_src,
                                 double scale, int N, int nE, int c0, int c1, size_t ld, double *__restrict__ U) {

@@ -69,7 +69,8 @@ struct AmgLevel {      // one coarse level of the aggregation hierarchy (device 
 
 struct pgb200_ert {
     // sizes
-    int dim = 0, nloc = 0, elem = 0, N = 0, C = 0, nE = 0, nK = 0, nS = 0, M = 0, D = 0, sr = 1, fullspace = 0;
+    int dim = 0, nloc = 0, elem = 0, N = 0, C = 0, nE = 0, nK = 0, nS = 0, M = 0, D = 0, sr = 1, fullspace = 0, topography = 0;
+    bool prim_set = false;
     size_t nnz = 0, ld = 0;
     double surface_z = 0.0;
     int device = 0;
@@ -489,6 +490,8 @@ int map_model(pgb200_ert *h, const double *model_dev, int n_in) {
 
 // assemble S(rho), right-hand sides, solve, total potentials  (calculateK, dcfemmodelling.cpp:2152-2296)
 int forward_solve(pgb200_ert *h) {
+    if (h->sr && !h->prim_set)
+        PGB_FAIL("topography: singularity removal needs numeric primary potentials (pgb200_ert_set_primary_dev) before the first solve");
     phase_begin(h, PH_ASM);
     CKR(assemble(h, h->rho.p, h->vals.p));
     k_count_singular<<<cdiv(h->N, 256), 256, 0, h->st>>>(h->diag_pos.p, h->N, h->nK, h->nnz, h->vals.p, h->flags.p + 1); LAUNCH(h);
@@ -834,7 +837,7 @@ int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
     CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     h->dim = p->dim; h->nloc = p->nloc; h->N = p->n_nodes; h->C = p->n_cells; h->nnz = (size_t)p->nnz;
     h->nE = p->n_elec; h->nK = p->n_k; h->nS = h->nE * h->nK; h->M = p->n_model; h->D = p->n_data; h->sr = p->sr;
-    h->fullspace = p->fullspace; h->surface_z = p->surface_z;
+    h->fullspace = p->fullspace; h->surface_z = p->surface_z; h->topography = p->topography;
     if (p->dim == 2 && p->nloc == 3) h->elem = TRI3; else if (p->dim == 2 && p->nloc == 6) h->elem = TRI6;
     else if (p->dim == 3 && p->nloc == 4) h->elem = TET4; else if (p->dim == 3 && p->nloc == 10) h->elem = TET10;
     else PGB_FAIL("unsupported cell type (need Tri3/Tri6/Tet4/Tet10)");
@@ -898,11 +901,14 @@ int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
     // geometry-only device work: primary potentials and the rho = 1 matrices
     CKR(h->prim.alloc(blk));
     CK(cudaMemsetAsync(h->prim.p, 0, blk * sizeof(double), st));
-    {
+    if (!h->topography) {
+        // flat earth: analytic primary potentials (exactDCSolution); with topography they are numeric and arrive
+        // through pgb200_ert_set_primary_dev
         dim3 b(32, 8), g(cdiv(N, 8), cdiv(h->nS, 32));
         k_primary<<<g, b, 0, st>>>(h->pos.p, N, h->el_pos.p, nE, h->sing_node.p, h->sing_val.p, h->kvals.p, nK, h->surface_z,
                                   h->fullspace, h->prim.p, h->ld); LAUNCH(h);
         CK(cudaGetLastError());
+        h->prim_set = true;
     }
     // rho = 1 matrices: the S1 of the singularity-removal right-hand side, and the (geometry-only) strength
     // information the multilevel hierarchy is built from
@@ -1091,12 +1097,26 @@ int pgb200_ert_pack_potentials(pgb200_ert *h, int c0, int c1, double *buf_dev, i
     return 0;
 }
 
+int pgb200_ert_set_primary_dev(pgb200_ert *h, const double *src_dev, long long src_ld, const int *row_map_host) {
+    if (!h || !src_dev || !row_map_host) PGB_FAIL("null argument");
+    if (src_ld < h->nS) PGB_FAIL("primary potentials: leading dimension smaller than the number of sources");
+    CK(cudaSetDevice(h->device));
+    DevBuf<int> map;
+    CKR(map.upload(row_map_host, (size_t)h->N, h->st));
+    dim3 b(32, 8), g(cdiv(h->N, 8), cdiv(h->nS, 32));
+    k_gather_rows<<<g, b, 0, h->st>>>(src_dev, (size_t)src_ld, map.p, h->N, h->nS, h->ld, h->prim.p); LAUNCH(h);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->st));
+    h->prim_set = true; h->pots_valid = false; h->jac_valid = false;
+    return 0;
+}
+
 // ---- Jacobian -------------------------------------------------------------------------
 static int create_jacobian_common(pgb200_ert *h, int n_in) {
     const double *rho_col = (n_in == h->M) ? h->model.p : nullptr;      // scaling only if len(model) == J.cols (:1377)
     if (!h->pots_valid) {
         // prepareJacobianT_ (:1246-1309): no potentials yet -> solve, analytically for a homogeneous model
-        const bool hetero = host_stddev(h->h_model) > 1e-12 * 1e5;
+        const bool hetero = h->topography || host_stddev(h->h_model) > 1e-12 * 1e5;     // setAnalytical(!(topography || het)) :1272
         phase_begin(h, PH_MAP);
         CKR(map_model(h, h->model.p, n_in));
         if (!hetero) { CKR(analytic_pots(h, h->h_model[0])); }

@@ -78,7 +78,8 @@ class ShardedERT:
         self.rows = split_range(self.D, world, rank) if world > 1 else (0, self.D)
         if world > 1:
             self.core.setShard(self.src[0], self.src[1], self.rows[0], self.rows[1])
-        self.core._ensure_handle()
+        self.core._ensure_handle()      # with topography every rank solves the (replicated) P2 primary problem here
+        self.core._resolve_k()
         self._bufs = None
 
     @property

@@ -24,8 +24,8 @@ import numpy as np
 from . import _capi
 from .amg_setup import build_hierarchy
 from .host_setup import build_plan, TOLERANCE
-from .mesh import MeshArrays, from_pg_mesh
-from .scheme import SchemeArrays, geometric_factors
+from .mesh import MeshArrays, from_pg_mesh, create_p2
+from .scheme import SchemeArrays, geometric_factors, electrode_matrix_data
 
 
 def _as_mesh(mesh) -> MeshArrays:
@@ -208,6 +208,8 @@ class CoreB200:
         self._tol, self._maxit, self._check = 1e-12, 50000, 25
         self._stream = None
         self._shard = None
+        self._prim_pm = None
+        self._placeholder_k = False
         self._J = JacobianB200(self)
 
     # ---- reference-style setters -----------------------------------------------------
@@ -259,9 +261,23 @@ class CoreB200:
             _capi.check(_capi.lib().pgb200_ert_set_shard(self._h, *self._shard))
 
     def calcGeometricFactor(self, data=None, nModel=0):
-        """analytic geometric factors (dcfemmodelling.cpp:1527-1533; numeric ones need topography support)"""
+        """geometric factors (dcfemmodelling.cpp:1527-1556): analytic for flat earth; with topography numeric,
+        1 / (u(rho = 1) + TOLERANCE) from the electrode potentials of a rho = 1 solve"""
         sch = self._scheme if data is None else _as_scheme(data)
-        return geometric_factors(sch, self._mesh.dim if self._mesh is not None else 3)
+        topo = False
+        if self._mesh is not None and self._scheme is not None:
+            topo = self._ensure_plan().topography
+        if not topo:
+            return geometric_factors(sch, self._mesh.dim if self._mesh is not None else 3)
+        self._ensure_handle()
+        if self.sr:
+            pm = self._prim_pm                       # SR with rho = 1: secondary field is zero, u = primary potentials
+        else:
+            P = self._plan
+            self.response(np.ones(nModel if nModel > 0 else P.M))
+            pm = self.get("pm").reshape(P.nE, P.nE)
+            self.clearPotentials()
+        return 1.0 / (electrode_matrix_data(pm, sch) + TOLERANCE)
 
     # ---- life cycle -------------------------------------------------------------------
     def _invalidate(self):
@@ -270,6 +286,8 @@ class CoreB200:
         self._h = None
         self._plan = None
         self._keep = None
+        self._prim_pm = None
+        self._placeholder_k = False
 
     def close(self):
         self._invalidate()
@@ -286,12 +304,65 @@ class CoreB200:
                 raise RuntimeError("Found no mesh, so cannot calculate a response.")
             if self._scheme is None:
                 raise RuntimeError("no response without data container")
-            sch = self._scheme
-            if sch.k is None or np.min(np.abs(sch.k)) < TOLERANCE:
-                # response() computes missing k-factors analytically for flat earth (:1088-1093)
-                sch.k = geometric_factors(sch, self._mesh.dim)
-            self._plan = build_plan(self._mesh, sch, self._k, self._w, color_fn=_capi.color_cells, panel_fn=_capi.build_panels)
+            # the plan is geometry only; missing k-factors are resolved at the first response()/createJacobian()
+            self._plan = build_plan(self._mesh, self._scheme, self._k, self._w, color_fn=_capi.color_cells,
+                                    panel_fn=_capi.build_panels)
+            self._placeholder_k = not self._have_k()
         return self._plan
+
+    def _have_k(self):
+        k = self._scheme.k
+        return k is not None and np.min(np.abs(k)) >= TOLERANCE
+
+    def _resolve_k(self):
+        """response() without k-factors (dcfemmodelling.cpp:1088-1098): analytic ones for flat earth, an error with
+        topography"""
+        if not getattr(self, "_placeholder_k", False):
+            return
+        P = self._plan
+        if P.topography:
+            raise RuntimeError(" data contains no K-factors ")
+        self._scheme.k = geometric_factors(self._scheme, self._mesh.dim)
+        self.setGeometricFactors(self._scheme.k)
+
+    def setGeometricFactors(self, k):
+        """install k-factors (data('k')) without rebuilding the geometry-only plan"""
+        k = np.ascontiguousarray(k, np.float64)
+        if self._scheme is None or k.size != self._scheme.size:
+            raise ValueError("k-factors must have one entry per datum")
+        self._scheme.k = k.copy()
+        self._placeholder_k = False
+        if self._h:
+            _capi.check(_capi.lib().pgb200_ert_set_kfac(self._h, self._scheme.k.ctypes.data))
+
+    def _ensure_primary(self):
+        """numeric primary potentials with topography (checkPrimpotentials_, dcfemmodelling.cpp:2009-2056): total-field
+        solve for rho = 1 on the P2-refined mesh (a second, temporary handle on the same GPU), taken at this mesh's
+        nodes -- createP2 keeps the vertex nodes, so the reference's interpolation to mesh_->positions() is a row pick.
+        The electrode-potential matrix of that solve also gives the numeric geometric factors (:1539-1556)."""
+        P = self._plan
+        if not (P.topography and self.sr) or self._prim_pm is not None:
+            return
+        if self._mesh.order != 1:
+            raise NotImplementedError("topography with a P2 secondary mesh: the reference refines with createP2, which "
+                                      "needs a P1 mesh")
+        prim = CoreB200(sr=False, verbose=self.verbose, device=self.device, preconditioner=self.preconditioner)
+        try:
+            prim.setMesh(create_p2(self._mesh))
+            sch = self._scheme
+            prim.setData(SchemeArrays(sch.sensors, sch.a, sch.b, sch.m, sch.n, np.ones(sch.size)))
+            prim.setkValues(P.k)
+            prim.setWeights(P.w)
+            prim.setSolverTolerance(self._tol, self._maxit, self._check)
+            P2 = prim._ensure_plan()
+            prim.response(np.ones(P2.M))
+            ptr, _, _, ld2 = prim._pots_info()
+            rows = np.ascontiguousarray(P2.node_inv[P.node_perm], np.int32)   # this handle's node i -> row of the P2 block
+            _capi.check(_capi.lib().pgb200_ert_set_primary_dev(self._h, C.c_void_p(ptr), int(ld2), rows.ctypes.data))
+            self._prim_pm = prim.get("pm").reshape(P.nE, P.nE)
+            self.primary_stats = prim.stats()
+        finally:
+            prim.close()
 
     def _ensure_handle(self):
         if self._h is None:
@@ -318,26 +389,38 @@ class CoreB200:
                 _capi.check(_capi.lib().pgb200_ert_set_preconditioner(h, 1 if self.hierarchy else 0, 8))
             else:
                 _capi.check(_capi.lib().pgb200_ert_set_preconditioner(h, 0, 8))
+            self._ensure_primary()
         return self._h
 
     # ---- the path ---------------------------------------------------------------------
     def response(self, model):
         h = self._ensure_handle()
+        self._resolve_k()
         m = np.ascontiguousarray(model, np.float64)
         out = np.zeros(self._scheme.size)
         _capi.check(_capi.lib().pgb200_ert_response(h, m.ctypes.data, int(m.size), out.ctypes.data))
         return out
 
+    def _jacobian_k(self, n_model):
+        if self._placeholder_k:
+            # prepareJacobianT_ fills missing k-factors first (:1286-1290): analytic, or numeric with topography
+            self.setGeometricFactors(self.calcGeometricFactor(nModel=int(n_model)))
+
     def createJacobian(self, model):
         h = self._ensure_handle()
+        self._jacobian_k(np.size(model))
         m = np.ascontiguousarray(model, np.float64)
         _capi.check(_capi.lib().pgb200_ert_create_jacobian(h, m.ctypes.data, int(m.size)))
         return None
 
     def response_dev(self, model_ptr: int, n: int, out_ptr: int):
+        self._ensure_handle()
+        self._resolve_k()
         _capi.check(_capi.lib().pgb200_ert_response_dev(self._ensure_handle(), C.c_void_p(model_ptr), int(n), C.c_void_p(out_ptr)))
 
     def createJacobian_dev(self, model_ptr: int, n: int):
+        self._ensure_handle()
+        self._jacobian_k(n)
         _capi.check(_capi.lib().pgb200_ert_create_jacobian_dev(self._ensure_handle(), C.c_void_p(model_ptr), int(n)))
 
     def jacobian(self):

@@ -453,10 +453,12 @@ def build_plan(mesh: MeshArrays, scheme, k_values=None, weights=None, color_fn=N
         if dim == 2:
             neumann_domain = False
     P.topography, P.surface_z, P.neumann_domain = topography, surface_z, neumann_domain
-    if topography:
+    if neumann_domain:
         raise NotImplementedError(
-            "topography / pure-Neumann domains need numeric primary potentials "
-            "(dcfemmodelling.cpp:2009-2056); not on the B200 path yet (SURVEY §8(f) item 2)")
+            "pure-Neumann 3-D domains (no mixed/Dirichlet boundary) need the calibration-node handling of "
+            "dcfemmodelling.cpp:1040-1075; not on the B200 path (SURVEY §8(f) item 2)")
+    # topography: the plan is the same; analytic primary potentials / analytic branches are switched off in the library
+    # and CoreB200 supplies numeric primary potentials from a P2 total-field solve (dcfemmodelling.cpp:2009-2056)
 
     # ---- pattern, scatter map, colours -------------------------------------------
     P.rowptr, P.colidx, pos = build_pattern(mesh)

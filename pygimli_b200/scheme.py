@@ -140,3 +140,11 @@ def geometric_factors(scheme: SchemeArrays, dim: int = 3) -> np.ndarray:
     a, b, m, n = scheme.a, scheme.b, scheme.m, scheme.n
     with np.errstate(divide="ignore"):
         return 1.0 / (u(a, m) - u(b, m) - u(a, n) + u(b, n))
+
+
+def electrode_matrix_data(pm: np.ndarray, scheme: SchemeArrays) -> np.ndarray:
+    """DataMap::data (core/src/bert/datamap.cpp:195-215): four-point voltages from the electrode-potential matrix
+    pm[source electrode, pick-up electrode]; electrode index -1 contributes nothing"""
+    def P(a, m):
+        return np.where((a >= 0) & (m >= 0), pm[np.maximum(a, 0), np.maximum(m, 0)], 0.0)
+    return (P(scheme.a, scheme.m) - P(scheme.a, scheme.n)) - (P(scheme.b, scheme.m) - P(scheme.b, scheme.n))

@@ -86,3 +86,28 @@ def coverage_case(dim: int, seed: int = 77):
     resp = 10.0 ** rng.uniform(1, 3, D)
     model = 10.0 ** rng.uniform(1, 3, M)
     return mesh, J, dd, mm, resp, model
+
+
+TOPO_CASES = ("topo_2d", "topo_3d")
+
+
+def make_topo_case(name: str):
+    """flat case with a smooth hill pressed into it: surface faces get different centre heights -> the reference's
+    topography branch (numeric primary potentials from a P2 solve, numeric geometric factors).
+    -> (MeshArrays, SchemeArrays WITHOUT k, model vector)"""
+    mesh, scheme, model = make_case("2d_p1" if name == "topo_2d" else "3d_p1")
+    v = mesh.dim - 1                                   # vertical coordinate: y in 2-D meshes, z in 3-D
+    x = mesh.pos[:, 0]
+    bump = 0.6 * np.exp(-((x - 4.3) / 3.0) ** 2)
+    if mesh.dim == 3:
+        bump = bump * np.exp(-((mesh.pos[:, 1] - 3.1) / 4.0) ** 2)
+    depth = -mesh.pos[:, v]
+    mesh.pos[:, v] += bump * np.clip(1.0 - depth / 6.0, 0.0, 1.0)      # fades out 6 m below the surface
+    mesh._cache.clear()
+    el = np.nonzero(mesh.node_marker == -99)[0]
+    sens = scheme.sensors.copy()
+    for i in range(sens.shape[0]):                     # electrodes ride on their (moved) surface nodes
+        j = el[np.argmin(np.abs(mesh.pos[el, 0] - sens[i, 0]) + (np.abs(mesh.pos[el, 1] - sens[i, 1]) if mesh.dim == 3 else 0.0))]
+        sens[i] = mesh.pos[j]
+    from pygimli_b200.scheme import SchemeArrays
+    return mesh, SchemeArrays(sens, scheme.a, scheme.b, scheme.m, scheme.n, None), model
