@@ -329,6 +329,7 @@ def run_b200(args):
             "phase_ms_per_step": {k: st[k] / args.steps for k in ("ms_map", "ms_assemble", "ms_rhs", "ms_solve", "ms_epilogue", "ms_jacobian")},
             "roofline": {"kernel": ("k_spmm_panel (%s-staged row panels" % ("cp.async" if args.spmm == "panel_cpasync" else "TMA") if args.spmm != "plain" else "k_spmm (plain gather") + ", CSR x dense block, inside block-PCG)", "bound": "hbm", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": ach / peak if peak else None,
+                         "peak_nominal": 8000.0, "frac_nominal": ach / 8000.0,
                          "traffic": _traffic(args.workload, "k_spmm_panel") if (world == 1 and args.scale == 1.0 and args.spmm == "panel") else None, "peak_source": peak_src,
                          "launches_timed": st["spmm_timed"], "avg_launch_ms": spmm_ms, "algorithmic_bytes_per_launch": spmm_bytes},
             "roofline_jacobian": {"kernel": "k_jacobian", "bound": "hbm", "achieved": jac_bytes / (jac_ms * 1e-3) / 1e9 if jac_ms > 0 else None,

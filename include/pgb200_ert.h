@@ -183,6 +183,13 @@ int pgb200_ert_jacobian_tmult_lr(pgb200_ert *h, const double *left_host, const d
  * to be summed over the ranks and divided afterwards).                                        */
 int pgb200_ert_coverage_trans(pgb200_ert *h, const double *dd_host, const double *mm_host, double *cov_host);
 
+/* Generic FEM matrices on the path's element kernels (SparseMatrix::fillStiffnessMatrix / fillMassMatrix,
+ * core/src/sparsematrix.h:1034-1065, as used by pygimli/solver/solver.py:1953, 2033):
+ *   vals = sum_c a[c] * int grad N_i . grad N_j  +  b[c] * int N_i N_j   over the handle's mesh, no boundary terms.
+ * a_cells_host / b_cells_host: [C] per-cell coefficients in the plan's cell order, either may be NULL (term absent);
+ * vals_host: [nnz] in the plan's CSR order.                                                  */
+int pgb200_ert_fill_matrix(pgb200_ert *h, const double *a_cells_host, const double *b_cells_host, double *vals_host);
+
 /* Numeric primary potentials for the singularity-removal path with topography (checkPrimpotentials_,
  * dcfemmodelling.cpp:2009-2056: total-field solve for rho = 1 on the P2-refined mesh, taken at the nodes of this mesh).
  * src_dev: node-major potentials of the primary handle ([n_src_nodes][src_ld], column = electrode + nE * k, see

@@ -137,6 +137,14 @@ class RefERT:
         w = np.ascontiguousarray(w, np.float64)
         lib().ref_set_kw(self.h, C.c_int(k.size), _d(k), _d(w))
 
+    def fill_matrix(self, kind, coef):
+        """CSR values of fillStiffnessMatrix (kind 0) / fillMassMatrix (kind 1), pattern as ``pattern()``"""
+        coef = np.ascontiguousarray(coef, np.float64)
+        n = lib().ref_fill_matrix(self.h, C.c_int(kind), _d(coef), None)
+        out = np.zeros(n)
+        lib().ref_fill_matrix(self.h, C.c_int(kind), _d(coef), _d(out))
+        return out
+
     def set_primary_from(self, p2_handle: "RefERT"):
         """numeric primary potentials from a total-field run on the P2 mesh (see ref_driver.cpp ref_set_primary_from)"""
         return int(lib().ref_set_primary_from(self.h, p2_handle.h))

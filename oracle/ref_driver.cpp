@@ -340,6 +340,18 @@ int ref_set_primary_from(void * vs, void * vp){
     dynamic_cast< DCSRMultiElectrodeModelling * >(s->fop)->setPrimaryPotential(*s->prim);
     return (int)s->prim->rows();
 }
+// SparseMatrix::fillStiffnessMatrix (kind 0) / fillMassMatrix (kind 1) with per-cell coefficients (sparsematrix.h:1034-1065)
+int ref_fill_matrix(void * vh, int kind, const double * coef, double * vals){
+    RefHandle * h = (RefHandle *)vh;
+    Mesh & mesh = *h->mesh;
+    RVector a(mesh.cellCount());
+    for (Index i = 0; i < mesh.cellCount(); i++) a[i] = coef[i];
+    RSparseMatrix S;
+    if (kind == 0) S.fillStiffnessMatrix(mesh, a); else S.fillMassMatrix(mesh, a);
+    if (vals) for (Index i = 0; i < S.nVals(); i++) vals[i] = S.vals()[i];
+    return (int)S.nVals();
+}
+
 // CSR pattern exactly as SparseMatrix::buildSparsityPattern (sparsematrix.h:966)
 int ref_pattern(void * vh, int * rowptr, int * colidx){
     RefHandle * h = (RefHandle *)vh;

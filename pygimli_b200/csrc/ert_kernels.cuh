@@ -95,6 +95,40 @@ k_assemble(const double *__restrict__ pos, const int *__restrict__ cells_col, co
     }
 }
 
+// generic FEM matrices on the same element kernels (SparseMatrix::fillStiffnessMatrix / fillMassMatrix,
+// core/src/sparsematrix.h:1034-1065):  vals += a_c * K_c + b_c * M_c  with per-cell coefficients in the ORIGINAL cell
+// order (a == nullptr / b == nullptr: that term is absent)
+template <int E>
+__global__ void __launch_bounds__(128)
+k_assemble_generic(const double *__restrict__ pos, const int *__restrict__ cells_col, const int *__restrict__ pos_col,
+                   const int *__restrict__ color_order, const double *__restrict__ a, const double *__restrict__ b, int C, int first,
+                   int count, double *__restrict__ vals) {
+    constexpr int NV = ElemTraits<E>::NV, NL = ElemTraits<E>::NL, DIM = ElemTraits<E>::DIM;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int slot = first + t;
+    const int cell = color_order[slot];
+    const double wa = a ? a[cell] : 0.0, wb = b ? b[cell] : 0.0;
+    double X[NV][3];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        const int n = cells_col[(size_t)v * C + slot];
+        X[v][0] = pos[3 * (size_t)n]; X[v][1] = pos[3 * (size_t)n + 1]; X[v][2] = pos[3 * (size_t)n + 2];
+    }
+    double size, G[NV][NV];
+    simplex_gram<DIM>(X, size, G);
+#pragma unroll
+    for (int i = 0; i < NL; i++) {
+#pragma unroll
+        for (int j = 0; j < NL; j++) {
+            double v = 0.0;
+            if (a) v = wa * stiff_entry<E>(i, j, size, G);
+            if (b) v = fma(wb, size * mass_unit<E>(i, j), v);
+            vals[pos_col[(size_t)(i * NL + j) * C + slot]] += v;
+        }
+    }
+}
+
 // mixed boundary faces (:243-299): vals[k][slot] += sum_e coef[k][e] / rho[owner[e]]
 __global__ void k_boundary_add(const int *__restrict__ slot, const int *__restrict__ ptr, const int *__restrict__ owner,
                                const double *__restrict__ coef, int n_slots, int n_entries, const double *__restrict__ rho,

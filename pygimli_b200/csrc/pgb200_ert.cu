@@ -143,6 +143,20 @@ int launch_assemble(pgb200_ert *h, const double *rho, double *vals) {
     return 0;
 }
 
+template <int E>
+int launch_assemble_generic(pgb200_ert *h, const double *a, const double *b, double *vals) {
+    CK(cudaMemsetAsync(vals, 0, sizeof(double) * h->nnz, h->st));
+    for (int c = 0; c < h->n_colors; c++) {
+        const int first = h->color_ptr[c], count = h->color_ptr[c + 1] - first;
+        if (count <= 0) continue;
+        k_assemble_generic<E><<<cdiv(count, 128), 128, 0, h->st>>>(h->pos.p, h->cells_col.p, h->pos_col.p, h->color_order.p, a, b,
+                                                                  h->C, first, count, vals);
+        LAUNCH(h);
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int assemble(pgb200_ert *h, const double *rho, double *vals) {
     switch (h->elem) {
         case TRI3:  CKR(launch_assemble<TRI3>(h, rho, vals)); break;
@@ -1094,6 +1108,26 @@ int pgb200_ert_pack_potentials(pgb200_ert *h, int c0, int c1, double *buf_dev, i
     dim3 b(32, 8), g(cdiv(h->N, 8), cdiv(c1 - c0, 32));
     k_pack_cols<<<g, b, 0, h->st>>>(h->U.p, h->ld, h->N, c0, c1, buf_dev, unpack, h->U.p); LAUNCH(h);
     CK(cudaGetLastError());
+    return 0;
+}
+
+int pgb200_ert_fill_matrix(pgb200_ert *h, const double *a_cells_host, const double *b_cells_host, double *vals_host) {
+    if (!h || !vals_host) PGB_FAIL("null argument");
+    if (!a_cells_host && !b_cells_host) PGB_FAIL("fill_matrix: neither a stiffness nor a mass coefficient given");
+    CK(cudaSetDevice(h->device));
+    DevBuf<double> a, b, out;
+    if (a_cells_host) CKR(a.upload(a_cells_host, (size_t)h->C, h->st));
+    if (b_cells_host) CKR(b.upload(b_cells_host, (size_t)h->C, h->st));
+    CKR(out.alloc(h->nnz));
+    switch (h->elem) {
+        case TRI3:  CKR(launch_assemble_generic<TRI3>(h, a.p, b.p, out.p)); break;
+        case TRI6:  CKR(launch_assemble_generic<TRI6>(h, a.p, b.p, out.p)); break;
+        case TET4:  CKR(launch_assemble_generic<TET4>(h, a.p, b.p, out.p)); break;
+        case TET10: CKR(launch_assemble_generic<TET10>(h, a.p, b.p, out.p)); break;
+        default: PGB_FAIL("unknown element type");
+    }
+    CK(cudaMemcpyAsync(vals_host, out.p, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
     return 0;
 }
 

@@ -446,6 +446,24 @@ class CoreB200:
         _capi.check(_capi.lib().pgb200_ert_map_model(h, m.ctypes.data, int(m.size), out.ctypes.data))
         return out
 
+    # ---- generic FEM matrices on the path's element kernels -----------------
+    def _fill(self, a, b):
+        h = self._ensure_handle()
+        P = self._plan
+        vec = [None if v is None else np.ascontiguousarray(np.broadcast_to(np.asarray(v, float), (P.C,)), np.float64) for v in (a, b)]
+        out = np.zeros(P.nnz)
+        _capi.check(_capi.lib().pgb200_ert_fill_matrix(h, *(None if v is None else v.ctypes.data for v in vec), out.ctypes.data))
+        return P.ref_rowptr, P.ref_colidx, out[P.ref_slot]
+
+    def fillStiffnessMatrix(self, a=1.0):
+        """(rowptr, colidx, vals) of  sum_c a_c int grad N_i . grad N_j  in the reference's CSR layout
+        (SparseMatrix::fillStiffnessMatrix, core/src/sparsematrix.h:1034-1049); ``a``: scalar or per-cell"""
+        return self._fill(a, None)
+
+    def fillMassMatrix(self, b=1.0):
+        """(rowptr, colidx, vals) of  sum_c b_c int N_i N_j  (SparseMatrix::fillMassMatrix, sparsematrix.h:1050-1065)"""
+        return self._fill(None, b)
+
     # ---- introspection ------------------------------------------------------------------
     def get(self, what: str, raw: bool = False) -> np.ndarray:
         h = self._h if (raw and self._h) else self._ensure_handle()

@@ -111,3 +111,15 @@ def make_topo_case(name: str):
         sens[i] = mesh.pos[j]
     from pygimli_b200.scheme import SchemeArrays
     return mesh, SchemeArrays(sens, scheme.a, scheme.b, scheme.m, scheme.n, None), model
+
+
+FEM_CASES = ("2d_p1", "2d_p2", "3d_p1", "3d_p2")
+
+
+def fem_inputs(mesh, seed: int = 31):
+    """seeded per-cell coefficients (stiffness a, mass b) and two probe vectors for the generic FEM matrices"""
+    rng = np.random.default_rng(seed)
+    a = 10.0 ** rng.uniform(-1, 1, mesh.cell_count)
+    b = 10.0 ** rng.uniform(-1, 1, mesh.cell_count)
+    X = rng.standard_normal((mesh.node_count, 2))
+    return a, b, X
