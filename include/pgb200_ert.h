@@ -232,6 +232,10 @@ long long pgb200_ert_get(pgb200_ert *h, const char *what, double *out_host, long
 int pgb200_ert_stats(pgb200_ert *h, double *stats, int n);
 int pgb200_ert_reset_stats(pgb200_ert *h);
 int pgb200_ert_set_profile(pgb200_ert *h, int on);
+/* on == 2 additionally records one CUDA event per kernel launch (no CUDA graph); pgb200_ert_get_trace returns, for the
+ * launches since then, (source line in csrc/pgb200_ert.cu) * 16 + multilevel level of each launch and the time since the previous launch
+ * finished [ms]: a warm per-kernel timeline of a step (profiles/summarize_trace.py).  Returns the entry count.  */
+int pgb200_ert_get_trace(pgb200_ert *h, int *lines, float *ms, int cap);
 /* 0: plain gather kernel; 1 / 2: panel-staged SpMM, one TMA bulk copy per halo row, with 1 / 2
  * (default) source columns per lane; 3: same as 2 but cp.async (LDGSTS) staging (A/B evidence)   */
 int pgb200_ert_set_spmm_variant(pgb200_ert *h, int panel_staged);

@@ -56,7 +56,7 @@ EXPORTS = [
     "pgb200_ert_jacobian_info", "pgb200_ert_clear_potentials", "pgb200_ert_potentials_info",
     "pgb200_ert_mark_potentials_valid", "pgb200_ert_forward_dev", "pgb200_ert_pm_info", "pgb200_ert_finish_response_dev",
     "pgb200_ert_pack_potentials", "pgb200_ert_get", "pgb200_ert_stats", "pgb200_ert_reset_stats", "pgb200_ert_set_profile",
-    "pgb200_spmm", "pgb200_ert_set_primary_dev", "pgb200_ert_fill_matrix", "pgb200_ert_jacobian_mult_lr", "pgb200_ert_jacobian_tmult_lr", "pgb200_ert_coverage_trans",
+    "pgb200_spmm", "pgb200_ert_get_trace", "pgb200_ert_set_primary_dev", "pgb200_ert_fill_matrix", "pgb200_ert_jacobian_mult_lr", "pgb200_ert_jacobian_tmult_lr", "pgb200_ert_coverage_trans",
 ]
 
 _lib = None
@@ -95,6 +95,7 @@ def lib():
         L.pgb200_ert_jacobian_mult_lr.argtypes = [C.c_void_p] * 5
         L.pgb200_ert_jacobian_tmult_lr.argtypes = [C.c_void_p] * 5
         L.pgb200_ert_coverage_trans.argtypes = [C.c_void_p] * 4
+        L.pgb200_ert_get_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.pgb200_ert_fill_matrix.argtypes = [C.c_void_p] * 4
         L.pgb200_ert_set_primary_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
         L.pgb200_ert_jacobian_info.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), c_int_p, c_int_p, C.POINTER(C.c_longlong)]

@@ -561,23 +561,54 @@ k_pcg_init(const double *__restrict__ B, const double *__restrict__ dinv, double
     }
     block_col_reduce(s0, s1, rz, bb, col, ok);
 }
+// Flat mapping for the element-wise block-vector kernels: the FLAT_T threads of a CTA tile the column window
+// [c0,c1) (chunks of at most cw columns along blockIdx.y) as rpp = FLAT_T / w consecutive rows of w columns, so that a
+// warp touches 32 consecutive elements of the row-major block whatever the window width (100 columns -> 5 rows per pass,
+// 14 columns of an 8-GPU shard -> 36), and every thread keeps ONE column (per-column scalars and dot partials stay in
+// registers).  A CTA covers rows_cta rows: r = roff, roff + rpp, ...
+constexpr int FLAT_T = 512;
+struct FlatMap { int col, roff, rpp, w; bool active; };
+__device__ __forceinline__ FlatMap flat_map(int c0, int c1, int cw) {
+    FlatMap f;
+    const int cs = c0 + blockIdx.y * cw;
+    f.w = min(cw, c1 - cs);
+    f.rpp = FLAT_T / f.w;
+    f.roff = threadIdx.x / f.w;
+    f.col = cs + threadIdx.x - f.roff * f.w;
+    f.active = f.roff < f.rpp;
+    return f;
+}
+// per-column sums over the CTA: shared-memory transpose-free reduction (threads t, t + w, t + 2w, ... share a column)
+__device__ __forceinline__ void flat_col_reduce(double v0, double v1, double *d0, double *d1, const FlatMap &f) {
+    __shared__ double red0[FLAT_T], red1[FLAT_T];
+    red0[threadIdx.x] = f.active ? v0 : 0.0; red1[threadIdx.x] = f.active ? v1 : 0.0;
+    __syncthreads();
+    if ((int)threadIdx.x < f.w) {
+        double a = 0.0, b = 0.0;
+        for (int j = 0; j < f.rpp; j++) { a += red0[threadIdx.x + j * f.w]; b += red1[threadIdx.x + j * f.w]; }
+        if (d0) atomicAdd(d0 + f.col, a);
+        if (d1) atomicAdd(d1 + f.col, b);
+    }
+}
+
 // alpha = rz/pAp;  x += alpha p;  r -= alpha Ap;  rz_new = r.Dinv r;  rr = r.r
 template <bool JACOBI>
-__global__ void __launch_bounds__(VEC_TX * VEC_TY)
+__global__ void __launch_bounds__(FLAT_T)
 k_pcg_update_xr(const double *__restrict__ P, const double *__restrict__ AP, const double *__restrict__ dinv,
                 double *__restrict__ Xv, double *__restrict__ R, int N, int nE, int c0, int c1, size_t ld,
-                const double *__restrict__ rz, const double *__restrict__ pAp, double *__restrict__ rz_new, double *__restrict__ rr) {
-    const int col = c0 + blockIdx.y * VEC_TX + threadIdx.x;
-    const bool ok = col < c1;
+                const double *__restrict__ rz, const double *__restrict__ pAp, double *__restrict__ rz_new, double *__restrict__ rr,
+                int cw, int rows_cta) {
+    const FlatMap f = flat_map(c0, c1, cw);
     double s0 = 0.0, s1 = 0.0;
-    if (ok) {
-        const double den = pAp[col], num = rz[col];
+    if (f.active) {
+        const double den = pAp[f.col], num = rz[f.col];
         const double alpha = (den > 0.0 && num > 0.0) ? num / den : 0.0;
-        const double *dk = dinv + (size_t)(col / nE) * N;
-        const int row0 = blockIdx.x * VEC_ROWS;
-        for (int r = threadIdx.y; r < VEC_ROWS; r += VEC_TY) {
-            const int row = row0 + r; if (row >= N) break;
-            const size_t o = (size_t)row * ld + col;
+        const double *dk = JACOBI ? dinv + (size_t)(f.col / nE) * N : nullptr;
+        const int row0 = blockIdx.x * rows_cta, nr = min(rows_cta, N - row0);
+#pragma unroll 4
+        for (int r = f.roff; r < nr; r += f.rpp) {
+            const int row = row0 + r;
+            const size_t o = (size_t)row * ld + f.col;
             const double rn = fma(-alpha, AP[o], R[o]);
             Xv[o] = fma(alpha, P[o], Xv[o]);
             R[o] = rn;
@@ -585,27 +616,29 @@ k_pcg_update_xr(const double *__restrict__ P, const double *__restrict__ AP, con
             s1 = fma(rn, rn, s1);
         }
     }
-    block_col_reduce(s0, s1, JACOBI ? rz_new : nullptr, rr, col, ok);
+    flat_col_reduce(s0, s1, JACOBI ? rz_new : nullptr, rr, f);
 }
 // beta = rz_new/rz;  p = Dinv r + beta p   (p = 0 once the column has converged: it freezes)
 // also clears the accumulators of the next iteration (buffers nobody reads in this launch)
 // JACOBI: z = Dinv r on the fly; otherwise R points at the preconditioned residual Z and dinv is unused
 template <bool JACOBI>
-__global__ void __launch_bounds__(VEC_TX * VEC_TY)
+__global__ void __launch_bounds__(FLAT_T)
 k_pcg_update_p(const double *__restrict__ R, const double *__restrict__ dinv, double *__restrict__ P, int N, int nE,
                int c0, int c1, size_t ld, const double *__restrict__ rz, const double *__restrict__ rz_new,
                const double *__restrict__ rr, const double *__restrict__ bb, double tol2,
-               double *__restrict__ zero_a, double *__restrict__ zero_b, double *__restrict__ zero_c) {
-    const int col = c0 + blockIdx.y * VEC_TX + threadIdx.x;
-    if (col >= c1) return;
-    if (blockIdx.x == 0 && threadIdx.y == 0) { zero_a[col] = 0.0; zero_b[col] = 0.0; zero_c[col] = 0.0; }
+               double *__restrict__ zero_a, double *__restrict__ zero_b, double *__restrict__ zero_c, int cw, int rows_cta) {
+    const FlatMap f = flat_map(c0, c1, cw);
+    if (!f.active) return;
+    const int col = f.col;
+    if (blockIdx.x == 0 && f.roff == 0) { zero_a[col] = 0.0; zero_b[col] = 0.0; zero_c[col] = 0.0; }
     const bool done = !(rr[col] > tol2 * bb[col]);
     const double den = rz[col];
     const double beta = (den > 0.0) ? rz_new[col] / den : 0.0;
-    const double *dk = dinv + (size_t)(col / nE) * N;
-    const int row0 = blockIdx.x * VEC_ROWS;
-    for (int r = threadIdx.y; r < VEC_ROWS; r += VEC_TY) {
-        const int row = row0 + r; if (row >= N) break;
+    const double *dk = JACOBI ? dinv + (size_t)(col / nE) * N : nullptr;
+    const int row0 = blockIdx.x * rows_cta, nr = min(rows_cta, N - row0);
+#pragma unroll 4
+    for (int r = f.roff; r < nr; r += f.rpp) {
+        const int row = row0 + r;
         const size_t o = (size_t)row * ld + col;
         P[o] = done ? 0.0 : fma(beta, P[o], JACOBI ? dk[row] * R[o] : R[o]);
     }
@@ -690,7 +723,25 @@ k_amg_post(const int *__restrict__ rowptr, const int *__restrict__ colidx, const
         double acc[CPT];
 #pragma unroll
         for (int m = 0; m < CPT; m++) acc[m] = 0.0;
-        for (int p = rowptr[row]; p < rowptr[row + 1]; p++) {
+        // the entries of a row are independent: batches of 4 keep 4 index loads, then 4*CPT gathers, in flight (the
+        // coarse levels are latency-bound, not bandwidth-bound: a few thousand rows, ~15 entries each)
+        const int pb = rowptr[row], pe = rowptr[row + 1];
+        int p = pb;
+        for (; p + 4 <= pe; p += 4) {
+            size_t xo[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) xo[u] = (size_t)__ldg(colidx + p + u) * ld;
+            double a[4][CPT], x[4][CPT];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int m = 0; m < CPT; m++) { a[u][m] = __ldg(vals + voff[m] + p + u); x[u][m] = __ldg(X + xo[u] + col[m]); }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int m = 0; m < CPT; m++) acc[m] = fma(a[u][m], x[u][m], acc[m]);
+        }
+        for (; p < pe; p++) {
             const size_t xo = (size_t)colidx[p] * ld;
 #pragma unroll
             for (int m = 0; m < CPT; m++) acc[m] = fma(__ldg(vals + voff[m] + p), __ldg(X + xo + col[m]), acc[m]);
@@ -752,7 +803,23 @@ k_amg_restrict(const int *__restrict__ rowptr, const int *__restrict__ colidx, c
             const int i = mem_idx[q];
 #pragma unroll
             for (int m = 0; m < CPT; m++) acc[m] += __ldg(R + (size_t)i * ld + col[m]);
-            for (int p = rowptr[i]; p < rowptr[i + 1]; p++) {
+            const int pb = rowptr[i], pe = rowptr[i + 1];
+            int p = pb;
+            for (; p + 4 <= pe; p += 4) {                      // batches of 4 independent entries (see k_amg_post)
+                size_t xo[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) xo[u] = (size_t)__ldg(colidx + p + u) * ld;
+                double a[4][CPT], x[4][CPT];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int m = 0; m < CPT; m++) { a[u][m] = __ldg(vals_dw + voff[m] + p + u); x[u][m] = __ldg(R + xo[u] + col[m]); }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+#pragma unroll
+                    for (int m = 0; m < CPT; m++) acc[m] = fma(-a[u][m], x[u][m], acc[m]);
+            }
+            for (; p < pe; p++) {
                 const size_t xo = (size_t)colidx[p] * ld;
 #pragma unroll
                 for (int m = 0; m < CPT; m++) acc[m] = fma(-__ldg(vals_dw + voff[m] + p), __ldg(R + xo + col[m]), acc[m]);
@@ -763,27 +830,130 @@ k_amg_restrict(const int *__restrict__ rowptr, const int *__restrict__ colidx, c
     }
 }
 
-// RC[I] = sum of RES over the members of aggregate I (deterministic restriction of a fine residual block)
-__global__ void k_amg_sum_members(const int *__restrict__ mem_ptr, const int *__restrict__ mem_idx, int n_c, const double *__restrict__ RES,
-                                  double *__restrict__ RC, int c0, int c1, size_t ld) {
-    const int col = c0 + blockIdx.y * blockDim.x + threadIdx.x;
-    const int I = blockIdx.x * blockDim.y + threadIdx.y;
-    if (col >= c1 || I >= n_c) return;
-    double acc = 0.0;
-    for (int q = mem_ptr[I]; q < mem_ptr[I + 1]; q++) acc += RES[(size_t)mem_idx[q] * ld + col];
-    RC[(size_t)I * ld + col] = acc;
+// Small levels (a few thousand rows and fewer) are latency-bound: one thread walking the ~15 entries of its row --
+// index load, gather, FMA, each dependent on the last -- takes longer than the data movement.  The "split" variants give
+// ONE row to a CTA and spread its entries over the AMG_TY thread rows (partial sums meet in shared memory), which cuts
+// the dependent chain by 8.
+template <int CPT>
+__global__ void __launch_bounds__(AMG_TX * AMG_TY)
+k_amg_post_split(const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals, size_t nnz,
+                 const double *__restrict__ dinvw, int n, const double *__restrict__ X, const double *__restrict__ R,
+                 double *__restrict__ Z, int nE, int c0, int c1, size_t ld) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int row = blockIdx.x;
+    const int cbase = c0 + blockIdx.y * (AMG_TX * CPT) + tx;
+    int col[CPT]; size_t voff[CPT];
+#pragma unroll
+    for (int m = 0; m < CPT; m++) {
+        const int c = cbase + m * AMG_TX;
+        col[m] = c < c1 ? c : c0;
+        voff[m] = (size_t)(col[m] / nE) * nnz;
+    }
+    double acc[CPT];
+#pragma unroll
+    for (int m = 0; m < CPT; m++) acc[m] = 0.0;
+    for (int p = rowptr[row] + ty; p < rowptr[row + 1]; p += AMG_TY) {
+        const size_t xo = (size_t)__ldg(colidx + p) * ld;
+#pragma unroll
+        for (int m = 0; m < CPT; m++) acc[m] = fma(__ldg(vals + voff[m] + p), __ldg(X + xo + col[m]), acc[m]);
+    }
+    __shared__ double red[AMG_TY][AMG_TX * CPT];
+#pragma unroll
+    for (int m = 0; m < CPT; m++) red[ty][m * AMG_TX + tx] = acc[m];
+    __syncthreads();
+    if (ty < CPT) {                                             // thread row m finishes column group m
+        const int c = cbase + ty * AMG_TX;
+        if (c < c1) {
+            double s = 0.0;
+#pragma unroll
+            for (int y = 0; y < AMG_TY; y++) s += red[y][ty * AMG_TX + tx];
+            const size_t o = (size_t)row * ld + c;
+            Z[o] = fma(dinvw[(size_t)(c / nE) * n + row], R[o] - s, X[o]);
+        }
+    }
+}
+template <int CPT>
+__global__ void __launch_bounds__(AMG_TX * AMG_TY)
+k_amg_restrict_split(const int *__restrict__ rowptr, const int *__restrict__ colidx, const double *__restrict__ vals_dw, size_t nnz,
+                     const int *__restrict__ mem_ptr, const int *__restrict__ mem_idx, int n_c,
+                     const double *__restrict__ R, double *__restrict__ RC, int nE, int c0, int c1, size_t ld) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int I = blockIdx.x;
+    const int cbase = c0 + blockIdx.y * (AMG_TX * CPT) + tx;
+    int col[CPT]; size_t voff[CPT];
+#pragma unroll
+    for (int m = 0; m < CPT; m++) {
+        const int c = cbase + m * AMG_TX;
+        col[m] = c < c1 ? c : c0;
+        voff[m] = (size_t)(col[m] / nE) * nnz;
+    }
+    double acc[CPT];
+#pragma unroll
+    for (int m = 0; m < CPT; m++) acc[m] = 0.0;
+    int cnt = 0;                                               // entries of the aggregate's rows seen so far
+    const int qb = mem_ptr[I], qe = mem_ptr[I + 1];
+    for (int q = qb; q < qe; q++) {
+        const int i = mem_idx[q];
+        if (((q - qb) & (AMG_TY - 1)) == ty) {
+#pragma unroll
+            for (int m = 0; m < CPT; m++) acc[m] += __ldg(R + (size_t)i * ld + col[m]);
+        }
+        const int pb = rowptr[i], pe = rowptr[i + 1];
+        for (int p = pb + ((ty - cnt) & (AMG_TY - 1)); p < pe; p += AMG_TY) {
+            const size_t xo = (size_t)__ldg(colidx + p) * ld;
+#pragma unroll
+            for (int m = 0; m < CPT; m++) acc[m] = fma(-__ldg(vals_dw + voff[m] + p), __ldg(R + xo + col[m]), acc[m]);
+        }
+        cnt += pe - pb;
+    }
+    __shared__ double red[AMG_TY][AMG_TX * CPT];
+#pragma unroll
+    for (int m = 0; m < CPT; m++) red[ty][m * AMG_TX + tx] = acc[m];
+    __syncthreads();
+    if (ty < CPT) {
+        const int c = cbase + ty * AMG_TX;
+        if (c < c1) {
+            double s = 0.0;
+#pragma unroll
+            for (int y = 0; y < AMG_TY; y++) s += red[y][ty * AMG_TX + tx];
+            RC[(size_t)I * ld + c] = s;
+        }
+    }
+    (void)n_c;
+}
+
+// RC[I] = sum of RES over the members of aggregate I (deterministic restriction of a fine residual block); flat mapping
+__global__ void __launch_bounds__(FLAT_T)
+k_amg_sum_members(const int *__restrict__ mem_ptr, const int *__restrict__ mem_idx, int n_c, const double *__restrict__ RES,
+                  double *__restrict__ RC, int c0, int c1, size_t ld, int cw, int rows_cta) {
+    const FlatMap f = flat_map(c0, c1, cw);
+    if (!f.active) return;
+    const int row0 = blockIdx.x * rows_cta, nr = min(rows_cta, n_c - row0);
+#pragma unroll 2
+    for (int r = f.roff; r < nr; r += f.rpp) {
+        const int I = row0 + r;
+        double acc = 0.0;
+        for (int q = mem_ptr[I]; q < mem_ptr[I + 1]; q++) acc += RES[(size_t)mem_idx[q] * ld + f.col];
+        RC[(size_t)I * ld + f.col] = acc;
+    }
 }
 
 // X = dw .* R + EC[agg]   (pre-smoothed iterate plus prolongated coarse correction); EC == nullptr -> X = dw .* R
-__global__ void k_amg_prolong(const double *__restrict__ dinvw, int n, const int *__restrict__ agg, const double *__restrict__ R,
-                              const double *__restrict__ EC, double *__restrict__ X, int nE, int c0, int c1, size_t ld) {
-    const int col = c0 + blockIdx.y * blockDim.x + threadIdx.x;
-    const int row = blockIdx.x * blockDim.y + threadIdx.y;
-    if (col >= c1 || row >= n) return;
-    const size_t o = (size_t)row * ld + col;
-    double x = dinvw[(size_t)(col / nE) * n + row] * R[o];
-    if (EC) x += EC[(size_t)agg[row] * ld + col];
-    X[o] = x;
+__global__ void __launch_bounds__(FLAT_T)
+k_amg_prolong(const double *__restrict__ dinvw, int n, const int *__restrict__ agg, const double *__restrict__ R,
+              const double *__restrict__ EC, double *__restrict__ X, int nE, int c0, int c1, size_t ld, int cw, int rows_cta) {
+    const FlatMap f = flat_map(c0, c1, cw);
+    if (!f.active) return;
+    const double *dk = dinvw + (size_t)(f.col / nE) * n;
+    const int row0 = blockIdx.x * rows_cta, nr = min(rows_cta, n - row0);
+#pragma unroll 4
+    for (int r = f.roff; r < nr; r += f.rpp) {
+        const int row = row0 + r;
+        const size_t o = (size_t)row * ld + f.col;
+        double x = dk[row] * R[o];
+        if (EC) x += EC[(size_t)agg[row] * ld + f.col];
+        X[o] = x;
+    }
 }
 
 // numeric primary potentials: prim[i][c] = SRC[map[i]][c]  (rows of the P2 primary solve at this mesh's nodes)

@@ -110,13 +110,20 @@ struct pgb200_ert {
     int last_iters = 0; double last_relres = 0.0; long long launches = 0;
     cudaEvent_t ev[PH_COUNT + 1]; bool ev_ok = false; float ph_ms[PH_COUNT] = {0};
     bool ph_rec[PH_COUNT + 1] = {false};
+    std::vector<cudaEvent_t> tev; std::vector<int> tline; int n_tev = 0; int trace = 0; int cur_tag = 0;   // tag: multilevel level of the launch
     int prof = 0; std::vector<cudaEvent_t> pev; int n_pev = 0; double spmm_ms = 0.0; int spmm_timed = 0; double jac_ms = 0.0;
     cudaEvent_t jev[2]; bool jac_timed = false; int jac_launches = 0; long long total_iters = 0; int solves = 0;
     double *h_pinned = nullptr; size_t h_pinned_n = 0;
     int num_sms = 148;
 };
 
-#define LAUNCH(h) ((h)->launches++)
+inline void note_launch(pgb200_ert *h, int line) {
+    h->launches++;
+    if (h->trace && h->n_tev < (int)h->tev.size()) { cudaEventRecord(h->tev[h->n_tev], h->st); h->tline[h->n_tev++] = line * 16 + (h->cur_tag & 15); }
+}
+// every kernel launch is counted; in trace mode (set_profile(h, 2)) an event is recorded after each one, tagged with
+// the source line of the launch, so that consecutive events give a warm per-kernel timeline of one step
+#define LAUNCH(h) note_launch((h), __LINE__)
 
 namespace {
 
@@ -237,12 +244,36 @@ bool panel_path_ok(const pgb200_ert *h, int c0) {
     return h->use_panels && h->n_panels > 0 && !(c0 & 1) && (h->nK == 1 || h->nE >= 32 * h->panel_nc);
 }
 
+// launch geometry of the flat element-wise kernels (ert_kernels.cuh, flat_map): column chunks of at most FLAT_T columns,
+// rows per CTA = 12 passes on big levels, fewer on small ones so that they still fill the GPU
+struct FlatCfg { int cw, rows_cta; dim3 grid; };
+inline FlatCfg flat_cfg(int n_rows, int c0, int c1) {
+    FlatCfg f;
+    const int w = std::max(1, c1 - c0);
+    const int nchunk = cdiv(w, FLAT_T);
+    f.cw = cdiv(w, nchunk);
+    const int rpp = FLAT_T / f.cw;
+    const int passes = n_rows >= 60000 ? 12 : (n_rows >= 4000 ? 4 : 1);
+    f.rows_cta = rpp * passes;
+    f.grid = dim3(cdiv(n_rows, f.rows_cta), nchunk);
+    return f;
+}
+
 // rows per CTA of the plain multilevel kernels: 32 on big levels, 8 on small ones so that they still fill the GPU
 inline int amg_rows_per_cta(int n) { return n >= 60000 ? 32 : 8; }
+
+constexpr int AMG_SPLIT_BELOW = 6000;      // levels smaller than this use the one-row-per-CTA kernels (latency-bound; measured: 11 k rows is already better off with the row-per-thread kernels)
 
 template <int CPT>
 int amg_post_cpt(pgb200_ert *h, const int *rowptr, const int *colidx, const double *vals, size_t nnz, const double *dinvw, int n,
                  const double *X, const double *R, double *Z, int c0, int c1, double *dots) {
+    static_assert(CPT <= AMG_TY, "split kernels finish column group m in thread row m");
+    if (!dots && n < AMG_SPLIT_BELOW) {
+        dim3 block(AMG_TX, AMG_TY), grid(n, cdiv(c1 - c0, AMG_TX * CPT));
+        k_amg_post_split<CPT><<<grid, block, 0, h->st>>>(rowptr, colidx, vals, nnz, dinvw, n, X, R, Z, h->nE, c0, c1, h->ld);
+        LAUNCH(h);
+        return 0;
+    }
     const int rows = amg_rows_per_cta(n);
     dim3 block(AMG_TX, AMG_TY), grid(cdiv(n, rows), cdiv(c1 - c0, AMG_TX * CPT));
     if (dots) k_amg_post<CPT, true><<<grid, block, 0, h->st>>>(rowptr, colidx, vals, nnz, dinvw, n, X, R, Z, h->nE, c0, c1, h->ld, dots, rows);
@@ -267,6 +298,14 @@ int amg_post(pgb200_ert *h, const int *rowptr, const int *colidx, const double *
 int amg_restrict(pgb200_ert *h, const int *rowptr, const int *colidx, const double *vals_dw, size_t nnz, int n_f,
                  const AmgLevel *L, const double *R, int c0, int c1) {
     const int cpt = pick_cpt(c1 - c0);
+    if (L->n < AMG_SPLIT_BELOW) {
+        dim3 block(AMG_TX, AMG_TY), grid(L->n, cdiv(c1 - c0, AMG_TX * cpt));
+#define RSGO(C) k_amg_restrict_split<C><<<grid, block, 0, h->st>>>(rowptr, colidx, vals_dw, nnz, L->mem_ptr.p, L->mem_idx.p, L->n, R, L->R.p, h->nE, c0, c1, h->ld)
+        if (cpt == 4) RSGO(4); else if (cpt == 2) RSGO(2); else RSGO(1);
+#undef RSGO
+        LAUNCH(h);
+        return 0;
+    }
     const int rows = amg_rows_per_cta(L->n);
     dim3 block(AMG_TX, AMG_TY), grid(cdiv(L->n, rows), cdiv(c1 - c0, AMG_TX * cpt));
 #define RGO(C) k_amg_restrict<C><<<grid, block, 0, h->st>>>(rowptr, colidx, vals_dw, nnz, n_f, L->mem_ptr.p, L->mem_idx.p, L->n, R, L->R.p, h->nE, c0, c1, h->ld, rows)
@@ -306,17 +345,18 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
     std::vector<Lv> lv(nl + 1);
     lv[0] = {h->rowptr.p, h->colidx.p, h->vals.p, h->vals_dw0.p, h->nnz, h->dinvw0.p, h->N, h->R.p, h->X0.p, h->Z0.p};
     for (int l = 0; l < nl; l++) { AmgLevel *L = h->amg[l]; lv[l + 1] = {L->rowptr.p, L->colidx.p, L->vals.p, L->vals_dw.p, L->nnz, L->dinvw.p, L->n, L->R.p, L->X.p, L->Z.p}; }
-    dim3 pb(32, 8);
     // downward: residual after one damped-Jacobi sweep from zero, restricted
     const bool fine_panels = nl > 0 && panel_path_ok(h, c0);
     for (int l = 0; l < nl; l++) {
+        h->cur_tag = l;
         if (l == 0 && fine_panels) {
             // fine level: residual through the panel-staged kernel (into X0, free until the prolongation), then a
             // deterministic member sum
             PanelExtra ex{};
             CKR(launch_panel<EPI_RESIDUAL>(h, h->vals_dw0.p, h->R.p, h->X0.p, c0, c1, nullptr, ex));
             AmgLevel *L = h->amg[0];
-            k_amg_sum_members<<<dim3(cdiv(L->n, 8), cdiv(c1 - c0, 32)), dim3(32, 8), 0, h->st>>>(L->mem_ptr.p, L->mem_idx.p, L->n, h->X0.p, L->R.p, c0, c1, h->ld); LAUNCH(h);
+            const FlatCfg fc = flat_cfg(L->n, c0, c1);
+            k_amg_sum_members<<<fc.grid, FLAT_T, 0, h->st>>>(L->mem_ptr.p, L->mem_idx.p, L->n, h->X0.p, L->R.p, c0, c1, h->ld, fc.cw, fc.rows_cta); LAUNCH(h);
         } else {
             CKR(amg_restrict(h, lv[l].rowptr, lv[l].colidx, lv[l].vals_dw, lv[l].nnz, lv[l].n, h->amg[l], lv[l].R, c0, c1));
         }
@@ -325,8 +365,9 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
     const double *E;
     {
         Lv &c = lv[nl];
-        dim3 pg(cdiv(c.n, 8), cdiv(c1 - c0, 32));
-        k_amg_prolong<<<pg, pb, 0, h->st>>>(c.dinvw, c.n, nullptr, c.R, nullptr, c.X, h->nE, c0, c1, h->ld); LAUNCH(h);
+        h->cur_tag = nl;
+        const FlatCfg fc = flat_cfg(c.n, c0, c1);
+        k_amg_prolong<<<fc.grid, FLAT_T, 0, h->st>>>(c.dinvw, c.n, nullptr, c.R, nullptr, c.X, h->nE, c0, c1, h->ld, fc.cw, fc.rows_cta); LAUNCH(h);
         double *a = c.X, *b = c.Z;
         const int sweeps = (nl == 0) ? 1 : h->coarse_sweeps;
         for (int s = 0; s + 1 < sweeps; s++) {
@@ -339,8 +380,9 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
     // upward: prolongate, post-smooth
     for (int l = nl - 1; l >= 0; l--) {
         Lv &f = lv[l];
-        dim3 pg(cdiv(f.n, 8), cdiv(c1 - c0, 32));
-        k_amg_prolong<<<pg, pb, 0, h->st>>>(f.dinvw, f.n, h->amg[l]->agg.p, f.R, E, f.X, h->nE, c0, c1, h->ld); LAUNCH(h);
+        h->cur_tag = l;
+        const FlatCfg fc = flat_cfg(f.n, c0, c1);
+        k_amg_prolong<<<fc.grid, FLAT_T, 0, h->st>>>(f.dinvw, f.n, h->amg[l]->agg.p, f.R, E, f.X, h->nE, c0, c1, h->ld, fc.cw, fc.rows_cta); LAUNCH(h);
         if (l == 0 && fine_panels) {
             PanelExtra ex{}; ex.R = f.R; ex.dinvw = f.dinvw; ex.n = f.n;
             CKR(launch_panel<EPI_POST>(h, f.vals, f.X, f.Z, c0, c1, dots, ex));
@@ -349,6 +391,7 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
         }
         E = f.Z;
     }
+    h->cur_tag = 0;
     CK(cudaGetLastError());
     return 0;
 }
@@ -364,8 +407,9 @@ int pcg_solve(pgb200_ert *h) {
     double *S = h->scal.p;
     auto sc = [&](int i) { return S + (size_t)i * ld; };
     CK(cudaMemsetAsync(S, 0, sizeof(double) * 7 * ld, h->st));
-    dim3 vb(VEC_TX, VEC_TY), vg(cdiv(h->N, VEC_ROWS), cdiv(ncols, VEC_TX));
-    auto regrid = [&]() { vg = dim3(cdiv(h->N, VEC_ROWS), cdiv(c1 - c0, VEC_TX)); };
+    dim3 vb(VEC_TX, VEC_TY), vg(cdiv(h->N, VEC_ROWS), cdiv(ncols, VEC_TX));   // k_pcg_init (once per solve)
+    FlatCfg fc = flat_cfg(h->N, c0, c1);                                      // per-iteration vector kernels
+    auto regrid = [&]() { fc = flat_cfg(h->N, c0, c1); };
     const bool amg = h->use_amg && !h->amg.empty();
     k_pcg_init<<<vg, vb, 0, h->st>>>(h->B.p, h->dinv.p, h->X.p, h->R.p, h->P.p, h->N, h->nE, c0, c1, ld, amg ? nullptr : sc(0), sc(6)); LAUNCH(h);
     if (amg) {
@@ -385,16 +429,16 @@ int pcg_solve(pgb200_ert *h) {
         else CKR((launch_spmm<0, true>(h, h->vals.p, nullptr, nullptr, h->P.p, h->AP.p, c0, c1, sc(3))));
         if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
         if (amg) {
-            k_pcg_update_xr<false><<<vg, vb, 0, h->st>>>(h->P.p, h->AP.p, nullptr, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
-                                                        sc(rz_old), sc(3), sc(rz_new), sc(rr_cur)); LAUNCH(h);
+            k_pcg_update_xr<false><<<fc.grid, FLAT_T, 0, h->st>>>(h->P.p, h->AP.p, nullptr, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
+                                                                 sc(rz_old), sc(3), sc(rz_new), sc(rr_cur), fc.cw, fc.rows_cta); LAUNCH(h);
             CKR(amg_vcycle(h, c0, c1, sc(rz_new)));
-            k_pcg_update_p<false><<<vg, vb, 0, h->st>>>(h->Z0.p, nullptr, h->P.p, h->N, h->nE, c0, c1, ld, sc(rz_old), sc(rz_new),
-                                                       sc(rr_cur), sc(6), tol2, sc(3), sc(rr_nxt), sc(rz_nxt)); LAUNCH(h);
+            k_pcg_update_p<false><<<fc.grid, FLAT_T, 0, h->st>>>(h->Z0.p, nullptr, h->P.p, h->N, h->nE, c0, c1, ld, sc(rz_old), sc(rz_new),
+                                                                sc(rr_cur), sc(6), tol2, sc(3), sc(rr_nxt), sc(rz_nxt), fc.cw, fc.rows_cta); LAUNCH(h);
         } else {
-            k_pcg_update_xr<true><<<vg, vb, 0, h->st>>>(h->P.p, h->AP.p, h->dinv.p, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
-                                                       sc(rz_old), sc(3), sc(rz_new), sc(rr_cur)); LAUNCH(h);
-            k_pcg_update_p<true><<<vg, vb, 0, h->st>>>(h->R.p, h->dinv.p, h->P.p, h->N, h->nE, c0, c1, ld, sc(rz_old), sc(rz_new),
-                                                      sc(rr_cur), sc(6), tol2, sc(3), sc(rr_nxt), sc(rz_nxt)); LAUNCH(h);
+            k_pcg_update_xr<true><<<fc.grid, FLAT_T, 0, h->st>>>(h->P.p, h->AP.p, h->dinv.p, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
+                                                                sc(rz_old), sc(3), sc(rz_new), sc(rr_cur), fc.cw, fc.rows_cta); LAUNCH(h);
+            k_pcg_update_p<true><<<fc.grid, FLAT_T, 0, h->st>>>(h->R.p, h->dinv.p, h->P.p, h->N, h->nE, c0, c1, ld, sc(rz_old), sc(rz_new),
+                                                               sc(rr_cur), sc(6), tol2, sc(3), sc(rr_nxt), sc(rz_nxt), fc.cw, fc.rows_cta); LAUNCH(h);
         }
         return 0;
     };
@@ -938,6 +982,7 @@ int pgb200_ert_destroy(pgb200_ert *h) {
     cudaDeviceSynchronize();
     if (h->ev_ok) { for (int i = 0; i <= PH_COUNT; i++) cudaEventDestroy(h->ev[i]); cudaEventDestroy(h->jev[0]); cudaEventDestroy(h->jev[1]); }
     for (auto e : h->pev) cudaEventDestroy(e);
+    for (auto e : h->tev) cudaEventDestroy(e);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     for (AmgLevel *L : h->amg) delete L;
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
@@ -1349,7 +1394,26 @@ int pgb200_ert_set_profile(pgb200_ert *h, int on) {
     CK(cudaSetDevice(h->device));
     h->prof = on;
     if (on && h->pev.empty()) { h->pev.resize(4096); for (auto &e : h->pev) CK(cudaEventCreate(&e)); }
+    h->trace = (on == 2);
+    if (h->trace && h->tev.empty()) { h->tev.resize(60000); h->tline.assign(60000, 0); for (auto &e : h->tev) CK(cudaEventCreate(&e)); }
+    if (h->trace) { h->n_tev = 0; note_launch(h, 0); h->launches--; }      // start marker
     return 0;
+}
+
+// trace of the launches since set_profile(h, 2): source line of each launch (of csrc/pgb200_ert.cu) and the time from
+// the previous launch's completion to its own, in ms.  Returns the number of entries (at most cap).
+int pgb200_ert_get_trace(pgb200_ert *h, int *lines, float *ms, int cap) {
+    if (!h) { g_err = "null handle"; return -1; }
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->st);
+    int n = 0;
+    for (int i = 1; i < h->n_tev && n < cap; i++, n++) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, h->tev[i - 1], h->tev[i]);
+        if (lines) lines[n] = h->tline[i];          // source line * 16 + multilevel level
+        if (ms) ms[n] = t;
+    }
+    return n;
 }
 
 int pgb200_spmm(const int *rowptr, const int *colidx, const double *vals, long long nnz, const double *X, double *Y,

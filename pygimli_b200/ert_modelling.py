@@ -497,7 +497,17 @@ class CoreB200:
         _capi.check(_capi.lib().pgb200_ert_reset_stats(self._ensure_handle()))
 
     def setProfile(self, on=True):
-        _capi.check(_capi.lib().pgb200_ert_set_profile(self._ensure_handle(), 1 if on else 0))
+        """True/1: CUDA events around every SpMM and the Jacobian kernel (no CUDA graph); 2: one event per launch (trace)"""
+        _capi.check(_capi.lib().pgb200_ert_set_profile(self._ensure_handle(), int(on)))
+
+    def trace(self):
+        """launches since setProfile(2): (source lines in csrc/pgb200_ert.cu, ms since the previous launch finished)"""
+        cap = 60000
+        lines, ms = np.zeros(cap, np.int32), np.zeros(cap, np.float32)
+        n = _capi.lib().pgb200_ert_get_trace(self._ensure_handle(), lines.ctypes.data, ms.ctypes.data, cap)
+        if n < 0:
+            raise _capi.PGB200Error(_capi.last_error())
+        return lines[:n].copy(), ms[:n].copy()
 
     def _jac_info(self):
         ptr, rows, cols, ld = C.c_void_p(), C.c_int(), C.c_int(), C.c_longlong()

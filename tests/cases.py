@@ -123,3 +123,19 @@ def fem_inputs(mesh, seed: int = 31):
     b = 10.0 ** rng.uniform(-1, 1, mesh.cell_count)
     X = rng.standard_normal((mesh.node_count, 2))
     return a, b, X
+
+
+def make_pole_case():
+    """2d_p1 mesh with pole-dipole, dipole-pole and pole-pole rows (electrode index -1 = electrode at infinity,
+    DataMap::data datamap.cpp:195-215, geometricFactors bertMisc.cpp:131-176) -> (mesh, scheme without k, model)"""
+    mesh, scheme, model = make_case("2d_p1")
+    ne = scheme.sensors.shape[0]
+    rows = []
+    for i in range(0, ne - 3):
+        rows.append((i, -1, i + 1, i + 2))          # pole-dipole
+        rows.append((i, i + 1, i + 3, -1))          # dipole-pole
+    for i in range(0, ne - 4, 2):
+        rows.append((i, -1, i + 4, -1))             # pole-pole
+    r = np.asarray(rows, np.int32)
+    from pygimli_b200.scheme import SchemeArrays
+    return mesh, SchemeArrays(scheme.sensors, r[:, 0], r[:, 1], r[:, 2], r[:, 3], None), model
