@@ -221,7 +221,7 @@ def run_b200(args):
     stream = torch.cuda.current_stream()
     fop.set_stream(stream.cuda_stream)
     from pygimli_b200 import _capi
-    _capi.check(_capi.lib().pgb200_ert_set_spmm_variant(fop.core._h, {"plain": 0, "panel1": 1, "panel": 2, "panel_cpasync": 3}[args.spmm]))
+    _capi.check(_capi.lib().pgb200_ert_set_spmm_variant(fop.core._h, {"plain": 0, "panel1": 1, "panel": 2, "panel_cpasync": 3, "panel4": 4}[args.spmm]))
     t_setup = time.perf_counter() - t_setup
     D, M = scheme.size, int(model.size)
 
@@ -377,7 +377,7 @@ def main():
     ap.add_argument("--ref-direct-max-nodes", type=int, default=60000, help="use the direct CPU stand-in solver up to this mesh size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precond", default="multilevel", choices=["multilevel", "jacobi"], help="block-PCG preconditioner")
-    ap.add_argument("--spmm", default="panel", choices=["panel", "panel1", "panel_cpasync", "plain"], help="SpMM kernel inside PCG (A/B measurement)")
+    ap.add_argument("--spmm", default="panel", choices=["panel", "panel1", "panel4", "panel_cpasync", "plain"], help="SpMM kernel inside PCG (A/B measurement)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

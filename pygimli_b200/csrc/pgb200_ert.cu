@@ -213,7 +213,7 @@ int launch_spmm_panel_nc(pgb200_ert *h, const double *vals, const double *X, dou
     int tw = cdiv(span, ntile); tw += tw & 1;                  // even tile width <= 32*NC (16-byte aligned bulk copies)
     const size_t smem = sizeof(double) * ((size_t)h->max_halo * tw + 32 * NC + 3 * (size_t)h->max_pnnz) +
                         sizeof(int) * ((size_t)h->max_rows + 2) + 16;
-    static size_t configured[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    static size_t configured[5][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     if (smem > configured[NC][EPI]) {
         CK(cudaFuncSetAttribute(k_spmm_panel<NC, true, 0, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(k_spmm_panel<NC, false, 0, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -233,7 +233,8 @@ int launch_spmm_panel_nc(pgb200_ert *h, const double *vals, const double *X, dou
 template <int EPI>
 int launch_panel(pgb200_ert *h, const double *vals, const double *X, double *Y, int c0, int c1, double *dots, const PanelExtra &ex) {
     if (c1 <= c0) return 0;
-    if (h->panel_nc == 2 && c1 - c0 > 32) return launch_spmm_panel_nc<2, EPI>(h, vals, X, Y, c0, c1, dots, ex);   // narrow shards: 1 column per lane
+    if (h->panel_nc == 4 && h->nK == 1 && c1 - c0 > 64) return launch_spmm_panel_nc<4, EPI>(h, vals, X, Y, c0, c1, dots, ex);   // one 128-wide tile
+    if (h->panel_nc >= 2 && c1 - c0 > 32) return launch_spmm_panel_nc<2, EPI>(h, vals, X, Y, c0, c1, dots, ex);   // narrow shards: 1 column per lane
     return launch_spmm_panel_nc<1, EPI>(h, vals, X, Y, c0, c1, dots, ex);
 }
 int launch_spmm_panel(pgb200_ert *h, const double *vals, const double *X, double *Y, int c0, int c1, double *dots) {
@@ -241,7 +242,7 @@ int launch_spmm_panel(pgb200_ert *h, const double *vals, const double *X, double
     return launch_panel<EPI_SPMM>(h, vals, X, Y, c0, c1, dots, ex);
 }
 bool panel_path_ok(const pgb200_ert *h, int c0) {
-    return h->use_panels && h->n_panels > 0 && !(c0 & 1) && (h->nK == 1 || h->nE >= 32 * h->panel_nc);
+    return h->use_panels && h->n_panels > 0 && !(c0 & 1) && (h->nK == 1 || h->nE >= 32 * std::min(2, h->panel_nc));
 }
 
 // launch geometry of the flat element-wise kernels (ert_kernels.cuh, flat_map): column chunks of at most FLAT_T columns,
@@ -1385,8 +1386,8 @@ int pgb200_ert_reset_stats(pgb200_ert *h) {
 }
 int pgb200_ert_set_spmm_variant(pgb200_ert *h, int panel_staged) {
     if (!h) PGB_FAIL("null handle");
-    h->use_panels = panel_staged != 0; h->panel_tma = (panel_staged == 1 || panel_staged == 2);
-    h->panel_nc = (panel_staged == 1) ? 1 : 2;
+    h->use_panels = panel_staged != 0; h->panel_tma = (panel_staged == 1 || panel_staged == 2 || panel_staged == 4);
+    h->panel_nc = (panel_staged == 1) ? 1 : (panel_staged == 4 ? 4 : 2);
     return 0;
 }
 int pgb200_ert_set_profile(pgb200_ert *h, int on) {

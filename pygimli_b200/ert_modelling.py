@@ -19,6 +19,8 @@ there is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
+
 import numpy as np
 
 from . import _capi
@@ -389,6 +391,8 @@ class CoreB200:
                 _capi.check(_capi.lib().pgb200_ert_set_preconditioner(h, 1 if self.hierarchy else 0, 8))
             else:
                 _capi.check(_capi.lib().pgb200_ert_set_preconditioner(h, 0, 8))
+            if os.environ.get("PGB200_SPMM_VARIANT"):      # A/B switch for measurements: 0 plain, 1/2/4 panel NC, 3 cp.async
+                _capi.check(_capi.lib().pgb200_ert_set_spmm_variant(h, int(os.environ["PGB200_SPMM_VARIANT"])))
             self._ensure_primary()
         return self._h
 
