@@ -246,7 +246,7 @@ bool panel_path_ok(const pgb200_ert *h, int c0) {
 }
 
 // launch geometry of the flat element-wise kernels (ert_kernels.cuh, flat_map): column chunks of at most FLAT_T columns,
-// rows per CTA = 12 passes on big levels, fewer on small ones so that they still fill the GPU
+// rows per CTA = rows per pass x passes
 struct FlatCfg { int cw, rows_cta; dim3 grid; };
 inline FlatCfg flat_cfg(int n_rows, int c0, int c1) {
     FlatCfg f;
@@ -254,7 +254,8 @@ inline FlatCfg flat_cfg(int n_rows, int c0, int c1) {
     const int nchunk = cdiv(w, FLAT_T);
     f.cw = cdiv(w, nchunk);
     const int rpp = FLAT_T / f.cw;
-    const int passes = n_rows >= 60000 ? 12 : (n_rows >= 4000 ? 4 : 1);
+    // up to 12 passes per CTA, fewer when that would leave less than ~4 CTAs per SM (small levels, narrow shards)
+    const int passes = std::max(1, std::min(12, n_rows / (rpp * 600)));
     f.rows_cta = rpp * passes;
     f.grid = dim3(cdiv(n_rows, f.rows_cta), nchunk);
     return f;
