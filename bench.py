@@ -122,14 +122,20 @@ def run_reference(args):
     mesh, scheme, model, desc, kw = build_workload(args.workload, args.scale)
     cores = os.cpu_count() or 1
     threads = max(1, min(8, cores - 2))          # reference default (modellingbase.cpp:77)
-    samples = []
     info = {}
     cache = {}
+    # every step is one bounded sample; the whole run is bounded too (--ref-time-budget): once another sample would not
+    # fit, the remaining steps reuse the measured ones (a c3 sample factorises a 180 k-node matrix: 1.5-4 min of CPU)
+    runs, last_wall, t_start = [], 0.0, time.perf_counter()
     with stdout_to_stderr():
         for step in range(args.warmup + args.steps):
+            if runs and (time.perf_counter() - t_start + last_wall) > args.ref_time_budget:
+                break
+            t0 = time.perf_counter()
             t, info = reference_sample(ref, mesh, scheme, model, threads, args, kw, cache)
-            if step >= args.warmup:
-                samples.append(t)
+            last_wall = time.perf_counter() - t0
+            runs.append(t)
+    samples = runs[args.warmup:] if len(runs) > args.warmup else runs[-1:]
     val = float(np.mean(samples))
     line = {"metric": "ert_forward_jacobian_s_per_iter", "value": val, "unit": "s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": val * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
@@ -137,7 +143,7 @@ def run_reference(args):
             "config": {"workload": args.workload + ": " + desc, "cells": mesh.cell_count, "nodes": mesh.node_count,
                        "electrodes": scheme.sensor_count, "data": scheme.size, "model_cells": int(model.size)},
             "cpu_baseline": {"value": val, "unit": "s", "cores": threads, "kind": "reference", "sample": info["sample"],
-                             "stages_s": info["stages"]},
+                             "stages_s": info["stages"], "samples_run": len(runs), "samples_measured": len(samples)},
             "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
@@ -374,6 +380,8 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-12, help="block-PCG relative residual tolerance")
     ap.add_argument("--ref-rows", type=int, default=24, help="data rows in the CPU sensitivity sample")
     ap.add_argument("--ref-sources", type=int, default=1, help="sources in the CPU solve sample")
+    ap.add_argument("--ref-time-budget", type=float, default=180.0,
+                    help="--impl reference: wall-clock budget [s] for re-running the CPU sample over the warm-up and timed steps")
     ap.add_argument("--ref-direct-max-nodes", type=int, default=250000,
                     help="use the direct CPU stand-in solver (scipy SuperLU; the reference factorises with CHOLMOD) up to this mesh "
                          "size -- c3 (180 k nodes) factorises in 1.5-4 min; larger meshes fall back to the Jacobi-PCG stand-in")
