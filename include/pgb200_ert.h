@@ -132,10 +132,13 @@ int pgb200_color_cells(int n_cells, int nloc, const int *cells, int n_nodes, int
 int pgb200_build_panels(int n_rows, const int *rowptr, const int *colidx, int rmax, int hmax,
                         int *panel_ptr, int *halo_ptr, int *halo_cols, unsigned short *lidx, unsigned short *self_idx);
 
-/* Greedy pairwise aggregation along the strongest negative coupling (multilevel preconditioner
- * set-up); agg[n] receives the aggregate id per node; returns the number of aggregates.  With
- * group != NULL only nodes of the same group are matched (aggregates stay inside SpMM row panels). */
-int pgb200_pairwise_aggregate(int n, const int *rowptr, const int *colidx, const double *vals, const int *group, int *agg);
+/* Greedy pairwise aggregation along the strongest negative coupling (multilevel preconditioner set-up); a pair is
+ * formed only if the coupling is at least theta times the strongest coupling of BOTH nodes, left-over nodes join a
+ * neighbouring aggregate only across such a strong coupling (theta = 0: unconditional matching).  agg[n] receives the
+ * aggregate id per node; returns the number of aggregates, -1 on a null argument.  With group != NULL only nodes of the
+ * same group are matched (aggregates stay inside SpMM row panels).                               */
+int pgb200_pairwise_aggregate(int n, const int *rowptr, const int *colidx, const double *vals, const int *group, double theta,
+                              int *agg);
 
 /* ---- life cycle ------------------------------------------------------------------- */
 int pgb200_ert_create(const pgb200_plan *plan, int device, pgb200_ert **out);

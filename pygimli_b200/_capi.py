@@ -113,7 +113,7 @@ def lib():
         L.pgb200_ert_set_preconditioner.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.pgb200_ert_set_graph.argtypes = [C.c_void_p, C.c_int]
         L.pgb200_ert_map_model.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
-        L.pgb200_pairwise_aggregate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pgb200_pairwise_aggregate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         L.pgb200_spmm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p]
         _lib = L
@@ -143,14 +143,20 @@ def color_cells(cells: np.ndarray, n_nodes: int):
     return color, int(n)
 
 
-def pairwise_aggregate(rowptr, colidx, vals, group=None):
+AGGREGATION_THETA = 0.25     # strength threshold of the pairwise matching (see pgb200_pairwise_aggregate)
+
+
+def pairwise_aggregate(rowptr, colidx, vals, group=None, theta=None):
     rowptr = np.ascontiguousarray(rowptr, np.int32)
     colidx = np.ascontiguousarray(colidx, np.int32)
     vals = np.ascontiguousarray(vals, np.float64)
     agg = np.zeros(rowptr.size - 1, np.int32)
     g = None if group is None else np.ascontiguousarray(group, np.int32)
     na = lib().pgb200_pairwise_aggregate(rowptr.size - 1, rowptr.ctypes.data, colidx.ctypes.data, vals.ctypes.data,
-                                         None if g is None else g.ctypes.data, agg.ctypes.data)
+                                         None if g is None else g.ctypes.data,
+                                         C.c_double(AGGREGATION_THETA if theta is None else float(theta)), agg.ctypes.data)
+    if na < 0:
+        raise PGB200Error(last_error())
     return agg, int(na)
 
 

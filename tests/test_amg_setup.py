@@ -100,3 +100,82 @@ def test_vcycle_is_spd_and_accelerates_pcg(hier):
     it_jac = pcg(lambda r: r / A.diagonal())
     it_ml = pcg(lambda r: _vcycle(mats, lv, 0, r))
     assert it_ml < 0.5 * it_jac
+
+
+def _aniso_grid(nx, ny, sx, sy):
+    """5-point matrix of -sx u_xx - sy u_yy on an nx x ny grid (+ a small shift): couplings -sx along x, -sy along y"""
+    idx = np.arange(nx * ny).reshape(ny, nx)
+    rows, cols, vals = [], [], []
+    for (a, b, s) in ((idx[:, :-1], idx[:, 1:], sx), (idx[:-1, :], idx[1:, :], sy)):
+        a, b = a.ravel(), b.ravel()
+        rows += [a, b]; cols += [b, a]; vals += [np.full(a.size, -s), np.full(a.size, -s)]
+    A = sp.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nx * ny, nx * ny)).tocsr()
+    A = A + sp.diags(-A.sum(1).A1 + 1e-3)
+    A.sort_indices()
+    return A, idx
+
+
+def test_strength_threshold_keeps_aggregates_in_the_strong_direction():
+    """stretched cells: with the threshold no aggregate crosses the weak (y) couplings, however many passes follow;
+    the unconditional matching (theta = 0) pairs across them as soon as the strong partners are used up"""
+    A, idx = _aniso_grid(9, 8, 100.0, 1.0)                           # odd row length: one node per row is left over
+    row_of = np.repeat(np.arange(8), 9)
+    agg, na = _capi.pairwise_aggregate(A.indptr, A.indices, A.data)               # default theta = 0.25
+    for a in range(na):
+        assert np.unique(row_of[agg == a]).size == 1                 # members share a grid row
+    assert np.bincount(agg).max() <= 3                               # pairs, the left-over node joins one of them
+    agg0, na0 = _capi.pairwise_aggregate(A.indptr, A.indices, A.data, theta=0.0)
+    assert np.bincount(agg0).min() >= 2                              # nobody stays alone without a threshold
+
+
+def test_weak_partner_is_not_matched_but_may_join():
+    """a coupling must be strong for BOTH nodes to form a pair; a left-over node joins across a coupling that is strong
+    for itself"""
+    A = sp.lil_matrix((5, 5))
+    for i, j, s in ((0, 1, 10.0), (2, 3, 10.0), (1, 4, 0.1), (3, 4, 0.1)):      # node 4 hangs on two strong pairs
+        A[i, j] = A[j, i] = -s
+    A.setdiag(-np.asarray(A.sum(1)).ravel() + 1e-3)
+    A = A.tocsr(); A.sort_indices()
+    agg, na = _capi.pairwise_aggregate(A.indptr, A.indices, A.data)
+    assert na == 2
+    # node 4's couplings (0.1) are strong for ITSELF (they are all it has) -> it joins a neighbouring aggregate
+    assert np.sum(agg == agg[4]) == 3
+    # but it is never chosen as a PARTNER: 0.1 < 0.25 * 10 for nodes 1 and 3
+    assert agg[0] == agg[1] and agg[2] == agg[3]
+
+
+def test_threshold_improves_the_preconditioner_on_a_graded_mesh():
+    """numpy emulation of the V-cycle: the thresholded matching needs fewer PCG iterations than the unconditional one
+    on the (graded, stretched-cell) 3-D test mesh"""
+    P, A = _matrix("3d_p1")
+    counts = {}
+    for theta in (0.0, 0.25):
+        lv = amg_setup.build_hierarchy(A.indptr, A.indices, A.data,
+                                       lambda rp, ci, v, theta=theta: _capi.pairwise_aggregate(rp, ci, v, theta=theta), min_size=64)
+        mats, v = [A], A.data
+        for L in lv:
+            v = amg_setup._sum_values(v, L["gal_ptr"], L["gal_idx"])
+            mats.append(sp.csr_matrix((v, L["colidx"], L["rowptr"]), shape=(L["n"], L["n"])))
+        dws = [(1.6 / max(2.0, (abs(M).sum(1).A1 / M.diagonal()).max())) / M.diagonal() for M in mats]
+
+        def vc(l, r):
+            Al, dw = mats[l], dws[l]
+            if l == len(lv):
+                x = dw * r
+                for _ in range(7):
+                    x = x + dw * (r - Al @ x)
+                return x
+            L = lv[l]
+            x = dw * r
+            x = x + vc(l + 1, np.add.reduceat((r - Al @ x)[L["mem_idx"]], L["mem_ptr"][:-1]))[L["agg"]]
+            return x + dw * (r - Al @ x)
+        b = np.random.default_rng(0).standard_normal(P.N)
+        x, r = np.zeros(P.N), b.copy()
+        z = vc(0, r); p = z.copy(); rz = r @ z
+        it = 0
+        while np.linalg.norm(r) > 1e-10 * np.linalg.norm(b) and it < 2000:
+            Ap = A @ p; al = rz / (p @ Ap); x += al * p; r -= al * Ap
+            z = vc(0, r); rzn = r @ z; p = z + (rzn / rz) * p; rz = rzn; it += 1
+        counts[theta] = it
+    assert counts[0.25] <= counts[0.0]
+    assert counts[0.25] < 2000
