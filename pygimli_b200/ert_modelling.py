@@ -188,6 +188,22 @@ def createCoverage(S: JacobianB200, mesh, response=None, model=None):
     return cov_model[marker] / mesh.cell_sizes()
 
 
+def managerCoverage(S, para_mesh, response, model):
+    """``ERTManager.coverage()`` (pygimli/physics/ert/ertManager.py:328-340): coverage under the logarithmic
+    transformation, log10(coverageDCtrans(J, 1/response, 1/model) / parameter sizes), looked up per cell of the parameter
+    mesh (markers 0..M-1, several cells may share a marker).  ``S`` is the HBM-resident Jacobian (or anything with a
+    ``coverageDCtrans(dd, mm)`` method); only M doubles leave the GPU."""
+    para_mesh = _as_mesh(para_mesh)
+    response, model = np.asarray(response, float), np.asarray(model, float)
+    cov_trans = S.coverageDCtrans(1.0 / response, 1.0 / model)
+    marker = np.asarray(para_mesh.cell_marker)
+    if marker.min() < 0 or marker.max() >= model.size:
+        raise IndexError("coverage: cell markers of the parameter mesh must index the model vector")
+    param_sizes = np.bincount(marker, weights=para_mesh.cell_sizes(), minlength=model.size)
+    with np.errstate(divide="ignore"):
+        return np.log10(cov_trans / param_sizes)[marker]
+
+
 class CoreB200:
     """Replacement for ``pg.core.DCSRMultiElectrodeModelling`` (sr=True) /
     ``DCMultiElectrodeModelling`` (sr=False) on one B200."""

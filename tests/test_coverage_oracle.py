@@ -41,3 +41,34 @@ def test_live_reference_when_present():
     np.testing.assert_allclose(coverage_dc_trans(J, dd, mm), ref.coverage_trans(J, dd, mm), rtol=1e-14)
     np.testing.assert_allclose(create_coverage(J, mesh.cell_marker, mesh.cell_sizes(), resp, model),
                                ref.create_coverage(J, mesh, resp, model), rtol=1e-13)
+
+
+def test_manager_coverage_host_part():
+    """ERTManager.coverage() (ertManager.py:328-340) on top of coverageDCtrans: the host part (parameter sizes per marker,
+    log10, per-cell look-up) with the oracle standing in for the GPU operator"""
+    from pygimli_b200.ert_modelling import managerCoverage
+    mesh, J, dd, mm, resp, model = coverage_case(2)
+
+    class Stub:
+        def coverageDCtrans(self, d, m):
+            return coverage_dc_trans(J, d, m)
+    got = managerCoverage(Stub(), mesh, resp, model)
+    cov = coverage_dc_trans(J, 1.0 / resp, 1.0 / model)
+    sizes = np.zeros(model.size)
+    for c, mk in enumerate(mesh.cell_marker):                         # the reference's loop over paraDomain.cells()
+        sizes[mk] += mesh.cell_sizes()[c]
+    np.testing.assert_allclose(got, np.log10(cov / sizes)[mesh.cell_marker], rtol=1e-14)
+    # several cells per marker: sizes add up
+    mesh.cell_marker = (mesh.cell_marker // 2).astype(np.int32)
+    M2 = int(mesh.cell_marker.max()) + 1
+    got2 = managerCoverage(Stub2(J[:, :M2]), mesh, resp, model[:M2])
+    sizes2 = np.bincount(mesh.cell_marker, weights=mesh.cell_sizes(), minlength=M2)
+    np.testing.assert_allclose(got2, np.log10(coverage_dc_trans(J[:, :M2], 1.0 / resp, 1.0 / model[:M2]) / sizes2)[mesh.cell_marker], rtol=1e-14)
+
+
+class Stub2:
+    def __init__(self, J):
+        self.J = J
+
+    def coverageDCtrans(self, d, m):
+        return coverage_dc_trans(self.J, d, m)
