@@ -77,6 +77,107 @@ class DirectSolver:
         self.n_solve += 1
 
 
+class ComplexDirectSolver:
+    """scipy SuperLU on the complex-symmetric system + 2 refinement steps (stands in for CHOLMOD/UMFPACK complex,
+    cholmodWrapper.cpp:167-222)"""
+
+    def __init__(self):
+        self.lu = None
+        self.n_factor = 0
+        self.n_solve = 0
+
+    def set_matrix(self, n, nnz, rowptr, colidx, vals):
+        import scipy.sparse as sp
+        import scipy.sparse.linalg as spla
+        rp = np.ctypeslib.as_array(rowptr, shape=(n + 1,)).copy()
+        ci = np.ctypeslib.as_array(colidx, shape=(nnz,)).copy()
+        v = np.ctypeslib.as_array(vals, shape=(2 * nnz,)).copy().view(np.complex128)
+        self.A = sp.csr_matrix((v, ci, rp), shape=(n, n))
+        self.lu = spla.splu(self.A.tocsc())
+        self.n_factor += 1
+
+    def solve(self, n, rhs, sol):
+        b = np.ctypeslib.as_array(rhs, shape=(2 * n,)).view(np.complex128)
+        x = self.lu.solve(b)
+        for _ in range(2):
+            x = x + self.lu.solve(b - self.A @ x)
+        np.ctypeslib.as_array(sol, shape=(2 * n,))[:] = np.ascontiguousarray(x).view(np.float64)
+        self.n_solve += 1
+
+
+class RefERTComplex:
+    """The reference's complex-resistivity path: ``DCMultiElectrodeModelling`` with ``setComplex(True)``
+    (total field; model = [re(rho); im(rho)], response = [re(rhoa); im(rhoa)], complex Jacobian)."""
+
+    def __init__(self, mesh, scheme):
+        L = lib()
+        L.ref_create_complex.restype = C.c_void_p
+        self.mesh, self.scheme = mesh, scheme
+        pos = np.ascontiguousarray(mesh.pos, np.float64)
+        nm = np.ascontiguousarray(mesh.node_marker, np.int32)
+        cells = np.ascontiguousarray(mesh.cells, np.int32)
+        cm = np.ascontiguousarray(mesh.cell_marker, np.int32)
+        bounds = np.ascontiguousarray(mesh.bounds, np.int32)
+        bm = np.ascontiguousarray(mesh.bound_marker, np.int32)
+        sens = np.ascontiguousarray(scheme.sensors, np.float64)
+        abmn = scheme.abmn()
+        self.h = C.c_void_p(L.ref_create_complex(
+            C.c_int(mesh.dim), C.c_int(pos.shape[0]), _d(pos), _i(nm),
+            C.c_int(cells.shape[0]), C.c_int(cells.shape[1]), _i(cells), _i(cm),
+            C.c_int(bounds.shape[0]), C.c_int(bounds.shape[1] if bounds.ndim == 2 else 0), _i(bounds), _i(bm),
+            C.c_int(sens.shape[0]), _d(sens), C.c_int(abmn.shape[0]), _i(abmn)))
+        self.N, self.D, self.nE = pos.shape[0], abmn.shape[0], sens.shape[0]
+        self.solver = ComplexDirectSolver()
+        self._cb1 = _SETM(self.solver.set_matrix)
+        self._cb2 = _SOLVE(self.solver.solve)
+        L.ref_set_complex_callbacks(self.h, self._cb1, self._cb2)
+        L.ref_set_threads(self.h, C.c_int(1))
+        if scheme.k is not None:
+            k = np.ascontiguousarray(scheme.k, np.float64)
+            L.ref_set_k(self.h, _d(k))
+
+    def close(self):
+        if self.h:
+            lib().ref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def kw(self):
+        n = lib().ref_n_k(self.h)
+        k, w = np.zeros(n), np.zeros(n)
+        lib().ref_get_kw(self.h, _d(k), _d(w))
+        return k, w
+
+    def response(self, model_c):
+        """model_c: complex cell/model resistivities -> complex apparent resistivities"""
+        mc = np.asarray(model_c, np.complex128)
+        m = np.ascontiguousarray(np.concatenate([mc.real, mc.imag]))
+        out = np.zeros(2 * self.D)
+        lib().ref_response_complex(self.h, C.c_int(m.size), _d(m), _d(out))
+        return out[: self.D] + 1j * out[self.D:]
+
+    def solutions(self):
+        """k-summed potentials, rows [re(e = 0..nE-1); im(e = 0..nE-1)] -> complex (nE, N)"""
+        r = lib().ref_solution_rows(self.h)
+        out = np.zeros((r, self.N))
+        lib().ref_get_solutions(self.h, _d(out))
+        return out[: self.nE] + 1j * out[self.nE:]
+
+    def create_jacobian(self, model_c):
+        mc = np.asarray(model_c, np.complex128)
+        m = np.ascontiguousarray(np.concatenate([mc.real, mc.imag]))
+        rc = np.zeros(2, np.int32)
+        lib().ref_create_jacobian_complex(self.h, C.c_int(m.size), _d(m), _i(rc), None)
+        J = np.zeros((int(rc[0]), 2 * int(rc[1])))
+        lib().ref_create_jacobian_complex(self.h, C.c_int(m.size), _d(m), _i(rc), _d(J))
+        return J.view(np.complex128)
+
+
 class RefERT:
     """The reference's ``DCSRMultiElectrodeModelling`` (sr=True) or ``DCMultiElectrodeModelling``
     on flat arrays.  ``mesh``/``scheme`` are duck-typed (pygimli_b200.MeshArrays / SchemeArrays)."""

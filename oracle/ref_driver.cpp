@@ -48,6 +48,9 @@ void dcfemBoundaryAssembleStiffnessMatrix(RSparseMatrix & S, const Mesh & mesh,
 extern "C" {
 typedef void (*set_matrix_cb)(int n, int nnz, const int * rowptr, const int * colidx, const double * vals);
 typedef void (*solve_cb)(int n, const double * rhs, double * sol);
+// complex variants: values / vectors are interleaved (re, im) doubles, i.e. std::complex<double> / numpy complex128
+typedef void (*set_matrix_c_cb)(int n, int nnz, const int * rowptr, const int * colidx, const double * vals);
+typedef void (*solve_c_cb)(int n, const double * rhs, double * sol);
 }
 
 namespace {
@@ -67,6 +70,19 @@ public:
             for (Index i = 0; i < n; i++) diag_[i] = S.getVal(i, i);
         }
         nSetMatrix++; tSetMatrix += sw.duration();
+    }
+    // complex resistivity (dcfemmodelling.cpp:1843-1866 with ValueType = Complex): only through the callbacks
+    virtual void setMatrix(const CSparseMatrix & S){
+        if (!setCbC_) throwError("oracle driver: complex solve needs the complex callbacks");
+        nC_ = S.rows();
+        setCbC_((int)S.rows(), (int)S.nVals(), &S.vecColPtr()[0], &S.vecRowIdx()[0], reinterpret_cast< const double * >(&S.vecVals()[0]));
+        nSetMatrix++;
+    }
+    virtual void solve(const CVector & b, CVector & x){
+        if (!solveCbC_) throwError("oracle driver: complex solve needs the complex callbacks");
+        if (x.size() != nC_) x.resize(nC_);
+        solveCbC_((int)nC_, reinterpret_cast< const double * >(&b[0]), reinterpret_cast< double * >(&x[0]));
+        nSolve++;
     }
     virtual void solve(const RVector & b, RVector & x){
         Stopwatch sw(true);
@@ -101,6 +117,9 @@ public:
     RVector diag_;
     set_matrix_cb setCb_;
     solve_cb solveCb_;
+    set_matrix_c_cb setCbC_ = 0;
+    solve_c_cb solveCbC_ = 0;
+    Index nC_ = 0;
     long nSetMatrix, nSolve;
     double tSetMatrix, tSolve;
     double tol_;
@@ -154,15 +173,50 @@ void * ref_create(int dim, int nNodes, const double * xyz, const int * nodeMarke
         h->data->createFourPointData(d, abmn[4*d], abmn[4*d+1], abmn[4*d+2], abmn[4*d+3]);
 
     h->sr = sr != 0;
-    if (h->sr) h->fop = new DCSRMultiElectrodeModelling(mesh, *h->data, verbose != 0);
-    else       h->fop = new DCMultiElectrodeModelling(mesh, *h->data, verbose != 0);
+    if (h->sr) h->fop = new DCSRMultiElectrodeModelling(mesh, *h->data, verbose > 0);
+    else       h->fop = new DCMultiElectrodeModelling(mesh, *h->data, verbose > 0);
     h->solver = new InjectedSolver();
     h->fop->setSolver(h->solver);
     h->fop->setThreadCount(1);
     h->subPots = new RMatrix();
-    h->fop->collectSubPotentials(*h->subPots);
+    if (verbose >= 0) h->fop->collectSubPotentials(*h->subPots);   // verbose < 0: complex handle, see ref_create_complex
     return h;
 }
+
+// Complex-resistivity handle (total field only: DCSRMultiElectrodeModelling::calculateK throws for complex,
+// dcfemmodelling.cpp:2156).  The k-resolved potentials cannot be collected (collectSubPotentials takes an RMatrix, the
+// complex run needs a CMatrix the fop creates itself, :1672-1676); solution() holds the k-summed [re; im] rows.
+void * ref_create_complex(int dim, int nNodes, const double * xyz, const int * nodeMarker,
+                          int nCells, int nloc, const int * cells, const int * cellMarker,
+                          int nBounds, int nlocb, const int * bounds, const int * boundMarker,
+                          int nSensors, const double * sensors, int nData, const int * abmn){
+    RefHandle * h = (RefHandle *)ref_create(dim, nNodes, xyz, nodeMarker, nCells, nloc, cells, cellMarker, nBounds, nlocb, bounds,
+                                            boundMarker, nSensors, sensors, nData, abmn, 0, -1);
+    h->fop->setVerbose(false);
+    h->fop->setComplex(true);
+    return h;
+}
+void ref_set_complex_callbacks(void * vh, set_matrix_c_cb a, solve_c_cb b){
+    RefHandle * h = (RefHandle *)vh; h->solver->setCbC_ = a; h->solver->solveCbC_ = b;
+}
+// complex response (dcfemmodelling.cpp:1103-1118): model = [re(rho); im(rho)], out = [re(rhoa); im(rhoa)]
+void ref_response_complex(void * vh, int nModel2, const double * model, double * out){
+    RefHandle * h = (RefHandle *)vh;
+    RVector m(nModel2); for (int i = 0; i < nModel2; i++) m[i] = model[i];
+    RVector r(h->fop->response(m));
+    for (Index i = 0; i < r.size(); i++) out[i] = r[i];
+}
+// complex Jacobian (dcfemmodelling.cpp:1447-1461, 1410-1444): out = interleaved (re, im) row-major [rows x cols]
+void ref_create_jacobian_complex(void * vh, int nModel2, const double * model, int * rowsCols, double * out){
+    RefHandle * h = (RefHandle *)vh;
+    RVector m(nModel2); for (int i = 0; i < nModel2; i++) m[i] = model[i];
+    if (!out) { h->fop->createJacobian(m); }
+    CMatrix * J = dynamic_cast< CMatrix * >(h->fop->jacobian());
+    rowsCols[0] = (int)J->rows(); rowsCols[1] = (int)J->cols();
+    if (out) for (Index i = 0; i < J->rows(); i++)
+        std::memcpy(out + 2*i*J->cols(), reinterpret_cast< const double * >(&(*J)[i][0]), 2*J->cols()*sizeof(double));
+}
+int ref_solution_rows(void * vh){ return (int)((RefHandle *)vh)->fop->solution().rows(); }
 
 void ref_destroy(void * vh){
     RefHandle * h = (RefHandle *)vh;

@@ -139,3 +139,13 @@ def make_pole_case():
     r = np.asarray(rows, np.int32)
     from pygimli_b200.scheme import SchemeArrays
     return mesh, SchemeArrays(scheme.sensors, r[:, 0], r[:, 1], r[:, 2], r[:, 3], None), model
+
+
+COMPLEX_CASES = ("2d_p1", "3d_p1")
+
+
+def complex_model(model, seed: int = 7):
+    """complex resistivities for the complex-resistivity (induced polarisation) cases: the real model with phases of
+    -10 ... -20 mrad per model cell"""
+    rng = np.random.default_rng(seed)
+    return model * np.exp(-0.01j * (1.0 + rng.random(model.size)))
