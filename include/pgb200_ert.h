@@ -210,7 +210,11 @@ int pgb200_ert_clear_potentials(pgb200_ert *h);
 /* device pointer + leading dimension of the k-resolved potentials U[node][ld], column
  * s = electrode + nE * kIdx (subSolutions_ transposed, :1681); used for the NCCL all-gather */
 int pgb200_ert_potentials_info(pgb200_ert *h, void **dev_ptr, int *n_nodes, int *n_src, long long *ld);
+/* after the caller's all-gather filled the other shards' columns; fails if this handle's own shard was never solved */
 int pgb200_ert_mark_potentials_valid(pgb200_ert *h);
+/* bit 0: this handle's source shard holds solved potentials; bit 1: all nS columns are valid (the Jacobian may use
+ * them).  < 0 on a null handle.                                                              */
+int pgb200_ert_potentials_state(pgb200_ert *h);
 
 /* ---- multi-GPU staging (one handle per GPU; the exchange itself is NCCL in the caller) - */
 /* solve this shard's sources; leaves U[:, shard] and the PARTIAL electrode matrix in HBM    */
@@ -234,6 +238,12 @@ long long pgb200_ert_get(pgb200_ert *h, const char *what, double *out_host, long
  * [12]=Jacobian passes timed, [13]=PCG iterations since reset, [14]=solves since reset       */
 int pgb200_ert_stats(pgb200_ert *h, double *stats, int n);
 int pgb200_ert_reset_stats(pgb200_ert *h);
+/* which code paths the last solve / Jacobian plan took (parity tests assert that the kernels the benchmark times are
+ * the ones compared with the reference): [0] source columns per lane of the panel-staged SpMM (0 = plain gather kernel),
+ * [1] column tiles per row panel, [2] 1 if a column tile straddled two wavenumber groups, [3] CUDA-graph launches of
+ * the last solve, [4] Jacobian chunks, [5] register tiles per thread of the widest chunk, [6] 1 if every chunk uses
+ * pre-resolved Gram offsets, [7] coarse levels of the multilevel preconditioner                              */
+int pgb200_ert_path_info(pgb200_ert *h, int *out, int n);
 int pgb200_ert_set_profile(pgb200_ert *h, int on);
 /* on == 2 additionally records one CUDA event per kernel launch (no CUDA graph); pgb200_ert_get_trace returns, for the
  * launches since then, (source line in csrc/pgb200_ert.cu) * 16 + multilevel level of each launch and the time since the previous launch

@@ -358,6 +358,16 @@ class RefERT:
         lib().ref_time_partial_solve(self.h, C.c_int(m.size), _d(m), C.c_int(int(n_src)), _d(out))
         return out if detail else float(out[1])
 
+    def partial_solve_pots(self, model, n_src):
+        """(times[4], pots[n_src * nK, N]): the reference's calculateK for the first n_src sources, every wavenumber;
+        row i + k * n_src holds the total potential of source i at wavenumber k"""
+        m = np.ascontiguousarray(model, np.float64)
+        out = np.zeros(4)
+        nK = lib().ref_n_k(self.h)
+        sol = np.zeros((int(n_src) * nK, self.N))
+        lib().ref_partial_solve_pots(self.h, C.c_int(m.size), _d(m), C.c_int(int(n_src)), _d(out), _d(sol))
+        return out, sol
+
     def solver_stats(self):
         out = np.zeros(4)
         lib().ref_solver_stats(self.h, _d(out))

@@ -249,6 +249,25 @@ void ref_time_partial_solve(void * vh, int nModel, const double * model, int nSr
     out[2] = sw.duration();
     out[0] = h->solver->tSetMatrix - t0s; out[1] = h->solver->tSolve - t0v; out[3] = (double)(h->solver->iters_ - it0);
 }
+// same bounded solve, but the k-resolved total potentials of the first nSrc sources are handed back
+// (row i + k * nSrc, node-major as the reference stores them): bench.py compares them with the GPU's potentials
+void ref_partial_solve_pots(void * vh, int nModel, const double * model, int nSrc, double * out, double * solOut){
+    RefHandle * h = (RefHandle *)vh;
+    RVector m(nModel); for (int i = 0; i < nModel; i++) m[i] = model[i];
+    h->fop->mapERTModel(m, -9e99);
+    std::vector < ElectrodeShape * > eA, eB;
+    h->fop->createCurrentPattern(eA, eB, true);
+    eA.resize(nSrc); eB.resize(nSrc);
+    h->fop->preCalculate(eA, eB);
+    const Index nK = h->fop->kValues().size(), N = h->fop->mesh()->nodeCount();
+    RMatrix sol(nSrc * nK, N);
+    double t0s = h->solver->tSetMatrix, t0v = h->solver->tSolve; long it0 = h->solver->iters_;
+    Stopwatch sw(true);
+    for (Index k = 0; k < nK; k++) h->fop->calculateK(eA, eB, sol, k);
+    out[2] = sw.duration();
+    out[0] = h->solver->tSetMatrix - t0s; out[1] = h->solver->tSolve - t0v; out[3] = (double)(h->solver->iters_ - it0);
+    if (solOut) for (Index r = 0; r < sol.rows(); r++) std::memcpy(solOut + (size_t)r * N, &sol[r][0], N * sizeof(double));
+}
 void ref_set_threads(void * vh, int n){ ((RefHandle *)vh)->fop->setThreadCount(n); }
 
 int ref_n_k(void * vh){ return (int)((RefHandle *)vh)->fop->kValues().size(); }

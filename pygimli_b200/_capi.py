@@ -57,6 +57,7 @@ EXPORTS = [
     "pgb200_ert_mark_potentials_valid", "pgb200_ert_forward_dev", "pgb200_ert_pm_info", "pgb200_ert_finish_response_dev",
     "pgb200_ert_pack_potentials", "pgb200_ert_get", "pgb200_ert_stats", "pgb200_ert_reset_stats", "pgb200_ert_set_profile",
     "pgb200_spmm", "pgb200_ert_get_trace", "pgb200_ert_set_primary_dev", "pgb200_ert_fill_matrix", "pgb200_ert_jacobian_mult_lr", "pgb200_ert_jacobian_tmult_lr", "pgb200_ert_coverage_trans",
+    "pgb200_ert_path_info", "pgb200_ert_potentials_state",
 ]
 
 _lib = None
@@ -79,7 +80,7 @@ def lib():
         L.pgb200_ert_get.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]
         L.pgb200_ert_create.argtypes = [C.POINTER(Plan), C.c_int, C.POINTER(C.c_void_p)]
         for name in ("pgb200_ert_destroy", "pgb200_ert_clear_potentials", "pgb200_ert_mark_potentials_valid",
-                     "pgb200_ert_reset_stats"):
+                     "pgb200_ert_reset_stats", "pgb200_ert_potentials_state"):
             getattr(L, name).argtypes = [C.c_void_p]
         L.pgb200_ert_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         L.pgb200_ert_set_solver.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int]
@@ -106,6 +107,7 @@ def lib():
         L.pgb200_ert_pack_potentials.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
         L.pgb200_ert_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.pgb200_ert_set_profile.argtypes = [C.c_void_p, C.c_int]
+        L.pgb200_ert_path_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.pgb200_color_cells.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.pgb200_build_panels.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
         L.pgb200_ert_set_spmm_variant.argtypes = [C.c_void_p, C.c_int]

@@ -92,7 +92,7 @@ struct pgb200_ert {
     // state (device)
     DevBuf<double> model, rho, rho_src, vals, vals1, dinv, prim, B, X, R, P, AP, U, scal, pM, resp, resp_rez, rhoa, Jt, tmp, xin, yout;
     DevBuf<int> flags;
-    bool pots_valid = false, have_vals = false;
+    bool pots_valid = false, shard_solved = false, have_vals = false;   // pots_valid: ALL nS columns of U hold potentials of one model
     int model_len = 0;
     std::vector<double> h_model;
     // jacobian plan
@@ -115,6 +115,8 @@ struct pgb200_ert {
     cudaEvent_t jev[2]; bool jac_timed = false; int jac_launches = 0; long long total_iters = 0; int solves = 0;
     double *h_pinned = nullptr; size_t h_pinned_n = 0;
     int num_sms = 148;
+    // which code paths the last solve / Jacobian took (pgb200_ert_path_info)
+    int pi_panel_nc = 0, pi_tiles = 0, pi_two_k = 0, pi_graph_launches = 0;
 };
 
 inline void note_launch(pgb200_ert *h, int line) {
@@ -222,6 +224,7 @@ int launch_spmm_panel_nc(pgb200_ert *h, const double *vals, const double *X, dou
         configured[NC][EPI] = smem;
     }
     dim3 grid(h->n_panels, ntile);
+    h->pi_panel_nc = NC; h->pi_tiles = ntile; if (h->nK > 1 && (tw % h->nE != 0 || c0 % h->nE != 0)) h->pi_two_k = 1;
 #define PANEL_GO(D, S) k_spmm_panel<NC, D, S, EPI><<<grid, PANEL_THREADS, smem, h->st>>>(h->rowptr.p, h->lidx.p, h->self_idx.p, h->panel_ptr.p, \
         h->halo_ptr.p, h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0, c1, tw, h->max_halo, h->max_pnnz, h->max_rows, h->ld, dots, ex)
     if (h->panel_tma) { if (dots) PANEL_GO(true, 1); else PANEL_GO(false, 1); }
@@ -403,6 +406,7 @@ int pcg_solve(pgb200_ert *h) {
     const int s0 = h->c0, s1 = h->c1, ncols = s1 - s0;      // this shard's source columns
     int c0 = s0, c1 = s1;                                    // ACTIVE window: shrinks as wavenumber groups converge
     h->last_iters = 0; h->last_relres = 0.0;
+    h->pi_panel_nc = 0; h->pi_tiles = 0; h->pi_two_k = 0; h->pi_graph_launches = 0;
     if (ncols <= 0) return 0;
     h->col_relres.assign(h->ld, 0.0);
     const size_t ld = h->ld;
@@ -501,6 +505,7 @@ int pcg_solve(pgb200_ert *h) {
                     h->gkey = key;
                 }
                 CK(cudaGraphLaunch(h->gexec, h->st));
+                h->pi_graph_launches++;
                 h->launches += h->launches_per_block;
             }
             it += 6; blocks++;
@@ -584,7 +589,10 @@ int forward_solve(pgb200_ert *h) {
         k_finalize_pots<<<g, b, 0, h->st>>>(h->X.p, h->sr ? h->prim.p : nullptr, h->rho_src.p, 0.0, h->N, h->nE, c0, c1, h->ld, h->U.p); LAUNCH(h);
     }
     CK(cudaGetLastError());
-    h->pots_valid = true;
+    // a source shard fills only its own columns: the Jacobian may use U only after the caller's all-gather
+    // (pgb200_ert_mark_potentials_valid)
+    h->shard_solved = true;
+    h->pots_valid = (c0 == 0 && c1 == h->nS);
     return 0;
 }
 
@@ -595,7 +603,8 @@ int analytic_pots(pgb200_ert *h, double scale) {
         k_finalize_pots<<<g, b, 0, h->st>>>(nullptr, h->prim.p, nullptr, scale, h->N, h->nE, c0, c1, h->ld, h->U.p); LAUNCH(h);
     }
     CK(cudaGetLastError());
-    h->pots_valid = true;
+    h->shard_solved = true;
+    h->pots_valid = (c0 == 0 && c1 == h->nS);
     return 0;
 }
 
@@ -1066,7 +1075,7 @@ int pgb200_ert_set_shard(pgb200_ert *h, int src_begin, int src_end, int row_begi
     if (!h) PGB_FAIL("null handle");
     if (src_begin < 0 || src_end > h->nS || src_begin > src_end || row_begin < 0 || row_end > h->D || row_begin > row_end) PGB_FAIL("invalid shard");
     CK(cudaSetDevice(h->device));
-    h->c0 = src_begin; h->c1 = src_end; h->pots_valid = false;
+    h->c0 = src_begin; h->c1 = src_end; h->pots_valid = false; h->shard_solved = false;
     if (row_begin != h->row0 || row_end != h->row1) { h->row0 = row_begin; h->row1 = row_end; CKR(build_jac_plan(h)); }
     return 0;
 }
@@ -1080,8 +1089,14 @@ int pgb200_ert_set_kfac(pgb200_ert *h, const double *k) {
     return 0;
 }
 
-int pgb200_ert_clear_potentials(pgb200_ert *h) { if (!h) PGB_FAIL("null handle"); h->pots_valid = false; return 0; }
-int pgb200_ert_mark_potentials_valid(pgb200_ert *h) { if (!h) PGB_FAIL("null handle"); h->pots_valid = true; return 0; }
+int pgb200_ert_clear_potentials(pgb200_ert *h) { if (!h) PGB_FAIL("null handle"); h->pots_valid = false; h->shard_solved = false; return 0; }
+int pgb200_ert_mark_potentials_valid(pgb200_ert *h) {
+    if (!h) PGB_FAIL("null handle");
+    if (!h->shard_solved) PGB_FAIL("potentials cannot be marked valid: this handle's source shard has not been solved (run the forward solve first)");
+    h->pots_valid = true;
+    return 0;
+}
+int pgb200_ert_potentials_state(pgb200_ert *h) { if (!h) return -1; return (h->shard_solved ? 1 : 0) | (h->pots_valid ? 2 : 0); }
 
 // ---- forward --------------------------------------------------------------------------
 static int response_common(pgb200_ert *h, int n_in, double *rhoa_dev) {
@@ -1201,7 +1216,7 @@ int pgb200_ert_set_primary_dev(pgb200_ert *h, const double *src_dev, long long s
     k_gather_rows<<<g, b, 0, h->st>>>(src_dev, (size_t)src_ld, map.p, h->N, h->nS, h->ld, h->prim.p); LAUNCH(h);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->st));
-    h->prim_set = true; h->pots_valid = false; h->jac_valid = false;
+    h->prim_set = true; h->pots_valid = false; h->shard_solved = false; h->jac_valid = false;
     return 0;
 }
 
@@ -1390,6 +1405,14 @@ int pgb200_ert_stats(pgb200_ert *h, double *s, int n) {
                     h->ph_ms[PH_SOLVE], h->ph_ms[PH_EPI], h->ph_ms[PH_JAC], (double)h->spmm_timed, h->spmm_ms, h->jac_ms,
                     (double)h->jac_launches, (double)h->total_iters, (double)h->solves};
     for (int i = 0; i < n && i < 15; i++) s[i] = v[i];
+    return 0;
+}
+int pgb200_ert_path_info(pgb200_ert *h, int *out, int n) {
+    if (!h || !out) PGB_FAIL("null argument");
+    int mt = 0, res = 1;
+    for (auto &c : h->chunks) { mt = std::max(mt, c.mt); res = res && c.resolved; }
+    const int v[8] = {h->pi_panel_nc, h->pi_tiles, h->pi_two_k, h->pi_graph_launches, (int)h->chunks.size(), mt, res, (int)h->amg.size()};
+    for (int i = 0; i < n && i < 8; i++) out[i] = v[i];
     return 0;
 }
 int pgb200_ert_reset_stats(pgb200_ert *h) {

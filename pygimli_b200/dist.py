@@ -142,7 +142,13 @@ class ShardedERT:
 
     def create_jacobian_dev(self, model_dev):
         if self.world > 1:
-            self._allgather_potentials()
+            state = _capi.lib().pgb200_ert_potentials_state(self.core._h)
+            if not (state & 2):
+                # prepareJacobianT_ (dcfemmodelling.cpp:1246-1309): no potentials (never solved, setShard, clearPotentials)
+                # -> solve this shard's sources for this model first; only then are the other shards' columns gathered
+                if not (state & 1):
+                    _capi.check(_capi.lib().pgb200_ert_forward_dev(self.core._h, C.c_void_p(model_dev.data_ptr()), int(model_dev.numel())))
+                self._allgather_potentials()
         self.core.createJacobian_dev(model_dev.data_ptr(), model_dev.numel())
 
     # ---- host-buffer path ----------------------------------------------------------------

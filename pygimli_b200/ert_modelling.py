@@ -291,8 +291,14 @@ class CoreB200:
         if self.sr:
             pm = self._prim_pm                       # SR with rho = 1: secondary field is zero, u = primary potentials
         else:
+            # total field: u(rho = 1) from a solve on this mesh (dcfemmodelling.cpp:1539-1556).  The k-factors are what is
+            # being computed, so the forward call must not ask for them (response() would raise without them, :1096)
             P = self._plan
-            self.response(np.ones(nModel if nModel > 0 else P.M))
+            placeholder, self._placeholder_k = self._placeholder_k, False
+            try:
+                self.response(np.ones(nModel if nModel > 0 else P.M))
+            finally:
+                self._placeholder_k = placeholder
             pm = self.get("pm").reshape(P.nE, P.nE)
             self.clearPotentials()
         return 1.0 / (electrode_matrix_data(pm, sch) + TOLERANCE)
@@ -512,6 +518,14 @@ class CoreB200:
                 "ms_epilogue", "ms_jacobian", "spmm_timed", "spmm_ms_total", "jacobian_kernel_ms", "jacobian_timed",
                 "pcg_iterations_total", "solves"]
         return dict(zip(keys, s.tolist()))
+
+    def pathInfo(self) -> dict:
+        """which kernels the last solve / Jacobian plan used (pgb200_ert_path_info)"""
+        v = np.zeros(8, np.int32)
+        _capi.check(_capi.lib().pgb200_ert_path_info(self._ensure_handle(), v.ctypes.data, 8))
+        keys = ["spmm_panel_nc", "spmm_tiles", "spmm_two_k", "graph_launches", "jac_chunks", "jac_tiles_per_thread",
+                "jac_resolved", "amg_levels"]
+        return dict(zip(keys, (int(x) for x in v)))
 
     def resetStats(self):
         _capi.check(_capi.lib().pgb200_ert_reset_stats(self._ensure_handle()))

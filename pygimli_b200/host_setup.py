@@ -625,7 +625,9 @@ def build_plan(mesh: MeshArrays, scheme, k_values=None, weights=None, color_fn=N
         raise NotImplementedError("fixed-value regions are not supported on the B200 path")
     P.M = int(cm.max()) + 1 if cm.size and cm.max() >= 0 else 0
     P.cell_marker = cm.copy()
-    empty = cm == -1
+    # every cell without a model value is filled by the prolongation: the reference zero-initialises the attributes and
+    # prolongateEmptyCellsValues (mesh.cpp:2247-2316) fills all |value| < TOLERANCE, whatever negative marker they carry
+    empty = cm < 0
     P.has_background = bool(empty.any())
     levels = []
     if P.has_background:

@@ -68,6 +68,52 @@ def make_case(name: str):
     return mesh, scheme, model
 
 
+# Cases sized so that the kernels bench.py times are the ones compared with the reference:
+#   3d_p1_wide  72 surface electrodes, complete dipole-dipole: > 64 source columns -> two column tiles of the NC = 2 panel
+#               SpMM in all three epilogue roles inside the CUDA graph, a 72 x 72 Gram block
+#   2d_p1_wide  65 electrodes, 2.5-D: column tiles that straddle two wavenumber groups (the two_k path of the panel SpMM)
+#   3d_p1_192   192 surface electrodes, every 7th row of the complete dipole-dipole scheme: the current-electrode list
+#               does not fit one Gram block -> several Jacobian chunks, two register tiles per thread
+WIDE_CASES = ("3d_p1_wide", "2d_p1_wide", "3d_p1_192")
+
+
+def make_wide_case(name: str):
+    """-> (MeshArrays, SchemeArrays with analytic k, model, rows): ``rows`` = the data rows whose Jacobian rows the golden
+    file holds (the reference computes only those; every row of J depends on the potentials alone)"""
+    from pygimli_b200.scheme import create_dd_complete
+    if name == "2d_p1_wide":
+        ne, sp = 65, 1.0
+        xs = graded_axis(0.0, (ne - 1) * sp, sp / 2, 1.4, 300.0)
+        ys = -graded_axis(0.0, 16.0, sp / 2, 1.4, 300.0, both=False)
+        mesh = grid_mesh_2d(xs, ys, para_box=(-2.0, (ne - 1) * sp + 2.0, -17.0))
+        sens = np.zeros((ne, 3))
+        sens[:, 0] = np.arange(ne) * sp
+        mark_electrode_nodes(mesh, sens)
+        scheme = create_dd(sens)
+        scheme.k = geometric_factors(scheme, 2)
+    else:
+        nx, ny = (9, 8) if name == "3d_p1_wide" else (16, 12)
+        sp = 1.0
+        xs = graded_axis(0.0, (nx - 1) * sp, sp, 1.6, 60.0)
+        ysx = graded_axis(0.0, (ny - 1) * sp, sp, 1.6, 60.0)
+        zs = -graded_axis(0.0, 4.0, sp, 1.6, 60.0, both=False)
+        pb = (-1.5, (nx - 1) * sp + 1.5, -1.5, (ny - 1) * sp + 1.5, -4.5)
+        mesh = grid_mesh_3d(xs, ysx, zs, para_box=pb, marker_per="cube")
+        gx, gy = np.meshgrid(np.arange(nx) * sp, np.arange(ny) * sp)
+        sens = np.stack([gx.ravel(), gy.ravel(), np.zeros(nx * ny)], 1)
+        mark_electrode_nodes(mesh, sens)
+        scheme = create_dd_complete(sens)
+        if name == "3d_p1_192":
+            scheme = scheme.subset(np.arange(0, scheme.size, 7))
+        scheme.k = geometric_factors(scheme, 3)
+        ok = np.isfinite(scheme.k) & (np.abs(scheme.k) < 1e9)
+        if not ok.all():
+            scheme = scheme.subset(np.nonzero(ok)[0])
+    M = int(mesh.cell_marker.max()) + 1
+    rows = np.unique(np.linspace(0, scheme.size - 1, 48).astype(int))
+    return mesh, scheme, _model(M, seed=4321), rows
+
+
 def coverage_case(dim: int, seed: int = 77):
     """-> (parameter mesh with one cell per model entry and shuffled markers, dense J, dd, mm, response, model):
     seeded inputs of the coverage tests (coverageDCtrans / createCoverage, bertJacobian.cpp:569-628)"""

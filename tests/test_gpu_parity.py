@@ -97,7 +97,7 @@ def test_jacobian(case):
     assert _relmax(J, ref) < TOL
     # row-wise too: every data row within tolerance of its own scale
     rs = np.max(np.abs(ref), axis=1)
-    assert np.max(np.max(np.abs(J - ref), axis=1) / rs) < 1e-7
+    assert np.max(np.max(np.abs(J - ref), axis=1) / rs) < TOL
 
 
 def test_jacobian_operator(case):

@@ -96,3 +96,35 @@ def test_jacobian_without_k_uses_numeric_factors():
     fop.createJacobian(model)
     assert _relmax(fop._core._scheme.k, g["kfac"]) < TOL
     assert _relmax(fop.jacobian().numpy(), g["J"]) < TOL
+
+
+def test_total_field_numeric_factors_without_k():
+    """sr=False on a topography mesh without k-factors: calcGeometricFactor takes 1 / (u(rho = 1) + TOLERANCE) from a
+    rho = 1 solve on this mesh (dcfemmodelling.cpp:1527-1556), and createJacobian fills the factors the same way
+    (:1286-1290) instead of raising"""
+    from oracle import ref
+    from pygimli_b200 import ERTModellingB200
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    mesh, scheme, model = make_topo_case("topo_2d")
+    R = ref.RefERT(mesh, scheme, sr=False)
+    k_ref = R.geometric_factors()
+    R.set_k(k_ref)
+    r_ref = R.response(model)
+    J_ref = R.create_jacobian(model)
+    R.close()
+    fop = ERTModellingB200(sr=False)
+    fop.setMesh(mesh)
+    fop.setData(scheme)
+    k = fop._core.calcGeometricFactor()
+    assert _relmax(k, k_ref) < TOL
+    fop2 = ERTModellingB200(sr=False)
+    fop2.setMesh(mesh)
+    fop2.setData(scheme)
+    fop2.createJacobian(model)                       # fills k numerically first
+    assert _relmax(fop2._core._scheme.k, k_ref) < TOL
+    rhoa = fop2.response(model)
+    assert np.all(np.abs(rhoa - r_ref) <= TOL * np.abs(r_ref) + np.abs(k_ref) * 2e-10)
+    assert _relmax(fop2.jacobian().numpy(), J_ref) < TOL
+    fop._core.close()
+    fop2._core.close()
