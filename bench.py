@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 
 
 def _traffic(workload, kernel):
-    """DRAM bytes per launch from the committed ncu capture (profiles/r01_traffic.json), or None"""
+    """DRAM bytes per launch from the committed ncu capture (profiles/r02_traffic.json), or None"""
     try:
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
             t = json.load(f)[workload][kernel]
@@ -250,7 +250,7 @@ def run_b200(args):
     stream = torch.cuda.current_stream()
     fop.set_stream(stream.cuda_stream)
     from pygimli_b200 import _capi
-    _capi.check(_capi.lib().pgb200_ert_set_spmm_variant(fop.core._h, {"plain": 0, "panel1": 1, "panel": 2, "panel_cpasync": 3, "panel4": 4}[args.spmm]))
+    _capi.check(_capi.lib().pgb200_ert_set_spmm_variant(fop.core._h, {"plain": 0, "stream": 1}[args.spmm]))
     t_setup = time.perf_counter() - t_setup
     D, M = scheme.size, int(model.size)
 
@@ -360,10 +360,10 @@ def run_b200(args):
                        "setup_s": t_setup},
             "pcg_iterations": st["pcg_iterations"], "pcg_max_rel_residual": st["max_rel_residual"],
             "phase_ms_per_step": {k: st[k] / args.steps for k in ("ms_map", "ms_assemble", "ms_rhs", "ms_solve", "ms_epilogue", "ms_jacobian")},
-            "roofline": {"kernel": ("k_spmm_panel (%s-staged row panels" % ("cp.async" if args.spmm == "panel_cpasync" else "TMA") if args.spmm != "plain" else "k_spmm (plain gather") + ", CSR x dense block, inside block-PCG)", "bound": "hbm", "achieved": ach, "peak": peak,
+            "roofline": {"kernel": ("k_spmm_stream (persistent, warp-specialised, TMA-staged row panels" if args.spmm != "plain" else "k_spmm (plain gather") + ", CSR x dense block, inside block-PCG)", "bound": "hbm", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": ach / peak if peak else None,
                          "peak_nominal": 8000.0, "frac_nominal": ach / 8000.0,
-                         "traffic": _traffic(args.workload, "k_spmm_panel") if (world == 1 and args.scale == 1.0 and args.spmm == "panel") else None, "peak_source": peak_src,
+                         "traffic": _traffic(args.workload, "k_spmm_stream") if (world == 1 and args.scale == 1.0 and args.spmm == "stream") else None, "peak_source": peak_src,
                          "launches_timed": st["spmm_timed"], "avg_launch_ms": spmm_ms, "algorithmic_bytes_per_launch": spmm_bytes},
             "roofline_jacobian": {"kernel": "k_jacobian", "bound": "hbm", "achieved": jac_bytes / (jac_ms * 1e-3) / 1e9 if jac_ms > 0 else None,
                                   "peak": peak, "unit": "GB/s", "frac": (jac_bytes / (jac_ms * 1e-3) / 1e9 / peak) if jac_ms > 0 else None,
@@ -424,7 +424,7 @@ def main():
                          "size -- c3 (180 k nodes) factorises in 1.5-4 min; larger meshes fall back to the Jacobi-PCG stand-in")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precond", default="multilevel", choices=["multilevel", "jacobi"], help="block-PCG preconditioner")
-    ap.add_argument("--spmm", default="panel", choices=["panel", "panel1", "panel4", "panel_cpasync", "plain"], help="SpMM kernel inside PCG (A/B measurement)")
+    ap.add_argument("--spmm", default="stream", choices=["stream", "plain"], help="SpMM kernel inside PCG (A/B measurement)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -85,15 +85,6 @@ typedef struct pgb200_plan {
     const int *pro_nb;          /* [n*pro_nf] neighbour cells                                */
     const double *pro_w;        /* [n*pro_nf] normalised weights (0 = unused)                */
 
-    int n_panels;               /* row panels of the staged SpMM (0 = use the plain kernel)  */
-    int max_halo;               /* largest halo (distinct columns) of a panel                */
-    int max_panel_nnz;          /* largest number of CSR entries of a panel                  */
-    const int *panel_ptr;       /* [n_panels+1] row ranges                                   */
-    const int *halo_ptr;        /* [n_panels+1] ranges into halo_cols                        */
-    const int *halo_cols;       /* distinct columns touched by each panel                    */
-    const unsigned short *lidx; /* [nnz] column of every entry as offset into its halo list  */
-    const unsigned short *self_idx; /* [N] offset of the row's own column (diagonal)         */
-
     int n_jac_cells;            /* cells with marker >= 0, sorted by marker (:298-299)       */
     const int *jac_cells;       /* [n_jac_cells]                                             */
     const int *jac_col_ptr;     /* [M+1] ranges into jac_cells                               */
@@ -127,10 +118,13 @@ int pgb200_version(void);
 /* Greedy conflict colouring: cells sharing a node get different colours.
  * Returns the number of colours (<= 0 on failure); color[C] receives the colour per cell. */
 int pgb200_color_cells(int n_cells, int nloc, const int *cells, int n_nodes, int *color);
-/* Row panels of the staged SpMM: consecutive rows grouped while rows <= rmax and distinct
- * columns <= hmax.  Returns the number of panels (< 0 on failure).                          */
-int pgb200_build_panels(int n_rows, const int *rowptr, const int *colidx, int rmax, int hmax,
-                        int *panel_ptr, int *halo_ptr, int *halo_cols, unsigned short *lidx, unsigned short *self_idx);
+/* Streamed row panels of the SpMM kernel (csrc/stream_panels.h) for a CSR pattern; the library builds them itself inside
+ * pgb200_ert_create / pgb200_ert_set_hierarchy, this entry point exists for the host-side tests.  Two calls: with
+ * panel_row_ptr == NULL only counts[8] = {panels, chunks, halo entries, crp_stride, max rows, max chunk halo, max chunk
+ * entries, nnz} is filled; then with arrays of those sizes.  Returns 0 on success.                            */
+int pgb200_build_stream_panels(int n_rows, const int *rowptr, const int *colidx, int rmax, int hc, int max_chunks, int *counts,
+                               int *panel_row_ptr, int *panel_chunk_ptr, int *chunk_halo_ptr, int *halo_cols, int *chunk_ent_ptr,
+                               int *ent_src, unsigned *ent_idx, int *crp);
 
 /* Greedy pairwise aggregation along the strongest negative coupling (multilevel preconditioner set-up); a pair is
  * formed only if the coupling is at least theta times the strongest coupling of BOTH nodes, left-over nodes join a
@@ -239,18 +233,18 @@ long long pgb200_ert_get(pgb200_ert *h, const char *what, double *out_host, long
 int pgb200_ert_stats(pgb200_ert *h, double *stats, int n);
 int pgb200_ert_reset_stats(pgb200_ert *h);
 /* which code paths the last solve / Jacobian plan took (parity tests assert that the kernels the benchmark times are
- * the ones compared with the reference): [0] source columns per lane of the panel-staged SpMM (0 = plain gather kernel),
- * [1] column tiles per row panel, [2] 1 if a column tile straddled two wavenumber groups, [3] CUDA-graph launches of
- * the last solve, [4] Jacobian chunks, [5] register tiles per thread of the widest chunk, [6] 1 if every chunk uses
- * pre-resolved Gram offsets, [7] coarse levels of the multilevel preconditioner                              */
+ * the ones compared with the reference): [0] column pairs per lane of the streamed SpMM (0 = plain gather kernel),
+ * [1] column tiles, [2] unused, [3] CUDA-graph launches of the last solve, [4] Jacobian chunks, [5] register tiles per
+ * thread of the widest chunk, [6] 1 if every chunk uses pre-resolved Gram offsets, [7] coarse levels of the multilevel
+ * preconditioner, [8] shared-memory slots of the streamed kernel's ring, [9] coarse levels on the streamed kernel  */
 int pgb200_ert_path_info(pgb200_ert *h, int *out, int n);
 int pgb200_ert_set_profile(pgb200_ert *h, int on);
 /* on == 2 additionally records one CUDA event per kernel launch (no CUDA graph); pgb200_ert_get_trace returns, for the
- * launches since then, (source line in csrc/pgb200_ert.cu) * 16 + multilevel level of each launch and the time since the previous launch
+ * launches since then, (source line in csrc/pgb200_ert.cu) * 256 + 16 * role + multilevel level of each launch (role of a
+ * streamed SpMM launch: 1 SpMM, 2 post-smoothing, 3 residual; 0 otherwise) and the time since the previous launch
  * finished [ms]: a warm per-kernel timeline of a step (profiles/summarize_trace.py).  Returns the entry count.  */
 int pgb200_ert_get_trace(pgb200_ert *h, int *lines, float *ms, int cap);
-/* 0: plain gather kernel; 1 / 2: panel-staged SpMM, one TMA bulk copy per halo row, with 1 / 2
- * (default) source columns per lane; 3: same as 2 but cp.async (LDGSTS) staging (A/B evidence)   */
+/* 0: plain gather kernels (A/B evidence); non-zero (default): the streamed, warp-specialised row-panel kernel */
 int pgb200_ert_set_spmm_variant(pgb200_ert *h, int panel_staged);
 
 /* ---- single-kernel entry points (device pointers; unit tests and micro-benchmarks) --- */

@@ -42,7 +42,8 @@ def main():
         return f"line {line}"
     agg = collections.OrderedDict()
     for code, t in zip(lines, ms):
-        key = (name(int(code) // 16), int(code) % 16, int(code) // 16)
+        role = {0: "", 1: " spmm", 2: " post", 3: " residual"}[(int(code) % 256) // 16]
+        key = (name(int(code) // 256) + role, int(code) % 16, int(code) // 256)
         a = agg.setdefault(key, [0, 0.0])
         a[0] += 1
         a[1] += float(t)
@@ -50,9 +51,9 @@ def main():
     iters = max(1.0, st["pcg_iterations"])
     print(f"# warm per-launch timeline, workload {args.workload}: {len(ms)} launches, {total:.1f} ms, {int(iters)} PCG iterations"
           f" ({total / iters * 1e3:.0f} us per iteration incl. set-up/epilogue; events add ~2 us per launch, CUDA graph off)")
-    print(f"{'kernel (launch site)':34s} {'level':>5s} {'launches':>9s} {'total ms':>10s} {'us/launch':>10s} {'us/iter':>9s} {'share':>7s}")
+    print(f"{'kernel (launch site)':38s} {'level':>5s} {'launches':>9s} {'total ms':>10s} {'us/launch':>10s} {'us/iter':>9s} {'share':>7s}")
     for (nm, lvl, line), (cnt, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print(f"{nm + ' @' + str(line):34s} {lvl:5d} {cnt:9d} {t:10.2f} {t / cnt * 1e3:10.1f} {t / iters * 1e3:9.1f} {100 * t / total:6.1f}%")
+        print(f"{nm + ' @' + str(line):38s} {lvl:5d} {cnt:9d} {t:10.2f} {t / cnt * 1e3:10.1f} {t / iters * 1e3:9.1f} {100 * t / total:6.1f}%")
 
 
 if __name__ == "__main__":

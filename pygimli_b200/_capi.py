@@ -34,8 +34,6 @@ class Plan(C.Structure):
         ("pick_w", c_dbl_p), ("src_cell_ptr", c_int_p), ("src_cells", c_int_p),
         ("n_pro_levels", C.c_int), ("pro_nf", C.c_int), ("pro_level_ptr", c_int_p), ("pro_cells", c_int_p), ("pro_nb", c_int_p),
         ("pro_w", c_dbl_p),
-        ("n_panels", C.c_int), ("max_halo", C.c_int), ("max_panel_nnz", C.c_int), ("panel_ptr", c_int_p), ("halo_ptr", c_int_p), ("halo_cols", c_int_p),
-        ("lidx", C.POINTER(C.c_ushort)), ("self_idx", C.POINTER(C.c_ushort)),
         ("n_jac_cells", C.c_int), ("jac_cells", c_int_p), ("jac_col_ptr", c_int_p),
         ("abmn", c_int_p), ("k_fac", c_dbl_p),
         ("topography", C.c_int),
@@ -49,7 +47,7 @@ class AmgLevel(C.Structure):
 
 # every symbol include/pgb200_ert.h declares (checked by tests/test_capi_symbols.py)
 EXPORTS = [
-    "pgb200_last_error", "pgb200_version", "pgb200_color_cells", "pgb200_build_panels", "pgb200_ert_set_spmm_variant", "pgb200_pairwise_aggregate", "pgb200_ert_set_hierarchy", "pgb200_ert_set_preconditioner", "pgb200_ert_set_graph", "pgb200_ert_map_model",
+    "pgb200_last_error", "pgb200_version", "pgb200_color_cells", "pgb200_build_stream_panels", "pgb200_ert_set_spmm_variant", "pgb200_pairwise_aggregate", "pgb200_ert_set_hierarchy", "pgb200_ert_set_preconditioner", "pgb200_ert_set_graph", "pgb200_ert_map_model",
     "pgb200_ert_create", "pgb200_ert_destroy", "pgb200_ert_set_stream", "pgb200_ert_set_solver", "pgb200_ert_set_shard",
     "pgb200_ert_set_kfac", "pgb200_ert_response", "pgb200_ert_create_jacobian", "pgb200_ert_jacobian_copy",
     "pgb200_ert_jacobian_mult", "pgb200_ert_jacobian_tmult", "pgb200_ert_response_dev", "pgb200_ert_create_jacobian_dev",
@@ -109,7 +107,7 @@ def lib():
         L.pgb200_ert_set_profile.argtypes = [C.c_void_p, C.c_int]
         L.pgb200_ert_path_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.pgb200_color_cells.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
-        L.pgb200_build_panels.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
+        L.pgb200_build_stream_panels.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 9
         L.pgb200_ert_set_spmm_variant.argtypes = [C.c_void_p, C.c_int]
         L.pgb200_ert_set_hierarchy.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.pgb200_ert_set_preconditioner.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -162,27 +160,26 @@ def pairwise_aggregate(rowptr, colidx, vals, group=None, theta=None):
     return agg, int(na)
 
 
-def build_panels(rowptr: np.ndarray, colidx: np.ndarray, rmax: int = 64, hmax: int = 208):
-    rmax = int(os.environ.get("PGB200_PANEL_ROWS", rmax))
-    hmax = int(os.environ.get("PGB200_PANEL_HALO", hmax))
-    """row panels + halo lists + 16-bit local column indices for the staged SpMM (C++ host helper)"""
+def build_stream_panels(rowptr: np.ndarray, colidx: np.ndarray, rmax: int = 64, hc: int = 104, max_chunks: int = 2) -> dict:
+    """streamed row panels of a CSR pattern (csrc/stream_panels.h); the library builds them itself, this wrapper serves
+    the host-side tests that replay the kernel's traversal"""
     rowptr = np.ascontiguousarray(rowptr, np.int32)
     colidx = np.ascontiguousarray(colidx, np.int32)
     n = rowptr.size - 1
-    panel_ptr = np.zeros(n + 1, np.int32)
-    halo_ptr = np.zeros(n + 1, np.int32)
-    halo_cols = np.zeros(max(1, colidx.size), np.int32)
-    lidx = np.zeros(max(1, colidx.size), np.uint16)
-    self_idx = np.zeros(n, np.uint16)
-    npan = lib().pgb200_build_panels(n, rowptr.ctypes.data, colidx.ctypes.data, int(rmax), int(hmax), panel_ptr.ctypes.data,
-                                     halo_ptr.ctypes.data, halo_cols.ctypes.data, lidx.ctypes.data, self_idx.ctypes.data)
-    if npan < 0:
+    counts = np.zeros(8, np.int32)
+    args = [n, rowptr.ctypes.data, colidx.ctypes.data, int(rmax), int(hc), int(max_chunks), counts.ctypes.data]
+    if lib().pgb200_build_stream_panels(*args, *([None] * 8)) != 0:
         raise PGB200Error(last_error())
-    panel_ptr = panel_ptr[: npan + 1].copy()
-    halo_ptr = halo_ptr[: npan + 1].copy()
-    return dict(n_panels=int(npan), panel_ptr=panel_ptr, halo_ptr=halo_ptr, halo_cols=halo_cols[: halo_ptr[-1]].copy(),
-                lidx=lidx, self_idx=self_idx, max_halo=int(np.diff(halo_ptr).max()),
-                max_panel_nnz=int(np.diff(rowptr[panel_ptr]).max()))
+    npan, nch, nh, stride, max_rows, mch, mce, nnz = (int(x) for x in counts)
+    out = dict(panel_row_ptr=np.zeros(npan + 1, np.int32), panel_chunk_ptr=np.zeros(npan + 1, np.int32),
+               chunk_halo_ptr=np.zeros(nch + 1, np.int32), halo_cols=np.zeros(max(1, nh), np.int32),
+               chunk_ent_ptr=np.zeros(nch + 1, np.int32), ent_src=np.zeros(max(1, nnz), np.int32),
+               ent_idx=np.zeros(max(1, nnz), np.uint32), crp=np.zeros(max(1, nch * stride), np.int32))
+    if lib().pgb200_build_stream_panels(*args, *(out[k].ctypes.data for k in ("panel_row_ptr", "panel_chunk_ptr", "chunk_halo_ptr",
+                                                                             "halo_cols", "chunk_ent_ptr", "ent_src", "ent_idx", "crp"))) != 0:
+        raise PGB200Error(last_error())
+    out.update(n_panels=npan, n_chunks=nch, crp_stride=stride, max_rows=max_rows, max_chunk_halo=mch, max_chunk_ent=mce, nnz=nnz)
+    return out
 
 
 def set_hierarchy(handle, levels):
@@ -248,15 +245,6 @@ def make_plan_struct(P, sr: bool):
     s.pro_cells = I(np.concatenate([c for c, _, _ in lv]) if lv else np.zeros(0, np.int32))
     s.pro_nb = I(np.concatenate([n for _, n, _ in lv]).ravel() if lv else np.zeros(0, np.int32))
     s.pro_w = D(np.concatenate([w for _, _, w in lv]).ravel() if lv else np.zeros(0))
-    pan = getattr(P, "panels", None)
-    if pan:
-        s.n_panels, s.max_halo, s.max_panel_nnz = pan["n_panels"], pan["max_halo"], pan["max_panel_nnz"]
-        s.panel_ptr, s.halo_ptr, s.halo_cols = I(pan["panel_ptr"]), I(pan["halo_ptr"]), I(pan["halo_cols"])
-        l16, s16 = np.ascontiguousarray(pan["lidx"], np.uint16), np.ascontiguousarray(pan["self_idx"], np.uint16)
-        keep.extend([l16, s16])
-        s.lidx, s.self_idx = l16.ctypes.data_as(C.POINTER(C.c_ushort)), s16.ctypes.data_as(C.POINTER(C.c_ushort))
-    else:
-        s.n_panels, s.max_halo = 0, 0
     s.n_jac_cells, s.jac_cells, s.jac_col_ptr = int(P.jac_cells.size), I(P.jac_cells), I(P.jac_col_ptr)
     s.abmn = I(P.scheme.abmn())
     kf = P.scheme.k if P.scheme.k is not None else np.zeros(P.scheme.size)

@@ -298,30 +298,32 @@ k_spmm(const int *__restrict__ rowptr, const int *__restrict__ colidx, const dou
 }
 
 // ---------------------------------------------------------------------------------
-// K2': panel-staged SpMM  Y = A X  (+ fused p.Ap), the PCG hot kernel.
-//   Rows are renumbered along a space-filling curve at set-up, so R consecutive rows form a
-//   compact patch of the mesh whose matrix rows touch only a small "halo" set of distinct
-//   columns (about 3 per row instead of 15 for Kuhn tetrahedra).  One CTA = one row panel x one
-//   tile of TW source columns:
-//     1. one thread arms an mbarrier with the byte count, then the CTA issues one TMA bulk copy
-//        (cp.async.bulk.shared.global, SASS UBLKCP) per halo row: X[halo][tile] -> shared memory;
-//     2. every warp takes rows of the panel; lane = source column.  Column indices were
-//        re-encoded at set-up as 16-bit offsets into the halo list, so the inner loop is
-//        one broadcast load of (value, local index) + one conflict-free shared-memory read
-//        of X + one DFMA;
-//     3. Y is written with coalesced stores; the p.Ap partials are reduced over the warps in
-//        shared memory and leave the CTA as one atomicAdd per column.
-//   Each gathered X row is read from L2/HBM once per panel instead of once per touching row.
+// K2': streamed row-panel SpMM  Y = A X  (+ fused epilogues), the PCG hot kernel.   Layout: stream_panels.h.
+//
+//   Persistent, warp-specialised: one CTA per SM = 1 PRODUCER warp + 15 CONSUMER warps, a ring of S shared-memory slots
+//   guarded by full/empty mbarriers.
+//     producer  for every stage (panel, chunk) of this CTA's work list: wait for the slot to be free, arm its mbarrier
+//               with the byte count, then issue the TMA bulk copies (cp.async.bulk.shared.global, SASS UBLKCP): one per
+//               halo row of the chunk (the tile's columns of X), one for the chunk's packed entries {value, row-in-chunk},
+//               one for its per-row entry ranges.  The copies of stage n+1 run while the consumers work on stage n.
+//     consumers every warp owns up to 4 rows of the panel and keeps their sums for all columns of the tile in registers
+//               across the chunks (lane l: columns 2l, 2l+1 and 64+2l, 64+2l+1 -> two conflict-free 128-bit LDS per entry
+//               and row: 7 shared-memory wavefronts per entry for 100 columns instead of 8 + a second pass over the
+//               entries).  Inner loop: one 128-bit broadcast LDS of the entry, the X loads, 2-4 DFMA.
+//               After chunk 0 (the panel's own X rows, processed last) the epilogue writes Y with 128-bit stores.
+//   Column tiles never straddle a wavenumber group (one CSR value set per tile); 2.5-D windows are tile lists.
+//   Per-column dot products (p.Ap, r.z) are DETERMINISTIC: lane partials -> fixed-order sum over the 15 warps -> one partial
+//   row per CTA in global memory -> the CTA that takes the last ticket adds the rows in index order (no float atomics).
 // ---------------------------------------------------------------------------------
-constexpr int PANEL_THREADS = 512;
-constexpr int PANEL_WARPS = PANEL_THREADS / 32;
-
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
     asm volatile(
@@ -338,35 +340,26 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
-// NC = source columns per lane (tile width <= 32*NC).  Shared memory: X tile [halo][tw] doubles
-// (+ one pad row so that lanes beyond the tile width read in-bounds garbage they never use),
-// then the panel's CSR slice as 16-byte entries {value, byte offset of the entry's X row}, the
-// values of a second wavenumber group (only if the tile straddles two), and the row pointers.
-struct __align__(16) PanelEntry { double a; uint32_t off; uint32_t pad; };
+struct __align__(16) PanelEntry { double a; uint32_t idx; uint32_t pad; };   // value, row of its column in the staged chunk
 
-// accumulate one matrix row of the panel against the staged X tile: acc[m] = sum_p a_p * X[col_p][lane + 32 m]
-template <int NC, bool TWO_K>
-__device__ __forceinline__ void panel_row_acc(const char *sx_lane, const PanelEntry *sE, const double *sA1, int pb, int pe,
-                                              const bool (&second)[NC], double (&acc)[NC]) {
-#pragma unroll
-    for (int m = 0; m < NC; m++) acc[m] = 0.0;
-#pragma unroll 4
-    for (int p = pb; p < pe; p++) {
-        const PanelEntry e = sE[p];                               // one 128-bit broadcast load
-        const double *xr = reinterpret_cast<const double *>(sx_lane + e.off);
-        if (TWO_K) {
-            const double a1 = sA1[p];
-#pragma unroll
-            for (int m = 0; m < NC; m++) acc[m] = fma(second[m] ? a1 : e.a, xr[32 * m], acc[m]);
-        } else {
-#pragma unroll
-            for (int m = 0; m < NC; m++) acc[m] = fma(e.a, xr[32 * m], acc[m]);
-        }
+// packed entries of one matrix in the streamed order: ent[k][p'] = {vals[k][ent_src[p']], ent_idx[p']}
+__global__ void k_pack_entries(const int *__restrict__ ent_src, const unsigned *__restrict__ ent_idx, size_t nnz, int nK,
+                               const double *__restrict__ vals, PanelEntry *__restrict__ ent) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    const int src = ent_src[p];
+    const uint32_t idx = ent_idx[p];
+    for (int kk = 0; kk < nK; kk++) {
+        PanelEntry e; e.a = vals[(size_t)kk * nnz + src]; e.idx = idx; e.pad = 0;
+        ent[(size_t)kk * nnz + p] = e;
     }
 }
 
-// what a panel CTA does with the row sums  acc = (A X)[row]:
+// what a consumer warp does with the row sums  acc = (A X)[row]:
 //   EPI_SPMM     Y = acc                         (+ optional dot  X_row . Y_row : p.Ap of PCG)
 //   EPI_POST     Y = X_row + dw_row (R_row - acc) (+ dot R_row . Y_row): damped-Jacobi post-smoothing, r.z of PCG
 //   EPI_RESIDUAL Y = X_row - acc: with values pre-scaled by dw this is the residual after the pre-smoothing sweep
@@ -375,197 +368,241 @@ enum PanelEpi : int { EPI_SPMM = 0, EPI_POST = 1, EPI_RESIDUAL = 2 };
 
 struct PanelExtra {
     const double *R;          // EPI_POST: residual block
-    const double *dinvw;      // EPI_POST: [nK][N] damped inverse diagonal
+    const double *dinvw;      // EPI_POST: [nK][n] damped inverse diagonal
     int n;                    // rows of the level (stride of dinvw per wavenumber)
 };
 
-template <int NC, bool TWO_K, int EPI>
-__device__ __forceinline__ void panel_rows(const char *sx_lane, const PanelEntry *sE, const double *sA1, const int *sRow,
-                                           const unsigned short *__restrict__ self_idx, int panel, int r0, int nrows, int warp, int tw,
-                                           const bool (&ok)[NC], const bool (&second)[NC], const int (&col)[NC], int nE,
-                                           size_t ld, double *__restrict__ Y, double (&part)[NC], bool dot, const PanelExtra &ex) {
-    const double *dw[NC];
-    if (EPI == EPI_POST) {
-#pragma unroll
-        for (int m = 0; m < NC; m++) dw[m] = ex.dinvw + (size_t)(col[m] / nE) * ex.n;
-    }
-    for (int r = warp; r < nrows; r += PANEL_WARPS) {
-        double acc[NC];
-        panel_row_acc<NC, TWO_K>(sx_lane, sE, sA1, sRow[r], sRow[r + 1], second, acc);
-        const int row = r0 + r;
-        const double *xs = reinterpret_cast<const double *>(sx_lane + (size_t)self_idx[row] * tw * 8);
-#pragma unroll
-        for (int m = 0; m < NC; m++) {
-            if (ok[m]) {
-                const size_t o = (size_t)row * ld + col[m];
-                if (EPI == EPI_POST) {
-                    const double rr = __ldg(ex.R + o);
-                    const double z = fma(dw[m][row], rr - acc[m], xs[32 * m]);
-                    Y[o] = z;
-                    if (dot) part[m] = fma(rr, z, part[m]);
-                } else if (EPI == EPI_RESIDUAL) {
-                    Y[o] = xs[32 * m] - acc[m];
-                } else {
-                    Y[o] = acc[m];
-                    if (dot) part[m] = fma(acc[m], xs[32 * m], part[m]);
-                }
-            }
-        }
-    }
+constexpr int ST_CONSUMER_WARPS = 15;              // + 1 producer warp = 512 threads (128 registers per thread available)
+constexpr int ST_CONSUMERS = ST_CONSUMER_WARPS * 32;
+constexpr int ST_THREADS = ST_CONSUMERS + 32;      // + the producer warp
+constexpr int ST_RPW = 4;                          // rows per consumer warp: panels have at most 60 rows
+constexpr int ST_MAX_SLOTS = 4;
+constexpr int ST_MAX_TILE_W = 128;                 // columns per tile (2 column pairs per lane)
+
+struct StreamLevel {       // device arrays of stream_panels.h
+    const int *panel_row_ptr, *panel_chunk_ptr, *chunk_halo_ptr, *halo_cols, *chunk_ent_ptr, *crp;
+    int n_panels, crp_stride;
+};
+
+struct StreamArgs {
+    StreamLevel L;
+    const PanelEntry *ent; size_t nnz;            // packed entries [nK][nnz]
+    const double *X; double *Y; size_t ld;
+    int nE, c0, c1;                               // active column window [c0, c1)
+    int k_lo, tpk, pw, n_tiles, cpt;              // tile geometry: first wavenumber, tiles per wavenumber, tile width, tiles, CTAs per tile
+    int slots; uint32_t slot_bytes, x_bytes, ent_bytes;    // slot = [X rows | entries | row ranges]
+    double *dot_part; unsigned *dot_counter; double *dots;  // deterministic dots (DOT kernels)
+    PanelExtra ex;
+};
+
+// tile t -> wavenumber kk, copied columns [cs, cs + wc), valid columns [v0, v1); false: nothing to do
+__device__ __forceinline__ bool stream_tile(const StreamArgs &A, int t, int &kk, int &cs, int &wc, int &v0, int &v1) {
+    const int q = t / A.tpk, j = t - q * A.tpk;
+    kk = A.k_lo + q;
+    const int gb = max(kk * A.nE, A.c0), ge = min((kk + 1) * A.nE, A.c1);    // this group's part of the window
+    cs = (gb & ~1) + j * A.pw;                                                // even start: 16-byte aligned bulk copies
+    const int ce = min(cs + A.pw, (ge + 1) & ~1);
+    v0 = max(cs, gb); v1 = min(ce, ge);
+    if (v1 <= v0) return false;
+    wc = ce - cs;
+    return true;
 }
 
-__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-
-// STAGE = 0: X rows arrive through cp.async (LDGSTS, 16 bytes per lane, one warp per halo row);
-// STAGE = 1: one TMA bulk copy (UBLKCP) per halo row, completion on an mbarrier.
-template <int NC, bool DOT, int STAGE, int EPI>
-__global__ void __launch_bounds__(PANEL_THREADS)
-k_spmm_panel(const int *__restrict__ rowptr, const unsigned short *__restrict__ lidx, const unsigned short *__restrict__ self_idx,
-             const int *__restrict__ panel_ptr, const int *__restrict__ halo_ptr, const int *__restrict__ halo_cols,
-             const double *__restrict__ vals, size_t nnz, const double *__restrict__ X, double *__restrict__ Y,
-             int nE, int c0, int c1, int tw, int max_halo, int max_pnnz, int max_rows, size_t ld, double *__restrict__ dots,
-             const PanelExtra ex) {
-    extern __shared__ __align__(16) double sm[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ double red[PANEL_WARPS][32 * NC];
-    const int panel = blockIdx.x;
-    const int tile0 = c0 + blockIdx.y * tw;                   // first column of this tile (even)
-    const int w = min(tw, (int)ld - tile0);                    // copied width (even; may include zero padding)
-    const int r0 = panel_ptr[panel], nrows = panel_ptr[panel + 1] - r0;
-    const int h0 = halo_ptr[panel], hn = halo_ptr[panel + 1] - h0;
+template <int NCP, int EPI, bool DOT>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+k_spmm_stream(const StreamArgs A) {
+    extern __shared__ __align__(128) unsigned char st_smem[];
+    __shared__ __align__(8) uint64_t full[ST_MAX_SLOTS], empty[ST_MAX_SLOTS];
+    __shared__ double sdot[ST_MAX_TILE_W];
+    __shared__ int s_ticket;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    PanelEntry *sE = reinterpret_cast<PanelEntry *>(sm + (size_t)max_halo * tw + 32 * NC);   // after the pad row
-    double *sA1 = reinterpret_cast<double *>(sE + max_pnnz);
-    int *sRow = reinterpret_cast<int *>(sA1 + max_pnnz);
-
-    if (STAGE == 1) {
-        if (threadIdx.x == 0) {
-            mbar_init(&bar, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            mbar_expect_tx(&bar, (uint32_t)(hn * w * 8));
-        }
-        __syncthreads();
-        // one TMA bulk copy per halo row, issued from all warps (the issue is serialised per warp)
-        for (int i = threadIdx.x; i < hn; i += PANEL_THREADS)
-            tma_bulk_g2s(sm + (size_t)i * tw, X + (size_t)halo_cols[h0 + i] * ld + tile0, (uint32_t)(w * 8), &bar);
-    } else {
-        // one warp per halo row, lane = 16-byte chunk (w <= 64 -> at most 32 chunks)
-        const int nchunk = w >> 1;
-        for (int i = warp; i < hn; i += 4 * PANEL_WARPS) {
-            int hc[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) hc[u] = (i + u * PANEL_WARPS < hn) ? __ldg(halo_cols + h0 + i + u * PANEL_WARPS) : -1;
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (hc[u] >= 0 && lane < nchunk)
-                    cp_async16(sm + (size_t)(i + u * PANEL_WARPS) * tw + 2 * lane, X + (size_t)hc[u] * ld + tile0 + 2 * lane);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+    const int S = A.slots;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], ST_CONSUMER_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // meanwhile: CSR slice of the panel -> shared memory (coalesced, loads batched before the stores)
-    const int p0 = rowptr[r0];
-    const int pn = rowptr[r0 + nrows] - p0;
-    const int last = min(tile0 + w, c1) - 1;
-    const int kk0 = tile0 / nE, kk1 = last / nE;
-    const bool two_k = kk1 != kk0;
-    const double *v0 = vals + (size_t)kk0 * nnz + p0, *v1 = vals + (size_t)kk1 * nnz + p0;
-    for (int i = threadIdx.x; i < pn; i += 2 * PANEL_THREADS) {
-        const int j = i + PANEL_THREADS;
-        const bool hj = j < pn;
-        const double a = __ldg(v0 + i), b = hj ? __ldg(v0 + j) : 0.0;
-        const unsigned short la = __ldg(lidx + p0 + i), lb = hj ? __ldg(lidx + p0 + j) : (unsigned short)0;
-        double c = 0.0, d = 0.0;
-        if (two_k) { c = __ldg(v1 + i); d = hj ? __ldg(v1 + j) : 0.0; }
-        sE[i].a = a; sE[i].off = (uint32_t)la * (uint32_t)(tw * 8);
-        if (two_k) sA1[i] = c;
-        if (hj) { sE[j].a = b; sE[j].off = (uint32_t)lb * (uint32_t)(tw * 8); if (two_k) sA1[j] = d; }
-    }
-    for (int i = threadIdx.x; i <= nrows; i += PANEL_THREADS) sRow[i] = __ldg(rowptr + r0 + i) - p0;
-    int col[NC]; bool ok[NC], second[NC];
-#pragma unroll
-    for (int m = 0; m < NC; m++) {
-        col[m] = tile0 + lane + 32 * m;
-        ok[m] = (lane + 32 * m) < w && col[m] < c1;
-        second[m] = ok[m] && (col[m] / nE != kk0);
-        if (!ok[m]) col[m] = tile0;
-    }
-    (void)max_rows;
-    if (STAGE == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    if (STAGE == 1) mbar_wait(&bar, 0);
+    // work list of this CTA: tiles t_first, t_first + t_step, ...; panels j, j + cpt, ...
+    int t_first, t_step, j;
+    if (A.n_tiles <= (int)gridDim.x) { t_first = blockIdx.x / A.cpt; t_step = A.n_tiles; j = blockIdx.x - t_first * A.cpt; }
+    else { t_first = blockIdx.x; t_step = gridDim.x; j = 0; }
+    const int pstep = A.cpt;
+    const StreamLevel &L = A.L;
 
-    double part[NC];
-#pragma unroll
-    for (int m = 0; m < NC; m++) part[m] = 0.0;
-    const char *sx_lane = reinterpret_cast<const char *>(sm + lane);
-    if (two_k) panel_rows<NC, true, EPI>(sx_lane, sE, sA1, sRow, self_idx, panel, r0, nrows, warp, tw, ok, second, col, nE, ld, Y, part, DOT, ex);
-    else panel_rows<NC, false, EPI>(sx_lane, sE, sA1, sRow, self_idx, panel, r0, nrows, warp, tw, ok, second, col, nE, ld, Y, part, DOT, ex);
-    if (DOT) {
-#pragma unroll
-        for (int m = 0; m < NC; m++) red[warp][lane + 32 * m] = part[m];
-        __syncthreads();
-        if (warp == 0) {
-#pragma unroll
-            for (int m = 0; m < NC; m++) {
-                if (ok[m]) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int y = 0; y < PANEL_WARPS; y++) s += red[y][lane + 32 * m];
-                    atomicAdd(dots + col[m], s);
+    if (warp == ST_CONSUMER_WARPS) {
+        // ------------------------------- producer -------------------------------
+        uint32_t n = 0;
+        for (int t = t_first; t < A.n_tiles; t += t_step) {
+            int kk, cs, wc, v0, v1;
+            if (!stream_tile(A, t, kk, cs, wc, v0, v1)) continue;
+            const uint32_t rowb = (uint32_t)wc * 8u;
+            const PanelEntry *entk = A.ent + (size_t)kk * A.nnz;
+            for (int p = j; p < L.n_panels; p += pstep) {
+                const int ch0 = L.panel_chunk_ptr[p], ch1 = L.panel_chunk_ptr[p + 1];
+                for (int ch = ch1 - 1; ch >= ch0; ch--, n++) {
+                    const uint32_t slot = n % (uint32_t)S, use = n / (uint32_t)S;
+                    if (use > 0) mbar_wait(&empty[slot], (use & 1u) ^ 1u);
+                    unsigned char *sb = st_smem + (size_t)slot * A.slot_bytes;
+                    const int h0 = L.chunk_halo_ptr[ch], hn = L.chunk_halo_ptr[ch + 1] - h0;
+                    const int e0 = L.chunk_ent_ptr[ch], ne = L.chunk_ent_ptr[ch + 1] - e0;
+                    if (lane == 0) {
+                        mbar_expect_tx(&full[slot], (uint32_t)hn * rowb + (uint32_t)ne * 16u + (uint32_t)L.crp_stride * 4u);
+                        if (ne > 0) tma_bulk_g2s(sb + A.x_bytes, entk + e0, (uint32_t)ne * 16u, &full[slot]);
+                        tma_bulk_g2s(sb + A.x_bytes + A.ent_bytes, L.crp + (size_t)ch * L.crp_stride, (uint32_t)L.crp_stride * 4u, &full[slot]);
+                    }
+                    __syncwarp();
+                    for (int i = lane; i < hn; i += 32)
+                        tma_bulk_g2s(sb + (size_t)i * rowb, A.X + (size_t)__ldg(L.halo_cols + h0 + i) * A.ld + cs, rowb, &full[slot]);
                 }
             }
         }
+        return;
     }
-}
 
-// ---------------------------------------------------------------------------------
-// block-PCG vector kernels (Jacobi preconditioner; one independent CG per source column,
-// all columns advance in the same launches).  Thread = 1 column x strided rows; per-column
-// partial dot products stay in registers, then a shared-memory tree + one atomic per CTA.
-// ---------------------------------------------------------------------------------
-constexpr int VEC_TX = 32, VEC_TY = 8, VEC_ROWS = 64;
-
-__device__ __forceinline__ void block_col_reduce(double v0, double v1, double *d0, double *d1, int col, bool ok) {
-    __shared__ double red0[VEC_TY][VEC_TX], red1[VEC_TY][VEC_TX];
-    red0[threadIdx.y][threadIdx.x] = v0; red1[threadIdx.y][threadIdx.x] = v1;
-    __syncthreads();
-    if (threadIdx.y == 0 && ok) {
-        double a = 0.0, b = 0.0;
+    // ------------------------------- consumers -------------------------------
+    uint32_t n = 0;
+    for (int t = t_first; t < A.n_tiles; t += t_step) {
+        int kk, cs, wc, v0, v1;
+        if (!stream_tile(A, t, kk, cs, wc, v0, v1)) continue;
+        const uint32_t rowb = (uint32_t)wc * 8u;
+        // lane's columns: pair q covers cs + 64 q + 2 lane, +1
+        int col[NCP]; bool has[NCP], ok_lo[NCP], ok_hi[NCP];
 #pragma unroll
-        for (int y = 0; y < VEC_TY; y++) { a += red0[y][threadIdx.x]; b += red1[y][threadIdx.x]; }
-        if (d0) atomicAdd(d0 + col, a);
-        if (d1) atomicAdd(d1 + col, b);
-    }
-}
+        for (int q = 0; q < NCP; q++) {
+            col[q] = cs + 64 * q + 2 * lane;
+            has[q] = (64 * q + 2 * lane) < wc;
+            ok_lo[q] = has[q] && col[q] >= v0 && col[q] < v1;
+            ok_hi[q] = has[q] && col[q] + 1 >= v0 && col[q] + 1 < v1;
+        }
+        double part[2 * NCP];
+#pragma unroll
+        for (int q = 0; q < 2 * NCP; q++) part[q] = 0.0;
+        const double *dwk = (EPI == EPI_POST) ? A.ex.dinvw + (size_t)kk * A.ex.n : nullptr;
 
-// r = b - (x == 0); z = Dinv r; p = z; rz = r.z; bb = b.b
-__global__ void __launch_bounds__(VEC_TX * VEC_TY)
-k_pcg_init(const double *__restrict__ B, const double *__restrict__ dinv, double *__restrict__ Xv, double *__restrict__ R,
-           double *__restrict__ P, int N, int nE, int c0, int c1, size_t ld, double *__restrict__ rz, double *__restrict__ bb) {
-    const int col = c0 + blockIdx.y * VEC_TX + threadIdx.x;
-    const bool ok = col < c1;
-    double s0 = 0.0, s1 = 0.0;
-    if (ok) {
-        const double *dk = dinv + (size_t)(col / nE) * N;
-        const int row0 = blockIdx.x * VEC_ROWS;
-        for (int r = threadIdx.y; r < VEC_ROWS; r += VEC_TY) {
-            const int row = row0 + r; if (row >= N) break;
-            const size_t o = (size_t)row * ld + col;
-            const double b = B[o];
-            const double z = dk[row] * b;
-            Xv[o] = 0.0; R[o] = b; P[o] = z;
-            s0 = fma(b, z, s0); s1 = fma(b, b, s1);
+        for (int p = j; p < L.n_panels; p += pstep) {
+            const int r0 = L.panel_row_ptr[p], nrows = L.panel_row_ptr[p + 1] - r0;
+            const int nch = L.panel_chunk_ptr[p + 1] - L.panel_chunk_ptr[p];
+            double acc[ST_RPW][2 * NCP];
+#pragma unroll
+            for (int rr = 0; rr < ST_RPW; rr++)
+#pragma unroll
+                for (int q = 0; q < 2 * NCP; q++) acc[rr][q] = 0.0;
+            for (int c = nch - 1; c >= 0; c--, n++) {
+                const uint32_t slot = n % (uint32_t)S, use = n / (uint32_t)S;
+                mbar_wait(&full[slot], use & 1u);
+                const unsigned char *sb = st_smem + (size_t)slot * A.slot_bytes;
+                const PanelEntry *sE = reinterpret_cast<const PanelEntry *>(sb + A.x_bytes);
+                const int *sR = reinterpret_cast<const int *>(sb + A.x_bytes + A.ent_bytes);
+                const unsigned char *xl = sb + 16 * lane;
+#pragma unroll
+                for (int rr = 0; rr < ST_RPW; rr++) {
+                    const int r = warp + ST_CONSUMER_WARPS * rr;
+                    if (r < nrows) {
+                        const int pb = sR[r], pe = sR[r + 1];
+#pragma unroll 2
+                        for (int e = pb; e < pe; e++) {
+                            const PanelEntry en = sE[e];                               // one 128-bit broadcast load
+                            const unsigned char *xr = xl + en.idx * rowb;
+#pragma unroll
+                            for (int q = 0; q < NCP; q++) {
+                                if (has[q]) {
+                                    const double2 x = *reinterpret_cast<const double2 *>(xr + 512 * q);
+                                    acc[rr][2 * q] = fma(en.a, x.x, acc[rr][2 * q]);
+                                    acc[rr][2 * q + 1] = fma(en.a, x.y, acc[rr][2 * q + 1]);
+                                }
+                            }
+                        }
+                    }
+                }
+                if (c == 0) {
+                    // epilogue: chunk 0 starts with the panel's own X rows (halo index == local row)
+#pragma unroll
+                    for (int rr = 0; rr < ST_RPW; rr++) {
+                        const int r = warp + ST_CONSUMER_WARPS * rr;
+                        if (r < nrows) {
+                            const int row = r0 + r;
+                            const unsigned char *xs = xl + (uint32_t)r * rowb;
+                            double dw = 0.0;
+                            if (EPI == EPI_POST) dw = dwk[row];
+#pragma unroll
+                            for (int q = 0; q < NCP; q++) {
+                                if (has[q]) {
+                                    const double2 x = *reinterpret_cast<const double2 *>(xs + 512 * q);
+                                    const size_t o = (size_t)row * A.ld + col[q];
+                                    double y0, y1;
+                                    if (EPI == EPI_POST) {
+                                        double r_lo = 0.0, r_hi = 0.0;
+                                        if (ok_lo[q] && ok_hi[q]) { const double2 rv = *reinterpret_cast<const double2 *>(A.ex.R + o); r_lo = rv.x; r_hi = rv.y; }
+                                        else { if (ok_lo[q]) r_lo = A.ex.R[o]; if (ok_hi[q]) r_hi = A.ex.R[o + 1]; }
+                                        y0 = fma(dw, r_lo - acc[rr][2 * q], x.x);
+                                        y1 = fma(dw, r_hi - acc[rr][2 * q + 1], x.y);
+                                        if (DOT) { if (ok_lo[q]) part[2 * q] = fma(r_lo, y0, part[2 * q]); if (ok_hi[q]) part[2 * q + 1] = fma(r_hi, y1, part[2 * q + 1]); }
+                                    } else if (EPI == EPI_RESIDUAL) {
+                                        y0 = x.x - acc[rr][2 * q]; y1 = x.y - acc[rr][2 * q + 1];
+                                    } else {
+                                        y0 = acc[rr][2 * q]; y1 = acc[rr][2 * q + 1];
+                                        if (DOT) { if (ok_lo[q]) part[2 * q] = fma(y0, x.x, part[2 * q]); if (ok_hi[q]) part[2 * q + 1] = fma(y1, x.y, part[2 * q + 1]); }
+                                    }
+                                    if (ok_lo[q] && ok_hi[q]) *reinterpret_cast<double2 *>(A.Y + o) = make_double2(y0, y1);
+                                    else { if (ok_lo[q]) A.Y[o] = y0; if (ok_hi[q]) A.Y[o + 1] = y1; }
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);
+            }
+        }
+        if (DOT) {
+            // fixed-order sum over the warps, one partial row per CTA, the last CTA of the tile adds the rows in order
+            const int nslot = (A.n_tiles <= (int)gridDim.x) ? A.cpt : 1;
+            for (int w = 0; w < ST_CONSUMER_WARPS; w++) {
+                if (warp == w) {
+#pragma unroll
+                    for (int q = 0; q < NCP; q++) {
+                        if (has[q]) {
+                            const int i = 64 * q + 2 * lane;
+                            sdot[i] = (w == 0 ? 0.0 : sdot[i]) + part[2 * q];
+                            sdot[i + 1] = (w == 0 ? 0.0 : sdot[i + 1]) + part[2 * q + 1];
+                        }
+                    }
+                }
+                named_bar_sync(1, ST_CONSUMERS);
+            }
+            double *mine = A.dot_part + (size_t)j * A.ld;
+            for (int i = threadIdx.x; i < wc; i += ST_CONSUMERS) if (cs + i >= v0 && cs + i < v1) mine[cs + i] = sdot[i];
+            __threadfence();
+            named_bar_sync(1, ST_CONSUMERS);
+            if (threadIdx.x == 0) s_ticket = (int)atomicAdd(A.dot_counter + t, 1u);
+            named_bar_sync(1, ST_CONSUMERS);
+            if (s_ticket == nslot - 1) {
+                __threadfence();
+                for (int i = threadIdx.x; i < wc; i += ST_CONSUMERS) {
+                    const int cc = cs + i;
+                    if (cc >= v0 && cc < v1) {
+                        double sum = 0.0;
+                        for (int s2 = 0; s2 < nslot; s2++) sum += __ldcg(A.dot_part + (size_t)s2 * A.ld + cc);
+                        A.dots[cc] = sum;
+                    }
+                }
+                if (threadIdx.x == 0) A.dot_counter[t] = 0u;
+            }
+            named_bar_sync(1, ST_CONSUMERS);
         }
     }
-    block_col_reduce(s0, s1, rz, bb, col, ok);
 }
-// Flat mapping for the element-wise block-vector kernels: the FLAT_T threads of a CTA tile the column window
-// [c0,c1) (chunks of at most cw columns along blockIdx.y) as rpp = FLAT_T / w consecutive rows of w columns, so that a
-// warp touches 32 consecutive elements of the row-major block whatever the window width (100 columns -> 5 rows per pass,
-// 14 columns of an 8-GPU shard -> 36), and every thread keeps ONE column (per-column scalars and dot partials stay in
-// registers).  A CTA covers rows_cta rows: r = roff, roff + rpp, ...
+
+// ---------------------------------------------------------------------------------
+// block-PCG vector kernels (one independent CG per source column, all columns advance in the same launches).
+// Flat mapping: the FLAT_T threads of a CTA tile the column window [c0,c1) (chunks of at most cw columns along
+// blockIdx.y) as rpp = FLAT_T / w consecutive rows of w columns, so that a warp touches 32 consecutive elements of the
+// row-major block whatever the window width (100 columns -> 5 rows per pass, 14 columns of an 8-GPU shard -> 36), and
+// every thread keeps ONE column (per-column scalars and dot partials stay in registers).  A CTA walks row blocks of
+// rows_cta rows with a grid stride: blk = blockIdx.x, blockIdx.x + gridDim.x, ...
+// Per-column dot products are DETERMINISTIC (no floating-point atomics): thread partials meet in shared memory in a
+// fixed order, every CTA writes one partial row, the CTA that draws the last ticket adds the rows in index order.
+// ---------------------------------------------------------------------------------
 constexpr int FLAT_T = 512;
 struct FlatMap { int col, roff, rpp, w; bool active; };
 __device__ __forceinline__ FlatMap flat_map(int c0, int c1, int cw) {
@@ -578,69 +615,126 @@ __device__ __forceinline__ FlatMap flat_map(int c0, int c1, int cw) {
     f.active = f.roff < f.rpp;
     return f;
 }
-// per-column sums over the CTA: shared-memory transpose-free reduction (threads t, t + w, t + 2w, ... share a column)
-__device__ __forceinline__ void flat_col_reduce(double v0, double v1, double *d0, double *d1, const FlatMap &f) {
+struct DotOut {
+    double *part;          // [2][slots][ld] partial rows (plane 0 / 1 for the two sums a kernel may produce)
+    size_t plane;          // slots * ld
+    unsigned *counter;     // [column chunks] tickets, zero between launches
+    double *out0, *out1;   // final per-column sums (nullptr: that sum is not wanted)
+    size_t ld;
+};
+// v0, v1: this thread's partial sums for its column.  All threads of the CTA must call.
+__device__ __forceinline__ void flat_col_finalize(double v0, double v1, const FlatMap &f, const DotOut &D) {
     __shared__ double red0[FLAT_T], red1[FLAT_T];
+    __shared__ int ticket;
     red0[threadIdx.x] = f.active ? v0 : 0.0; red1[threadIdx.x] = f.active ? v1 : 0.0;
     __syncthreads();
     if ((int)threadIdx.x < f.w) {
         double a = 0.0, b = 0.0;
         for (int j = 0; j < f.rpp; j++) { a += red0[threadIdx.x + j * f.w]; b += red1[threadIdx.x + j * f.w]; }
-        if (d0) atomicAdd(d0 + f.col, a);
-        if (d1) atomicAdd(d1 + f.col, b);
+        double *row = D.part + (size_t)blockIdx.x * D.ld + f.col;
+        if (D.out0) row[0] = a;
+        if (D.out1) row[D.plane] = b;
     }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) ticket = (int)atomicAdd(D.counter + blockIdx.y, 1u);
+    __syncthreads();
+    if (ticket != (int)gridDim.x - 1) return;
+    __threadfence();
+    // last CTA of this column chunk: thread (roff, col) adds rows roff, roff + rpp, ...; then the roff partials in order
+    double a = 0.0, b = 0.0;
+    if (f.active) {
+        for (int sl = f.roff; sl < (int)gridDim.x; sl += f.rpp) {
+            const double *row = D.part + (size_t)sl * D.ld + f.col;
+            if (D.out0) a += __ldcg(row);
+            if (D.out1) b += __ldcg(row + D.plane);
+        }
+    }
+    __syncthreads();
+    red0[threadIdx.x] = a; red1[threadIdx.x] = b;
+    __syncthreads();
+    if ((int)threadIdx.x < f.w) {
+        double sa = 0.0, sb = 0.0;
+        for (int j = 0; j < f.rpp; j++) { sa += red0[threadIdx.x + j * f.w]; sb += red1[threadIdx.x + j * f.w]; }
+        if (D.out0) D.out0[f.col] = sa;
+        if (D.out1) D.out1[f.col] = sb;
+    }
+    if (threadIdx.x == 0) D.counter[blockIdx.y] = 0u;
 }
 
-// alpha = rz/pAp;  x += alpha p;  r -= alpha Ap;  rz_new = r.Dinv r;  rr = r.r
+// x = 0; r = b; p = z = Dinv r (Jacobi; with the multilevel preconditioner p is set by the first cycle); rz = r.z; bb = b.b
+__global__ void __launch_bounds__(FLAT_T)
+k_pcg_init(const double *__restrict__ B, const double *__restrict__ dinv, double *__restrict__ Xv, double *__restrict__ R,
+           double *__restrict__ P, int N, int nE, int c0, int c1, size_t ld, int cw, int rows_cta, int nblk, const DotOut D) {
+    const FlatMap f = flat_map(c0, c1, cw);
+    double s0 = 0.0, s1 = 0.0;
+    if (f.active) {
+        const double *dk = dinv + (size_t)(f.col / nE) * N;
+        for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+            const int row0 = blk * rows_cta, nr = min(rows_cta, N - row0);
+            for (int r = f.roff; r < nr; r += f.rpp) {
+                const int row = row0 + r;
+                const size_t o = (size_t)row * ld + f.col;
+                const double b = B[o];
+                const double z = dk[row] * b;
+                Xv[o] = 0.0; R[o] = b; P[o] = z;
+                s0 = fma(b, z, s0); s1 = fma(b, b, s1);
+            }
+        }
+    }
+    flat_col_finalize(s0, s1, f, D);
+}
+
+// alpha = rz/pAp;  x += alpha p;  r -= alpha Ap;  rz_new = r.Dinv r (Jacobi only);  rr = r.r
 template <bool JACOBI>
 __global__ void __launch_bounds__(FLAT_T)
 k_pcg_update_xr(const double *__restrict__ P, const double *__restrict__ AP, const double *__restrict__ dinv,
                 double *__restrict__ Xv, double *__restrict__ R, int N, int nE, int c0, int c1, size_t ld,
-                const double *__restrict__ rz, const double *__restrict__ pAp, double *__restrict__ rz_new, double *__restrict__ rr,
-                int cw, int rows_cta) {
+                const double *__restrict__ rz, const double *__restrict__ pAp, int cw, int rows_cta, int nblk, const DotOut D) {
     const FlatMap f = flat_map(c0, c1, cw);
     double s0 = 0.0, s1 = 0.0;
     if (f.active) {
         const double den = pAp[f.col], num = rz[f.col];
         const double alpha = (den > 0.0 && num > 0.0) ? num / den : 0.0;
         const double *dk = JACOBI ? dinv + (size_t)(f.col / nE) * N : nullptr;
-        const int row0 = blockIdx.x * rows_cta, nr = min(rows_cta, N - row0);
+        for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+            const int row0 = blk * rows_cta, nr = min(rows_cta, N - row0);
 #pragma unroll 4
-        for (int r = f.roff; r < nr; r += f.rpp) {
-            const int row = row0 + r;
-            const size_t o = (size_t)row * ld + f.col;
-            const double rn = fma(-alpha, AP[o], R[o]);
-            Xv[o] = fma(alpha, P[o], Xv[o]);
-            R[o] = rn;
-            if (JACOBI) s0 = fma(rn * dk[row], rn, s0);
-            s1 = fma(rn, rn, s1);
+            for (int r = f.roff; r < nr; r += f.rpp) {
+                const int row = row0 + r;
+                const size_t o = (size_t)row * ld + f.col;
+                const double rn = fma(-alpha, AP[o], R[o]);
+                Xv[o] = fma(alpha, P[o], Xv[o]);
+                R[o] = rn;
+                if (JACOBI) s0 = fma(rn * dk[row], rn, s0);
+                s1 = fma(rn, rn, s1);
+            }
         }
     }
-    flat_col_reduce(s0, s1, JACOBI ? rz_new : nullptr, rr, f);
+    flat_col_finalize(s0, s1, f, D);     // D.out0 = rz_new (Jacobi) or nullptr, D.out1 = rr
 }
-// beta = rz_new/rz;  p = Dinv r + beta p   (p = 0 once the column has converged: it freezes)
-// also clears the accumulators of the next iteration (buffers nobody reads in this launch)
+// beta = rz_new/rz;  p = z + beta p   (p = 0 once the column has converged: it freezes)
 // JACOBI: z = Dinv r on the fly; otherwise R points at the preconditioned residual Z and dinv is unused
 template <bool JACOBI>
 __global__ void __launch_bounds__(FLAT_T)
 k_pcg_update_p(const double *__restrict__ R, const double *__restrict__ dinv, double *__restrict__ P, int N, int nE,
                int c0, int c1, size_t ld, const double *__restrict__ rz, const double *__restrict__ rz_new,
-               const double *__restrict__ rr, const double *__restrict__ bb, double tol2,
-               double *__restrict__ zero_a, double *__restrict__ zero_b, double *__restrict__ zero_c, int cw, int rows_cta) {
+               const double *__restrict__ rr, const double *__restrict__ bb, double tol2, int cw, int rows_cta, int nblk) {
     const FlatMap f = flat_map(c0, c1, cw);
     if (!f.active) return;
     const int col = f.col;
-    if (blockIdx.x == 0 && f.roff == 0) { zero_a[col] = 0.0; zero_b[col] = 0.0; zero_c[col] = 0.0; }
     const bool done = !(rr[col] > tol2 * bb[col]);
     const double den = rz[col];
     const double beta = (den > 0.0) ? rz_new[col] / den : 0.0;
     const double *dk = JACOBI ? dinv + (size_t)(col / nE) * N : nullptr;
-    const int row0 = blockIdx.x * rows_cta, nr = min(rows_cta, N - row0);
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int row0 = blk * rows_cta, nr = min(rows_cta, N - row0);
 #pragma unroll 4
-    for (int r = f.roff; r < nr; r += f.rpp) {
-        const int row = row0 + r;
-        const size_t o = (size_t)row * ld + col;
-        P[o] = done ? 0.0 : fma(beta, P[o], JACOBI ? dk[row] * R[o] : R[o]);
+        for (int r = f.roff; r < nr; r += f.rpp) {
+            const int row = row0 + r;
+            const size_t o = (size_t)row * ld + col;
+            P[o] = done ? 0.0 : fma(beta, P[o], JACOBI ? dk[row] * R[o] : R[o]);
+        }
     }
 }
 
@@ -925,34 +1019,38 @@ k_amg_restrict_split(const int *__restrict__ rowptr, const int *__restrict__ col
 // RC[I] = sum of RES over the members of aggregate I (deterministic restriction of a fine residual block); flat mapping
 __global__ void __launch_bounds__(FLAT_T)
 k_amg_sum_members(const int *__restrict__ mem_ptr, const int *__restrict__ mem_idx, int n_c, const double *__restrict__ RES,
-                  double *__restrict__ RC, int c0, int c1, size_t ld, int cw, int rows_cta) {
+                  double *__restrict__ RC, int c0, int c1, size_t ld, int cw, int rows_cta, int nblk) {
     const FlatMap f = flat_map(c0, c1, cw);
     if (!f.active) return;
-    const int row0 = blockIdx.x * rows_cta, nr = min(rows_cta, n_c - row0);
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int row0 = blk * rows_cta, nr = min(rows_cta, n_c - row0);
 #pragma unroll 2
-    for (int r = f.roff; r < nr; r += f.rpp) {
-        const int I = row0 + r;
-        double acc = 0.0;
-        for (int q = mem_ptr[I]; q < mem_ptr[I + 1]; q++) acc += RES[(size_t)mem_idx[q] * ld + f.col];
-        RC[(size_t)I * ld + f.col] = acc;
+        for (int r = f.roff; r < nr; r += f.rpp) {
+            const int I = row0 + r;
+            double acc = 0.0;
+            for (int q = mem_ptr[I]; q < mem_ptr[I + 1]; q++) acc += RES[(size_t)mem_idx[q] * ld + f.col];
+            RC[(size_t)I * ld + f.col] = acc;
+        }
     }
 }
 
 // X = dw .* R + EC[agg]   (pre-smoothed iterate plus prolongated coarse correction); EC == nullptr -> X = dw .* R
 __global__ void __launch_bounds__(FLAT_T)
 k_amg_prolong(const double *__restrict__ dinvw, int n, const int *__restrict__ agg, const double *__restrict__ R,
-              const double *__restrict__ EC, double *__restrict__ X, int nE, int c0, int c1, size_t ld, int cw, int rows_cta) {
+              const double *__restrict__ EC, double *__restrict__ X, int nE, int c0, int c1, size_t ld, int cw, int rows_cta, int nblk) {
     const FlatMap f = flat_map(c0, c1, cw);
     if (!f.active) return;
     const double *dk = dinvw + (size_t)(f.col / nE) * n;
-    const int row0 = blockIdx.x * rows_cta, nr = min(rows_cta, n - row0);
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int row0 = blk * rows_cta, nr = min(rows_cta, n - row0);
 #pragma unroll 4
-    for (int r = f.roff; r < nr; r += f.rpp) {
-        const int row = row0 + r;
-        const size_t o = (size_t)row * ld + f.col;
-        double x = dk[row] * R[o];
-        if (EC) x += EC[(size_t)agg[row] * ld + f.col];
-        X[o] = x;
+        for (int r = f.roff; r < nr; r += f.rpp) {
+            const int row = row0 + r;
+            const size_t o = (size_t)row * ld + f.col;
+            double x = dk[row] * R[o];
+            if (EC) x += EC[(size_t)agg[row] * ld + f.col];
+            X[o] = x;
+        }
     }
 }
 

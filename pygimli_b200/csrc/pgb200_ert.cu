@@ -4,11 +4,13 @@
 // point needs a CUDA device and fails loudly otherwise.
 #include "../../include/pgb200_ert.h"
 #include "ert_kernels.cuh"
+#include "stream_panels.h"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <initializer_list>
 #include <string>
 #include <vector>
@@ -54,10 +56,24 @@ enum Phase { PH_MAP = 0, PH_ASM, PH_RHS, PH_SOLVE, PH_EPI, PH_JAC, PH_COUNT };
 } // namespace
 
 struct GraphKey {
-    int c0, c1; double tol; int use_panels, panel_nc, panel_tma, levels, sweeps; void *stream; void *vals;
+    int c0, c1; double tol; int use_panels, levels, sweeps; void *stream; void *vals;
     bool operator==(const GraphKey &o) const {
-        return c0 == o.c0 && c1 == o.c1 && tol == o.tol && use_panels == o.use_panels && panel_nc == o.panel_nc && panel_tma == o.panel_tma &&
+        return c0 == o.c0 && c1 == o.c1 && tol == o.tol && use_panels == o.use_panels &&
                levels == o.levels && sweeps == o.sweeps && stream == o.stream && vals == o.vals;
+    }
+};
+
+// device side of stream_panels.h for one matrix level, plus the packed entry arrays of its two value sets
+struct StreamDev {
+    bool ok = false;
+    int n_panels = 0, n_chunks = 0, crp_stride = 0, max_chunk_halo = 0, max_chunk_ent = 0; size_t nnz = 0;
+    DevBuf<int> panel_row_ptr, panel_chunk_ptr, chunk_halo_ptr, halo_cols, chunk_ent_ptr, crp, ent_src;
+    DevBuf<unsigned> ent_idx;
+    DevBuf<PanelEntry> ent_a, ent_dw;       // [nK][nnz]: A (SpMM, post-smoothing) and A * diag(dw) (pre-smoothing residual)
+    StreamLevel level() const {
+        StreamLevel L; L.panel_row_ptr = panel_row_ptr.p; L.panel_chunk_ptr = panel_chunk_ptr.p; L.chunk_halo_ptr = chunk_halo_ptr.p;
+        L.halo_cols = halo_cols.p; L.chunk_ent_ptr = chunk_ent_ptr.p; L.crp = crp.p; L.n_panels = n_panels; L.crp_stride = crp_stride;
+        return L;
     }
 };
 
@@ -65,6 +81,7 @@ struct AmgLevel {      // one coarse level of the aggregation hierarchy (device 
     int n = 0; size_t nnz = 0; int n_finer = 0;
     DevBuf<int> rowptr, colidx, diag_pos, gal_ptr, gal_idx, agg, mem_ptr, mem_idx;
     DevBuf<double> vals, vals_dw, dinvw, R, X, Z;
+    StreamDev stream;      // streamed row panels (levels that are large enough)
 };
 
 struct pgb200_ert {
@@ -85,7 +102,10 @@ struct pgb200_ert {
         dir_zero, dir_diag, dir_nodes, sing_node, pick_ptr, pick_idx, src_cell_ptr, src_cells, pro_cells, pro_nb,
         jac_cells, jac_col_ptr, abmn;
     std::vector<int> color_ptr, pro_level_ptr;
-    DevBuf<int> panel_ptr, halo_ptr, halo_cols; DevBuf<unsigned short> lidx, self_idx; int n_panels = 0, max_halo = 0, max_pnnz = 0, max_rows = 0, panel_nc = 2, panel_tma = 1; int use_panels = 1;
+    StreamDev stream; int use_panels = 1, use_panels_build = 1;   // streamed row panels of the fine level (use_panels 0: plain gather SpMM, A/B evidence)
+    int stream_rmax = ST_CONSUMER_WARPS * ST_RPW, stream_hc = 104, stream_chunks = 2; // panel limits (stream_panels.h)
+    DevBuf<double> dot_part; DevBuf<unsigned> dot_counter;    // deterministic column dots: per-CTA partial rows + tickets
+    int dot_slots = 0; size_t smem_optin = 0;
     std::vector<double> h_kvals;
     int n_colors = 0, n_bc_slots = 0, n_bc_entries = 0, n_dir_zero = 0, n_dir_nodes = 0, pro_nf = 0, n_jac_cells = 0;
     std::vector<int> h_abmn; std::vector<double> h_kfac;
@@ -111,17 +131,18 @@ struct pgb200_ert {
     cudaEvent_t ev[PH_COUNT + 1]; bool ev_ok = false; float ph_ms[PH_COUNT] = {0};
     bool ph_rec[PH_COUNT + 1] = {false};
     std::vector<cudaEvent_t> tev; std::vector<int> tline; int n_tev = 0; int trace = 0; int cur_tag = 0;   // tag: multilevel level of the launch
+    int cur_role = 0;   // trace only: epilogue role of a streamed SpMM launch (1 SpMM, 2 post-smoothing, 3 residual)
     int prof = 0; std::vector<cudaEvent_t> pev; int n_pev = 0; double spmm_ms = 0.0; int spmm_timed = 0; double jac_ms = 0.0;
     cudaEvent_t jev[2]; bool jac_timed = false; int jac_launches = 0; long long total_iters = 0; int solves = 0;
     double *h_pinned = nullptr; size_t h_pinned_n = 0;
     int num_sms = 148;
     // which code paths the last solve / Jacobian took (pgb200_ert_path_info)
-    int pi_panel_nc = 0, pi_tiles = 0, pi_two_k = 0, pi_graph_launches = 0;
+    int pi_panel_nc = 0, pi_tiles = 0, pi_two_k = 0, pi_graph_launches = 0, pi_slots = 0, pi_stream_levels = 0;
 };
 
 inline void note_launch(pgb200_ert *h, int line) {
     h->launches++;
-    if (h->trace && h->n_tev < (int)h->tev.size()) { cudaEventRecord(h->tev[h->n_tev], h->st); h->tline[h->n_tev++] = line * 16 + (h->cur_tag & 15); }
+    if (h->trace && h->n_tev < (int)h->tev.size()) { cudaEventRecord(h->tev[h->n_tev], h->st); h->tline[h->n_tev++] = line * 256 + ((h->cur_role & 15) << 4) + (h->cur_tag & 15); }
 }
 // every kernel launch is counted; in trace mode (set_profile(h, 2)) an event is recorded after each one, tagged with
 // the source line of the launch, so that consecutive events give a warm per-kernel timeline of one step
@@ -206,67 +227,130 @@ int launch_spmm(pgb200_ert *h, const double *vals, const double *vals1, const do
     return 0;
 }
 
-// panel-staged SpMM (the PCG hot kernel): Y = A X on columns [c0,c1), fused p.Ap; the same kernel with other
-// epilogues is the fine-level smoother / residual-restriction of the multilevel preconditioner
-template <int NC, int EPI>
-int launch_spmm_panel_nc(pgb200_ert *h, const double *vals, const double *X, double *Y, int c0, int c1, double *dots, const PanelExtra &ex) {
-    const int span = c1 - c0;
-    const int ntile = cdiv(span, 32 * NC);
-    int tw = cdiv(span, ntile); tw += tw & 1;                  // even tile width <= 32*NC (16-byte aligned bulk copies)
-    const size_t smem = sizeof(double) * ((size_t)h->max_halo * tw + 32 * NC + 3 * (size_t)h->max_pnnz) +
-                        sizeof(int) * ((size_t)h->max_rows + 2) + 16;
-    static size_t configured[5][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    if (smem > configured[NC][EPI]) {
-        CK(cudaFuncSetAttribute(k_spmm_panel<NC, true, 0, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_spmm_panel<NC, false, 0, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_spmm_panel<NC, true, 1, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_spmm_panel<NC, false, 1, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[NC][EPI] = smem;
-    }
-    dim3 grid(h->n_panels, ntile);
-    h->pi_panel_nc = NC; h->pi_tiles = ntile; if (h->nK > 1 && (tw % h->nE != 0 || c0 % h->nE != 0)) h->pi_two_k = 1;
-#define PANEL_GO(D, S) k_spmm_panel<NC, D, S, EPI><<<grid, PANEL_THREADS, smem, h->st>>>(h->rowptr.p, h->lidx.p, h->self_idx.p, h->panel_ptr.p, \
-        h->halo_ptr.p, h->halo_cols.p, vals, h->nnz, X, Y, h->nE, c0, c1, tw, h->max_halo, h->max_pnnz, h->max_rows, h->ld, dots, ex)
-    if (h->panel_tma) { if (dots) PANEL_GO(true, 1); else PANEL_GO(false, 1); }
-    else { if (dots) PANEL_GO(true, 0); else PANEL_GO(false, 0); }
-#undef PANEL_GO
-    LAUNCH(h);
+// ---- streamed row-panel SpMM (the PCG hot kernel; ert_kernels.cuh k_spmm_stream) -------------------------------------
+// host layout -> device, once per pattern
+int stream_upload(pgb200_ert *h, StreamDev &D, int n, const int *rowptr_host, const int *colidx_host) {
+    D.ok = false;
+    if (!h->use_panels_build) return 0;
+    StreamPanelsHost S;
+    const std::string err = build_stream_panels(n, rowptr_host, colidx_host, h->stream_rmax, h->stream_hc, h->stream_chunks, S);
+    if (!err.empty()) return 0;                  // (a row wider than the halo limit) -> plain kernels for this level
+    cudaStream_t st = h->st;
+    CKR(D.panel_row_ptr.upload(S.panel_row_ptr.data(), S.panel_row_ptr.size(), st));
+    CKR(D.panel_chunk_ptr.upload(S.panel_chunk_ptr.data(), S.panel_chunk_ptr.size(), st));
+    CKR(D.chunk_halo_ptr.upload(S.chunk_halo_ptr.data(), S.chunk_halo_ptr.size(), st));
+    CKR(D.halo_cols.upload(S.halo_cols.data(), S.halo_cols.size(), st));
+    CKR(D.chunk_ent_ptr.upload(S.chunk_ent_ptr.data(), S.chunk_ent_ptr.size(), st));
+    CKR(D.crp.upload(S.crp.data(), S.crp.size(), st));
+    CKR(D.ent_src.upload(S.ent_src.data(), S.ent_src.size(), st));
+    CKR(D.ent_idx.upload(S.ent_idx.data(), S.ent_idx.size(), st));
+    CK(cudaStreamSynchronize(st));               // the host vectors go out of scope
+    D.n_panels = S.n_panels; D.n_chunks = S.n_chunks; D.crp_stride = S.crp_stride; D.max_chunk_halo = S.max_chunk_halo;
+    D.max_chunk_ent = S.max_chunk_ent; D.nnz = (size_t)S.nnz;
+    CKR(D.ent_a.alloc(D.nnz * h->nK)); CKR(D.ent_dw.alloc(D.nnz * h->nK));
+    D.ok = true;
+    return 0;
+}
+int stream_pack(pgb200_ert *h, StreamDev &D, const double *vals, PanelEntry *ent) {
+    if (!D.ok || D.nnz == 0) return 0;
+    k_pack_entries<<<cdiv((long long)D.nnz, 256), 256, 0, h->st>>>(D.ent_src.p, D.ent_idx.p, D.nnz, h->nK, vals, ent); LAUNCH(h);
+    return 0;
+}
+inline size_t up128(size_t x) { return (x + 127) / 128 * 128; }
+
+template <int NCP, int EPI, bool DOT>
+int stream_go(pgb200_ert *h, const StreamArgs &A, size_t smem) {
+    k_spmm_stream<NCP, EPI, DOT><<<h->num_sms, ST_THREADS, smem, h->st>>>(A);
+    h->cur_role = EPI + 1; LAUNCH(h); h->cur_role = 0;
     return 0;
 }
 template <int EPI>
-int launch_panel(pgb200_ert *h, const double *vals, const double *X, double *Y, int c0, int c1, double *dots, const PanelExtra &ex) {
+int stream_configure_epi(size_t smem) {
+    CK(cudaFuncSetAttribute(k_spmm_stream<1, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_spmm_stream<2, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_spmm_stream<1, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_spmm_stream<2, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return 0;
+}
+// per handle (the attribute is per device/context): dynamic shared memory of the streamed kernels
+int stream_configure(pgb200_ert *h) {
+    int optin = 0;
+    CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, k_spmm_stream<2, EPI_POST, true>));
+    h->smem_optin = (size_t)optin - fa.sharedSizeBytes - 256;          // static: mbarriers, dot scratch
+    CKR(stream_configure_epi<EPI_SPMM>(h->smem_optin));
+    CKR(stream_configure_epi<EPI_POST>(h->smem_optin));
+    CKR(stream_configure_epi<EPI_RESIDUAL>(h->smem_optin));
+    return 0;
+}
+
+// Y = op(A X) on the column window [c0, c1); dots != nullptr: deterministic per-column dot of the epilogue
+template <int EPI>
+int launch_stream(pgb200_ert *h, const StreamDev &D, const PanelEntry *ent, const double *X, double *Y, int c0, int c1, double *dots,
+                  const PanelExtra &ex) {
     if (c1 <= c0) return 0;
-    if (h->panel_nc == 4 && h->nK == 1 && c1 - c0 > 64) return launch_spmm_panel_nc<4, EPI>(h, vals, X, Y, c0, c1, dots, ex);   // one 128-wide tile
-    if (h->panel_nc >= 2 && c1 - c0 > 32) return launch_spmm_panel_nc<2, EPI>(h, vals, X, Y, c0, c1, dots, ex);   // narrow shards: 1 column per lane
-    return launch_spmm_panel_nc<1, EPI>(h, vals, X, Y, c0, c1, dots, ex);
+    const int nE = h->nE;
+    StreamArgs A;
+    A.L = D.level(); A.ent = ent; A.nnz = D.nnz; A.X = X; A.Y = Y; A.ld = h->ld; A.nE = nE; A.c0 = c0; A.c1 = c1; A.ex = ex;
+    A.k_lo = c0 / nE;
+    const int k_hi = (c1 - 1) / nE;
+    // widest column span of one wavenumber group inside the window, from an even start
+    int span;
+    if (k_hi == A.k_lo) span = ((c1 + 1) & ~1) - (c0 & ~1);
+    else span = nE + ((nE & 1) ? 1 : 0);
+    // tile width: at least two slots must fit
+    const size_t ent_b = up128((size_t)std::max(1, D.max_chunk_ent) * sizeof(PanelEntry)), crp_b = up128((size_t)D.crp_stride * 4);
+    const size_t per_col = (size_t)D.max_chunk_halo * 8;
+    long long wfit = ((long long)(h->smem_optin / 2) - (long long)ent_b - (long long)crp_b - 128) / (long long)per_col;
+    int wmax = (int)std::min<long long>(ST_MAX_TILE_W, wfit) & ~1;
+    if (wmax < 2) PGB_FAIL("streamed SpMM: a halo chunk does not fit shared memory");
+    A.tpk = cdiv(span, wmax);
+    A.pw = (cdiv(span, A.tpk) + 1) & ~1;
+    A.n_tiles = (k_hi - A.k_lo + 1) * A.tpk;
+    A.x_bytes = (uint32_t)up128((size_t)D.max_chunk_halo * A.pw * 8);
+    A.ent_bytes = (uint32_t)ent_b;
+    A.slot_bytes = (uint32_t)(A.x_bytes + ent_b + crp_b);
+    A.slots = (int)std::min<size_t>(ST_MAX_SLOTS, h->smem_optin / A.slot_bytes);
+    if (A.slots < 2) PGB_FAIL("streamed SpMM: internal slot sizing error");
+    const size_t smem = (size_t)A.slots * A.slot_bytes;
+    const int G = h->num_sms;
+    A.cpt = A.n_tiles <= G ? std::max(1, G / A.n_tiles) : 1;
+    A.dot_part = h->dot_part.p; A.dot_counter = h->dot_counter.p; A.dots = dots;
+    if (dots && A.n_tiles > (int)h->dot_counter.n) PGB_FAIL("streamed SpMM: too many column tiles for the dot tickets");
+    h->pi_panel_nc = A.pw > 64 ? 2 : 1; h->pi_tiles = A.n_tiles; h->pi_slots = A.slots;
+    if (A.pw > 64) { if (dots) return stream_go<2, EPI, true>(h, A, smem); return stream_go<2, EPI, false>(h, A, smem); }
+    if (dots) return stream_go<1, EPI, true>(h, A, smem);
+    return stream_go<1, EPI, false>(h, A, smem);
 }
-int launch_spmm_panel(pgb200_ert *h, const double *vals, const double *X, double *Y, int c0, int c1, double *dots) {
-    PanelExtra ex{}; 
-    return launch_panel<EPI_SPMM>(h, vals, X, Y, c0, c1, dots, ex);
-}
-bool panel_path_ok(const pgb200_ert *h, int c0) {
-    return h->use_panels && h->n_panels > 0 && !(c0 & 1) && (h->nK == 1 || h->nE >= 32 * std::min(2, h->panel_nc));
-}
+bool panel_path_ok(const pgb200_ert *h) { return h->use_panels && h->stream.ok; }
 
 // launch geometry of the flat element-wise kernels (ert_kernels.cuh, flat_map): column chunks of at most FLAT_T columns,
 // rows per CTA = rows per pass x passes
-struct FlatCfg { int cw, rows_cta; dim3 grid; };
+constexpr int FLAT_MAX_GX = 1184;          // 8 CTAs per SM: bounds the partial rows of the deterministic dots
+struct FlatCfg { int cw, rows_cta, nblk; dim3 grid; };
 inline FlatCfg flat_cfg(int n_rows, int c0, int c1) {
     FlatCfg f;
     const int w = std::max(1, c1 - c0);
     const int nchunk = cdiv(w, FLAT_T);
     f.cw = cdiv(w, nchunk);
     const int rpp = FLAT_T / f.cw;
-    // up to 12 passes per CTA, fewer when that would leave less than ~4 CTAs per SM (small levels, narrow shards)
+    // up to 12 passes per row block, fewer when that would leave less than ~4 CTAs per SM (small levels, narrow shards)
     const int passes = std::max(1, std::min(12, n_rows / (rpp * 600)));
     f.rows_cta = rpp * passes;
-    f.grid = dim3(cdiv(n_rows, f.rows_cta), nchunk);
+    f.nblk = cdiv(n_rows, f.rows_cta);
+    f.grid = dim3(std::min(f.nblk, FLAT_MAX_GX), nchunk);      // CTAs walk the row blocks with a grid stride
     return f;
+}
+inline DotOut dot_out(pgb200_ert *h, double *out0, double *out1) {
+    DotOut D; D.part = h->dot_part.p; D.plane = (size_t)h->dot_slots * h->ld; D.counter = h->dot_counter.p; D.out0 = out0; D.out1 = out1; D.ld = h->ld;
+    return D;
 }
 
 // rows per CTA of the plain multilevel kernels: 32 on big levels, 8 on small ones so that they still fill the GPU
 inline int amg_rows_per_cta(int n) { return n >= 60000 ? 32 : 8; }
 
+constexpr int STREAM_MIN_ROWS = 6000;     // coarse levels with at least this many rows use the streamed row-panel kernel
 constexpr int AMG_SPLIT_BELOW = 6000;      // levels smaller than this use the one-row-per-CTA kernels (latency-bound; measured: 11 k rows is already better off with the row-per-thread kernels)
 
 template <int CPT>
@@ -294,6 +378,8 @@ int pick_cpt(int ncols) {
 }
 int amg_post(pgb200_ert *h, const int *rowptr, const int *colidx, const double *vals, size_t nnz, const double *dinvw, int n,
              const double *X, const double *R, double *Z, int c0, int c1, double *dots) {
+    // (plain-kernel path only: the column dots are accumulated with atomics into a zeroed buffer)
+    if (dots) CK(cudaMemsetAsync(dots + c0, 0, sizeof(double) * (c1 - c0), h->st));
     switch (pick_cpt(c1 - c0)) {
         case 4: return amg_post_cpt<4>(h, rowptr, colidx, vals, nnz, dinvw, n, X, R, Z, c0, c1, dots);
         case 2: return amg_post_cpt<2>(h, rowptr, colidx, vals, nnz, dinvw, n, X, R, Z, c0, c1, dots);
@@ -333,35 +419,39 @@ int amg_setup_values(pgb200_ert *h) {
         return 0;
     };
     CKR(smoother(h->rowptr.p, h->colidx.p, h->diag_pos.p, h->N, h->nnz, h->vals.p, h->dinvw0.p, h->vals_dw0.p));
+    CKR(stream_pack(h, h->stream, h->vals_dw0.p, h->stream.ent_dw.p));
     const double *vf = h->vals.p; size_t nnz_f = h->nnz;
     for (AmgLevel *L : h->amg) {
         k_galerkin<<<cdiv((long long)L->nnz, 128), 128, 0, h->st>>>(L->gal_ptr.p, L->gal_idx.p, (int)L->nnz, nK, nnz_f, L->nnz, vf, L->vals.p); LAUNCH(h);
         CKR(smoother(L->rowptr.p, L->colidx.p, L->diag_pos.p, L->n, L->nnz, L->vals.p, L->dinvw.p, L->vals_dw.p));
+        CKR(stream_pack(h, L->stream, L->vals.p, L->stream.ent_a.p));
+        CKR(stream_pack(h, L->stream, L->vals_dw.p, L->stream.ent_dw.p));
         vf = L->vals.p; nnz_f = L->nnz;
     }
     CK(cudaGetLastError());
     return 0;
 }
 
-// one V(1,1) cycle: Z0 = M^-1 R (level 0 residual = h->R); optionally accumulates dots[c] += R.Z
+// one V(1,1) cycle: Z0 = M^-1 R (level 0 residual = h->R); dots != nullptr: dots[c] = R.Z per column (deterministic on the
+// streamed path)
 int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
     const int nl = (int)h->amg.size();
-    struct Lv { const int *rowptr, *colidx; const double *vals, *vals_dw; size_t nnz; const double *dinvw; int n; const double *R; double *X, *Z; };
+    struct Lv { const int *rowptr, *colidx; const double *vals, *vals_dw; size_t nnz; const double *dinvw; int n; const double *R; double *X, *Z; const StreamDev *st; };
     std::vector<Lv> lv(nl + 1);
-    lv[0] = {h->rowptr.p, h->colidx.p, h->vals.p, h->vals_dw0.p, h->nnz, h->dinvw0.p, h->N, h->R.p, h->X0.p, h->Z0.p};
-    for (int l = 0; l < nl; l++) { AmgLevel *L = h->amg[l]; lv[l + 1] = {L->rowptr.p, L->colidx.p, L->vals.p, L->vals_dw.p, L->nnz, L->dinvw.p, L->n, L->R.p, L->X.p, L->Z.p}; }
+    lv[0] = {h->rowptr.p, h->colidx.p, h->vals.p, h->vals_dw0.p, h->nnz, h->dinvw0.p, h->N, h->R.p, h->X0.p, h->Z0.p, &h->stream};
+    for (int l = 0; l < nl; l++) { AmgLevel *L = h->amg[l]; lv[l + 1] = {L->rowptr.p, L->colidx.p, L->vals.p, L->vals_dw.p, L->nnz, L->dinvw.p, L->n, L->R.p, L->X.p, L->Z.p, &L->stream}; }
+    auto streamed = [&](int l) { return h->use_panels && lv[l].st->ok; };
     // downward: residual after one damped-Jacobi sweep from zero, restricted
-    const bool fine_panels = nl > 0 && panel_path_ok(h, c0);
     for (int l = 0; l < nl; l++) {
         h->cur_tag = l;
-        if (l == 0 && fine_panels) {
-            // fine level: residual through the panel-staged kernel (into X0, free until the prolongation), then a
+        if (streamed(l)) {
+            // residual through the streamed kernel (into X of this level, free until the prolongation), then a
             // deterministic member sum
             PanelExtra ex{};
-            CKR(launch_panel<EPI_RESIDUAL>(h, h->vals_dw0.p, h->R.p, h->X0.p, c0, c1, nullptr, ex));
-            AmgLevel *L = h->amg[0];
+            CKR(launch_stream<EPI_RESIDUAL>(h, *lv[l].st, lv[l].st->ent_dw.p, lv[l].R, lv[l].X, c0, c1, nullptr, ex));
+            AmgLevel *L = h->amg[l];
             const FlatCfg fc = flat_cfg(L->n, c0, c1);
-            k_amg_sum_members<<<fc.grid, FLAT_T, 0, h->st>>>(L->mem_ptr.p, L->mem_idx.p, L->n, h->X0.p, L->R.p, c0, c1, h->ld, fc.cw, fc.rows_cta); LAUNCH(h);
+            k_amg_sum_members<<<fc.grid, FLAT_T, 0, h->st>>>(L->mem_ptr.p, L->mem_idx.p, L->n, lv[l].X, L->R.p, c0, c1, h->ld, fc.cw, fc.rows_cta, fc.nblk); LAUNCH(h);
         } else {
             CKR(amg_restrict(h, lv[l].rowptr, lv[l].colidx, lv[l].vals_dw, lv[l].nnz, lv[l].n, h->amg[l], lv[l].R, c0, c1));
         }
@@ -372,7 +462,7 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
         Lv &c = lv[nl];
         h->cur_tag = nl;
         const FlatCfg fc = flat_cfg(c.n, c0, c1);
-        k_amg_prolong<<<fc.grid, FLAT_T, 0, h->st>>>(c.dinvw, c.n, nullptr, c.R, nullptr, c.X, h->nE, c0, c1, h->ld, fc.cw, fc.rows_cta); LAUNCH(h);
+        k_amg_prolong<<<fc.grid, FLAT_T, 0, h->st>>>(c.dinvw, c.n, nullptr, c.R, nullptr, c.X, h->nE, c0, c1, h->ld, fc.cw, fc.rows_cta, fc.nblk); LAUNCH(h);
         double *a = c.X, *b = c.Z;
         const int sweeps = (nl == 0) ? 1 : h->coarse_sweeps;
         for (int s = 0; s + 1 < sweeps; s++) {
@@ -387,10 +477,11 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
         Lv &f = lv[l];
         h->cur_tag = l;
         const FlatCfg fc = flat_cfg(f.n, c0, c1);
-        k_amg_prolong<<<fc.grid, FLAT_T, 0, h->st>>>(f.dinvw, f.n, h->amg[l]->agg.p, f.R, E, f.X, h->nE, c0, c1, h->ld, fc.cw, fc.rows_cta); LAUNCH(h);
-        if (l == 0 && fine_panels) {
+        k_amg_prolong<<<fc.grid, FLAT_T, 0, h->st>>>(f.dinvw, f.n, h->amg[l]->agg.p, f.R, E, f.X, h->nE, c0, c1, h->ld, fc.cw, fc.rows_cta, fc.nblk); LAUNCH(h);
+        if (streamed(l)) {
             PanelExtra ex{}; ex.R = f.R; ex.dinvw = f.dinvw; ex.n = f.n;
-            CKR(launch_panel<EPI_POST>(h, f.vals, f.X, f.Z, c0, c1, dots, ex));
+            const PanelEntry *ea = (l == 0) ? h->stream.ent_a.p : f.st->ent_a.p;
+            CKR(launch_stream<EPI_POST>(h, *f.st, ea, f.X, f.Z, c0, c1, l == 0 ? dots : nullptr, ex));
         } else {
             CKR(amg_post(h, f.rowptr, f.colidx, f.vals, f.nnz, f.dinvw, f.n, f.X, f.R, f.Z, c0, c1, l == 0 ? dots : nullptr));
         }
@@ -413,11 +504,11 @@ int pcg_solve(pgb200_ert *h) {
     double *S = h->scal.p;
     auto sc = [&](int i) { return S + (size_t)i * ld; };
     CK(cudaMemsetAsync(S, 0, sizeof(double) * 7 * ld, h->st));
-    dim3 vb(VEC_TX, VEC_TY), vg(cdiv(h->N, VEC_ROWS), cdiv(ncols, VEC_TX));   // k_pcg_init (once per solve)
     FlatCfg fc = flat_cfg(h->N, c0, c1);                                      // per-iteration vector kernels
     auto regrid = [&]() { fc = flat_cfg(h->N, c0, c1); };
     const bool amg = h->use_amg && !h->amg.empty();
-    k_pcg_init<<<vg, vb, 0, h->st>>>(h->B.p, h->dinv.p, h->X.p, h->R.p, h->P.p, h->N, h->nE, c0, c1, ld, amg ? nullptr : sc(0), sc(6)); LAUNCH(h);
+    k_pcg_init<<<fc.grid, FLAT_T, 0, h->st>>>(h->B.p, h->dinv.p, h->X.p, h->R.p, h->P.p, h->N, h->nE, c0, c1, ld, fc.cw, fc.rows_cta, fc.nblk,
+                                              dot_out(h, amg ? nullptr : sc(0), sc(6))); LAUNCH(h);
     if (amg) {
         CKR(amg_vcycle(h, c0, c1, sc(0)));
         CK(cudaMemcpyAsync(h->P.p, h->Z0.p, sizeof(double) * (size_t)h->N * ld, cudaMemcpyDeviceToDevice, h->st));
@@ -428,23 +519,28 @@ int pcg_solve(pgb200_ert *h) {
     int it = 0; bool converged = false;
     // one PCG iteration; the scalar buffers rotate with the iteration number (rz: period 3, rr: period 2)
     auto body = [&](int i, bool timed) -> int {
-        const int rz_old = i % 3, rz_new = (i + 1) % 3, rz_nxt = (i + 2) % 3;
-        const int rr_cur = 4 + (i % 2), rr_nxt = 4 + ((i + 1) % 2);
+        const int rz_old = i % 3, rz_new = (i + 1) % 3;
+        const int rr_cur = 4 + (i % 2);
         if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
-        if (panel_path_ok(h, c0)) CKR(launch_spmm_panel(h, h->vals.p, h->P.p, h->AP.p, c0, c1, sc(3)));
-        else CKR((launch_spmm<0, true>(h, h->vals.p, nullptr, nullptr, h->P.p, h->AP.p, c0, c1, sc(3))));
+        if (panel_path_ok(h)) {
+            PanelExtra ex{};
+            CKR(launch_stream<EPI_SPMM>(h, h->stream, h->stream.ent_a.p, h->P.p, h->AP.p, c0, c1, sc(3), ex));
+        } else {
+            CK(cudaMemsetAsync(sc(3) + c0, 0, sizeof(double) * (c1 - c0), h->st));
+            CKR((launch_spmm<0, true>(h, h->vals.p, nullptr, nullptr, h->P.p, h->AP.p, c0, c1, sc(3))));
+        }
         if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
         if (amg) {
             k_pcg_update_xr<false><<<fc.grid, FLAT_T, 0, h->st>>>(h->P.p, h->AP.p, nullptr, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
-                                                                 sc(rz_old), sc(3), sc(rz_new), sc(rr_cur), fc.cw, fc.rows_cta); LAUNCH(h);
+                                                                 sc(rz_old), sc(3), fc.cw, fc.rows_cta, fc.nblk, dot_out(h, nullptr, sc(rr_cur))); LAUNCH(h);
             CKR(amg_vcycle(h, c0, c1, sc(rz_new)));
             k_pcg_update_p<false><<<fc.grid, FLAT_T, 0, h->st>>>(h->Z0.p, nullptr, h->P.p, h->N, h->nE, c0, c1, ld, sc(rz_old), sc(rz_new),
-                                                                sc(rr_cur), sc(6), tol2, sc(3), sc(rr_nxt), sc(rz_nxt), fc.cw, fc.rows_cta); LAUNCH(h);
+                                                                sc(rr_cur), sc(6), tol2, fc.cw, fc.rows_cta, fc.nblk); LAUNCH(h);
         } else {
             k_pcg_update_xr<true><<<fc.grid, FLAT_T, 0, h->st>>>(h->P.p, h->AP.p, h->dinv.p, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
-                                                                sc(rz_old), sc(3), sc(rz_new), sc(rr_cur), fc.cw, fc.rows_cta); LAUNCH(h);
+                                                                sc(rz_old), sc(3), fc.cw, fc.rows_cta, fc.nblk, dot_out(h, sc(rz_new), sc(rr_cur))); LAUNCH(h);
             k_pcg_update_p<true><<<fc.grid, FLAT_T, 0, h->st>>>(h->R.p, h->dinv.p, h->P.p, h->N, h->nE, c0, c1, ld, sc(rz_old), sc(rz_new),
-                                                               sc(rr_cur), sc(6), tol2, sc(3), sc(rr_nxt), sc(rz_nxt), fc.cw, fc.rows_cta); LAUNCH(h);
+                                                               sc(rr_cur), sc(6), tol2, fc.cw, fc.rows_cta, fc.nblk); LAUNCH(h);
         }
         return 0;
     };
@@ -483,7 +579,7 @@ int pcg_solve(pgb200_ert *h) {
         const int blocks_per_check = std::max(1, h->check_every / 6);
         int blocks = 0;
         while (it < h->max_iter && !converged) {
-            GraphKey key{c0, c1, h->tol, h->use_panels, h->panel_nc, h->panel_tma, (int)h->amg.size(), h->coarse_sweeps, (void *)h->st, (void *)h->vals.p};
+            GraphKey key{c0, c1, h->tol, h->use_panels, (int)h->amg.size(), h->coarse_sweeps, (void *)h->st, (void *)h->vals.p};
             if (it == 0) {
                 const long long before = h->launches;
                 for (int j = 0; j < 6; j++) CKR(body(j, false));          // warm-up block (also sets kernel attributes)
@@ -562,6 +658,7 @@ int forward_solve(pgb200_ert *h) {
     k_count_singular<<<cdiv(h->N, 256), 256, 0, h->st>>>(h->diag_pos.p, h->N, h->nK, h->nnz, h->vals.p, h->flags.p + 1); LAUNCH(h);
     k_inv_diag<<<cdiv(h->N, 256), 256, 0, h->st>>>(h->diag_pos.p, h->N, h->nK, h->nnz, h->vals.p, h->dinv.p); LAUNCH(h);
     h->have_vals = true;
+    CKR(stream_pack(h, h->stream, h->vals.p, h->stream.ent_a.p));
     if (h->use_amg) CKR(amg_setup_values(h));
     phase_begin(h, PH_RHS);
     const int c0 = h->c0, c1 = h->c1;
@@ -824,39 +921,30 @@ int pgb200_color_cells(int n_cells, int nloc, const int *cells, int n_nodes, int
     return ncol;
 }
 
-// Row panels for the staged SpMM: consecutive rows are grouped while the panel has at most rmax rows
-// and its halo (distinct columns) at most hmax entries.  Outputs: panel_ptr[<=N+1], halo_ptr[<=N+1],
-// halo_cols[<=nnz], lidx[nnz] (16-bit offset of every entry's column in its panel's halo list),
-// self_idx[N] (offset of the row itself).  Returns the number of panels (< 0 on failure).
-int pgb200_build_panels(int n_rows, const int *rowptr, const int *colidx, int rmax, int hmax,
-                        int *panel_ptr, int *halo_ptr, int *halo_cols, unsigned short *lidx, unsigned short *self_idx) {
-    if (hmax > 65535 || rmax < 1) { g_err = "invalid panel limits"; return -1; }
-    std::vector<int> stamp((size_t)n_rows, -1), slot((size_t)n_rows, 0);
-    int np = 0, hcount = 0, row = 0;
-    panel_ptr[0] = 0; halo_ptr[0] = 0;
-    while (row < n_rows) {
-        const int start = row, hstart = hcount;
-        int h = 0;
-        while (row < n_rows && row - start < rmax) {
-            int add = 0;
-            for (int p = rowptr[row]; p < rowptr[row + 1]; p++) if (stamp[colidx[p]] != np) add++;
-            if (h + add > hmax) {
-                if (row == start) { g_err = "a single matrix row exceeds the halo limit"; return -1; }
-                break;
-            }
-            for (int p = rowptr[row]; p < rowptr[row + 1]; p++) {
-                const int c = colidx[p];
-                if (stamp[c] != np) { stamp[c] = np; slot[c] = h; halo_cols[hstart + h] = c; h++; }
-                lidx[p] = (unsigned short)slot[c];
-            }
-            if (stamp[row] != np) { g_err = "matrix row without diagonal entry"; return -1; }
-            self_idx[row] = (unsigned short)slot[row];
-            row++;
-        }
-        hcount += h; np++;
-        panel_ptr[np] = row; halo_ptr[np] = hcount;
-    }
-    return np;
+// Streamed row panels (stream_panels.h) of a CSR pattern -- exported for the host-side tests, which replay the kernel's
+// traversal on the CPU.  Two calls: with out == NULL the sizes are returned in counts[8] = {n_panels, n_chunks, halo
+// entries, crp_stride, max_rows, max_chunk_halo, max_chunk_ent, nnz}; with the arrays allocated they are filled
+// (panel_row_ptr[n_panels+1], panel_chunk_ptr[n_panels+1], chunk_halo_ptr[n_chunks+1], halo_cols[halo entries],
+// chunk_ent_ptr[n_chunks+1], ent_src[nnz], ent_idx[nnz], crp[n_chunks*crp_stride]).
+int pgb200_build_stream_panels(int n_rows, const int *rowptr, const int *colidx, int rmax, int hc, int max_chunks, int *counts,
+                               int *panel_row_ptr, int *panel_chunk_ptr, int *chunk_halo_ptr, int *halo_cols, int *chunk_ent_ptr,
+                               int *ent_src, unsigned *ent_idx, int *crp) {
+    if (!rowptr || !colidx || !counts) { g_err = "null argument"; return 1; }
+    StreamPanelsHost S;
+    const std::string err = build_stream_panels(n_rows, rowptr, colidx, rmax, hc, max_chunks, S);
+    if (!err.empty()) { g_err = err; return 1; }
+    const int c[8] = {S.n_panels, S.n_chunks, (int)S.halo_cols.size(), S.crp_stride, S.max_rows, S.max_chunk_halo, S.max_chunk_ent, (int)S.nnz};
+    for (int i = 0; i < 8; i++) counts[i] = c[i];
+    if (!panel_row_ptr) return 0;
+    std::copy(S.panel_row_ptr.begin(), S.panel_row_ptr.end(), panel_row_ptr);
+    std::copy(S.panel_chunk_ptr.begin(), S.panel_chunk_ptr.end(), panel_chunk_ptr);
+    std::copy(S.chunk_halo_ptr.begin(), S.chunk_halo_ptr.end(), chunk_halo_ptr);
+    std::copy(S.halo_cols.begin(), S.halo_cols.end(), halo_cols);
+    std::copy(S.chunk_ent_ptr.begin(), S.chunk_ent_ptr.end(), chunk_ent_ptr);
+    std::copy(S.ent_src.begin(), S.ent_src.end(), ent_src);
+    std::copy(S.ent_idx.begin(), S.ent_idx.end(), ent_idx);
+    std::copy(S.crp.begin(), S.crp.end(), crp);
+    return 0;
 }
 
 // Pairwise aggregation for the multilevel preconditioner: nodes are visited in order; an unaggregated node is matched
@@ -954,13 +1042,18 @@ int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
     const size_t npro = p->n_pro_levels ? (size_t)p->pro_level_ptr[p->n_pro_levels] : 0;
     CKR(h->pro_cells.upload(p->pro_cells, npro, st)); CKR(h->pro_nb.upload(p->pro_nb, npro * p->pro_nf, st));
     CKR(h->pro_w.upload(p->pro_w, npro * p->pro_nf, st));
-    h->n_panels = p->n_panels; h->max_halo = p->max_halo; h->max_pnnz = p->max_panel_nnz; h->max_rows = 0;
-    for (int i = 0; i < p->n_panels; i++) h->max_rows = std::max(h->max_rows, p->panel_ptr[i + 1] - p->panel_ptr[i]);
-    if (p->n_panels > 0) {
-        CKR(h->panel_ptr.upload(p->panel_ptr, (size_t)p->n_panels + 1, st)); CKR(h->halo_ptr.upload(p->halo_ptr, (size_t)p->n_panels + 1, st));
-        CKR(h->halo_cols.upload(p->halo_cols, (size_t)p->halo_ptr[p->n_panels], st));
-        CKR(h->lidx.upload(p->lidx, h->nnz, st)); CKR(h->self_idx.upload(p->self_idx, N, st));
-    }
+    // streamed row panels of the fine matrix (internal layout, built here from the pattern), their kernels' shared-memory
+    // opt-in, and the partial rows / tickets of the deterministic column dots
+    if (const char *e = getenv("PGB200_STREAM_HC")) h->stream_hc = std::max(h->stream_rmax, atoi(e));
+    if (const char *e = getenv("PGB200_STREAM_CHUNKS")) h->stream_chunks = std::max(1, atoi(e));
+    if (const char *e = getenv("PGB200_STREAM_ROWS")) h->stream_rmax = std::min(ST_CONSUMER_WARPS * ST_RPW, std::max(1, atoi(e)));
+    h->stream_hc = std::max(h->stream_hc, h->stream_rmax);
+    CKR(stream_configure(h));
+    CKR(stream_upload(h, h->stream, N, p->rowptr, p->colidx));
+    h->dot_slots = std::max(FLAT_MAX_GX, h->num_sms);
+    CKR(h->dot_part.alloc(2 * (size_t)h->dot_slots * h->ld));
+    CKR(h->dot_counter.alloc((size_t)std::max(64, h->nS + 8)));
+    CK(cudaMemsetAsync(h->dot_counter.p, 0, sizeof(unsigned) * h->dot_counter.n, st));
     h->n_jac_cells = p->n_jac_cells;
     CKR(h->jac_cells.upload(p->jac_cells, p->n_jac_cells, st)); CKR(h->jac_col_ptr.upload(p->jac_col_ptr, (size_t)h->M + 1, st));
     h->h_jac_col_ptr.assign(p->jac_col_ptr, p->jac_col_ptr + h->M + 1);
@@ -1037,6 +1130,7 @@ int pgb200_ert_set_hierarchy(pgb200_ert *h, int n_levels, const pgb200_amg_level
         CKR(L->vals.alloc(L->nnz * h->nK)); CKR(L->vals_dw.alloc(L->nnz * h->nK)); CKR(L->dinvw.alloc((size_t)s.n * h->nK));
         const size_t blk = (size_t)s.n * h->ld;
         CKR(L->R.alloc(blk)); CKR(L->X.alloc(blk)); CKR(L->Z.alloc(blk));
+        if (s.n >= STREAM_MIN_ROWS) CKR(stream_upload(h, L->stream, s.n, s.rowptr, s.colidx));   // large coarse levels run on the streamed kernel too
         CK(cudaMemsetAsync(L->R.p, 0, blk * sizeof(double), st)); CK(cudaMemsetAsync(L->X.p, 0, blk * sizeof(double), st));
         CK(cudaMemsetAsync(L->Z.p, 0, blk * sizeof(double), st));
         n_finer = s.n; nnz_finer = L->nnz;
@@ -1411,8 +1505,10 @@ int pgb200_ert_path_info(pgb200_ert *h, int *out, int n) {
     if (!h || !out) PGB_FAIL("null argument");
     int mt = 0, res = 1;
     for (auto &c : h->chunks) { mt = std::max(mt, c.mt); res = res && c.resolved; }
-    const int v[8] = {h->pi_panel_nc, h->pi_tiles, h->pi_two_k, h->pi_graph_launches, (int)h->chunks.size(), mt, res, (int)h->amg.size()};
-    for (int i = 0; i < n && i < 8; i++) out[i] = v[i];
+    int sl = 0;
+    for (AmgLevel *L : h->amg) sl += (h->use_panels && L->stream.ok) ? 1 : 0;
+    const int v[10] = {h->pi_panel_nc, h->pi_tiles, h->pi_two_k, h->pi_graph_launches, (int)h->chunks.size(), mt, res, (int)h->amg.size(), h->pi_slots, sl};
+    for (int i = 0; i < n && i < 10; i++) out[i] = v[i];
     return 0;
 }
 int pgb200_ert_reset_stats(pgb200_ert *h) {
@@ -1423,8 +1519,7 @@ int pgb200_ert_reset_stats(pgb200_ert *h) {
 }
 int pgb200_ert_set_spmm_variant(pgb200_ert *h, int panel_staged) {
     if (!h) PGB_FAIL("null handle");
-    h->use_panels = panel_staged != 0; h->panel_tma = (panel_staged == 1 || panel_staged == 2 || panel_staged == 4);
-    h->panel_nc = (panel_staged == 1) ? 1 : (panel_staged == 4 ? 4 : 2);
+    h->use_panels = panel_staged != 0;
     return 0;
 }
 int pgb200_ert_set_profile(pgb200_ert *h, int on) {
@@ -1448,7 +1543,7 @@ int pgb200_ert_get_trace(pgb200_ert *h, int *lines, float *ms, int cap) {
     for (int i = 1; i < h->n_tev && n < cap; i++, n++) {
         float t = 0.f;
         cudaEventElapsedTime(&t, h->tev[i - 1], h->tev[i]);
-        if (lines) lines[n] = h->tline[i];          // source line * 16 + multilevel level
+        if (lines) lines[n] = h->tline[i];          // source line * 256 + role * 16 + multilevel level
         if (ms) ms[n] = t;
     }
     return n;

@@ -329,8 +329,7 @@ class CoreB200:
             if self._scheme is None:
                 raise RuntimeError("no response without data container")
             # the plan is geometry only; missing k-factors are resolved at the first response()/createJacobian()
-            self._plan = build_plan(self._mesh, self._scheme, self._k, self._w, color_fn=_capi.color_cells,
-                                    panel_fn=_capi.build_panels)
+            self._plan = build_plan(self._mesh, self._scheme, self._k, self._w, color_fn=_capi.color_cells)
             self._placeholder_k = not self._have_k()
         return self._plan
 
@@ -413,7 +412,7 @@ class CoreB200:
                 _capi.check(_capi.lib().pgb200_ert_set_preconditioner(h, 1 if self.hierarchy else 0, 8))
             else:
                 _capi.check(_capi.lib().pgb200_ert_set_preconditioner(h, 0, 8))
-            if os.environ.get("PGB200_SPMM_VARIANT"):      # A/B switch for measurements: 0 plain, 1/2/4 panel NC, 3 cp.async
+            if os.environ.get("PGB200_SPMM_VARIANT"):      # A/B switch for measurements: 0 plain gather kernels, 1 streamed
                 _capi.check(_capi.lib().pgb200_ert_set_spmm_variant(h, int(os.environ["PGB200_SPMM_VARIANT"])))
             self._ensure_primary()
         return self._h
@@ -521,10 +520,10 @@ class CoreB200:
 
     def pathInfo(self) -> dict:
         """which kernels the last solve / Jacobian plan used (pgb200_ert_path_info)"""
-        v = np.zeros(8, np.int32)
-        _capi.check(_capi.lib().pgb200_ert_path_info(self._ensure_handle(), v.ctypes.data, 8))
+        v = np.zeros(10, np.int32)
+        _capi.check(_capi.lib().pgb200_ert_path_info(self._ensure_handle(), v.ctypes.data, 10))
         keys = ["spmm_panel_nc", "spmm_tiles", "spmm_two_k", "graph_launches", "jac_chunks", "jac_tiles_per_thread",
-                "jac_resolved", "amg_levels"]
+                "jac_resolved", "amg_levels", "spmm_slots", "stream_levels"]
         return dict(zip(keys, (int(x) for x in v)))
 
     def resetStats(self):

@@ -422,8 +422,7 @@ class ERTPlan:
     slot -> internal slot) and ``node_inv`` (old -> new)."""
 
 
-def build_plan(mesh: MeshArrays, scheme, k_values=None, weights=None, color_fn=None, panel_fn=None,
-               reorder: bool = True) -> ERTPlan:
+def build_plan(mesh: MeshArrays, scheme, k_values=None, weights=None, color_fn=None, reorder: bool = True) -> ERTPlan:
     P = ERTPlan()
     P.mesh_ref = mesh
     perm = node_ordering(mesh) if reorder else np.arange(mesh.node_count, dtype=np.int64)
@@ -481,7 +480,6 @@ def build_plan(mesh: MeshArrays, scheme, k_values=None, weights=None, color_fn=N
     P.ref_slot = o.astype(np.int64)
     P.ref_colidx = perm[P.colidx][o].astype(np.int32)
     P.ref_rowptr = np.concatenate([[0], np.cumsum(np.bincount(perm[rowof_i], minlength=N))]).astype(np.int32)
-    P.panels = panel_fn(P.rowptr, P.colidx) if panel_fn is not None else None
 
     # ---- electrodes (dcfemmodelling.cpp:845-940) ------------------------------------
     sens = np.array(scheme.sensors, float).reshape(-1, 3)

@@ -12,7 +12,7 @@ from pygimli_b200 import _capi, amg_setup, host_setup as hs
 def _matrix(name):
     """rho = 1 stiffness matrix of a test mesh assembled with numpy (P1 closed form), internal numbering"""
     mesh, scheme, _ = make_case(name)
-    P = hs.build_plan(mesh, scheme, color_fn=_capi.color_cells, panel_fn=_capi.build_panels)
+    P = hs.build_plan(mesh, scheme, color_fn=_capi.color_cells)
     m = P.mesh
     X = m.pos[m.cells[:, : m.dim + 1], : m.dim]
     J = np.transpose(X[:, 1:] - X[:, :1], (0, 2, 1))

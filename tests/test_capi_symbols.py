@@ -42,22 +42,62 @@ def test_color_cells_is_conflict_free():
         assert np.unique(nodes).size == nodes.size
 
 
-def test_build_panels_covers_matrix():
+def _replay_stream_spmm(pan, vals, X, tile):
+    """CPU replay of k_spmm_stream's traversal: panels -> chunks (last to first) -> rows -> re-ordered entries, reading X
+    only through the staged halo rows of the chunk and the tile's columns"""
+    c0, c1 = tile
+    Y = np.zeros_like(X)
+    for p in range(pan["n_panels"]):
+        r0, r1 = pan["panel_row_ptr"][p], pan["panel_row_ptr"][p + 1]
+        acc = np.zeros((r1 - r0, c1 - c0))
+        for ch in range(pan["panel_chunk_ptr"][p + 1] - 1, pan["panel_chunk_ptr"][p] - 1, -1):
+            h0, h1 = pan["chunk_halo_ptr"][ch], pan["chunk_halo_ptr"][ch + 1]
+            staged = X[pan["halo_cols"][h0:h1], c0:c1]                      # what the TMA copies bring
+            e0 = pan["chunk_ent_ptr"][ch]
+            crp = pan["crp"][ch * pan["crp_stride"]: (ch + 1) * pan["crp_stride"]]
+            for r in range(r1 - r0):
+                for e in range(e0 + crp[r], e0 + crp[r + 1]):
+                    acc[r] += vals[pan["ent_src"][e]] * staged[pan["ent_idx"][e]]
+            if ch == pan["panel_chunk_ptr"][p]:
+                # chunk 0 starts with the panel's own rows
+                assert np.array_equal(pan["halo_cols"][h0:h0 + (r1 - r0)], np.arange(r0, r1))
+        Y[r0:r1, c0:c1] = acc
+    return Y
+
+
+@pytest.mark.parametrize("name,limits", [("3d_p1", (60, 104, 2)), ("3d_p2", (60, 104, 2)), ("2d_p1", (60, 104, 2)),
+                                         ("3d_p1", (16, 40, 3)), ("2d_p2", (8, 30, 4))])
+def test_stream_panels_reproduce_spmm(name, limits):
+    """the streamed row-panel layout (csrc/stream_panels.h) visits every CSR entry exactly once and its staged-halo
+    indices resolve to the right columns: a CPU replay of the kernel's traversal equals A @ X"""
+    import scipy.sparse as sp
     from cases import make_case
     from pygimli_b200.host_setup import build_pattern
-    mesh, _, _ = make_case("3d_p1")
+    mesh, _, _ = make_case(name)
     rowptr, colidx, _ = build_pattern(mesh)
-    pan = _capi.build_panels(rowptr, colidx, 64, 208)
-    pp, hp = pan["panel_ptr"], pan["halo_ptr"]
-    assert pp[0] == 0 and pp[-1] == mesh.node_count and np.all(np.diff(pp) > 0) and np.all(np.diff(pp) <= 64)
-    assert np.all(np.diff(hp) <= 208)
-    # local indices resolve to the original columns, self index to the diagonal
-    rowof = np.repeat(np.arange(mesh.node_count), np.diff(rowptr))
-    panel_of_row = np.repeat(np.arange(pan["n_panels"]), np.diff(pp))
-    col_back = pan["halo_cols"][hp[panel_of_row[rowof]] + pan["lidx"][: colidx.size]]
-    assert np.array_equal(col_back, colidx)
-    self_back = pan["halo_cols"][hp[panel_of_row] + pan["self_idx"]]
-    assert np.array_equal(self_back, np.arange(mesh.node_count))
+    rmax, hc, nch = limits
+    pan = _capi.build_stream_panels(rowptr, colidx, rmax, hc, nch)
+    N = mesh.node_count
+    pr = pan["panel_row_ptr"]
+    assert pr[0] == 0 and pr[-1] == N and np.all(np.diff(pr) > 0) and np.all(np.diff(pr) <= rmax)
+    assert np.all(np.diff(pan["chunk_halo_ptr"]) <= hc) and np.all(np.diff(pan["panel_chunk_ptr"]) <= nch)
+    assert pan["crp_stride"] % 4 == 0 and pan["nnz"] == colidx.size
+    assert np.array_equal(np.sort(pan["ent_src"][:colidx.size]), np.arange(colidx.size))       # a permutation of the CSR slots
+    rng = np.random.default_rng(0)
+    vals = rng.standard_normal(colidx.size)
+    X = rng.standard_normal((N, 6))
+    A = sp.csr_matrix((vals, colidx, rowptr), shape=(N, N))
+    Y = _replay_stream_spmm(pan, vals, X, (1, 5))
+    ref = np.zeros_like(X)
+    ref[:, 1:5] = (A @ X)[:, 1:5]
+    assert np.max(np.abs(Y - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+def test_stream_panels_reject_too_wide_rows():
+    rowptr = np.array([0, 5, 6, 7, 8, 9], np.int32)
+    colidx = np.array([0, 1, 2, 3, 4, 1, 2, 3, 4], np.int32)
+    with pytest.raises(_capi.PGB200Error, match="halo limit"):
+        _capi.build_stream_panels(rowptr, colidx, 2, 2, 2)
 
 
 def test_compute_fails_loudly_without_gpu():

@@ -16,7 +16,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 @pytest.fixture(scope="module", params=CASES)
 def plan(request):
     mesh, scheme, model = make_case(request.param)
-    P = hs.build_plan(mesh, scheme, color_fn=_capi.color_cells, panel_fn=_capi.build_panels)
+    P = hs.build_plan(mesh, scheme, color_fn=_capi.color_cells)
     return request.param, mesh, scheme, model, P, np.load(os.path.join(GOLD, request.param + ".npz"))
 
 
