@@ -120,11 +120,12 @@ int pgb200_version(void);
 int pgb200_color_cells(int n_cells, int nloc, const int *cells, int n_nodes, int *color);
 /* Streamed row panels of the SpMM kernel (csrc/stream_panels.h) for a CSR pattern; the library builds them itself inside
  * pgb200_ert_create / pgb200_ert_set_hierarchy, this entry point exists for the host-side tests.  Two calls: with
- * panel_row_ptr == NULL only counts[8] = {panels, chunks, halo entries, crp_stride, max rows, max chunk halo, max chunk
- * entries, nnz} is filled; then with arrays of those sizes.  Returns 0 on success.                            */
+ * panel_row_ptr == NULL only counts[10] = {panels, chunks, halo entries, crp_stride, max rows, max chunk halo, max chunk
+ * entries, nnz, runs, max runs per chunk} is filled; then with arrays of those sizes (runs[3 * runs] = {first halo entry
+ * in its chunk, column, length}).  Returns 0 on success.                                                       */
 int pgb200_build_stream_panels(int n_rows, const int *rowptr, const int *colidx, int rmax, int hc, int max_chunks, int *counts,
                                int *panel_row_ptr, int *panel_chunk_ptr, int *chunk_halo_ptr, int *halo_cols, int *chunk_ent_ptr,
-                               int *ent_src, unsigned *ent_idx, int *crp);
+                               int *ent_src, unsigned *ent_idx, int *crp, int *chunk_run_ptr, int *runs);
 
 /* Greedy pairwise aggregation along the strongest negative coupling (multilevel preconditioner set-up); a pair is
  * formed only if the coupling is at least theta times the strongest coupling of BOTH nodes, left-over nodes join a

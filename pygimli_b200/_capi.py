@@ -107,7 +107,7 @@ def lib():
         L.pgb200_ert_set_profile.argtypes = [C.c_void_p, C.c_int]
         L.pgb200_ert_path_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.pgb200_color_cells.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
-        L.pgb200_build_stream_panels.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 9
+        L.pgb200_build_stream_panels.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 11
         L.pgb200_ert_set_spmm_variant.argtypes = [C.c_void_p, C.c_int]
         L.pgb200_ert_set_hierarchy.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.pgb200_ert_set_preconditioner.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -166,18 +166,21 @@ def build_stream_panels(rowptr: np.ndarray, colidx: np.ndarray, rmax: int = 64, 
     rowptr = np.ascontiguousarray(rowptr, np.int32)
     colidx = np.ascontiguousarray(colidx, np.int32)
     n = rowptr.size - 1
-    counts = np.zeros(8, np.int32)
+    counts = np.zeros(10, np.int32)
     args = [n, rowptr.ctypes.data, colidx.ctypes.data, int(rmax), int(hc), int(max_chunks), counts.ctypes.data]
-    if lib().pgb200_build_stream_panels(*args, *([None] * 8)) != 0:
+    if lib().pgb200_build_stream_panels(*args, *([None] * 10)) != 0:
         raise PGB200Error(last_error())
-    npan, nch, nh, stride, max_rows, mch, mce, nnz = (int(x) for x in counts)
+    npan, nch, nh, stride, max_rows, mch, mce, nnz, nruns, mruns = (int(x) for x in counts)
     out = dict(panel_row_ptr=np.zeros(npan + 1, np.int32), panel_chunk_ptr=np.zeros(npan + 1, np.int32),
                chunk_halo_ptr=np.zeros(nch + 1, np.int32), halo_cols=np.zeros(max(1, nh), np.int32),
                chunk_ent_ptr=np.zeros(nch + 1, np.int32), ent_src=np.zeros(max(1, nnz), np.int32),
-               ent_idx=np.zeros(max(1, nnz), np.uint32), crp=np.zeros(max(1, nch * stride), np.int32))
+               ent_idx=np.zeros(max(1, nnz), np.uint32), crp=np.zeros(max(1, nch * stride), np.int32),
+               chunk_run_ptr=np.zeros(nch + 1, np.int32), runs=np.zeros((max(1, nruns), 3), np.int32))
     if lib().pgb200_build_stream_panels(*args, *(out[k].ctypes.data for k in ("panel_row_ptr", "panel_chunk_ptr", "chunk_halo_ptr",
-                                                                             "halo_cols", "chunk_ent_ptr", "ent_src", "ent_idx", "crp"))) != 0:
+                                                                             "halo_cols", "chunk_ent_ptr", "ent_src", "ent_idx", "crp",
+                                                                             "chunk_run_ptr", "runs"))) != 0:
         raise PGB200Error(last_error())
+    out.update(n_runs=nruns, max_chunk_runs=mruns)
     out.update(n_panels=npan, n_chunks=nch, crp_stride=stride, max_rows=max_rows, max_chunk_halo=mch, max_chunk_ent=mce, nnz=nnz)
     return out
 

@@ -315,6 +315,21 @@ k_spmm(const int *__restrict__ rowptr, const int *__restrict__ colidx, const dou
 //   Per-column dot products (p.Ap, r.z) are DETERMINISTIC: lane partials -> fixed-order sum over the 15 warps -> one partial
 //   row per CTA in global memory -> the CTA that takes the last ticket adds the rows in index order (no float atomics).
 // ---------------------------------------------------------------------------------
+// sum of base[sl * ld] over sl = first, first + step, ... < n, added in that order; the loads of 8 rows are issued
+// together (the last CTA runs alone on the GPU: without this it would pay one L2 round trip per row)
+__device__ __forceinline__ double ordered_row_sum(const double *base, size_t ld, int first, int step, int n) {
+    double acc = 0.0;
+    int sl = first;
+    for (; sl + 7 * step < n; sl += 8 * step) {
+        double t[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) t[u] = __ldcg(base + (size_t)(sl + u * step) * ld);
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc += t[u];
+    }
+    for (; sl < n; sl += step) acc += __ldcg(base + (size_t)sl * ld);
+    return acc;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -380,7 +395,7 @@ constexpr int ST_MAX_SLOTS = 4;
 constexpr int ST_MAX_TILE_W = 128;                 // columns per tile (2 column pairs per lane)
 
 struct StreamLevel {       // device arrays of stream_panels.h
-    const int *panel_row_ptr, *panel_chunk_ptr, *chunk_halo_ptr, *halo_cols, *chunk_ent_ptr, *crp;
+    const int *panel_row_ptr, *panel_chunk_ptr, *chunk_halo_ptr, *halo_cols, *chunk_ent_ptr, *crp, *chunk_run_ptr, *runs;
     int n_panels, crp_stride;
 };
 
@@ -436,23 +451,43 @@ k_spmm_stream(const StreamArgs A) {
             int kk, cs, wc, v0, v1;
             if (!stream_tile(A, t, kk, cs, wc, v0, v1)) continue;
             const uint32_t rowb = (uint32_t)wc * 8u;
+            const bool fullrows = (cs == 0 && wc == (int)A.ld);
             const PanelEntry *entk = A.ent + (size_t)kk * A.nnz;
             for (int p = j; p < L.n_panels; p += pstep) {
                 const int ch0 = L.panel_chunk_ptr[p], ch1 = L.panel_chunk_ptr[p + 1];
                 for (int ch = ch1 - 1; ch >= ch0; ch--, n++) {
                     const uint32_t slot = n % (uint32_t)S, use = n / (uint32_t)S;
-                    if (use > 0) mbar_wait(&empty[slot], (use & 1u) ^ 1u);
                     unsigned char *sb = st_smem + (size_t)slot * A.slot_bytes;
                     const int h0 = L.chunk_halo_ptr[ch], hn = L.chunk_halo_ptr[ch + 1] - h0;
                     const int e0 = L.chunk_ent_ptr[ch], ne = L.chunk_ent_ptr[ch + 1] - e0;
+                    // what to copy is read BEFORE waiting for the slot: the index loads overlap the consumers' work
+                    int src_row[4], dst_row[4], len[4], ncopy = 0;
+                    if (fullrows) {
+                        // the tile spans whole rows of X: one bulk copy per run of consecutive halo rows
+                        const int q0 = L.chunk_run_ptr[ch], q1 = L.chunk_run_ptr[ch + 1];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int i = q0 + lane + 32 * u;
+                            if (i < q1) { dst_row[u] = __ldg(L.runs + 3 * i); src_row[u] = __ldg(L.runs + 3 * i + 1); len[u] = __ldg(L.runs + 3 * i + 2); ncopy = u + 1; }
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int i = lane + 32 * u;
+                            if (i < hn) { dst_row[u] = i; src_row[u] = __ldg(L.halo_cols + h0 + i); len[u] = 1; ncopy = u + 1; }
+                        }
+                    }
+                    if (use > 0) mbar_wait(&empty[slot], (use & 1u) ^ 1u);
                     if (lane == 0) {
                         mbar_expect_tx(&full[slot], (uint32_t)hn * rowb + (uint32_t)ne * 16u + (uint32_t)L.crp_stride * 4u);
                         if (ne > 0) tma_bulk_g2s(sb + A.x_bytes, entk + e0, (uint32_t)ne * 16u, &full[slot]);
                         tma_bulk_g2s(sb + A.x_bytes + A.ent_bytes, L.crp + (size_t)ch * L.crp_stride, (uint32_t)L.crp_stride * 4u, &full[slot]);
                     }
                     __syncwarp();
-                    for (int i = lane; i < hn; i += 32)
-                        tma_bulk_g2s(sb + (size_t)i * rowb, A.X + (size_t)__ldg(L.halo_cols + h0 + i) * A.ld + cs, rowb, &full[slot]);
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (u < ncopy)
+                            tma_bulk_g2s(sb + (size_t)dst_row[u] * rowb, A.X + (size_t)src_row[u] * A.ld + cs, (uint32_t)len[u] * rowb, &full[slot]);
                 }
             }
         }
@@ -499,16 +534,17 @@ k_spmm_stream(const StreamArgs A) {
                     const int r = warp + ST_CONSUMER_WARPS * rr;
                     if (r < nrows) {
                         const int pb = sR[r], pe = sR[r + 1];
-#pragma unroll 2
+#pragma unroll 4
                         for (int e = pb; e < pe; e++) {
-                            const PanelEntry en = sE[e];                               // one 128-bit broadcast load
-                            const unsigned char *xr = xl + en.idx * rowb;
+                            const int4 raw = *reinterpret_cast<const int4 *>(sE + e);      // one 128-bit broadcast load: {value, row}
+                            const double a = __hiloint2double(raw.y, raw.x);
+                            const unsigned char *xr = xl + (uint32_t)raw.z * rowb;
 #pragma unroll
                             for (int q = 0; q < NCP; q++) {
                                 if (has[q]) {
                                     const double2 x = *reinterpret_cast<const double2 *>(xr + 512 * q);
-                                    acc[rr][2 * q] = fma(en.a, x.x, acc[rr][2 * q]);
-                                    acc[rr][2 * q + 1] = fma(en.a, x.y, acc[rr][2 * q + 1]);
+                                    acc[rr][2 * q] = fma(a, x.x, acc[rr][2 * q]);
+                                    acc[rr][2 * q + 1] = fma(a, x.y, acc[rr][2 * q + 1]);
                                 }
                             }
                         }
@@ -581,9 +617,7 @@ k_spmm_stream(const StreamArgs A) {
                 for (int i = threadIdx.x; i < wc; i += ST_CONSUMERS) {
                     const int cc = cs + i;
                     if (cc >= v0 && cc < v1) {
-                        double sum = 0.0;
-                        for (int s2 = 0; s2 < nslot; s2++) sum += __ldcg(A.dot_part + (size_t)s2 * A.ld + cc);
-                        A.dots[cc] = sum;
+                        A.dots[cc] = ordered_row_sum(A.dot_part + cc, A.ld, 0, 1, nslot);
                     }
                 }
                 if (threadIdx.x == 0) A.dot_counter[t] = 0u;
@@ -644,11 +678,8 @@ __device__ __forceinline__ void flat_col_finalize(double v0, double v1, const Fl
     // last CTA of this column chunk: thread (roff, col) adds rows roff, roff + rpp, ...; then the roff partials in order
     double a = 0.0, b = 0.0;
     if (f.active) {
-        for (int sl = f.roff; sl < (int)gridDim.x; sl += f.rpp) {
-            const double *row = D.part + (size_t)sl * D.ld + f.col;
-            if (D.out0) a += __ldcg(row);
-            if (D.out1) b += __ldcg(row + D.plane);
-        }
+        if (D.out0) a = ordered_row_sum(D.part + f.col, D.ld, f.roff, f.rpp, (int)gridDim.x);
+        if (D.out1) b = ordered_row_sum(D.part + D.plane + f.col, D.ld, f.roff, f.rpp, (int)gridDim.x);
     }
     __syncthreads();
     red0[threadIdx.x] = a; red1[threadIdx.x] = b;

@@ -67,12 +67,13 @@ struct GraphKey {
 struct StreamDev {
     bool ok = false;
     int n_panels = 0, n_chunks = 0, crp_stride = 0, max_chunk_halo = 0, max_chunk_ent = 0; size_t nnz = 0;
-    DevBuf<int> panel_row_ptr, panel_chunk_ptr, chunk_halo_ptr, halo_cols, chunk_ent_ptr, crp, ent_src;
+    DevBuf<int> panel_row_ptr, panel_chunk_ptr, chunk_halo_ptr, halo_cols, chunk_ent_ptr, crp, ent_src, chunk_run_ptr, runs;
     DevBuf<unsigned> ent_idx;
     DevBuf<PanelEntry> ent_a, ent_dw;       // [nK][nnz]: A (SpMM, post-smoothing) and A * diag(dw) (pre-smoothing residual)
     StreamLevel level() const {
         StreamLevel L; L.panel_row_ptr = panel_row_ptr.p; L.panel_chunk_ptr = panel_chunk_ptr.p; L.chunk_halo_ptr = chunk_halo_ptr.p;
         L.halo_cols = halo_cols.p; L.chunk_ent_ptr = chunk_ent_ptr.p; L.crp = crp.p; L.n_panels = n_panels; L.crp_stride = crp_stride;
+        L.chunk_run_ptr = chunk_run_ptr.p; L.runs = runs.p;
         return L;
     }
 };
@@ -244,6 +245,11 @@ int stream_upload(pgb200_ert *h, StreamDev &D, int n, const int *rowptr_host, co
     CKR(D.crp.upload(S.crp.data(), S.crp.size(), st));
     CKR(D.ent_src.upload(S.ent_src.data(), S.ent_src.size(), st));
     CKR(D.ent_idx.upload(S.ent_idx.data(), S.ent_idx.size(), st));
+    CKR(D.chunk_run_ptr.upload(S.chunk_run_ptr.data(), S.chunk_run_ptr.size(), st));
+    std::vector<int> runs(3 * S.run_start.size());
+    for (size_t i = 0; i < S.run_start.size(); i++) { runs[3 * i] = S.run_start[i]; runs[3 * i + 1] = S.run_col[i]; runs[3 * i + 2] = S.run_len[i]; }
+    CKR(D.runs.upload(runs.data(), runs.size(), st));
+    if (S.max_chunk_halo > 128) return 0;         // the producer warp handles at most 4 x 32 copies per stage
     CK(cudaStreamSynchronize(st));               // the host vectors go out of scope
     D.n_panels = S.n_panels; D.n_chunks = S.n_chunks; D.crp_stride = S.crp_stride; D.max_chunk_halo = S.max_chunk_halo;
     D.max_chunk_ent = S.max_chunk_ent; D.nnz = (size_t)S.nnz;
@@ -318,7 +324,7 @@ int launch_stream(pgb200_ert *h, const StreamDev &D, const PanelEntry *ent, cons
     A.cpt = A.n_tiles <= G ? std::max(1, G / A.n_tiles) : 1;
     A.dot_part = h->dot_part.p; A.dot_counter = h->dot_counter.p; A.dots = dots;
     if (dots && A.n_tiles > (int)h->dot_counter.n) PGB_FAIL("streamed SpMM: too many column tiles for the dot tickets");
-    h->pi_panel_nc = A.pw > 64 ? 2 : 1; h->pi_tiles = A.n_tiles; h->pi_slots = A.slots;
+    h->pi_panel_nc = A.pw > 64 ? 2 : 1; h->pi_tiles = std::max(h->pi_tiles, A.n_tiles); h->pi_slots = A.slots;
     if (A.pw > 64) { if (dots) return stream_go<2, EPI, true>(h, A, smem); return stream_go<2, EPI, false>(h, A, smem); }
     if (dots) return stream_go<1, EPI, true>(h, A, smem);
     return stream_go<1, EPI, false>(h, A, smem);
@@ -327,9 +333,9 @@ bool panel_path_ok(const pgb200_ert *h) { return h->use_panels && h->stream.ok; 
 
 // launch geometry of the flat element-wise kernels (ert_kernels.cuh, flat_map): column chunks of at most FLAT_T columns,
 // rows per CTA = rows per pass x passes
-constexpr int FLAT_MAX_GX = 1184;          // 8 CTAs per SM: bounds the partial rows of the deterministic dots
+constexpr int FLAT_MAX_GX = 296;           // 2 CTAs of 512 threads per SM: bounds the partial rows of the deterministic dots
 struct FlatCfg { int cw, rows_cta, nblk; dim3 grid; };
-inline FlatCfg flat_cfg(int n_rows, int c0, int c1) {
+inline FlatCfg flat_cfg(int n_rows, int c0, int c1, int gx_cap = 8 * FLAT_MAX_GX) {
     FlatCfg f;
     const int w = std::max(1, c1 - c0);
     const int nchunk = cdiv(w, FLAT_T);
@@ -339,7 +345,7 @@ inline FlatCfg flat_cfg(int n_rows, int c0, int c1) {
     const int passes = std::max(1, std::min(12, n_rows / (rpp * 600)));
     f.rows_cta = rpp * passes;
     f.nblk = cdiv(n_rows, f.rows_cta);
-    f.grid = dim3(std::min(f.nblk, FLAT_MAX_GX), nchunk);      // CTAs walk the row blocks with a grid stride
+    f.grid = dim3(std::min(f.nblk, gx_cap), nchunk);           // CTAs walk the row blocks with a grid stride
     return f;
 }
 inline DotOut dot_out(pgb200_ert *h, double *out0, double *out1) {
@@ -504,10 +510,10 @@ int pcg_solve(pgb200_ert *h) {
     double *S = h->scal.p;
     auto sc = [&](int i) { return S + (size_t)i * ld; };
     CK(cudaMemsetAsync(S, 0, sizeof(double) * 7 * ld, h->st));
-    FlatCfg fc = flat_cfg(h->N, c0, c1);                                      // per-iteration vector kernels
-    auto regrid = [&]() { fc = flat_cfg(h->N, c0, c1); };
+    FlatCfg fc = flat_cfg(h->N, c0, c1), fd = flat_cfg(h->N, c0, c1, FLAT_MAX_GX);   // per-iteration vector kernels; fd: those with column dots
+    auto regrid = [&]() { fc = flat_cfg(h->N, c0, c1); fd = flat_cfg(h->N, c0, c1, FLAT_MAX_GX); };
     const bool amg = h->use_amg && !h->amg.empty();
-    k_pcg_init<<<fc.grid, FLAT_T, 0, h->st>>>(h->B.p, h->dinv.p, h->X.p, h->R.p, h->P.p, h->N, h->nE, c0, c1, ld, fc.cw, fc.rows_cta, fc.nblk,
+    k_pcg_init<<<fd.grid, FLAT_T, 0, h->st>>>(h->B.p, h->dinv.p, h->X.p, h->R.p, h->P.p, h->N, h->nE, c0, c1, ld, fd.cw, fd.rows_cta, fd.nblk,
                                               dot_out(h, amg ? nullptr : sc(0), sc(6))); LAUNCH(h);
     if (amg) {
         CKR(amg_vcycle(h, c0, c1, sc(0)));
@@ -531,14 +537,14 @@ int pcg_solve(pgb200_ert *h) {
         }
         if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
         if (amg) {
-            k_pcg_update_xr<false><<<fc.grid, FLAT_T, 0, h->st>>>(h->P.p, h->AP.p, nullptr, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
-                                                                 sc(rz_old), sc(3), fc.cw, fc.rows_cta, fc.nblk, dot_out(h, nullptr, sc(rr_cur))); LAUNCH(h);
+            k_pcg_update_xr<false><<<fd.grid, FLAT_T, 0, h->st>>>(h->P.p, h->AP.p, nullptr, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
+                                                                 sc(rz_old), sc(3), fd.cw, fd.rows_cta, fd.nblk, dot_out(h, nullptr, sc(rr_cur))); LAUNCH(h);
             CKR(amg_vcycle(h, c0, c1, sc(rz_new)));
             k_pcg_update_p<false><<<fc.grid, FLAT_T, 0, h->st>>>(h->Z0.p, nullptr, h->P.p, h->N, h->nE, c0, c1, ld, sc(rz_old), sc(rz_new),
                                                                 sc(rr_cur), sc(6), tol2, fc.cw, fc.rows_cta, fc.nblk); LAUNCH(h);
         } else {
-            k_pcg_update_xr<true><<<fc.grid, FLAT_T, 0, h->st>>>(h->P.p, h->AP.p, h->dinv.p, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
-                                                                sc(rz_old), sc(3), fc.cw, fc.rows_cta, fc.nblk, dot_out(h, sc(rz_new), sc(rr_cur))); LAUNCH(h);
+            k_pcg_update_xr<true><<<fd.grid, FLAT_T, 0, h->st>>>(h->P.p, h->AP.p, h->dinv.p, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
+                                                                sc(rz_old), sc(3), fd.cw, fd.rows_cta, fd.nblk, dot_out(h, sc(rz_new), sc(rr_cur))); LAUNCH(h);
             k_pcg_update_p<true><<<fc.grid, FLAT_T, 0, h->st>>>(h->R.p, h->dinv.p, h->P.p, h->N, h->nE, c0, c1, ld, sc(rz_old), sc(rz_new),
                                                                sc(rr_cur), sc(6), tol2, fc.cw, fc.rows_cta, fc.nblk); LAUNCH(h);
         }
@@ -922,19 +928,21 @@ int pgb200_color_cells(int n_cells, int nloc, const int *cells, int n_nodes, int
 }
 
 // Streamed row panels (stream_panels.h) of a CSR pattern -- exported for the host-side tests, which replay the kernel's
-// traversal on the CPU.  Two calls: with out == NULL the sizes are returned in counts[8] = {n_panels, n_chunks, halo
-// entries, crp_stride, max_rows, max_chunk_halo, max_chunk_ent, nnz}; with the arrays allocated they are filled
-// (panel_row_ptr[n_panels+1], panel_chunk_ptr[n_panels+1], chunk_halo_ptr[n_chunks+1], halo_cols[halo entries],
-// chunk_ent_ptr[n_chunks+1], ent_src[nnz], ent_idx[nnz], crp[n_chunks*crp_stride]).
+// traversal on the CPU.  Two calls: with out == NULL the sizes are returned in counts[10] = {n_panels, n_chunks, halo
+// entries, crp_stride, max_rows, max_chunk_halo, max_chunk_ent, nnz, runs, max runs per chunk}; with the arrays allocated
+// they are filled (panel_row_ptr[n_panels+1], panel_chunk_ptr[n_panels+1], chunk_halo_ptr[n_chunks+1], halo_cols[halo
+// entries], chunk_ent_ptr[n_chunks+1], ent_src[nnz], ent_idx[nnz], crp[n_chunks*crp_stride], chunk_run_ptr[n_chunks+1],
+// runs[3*runs] = {first halo entry in the chunk, column, length}).
 int pgb200_build_stream_panels(int n_rows, const int *rowptr, const int *colidx, int rmax, int hc, int max_chunks, int *counts,
                                int *panel_row_ptr, int *panel_chunk_ptr, int *chunk_halo_ptr, int *halo_cols, int *chunk_ent_ptr,
-                               int *ent_src, unsigned *ent_idx, int *crp) {
+                               int *ent_src, unsigned *ent_idx, int *crp, int *chunk_run_ptr, int *runs) {
     if (!rowptr || !colidx || !counts) { g_err = "null argument"; return 1; }
     StreamPanelsHost S;
     const std::string err = build_stream_panels(n_rows, rowptr, colidx, rmax, hc, max_chunks, S);
     if (!err.empty()) { g_err = err; return 1; }
-    const int c[8] = {S.n_panels, S.n_chunks, (int)S.halo_cols.size(), S.crp_stride, S.max_rows, S.max_chunk_halo, S.max_chunk_ent, (int)S.nnz};
-    for (int i = 0; i < 8; i++) counts[i] = c[i];
+    const int c[10] = {S.n_panels, S.n_chunks, (int)S.halo_cols.size(), S.crp_stride, S.max_rows, S.max_chunk_halo, S.max_chunk_ent, (int)S.nnz,
+                       (int)S.run_start.size(), S.max_chunk_runs};
+    for (int i = 0; i < 10; i++) counts[i] = c[i];
     if (!panel_row_ptr) return 0;
     std::copy(S.panel_row_ptr.begin(), S.panel_row_ptr.end(), panel_row_ptr);
     std::copy(S.panel_chunk_ptr.begin(), S.panel_chunk_ptr.end(), panel_chunk_ptr);
@@ -944,6 +952,8 @@ int pgb200_build_stream_panels(int n_rows, const int *rowptr, const int *colidx,
     std::copy(S.ent_src.begin(), S.ent_src.end(), ent_src);
     std::copy(S.ent_idx.begin(), S.ent_idx.end(), ent_idx);
     std::copy(S.crp.begin(), S.crp.end(), crp);
+    std::copy(S.chunk_run_ptr.begin(), S.chunk_run_ptr.end(), chunk_run_ptr);
+    for (size_t i = 0; i < S.run_start.size(); i++) { runs[3 * i] = S.run_start[i]; runs[3 * i + 1] = S.run_col[i]; runs[3 * i + 2] = S.run_len[i]; }
     return 0;
 }
 

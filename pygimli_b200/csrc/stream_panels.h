@@ -2,11 +2,11 @@
 //
 // A matrix level (the fine stiffness matrix or a coarse level of the multilevel preconditioner) is cut into ROW PANELS of
 // consecutive rows (rows are numbered along a space-filling curve, so a panel is a compact patch of the mesh).  The
-// distinct columns a panel touches form its HALO list, ordered  [the panel's own rows | other columns in first-touch
-// order].  The halo list is cut into CHUNKS of at most `hc` entries; chunk 0 always holds the panel's own rows.  The CSR
+// distinct columns a panel touches form its HALO list, ordered  [the panel's own rows | other columns ascending].  The halo list is cut into CHUNKS of at most `hc` entries; chunk 0 always holds the panel's own rows.  The CSR
 // entries of a panel are re-ordered chunk-major: (chunk, row, ascending column), so that
 //     one pipeline stage of the kernel = one (panel, chunk):
-//        * the chunk's rows of the block vector X          -> one TMA bulk copy per halo row
+//        * the chunk's rows of the block vector X          -> one TMA bulk copy per RUN of consecutive halo rows when a
+//                                                             tile spans whole rows of X (runs are listed here), else per row
 //        * the chunk's packed entries {value, row-in-chunk} -> ONE contiguous TMA bulk copy
 //        * the chunk's per-row entry ranges (crp)            -> ONE contiguous TMA bulk copy
 // Accumulators stay in registers across the chunks of a panel; chunks are processed last-to-first so that the panel's own
@@ -29,6 +29,11 @@ struct StreamPanelsHost {
     std::vector<int> ent_src;           // [nnz] CSR slot of the re-ordered entry
     std::vector<unsigned> ent_idx;      // [nnz] row of the entry's column inside its chunk's staged X tile
     std::vector<int> crp;               // [n_chunks * crp_stride] entry range starts per row, relative to the chunk
+    std::vector<int> chunk_run_ptr;     // [n_chunks + 1] runs of consecutive columns inside a chunk's halo list ...
+    std::vector<int> run_start;         // ... first halo entry of the run, relative to the chunk
+    std::vector<int> run_col;           // ... its column
+    std::vector<int> run_len;           // ... number of consecutive columns
+    int max_chunk_runs = 0;
 };
 
 // rmax: rows per panel (<= hc), hc: halo entries per chunk, max_chunks: chunks per panel.  Returns "" or an error text.
@@ -42,6 +47,7 @@ inline std::string build_stream_panels(int n, const int *rowptr, const int *coli
     std::vector<int> stamp((size_t)std::max(n, 1), -1), slot((size_t)std::max(n, 1), 0);
     S.ent_src.resize((size_t)S.nnz); S.ent_idx.resize((size_t)S.nnz);
     S.panel_row_ptr.push_back(0); S.panel_chunk_ptr.push_back(0); S.chunk_halo_ptr.push_back(0); S.chunk_ent_ptr.push_back(0);
+    S.chunk_run_ptr.push_back(0);
     std::vector<int> others;
     long long ent_pos = 0;
     int row = 0, np = 0;
@@ -67,15 +73,17 @@ inline std::string build_stream_panels(int n, const int *rowptr, const int *coli
             row++;
         }
         const int nrows = row - start;
-        // 2. halo order: own rows first, then the other columns in first-touch order
+        // 2. halo order: own rows first, then the other columns ascending (neighbouring patches of the space-filling
+        //    curve appear as runs of consecutive rows of X -> few, large bulk copies)
         for (int r = start; r < row; r++) slot[r] = r - start;
-        int hn = nrows;
         for (int r = start; r < row; r++)
             for (int p = rowptr[r]; p < rowptr[r + 1]; p++) {
                 const int c = colidx[p];
-                if ((c < start || c >= row) && stamp[c] == np) { stamp[c] = -2 - np; slot[c] = hn++; others.push_back(c); }
+                if ((c < start || c >= row) && stamp[c] == np) { stamp[c] = -2 - np; others.push_back(c); }
             }
-        // (columns of other rows that are own rows keep stamp == np; the re-stamp above marks "listed")
+        std::sort(others.begin(), others.end());
+        int hn = nrows;
+        for (int c : others) slot[c] = hn++;
         const int nch = (hn + hc - 1) / hc;
         // chunk boundaries: balanced, chunk 0 holds at least the own rows
         std::vector<int> cb((size_t)nch + 1, hn);
@@ -90,6 +98,19 @@ inline std::string build_stream_panels(int n, const int *rowptr, const int *coli
             for (int i = cb[c]; i < cb[c + 1]; i++) S.halo_cols.push_back(i < nrows ? start + i : others[(size_t)(i - nrows)]);
             S.chunk_halo_ptr.push_back((int)S.halo_cols.size());
             S.max_chunk_halo = std::max(S.max_chunk_halo, cb[c + 1] - cb[c]);
+            {   // runs of consecutive columns
+                const int *hc0 = S.halo_cols.data() + (S.halo_cols.size() - (size_t)(cb[c + 1] - cb[c]));
+                const int len = cb[c + 1] - cb[c];
+                int nr = 0;
+                for (int i = 0; i < len;) {
+                    int e = i + 1;
+                    while (e < len && hc0[e] == hc0[e - 1] + 1) e++;
+                    S.run_start.push_back(i); S.run_col.push_back(hc0[i]); S.run_len.push_back(e - i);
+                    i = e; nr++;
+                }
+                S.chunk_run_ptr.push_back((int)S.run_start.size());
+                S.max_chunk_runs = std::max(S.max_chunk_runs, nr);
+            }
             // entries of this chunk, row by row
             const size_t crp0 = S.crp.size();
             S.crp.resize(crp0 + (size_t)S.crp_stride, 0);
