@@ -552,14 +552,35 @@ k_spmm_stream(const StreamArgs A) {
                 }
                 if (c == 0) {
                     // epilogue: chunk 0 starts with the panel's own X rows (halo index == local row)
+                    double rres[EPI == EPI_POST ? ST_RPW : 1][2 * NCP], dwr[ST_RPW];
+                    if (EPI == EPI_POST) {
+                        // all global loads of the epilogue are issued before the first store (Y may alias nothing, but the
+                        // compiler cannot know): one L2 round trip per panel instead of one per row
+#pragma unroll
+                        for (int rr = 0; rr < ST_RPW; rr++) {
+                            const int r = warp + ST_CONSUMER_WARPS * rr;
+                            dwr[rr] = 0.0;
+#pragma unroll
+                            for (int q = 0; q < 2 * NCP; q++) rres[rr][q] = 0.0;
+                            if (r < nrows) {
+                                const int row = r0 + r;
+                                dwr[rr] = __ldg(dwk + row);
+#pragma unroll
+                                for (int q = 0; q < NCP; q++) {
+                                    const size_t o = (size_t)row * A.ld + col[q];
+                                    if (ok_lo[q] && ok_hi[q]) { const double2 rv = __ldg(reinterpret_cast<const double2 *>(A.ex.R + o)); rres[rr][2 * q] = rv.x; rres[rr][2 * q + 1] = rv.y; }
+                                    else { if (ok_lo[q]) rres[rr][2 * q] = __ldg(A.ex.R + o); if (ok_hi[q]) rres[rr][2 * q + 1] = __ldg(A.ex.R + o + 1); }
+                                }
+                            }
+                        }
+                    }
 #pragma unroll
                     for (int rr = 0; rr < ST_RPW; rr++) {
                         const int r = warp + ST_CONSUMER_WARPS * rr;
                         if (r < nrows) {
                             const int row = r0 + r;
                             const unsigned char *xs = xl + (uint32_t)r * rowb;
-                            double dw = 0.0;
-                            if (EPI == EPI_POST) dw = dwk[row];
+                            const double dw = (EPI == EPI_POST) ? dwr[rr] : 0.0;
 #pragma unroll
                             for (int q = 0; q < NCP; q++) {
                                 if (has[q]) {
@@ -567,9 +588,7 @@ k_spmm_stream(const StreamArgs A) {
                                     const size_t o = (size_t)row * A.ld + col[q];
                                     double y0, y1;
                                     if (EPI == EPI_POST) {
-                                        double r_lo = 0.0, r_hi = 0.0;
-                                        if (ok_lo[q] && ok_hi[q]) { const double2 rv = *reinterpret_cast<const double2 *>(A.ex.R + o); r_lo = rv.x; r_hi = rv.y; }
-                                        else { if (ok_lo[q]) r_lo = A.ex.R[o]; if (ok_hi[q]) r_hi = A.ex.R[o + 1]; }
+                                        const double r_lo = rres[rr][2 * q], r_hi = rres[rr][2 * q + 1];
                                         y0 = fma(dw, r_lo - acc[rr][2 * q], x.x);
                                         y1 = fma(dw, r_hi - acc[rr][2 * q + 1], x.y);
                                         if (DOT) { if (ok_lo[q]) part[2 * q] = fma(r_lo, y0, part[2 * q]); if (ok_hi[q]) part[2 * q + 1] = fma(r_hi, y1, part[2 * q + 1]); }
@@ -632,8 +651,8 @@ k_spmm_stream(const StreamArgs A) {
 // Flat mapping: the FLAT_T threads of a CTA tile the column window [c0,c1) (chunks of at most cw columns along
 // blockIdx.y) as rpp = FLAT_T / w consecutive rows of w columns, so that a warp touches 32 consecutive elements of the
 // row-major block whatever the window width (100 columns -> 5 rows per pass, 14 columns of an 8-GPU shard -> 36), and
-// every thread keeps ONE column (per-column scalars and dot partials stay in registers).  A CTA walks row blocks of
-// rows_cta rows with a grid stride: blk = blockIdx.x, blockIdx.x + gridDim.x, ...
+// every thread keeps ONE column (per-column scalars and dot partials stay in registers).  The rows are split evenly
+// over the CTAs of a column chunk (contiguous ranges, flat_rows).
 // Per-column dot products are DETERMINISTIC (no floating-point atomics): thread partials meet in shared memory in a
 // fixed order, every CTA writes one partial row, the CTA that draws the last ticket adds the rows in index order.
 // ---------------------------------------------------------------------------------
@@ -648,6 +667,11 @@ __device__ __forceinline__ FlatMap flat_map(int c0, int c1, int cw) {
     f.col = cs + threadIdx.x - f.roff * f.w;
     f.active = f.roff < f.rpp;
     return f;
+}
+// contiguous, balanced row range of this CTA
+__device__ __forceinline__ void flat_rows(int n, int &lo, int &hi) {
+    lo = (int)(((long long)n * blockIdx.x) / gridDim.x);
+    hi = (int)(((long long)n * (blockIdx.x + 1)) / gridDim.x);
 }
 struct DotOut {
     double *part;          // [2][slots][ld] partial rows (plane 0 / 1 for the two sums a kernel may produce)
@@ -696,21 +720,18 @@ __device__ __forceinline__ void flat_col_finalize(double v0, double v1, const Fl
 // x = 0; r = b; p = z = Dinv r (Jacobi; with the multilevel preconditioner p is set by the first cycle); rz = r.z; bb = b.b
 __global__ void __launch_bounds__(FLAT_T)
 k_pcg_init(const double *__restrict__ B, const double *__restrict__ dinv, double *__restrict__ Xv, double *__restrict__ R,
-           double *__restrict__ P, int N, int nE, int c0, int c1, size_t ld, int cw, int rows_cta, int nblk, const DotOut D) {
+           double *__restrict__ P, int N, int nE, int c0, int c1, size_t ld, int cw, const DotOut D) {
     const FlatMap f = flat_map(c0, c1, cw);
     double s0 = 0.0, s1 = 0.0;
     if (f.active) {
         const double *dk = dinv + (size_t)(f.col / nE) * N;
-        for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-            const int row0 = blk * rows_cta, nr = min(rows_cta, N - row0);
-            for (int r = f.roff; r < nr; r += f.rpp) {
-                const int row = row0 + r;
-                const size_t o = (size_t)row * ld + f.col;
-                const double b = B[o];
-                const double z = dk[row] * b;
-                Xv[o] = 0.0; R[o] = b; P[o] = z;
-                s0 = fma(b, z, s0); s1 = fma(b, b, s1);
-            }
+        int lo, hi; flat_rows(N, lo, hi);
+        for (int row = lo + f.roff; row < hi; row += f.rpp) {
+            const size_t o = (size_t)row * ld + f.col;
+            const double b = B[o];
+            const double z = dk[row] * b;
+            Xv[o] = 0.0; R[o] = b; P[o] = z;
+            s0 = fma(b, z, s0); s1 = fma(b, b, s1);
         }
     }
     flat_col_finalize(s0, s1, f, D);
@@ -721,25 +742,22 @@ template <bool JACOBI>
 __global__ void __launch_bounds__(FLAT_T)
 k_pcg_update_xr(const double *__restrict__ P, const double *__restrict__ AP, const double *__restrict__ dinv,
                 double *__restrict__ Xv, double *__restrict__ R, int N, int nE, int c0, int c1, size_t ld,
-                const double *__restrict__ rz, const double *__restrict__ pAp, int cw, int rows_cta, int nblk, const DotOut D) {
+                const double *__restrict__ rz, const double *__restrict__ pAp, int cw, const DotOut D) {
     const FlatMap f = flat_map(c0, c1, cw);
     double s0 = 0.0, s1 = 0.0;
     if (f.active) {
         const double den = pAp[f.col], num = rz[f.col];
         const double alpha = (den > 0.0 && num > 0.0) ? num / den : 0.0;
         const double *dk = JACOBI ? dinv + (size_t)(f.col / nE) * N : nullptr;
-        for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-            const int row0 = blk * rows_cta, nr = min(rows_cta, N - row0);
+        int lo, hi; flat_rows(N, lo, hi);
 #pragma unroll 4
-            for (int r = f.roff; r < nr; r += f.rpp) {
-                const int row = row0 + r;
-                const size_t o = (size_t)row * ld + f.col;
-                const double rn = fma(-alpha, AP[o], R[o]);
-                Xv[o] = fma(alpha, P[o], Xv[o]);
-                R[o] = rn;
-                if (JACOBI) s0 = fma(rn * dk[row], rn, s0);
-                s1 = fma(rn, rn, s1);
-            }
+        for (int row = lo + f.roff; row < hi; row += f.rpp) {
+            const size_t o = (size_t)row * ld + f.col;
+            const double rn = fma(-alpha, AP[o], R[o]);
+            Xv[o] = fma(alpha, P[o], Xv[o]);
+            R[o] = rn;
+            if (JACOBI) s0 = fma(rn * dk[row], rn, s0);
+            s1 = fma(rn, rn, s1);
         }
     }
     flat_col_finalize(s0, s1, f, D);     // D.out0 = rz_new (Jacobi) or nullptr, D.out1 = rr
@@ -750,7 +768,7 @@ template <bool JACOBI>
 __global__ void __launch_bounds__(FLAT_T)
 k_pcg_update_p(const double *__restrict__ R, const double *__restrict__ dinv, double *__restrict__ P, int N, int nE,
                int c0, int c1, size_t ld, const double *__restrict__ rz, const double *__restrict__ rz_new,
-               const double *__restrict__ rr, const double *__restrict__ bb, double tol2, int cw, int rows_cta, int nblk) {
+               const double *__restrict__ rr, const double *__restrict__ bb, double tol2, int cw) {
     const FlatMap f = flat_map(c0, c1, cw);
     if (!f.active) return;
     const int col = f.col;
@@ -758,14 +776,11 @@ k_pcg_update_p(const double *__restrict__ R, const double *__restrict__ dinv, do
     const double den = rz[col];
     const double beta = (den > 0.0) ? rz_new[col] / den : 0.0;
     const double *dk = JACOBI ? dinv + (size_t)(col / nE) * N : nullptr;
-    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        const int row0 = blk * rows_cta, nr = min(rows_cta, N - row0);
+    int lo, hi; flat_rows(N, lo, hi);
 #pragma unroll 4
-        for (int r = f.roff; r < nr; r += f.rpp) {
-            const int row = row0 + r;
-            const size_t o = (size_t)row * ld + col;
-            P[o] = done ? 0.0 : fma(beta, P[o], JACOBI ? dk[row] * R[o] : R[o]);
-        }
+    for (int row = lo + f.roff; row < hi; row += f.rpp) {
+        const size_t o = (size_t)row * ld + col;
+        P[o] = done ? 0.0 : fma(beta, P[o], JACOBI ? dk[row] * R[o] : R[o]);
     }
 }
 
@@ -1050,38 +1065,32 @@ k_amg_restrict_split(const int *__restrict__ rowptr, const int *__restrict__ col
 // RC[I] = sum of RES over the members of aggregate I (deterministic restriction of a fine residual block); flat mapping
 __global__ void __launch_bounds__(FLAT_T)
 k_amg_sum_members(const int *__restrict__ mem_ptr, const int *__restrict__ mem_idx, int n_c, const double *__restrict__ RES,
-                  double *__restrict__ RC, int c0, int c1, size_t ld, int cw, int rows_cta, int nblk) {
+                  double *__restrict__ RC, int c0, int c1, size_t ld, int cw) {
     const FlatMap f = flat_map(c0, c1, cw);
     if (!f.active) return;
-    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        const int row0 = blk * rows_cta, nr = min(rows_cta, n_c - row0);
+    int lo, hi; flat_rows(n_c, lo, hi);
 #pragma unroll 2
-        for (int r = f.roff; r < nr; r += f.rpp) {
-            const int I = row0 + r;
-            double acc = 0.0;
-            for (int q = mem_ptr[I]; q < mem_ptr[I + 1]; q++) acc += RES[(size_t)mem_idx[q] * ld + f.col];
-            RC[(size_t)I * ld + f.col] = acc;
-        }
+    for (int I = lo + f.roff; I < hi; I += f.rpp) {
+        double acc = 0.0;
+        for (int q = mem_ptr[I]; q < mem_ptr[I + 1]; q++) acc += RES[(size_t)mem_idx[q] * ld + f.col];
+        RC[(size_t)I * ld + f.col] = acc;
     }
 }
 
 // X = dw .* R + EC[agg]   (pre-smoothed iterate plus prolongated coarse correction); EC == nullptr -> X = dw .* R
 __global__ void __launch_bounds__(FLAT_T)
 k_amg_prolong(const double *__restrict__ dinvw, int n, const int *__restrict__ agg, const double *__restrict__ R,
-              const double *__restrict__ EC, double *__restrict__ X, int nE, int c0, int c1, size_t ld, int cw, int rows_cta, int nblk) {
+              const double *__restrict__ EC, double *__restrict__ X, int nE, int c0, int c1, size_t ld, int cw) {
     const FlatMap f = flat_map(c0, c1, cw);
     if (!f.active) return;
     const double *dk = dinvw + (size_t)(f.col / nE) * n;
-    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        const int row0 = blk * rows_cta, nr = min(rows_cta, n - row0);
+    int lo, hi; flat_rows(n, lo, hi);
 #pragma unroll 4
-        for (int r = f.roff; r < nr; r += f.rpp) {
-            const int row = row0 + r;
-            const size_t o = (size_t)row * ld + f.col;
-            double x = dk[row] * R[o];
-            if (EC) x += EC[(size_t)agg[row] * ld + f.col];
-            X[o] = x;
-        }
+    for (int row = lo + f.roff; row < hi; row += f.rpp) {
+        const size_t o = (size_t)row * ld + f.col;
+        double x = dk[row] * R[o];
+        if (EC) x += EC[(size_t)agg[row] * ld + f.col];
+        X[o] = x;
     }
 }
 
@@ -1435,6 +1444,307 @@ k_jacobian(const JacArgs A) {
         if (nn.valid()) nn.advance(A);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------
+// K3': Jacobian, second generation (bertJacobian.cpp:70-119, elementmatrix.h:280-293, dcfemmodelling.cpp:1377-1383)
+//   J[d][col] = k_d / rho_col^2 * sum_{cells c of col} sum_k w_k (u_a-u_b)^T (K_c + k^2 M_c) (u_m-u_n)
+//
+//   * BASIS: the host picks, per side of the measurement, either the electrodes or the distinct dipoles as basis
+//     (k_basis_pots writes  UD[node][k][i] = u_a - u_b  once per Jacobian).  In dipole space a datum of a dipole-dipole
+//     scheme is ONE entry of the Gram block instead of four; when both sides share one basis list the block is
+//     symmetric and only the tiles on and above the diagonal are computed.
+//   * TILE LIST: only the 4x4 register tiles that some datum needs are computed (block-sparse schemes, e.g. crosshole).
+//   * WARP SPECIALISATION inside one persistent CTA per SM:
+//       producer warp   TMA bulk copies of the next items (cell, wavenumber): the cell's precomputed element record
+//                       (stiffness K_c and size, geometry-only, built at create) and the basis potentials of its nodes
+//                       -- one copy per node row -- into a ring of slots (full/empty mbarriers)
+//       Gram warps      V = w_k (K + k^2 M) U_Q for the NEXT item, then the register-tile update of the CURRENT one
+//                       (one named barrier per item); at the end of a model column the tiles go to one of two
+//                       shared-memory Gram buffers
+//       epilogue warps  turn the finished Gram buffer into the column of J: 1 / 2 / 4 signed look-ups per datum through
+//                       pre-resolved 16-bit offsets, times k_d / rho^2, 128-bit stores -- while the Gram warps are
+//                       already working on the next column.
+// ---------------------------------------------------------------------------------
+constexpr int J2_THREADS = 512;
+constexpr int J2_GRAM_WARPS = 11, J2_EPI_WARPS = 4;            // + 1 producer warp = 16 warps
+constexpr int J2_GT = J2_GRAM_WARPS * 32, J2_ET = J2_EPI_WARPS * 32;
+constexpr int J2_SLOTS = 3;
+constexpr int J2_MAX_MT = 2;                                   // register tiles per Gram thread
+
+// per-cell element record [NL*NL stiffness | size | pad]: geometry only
+template <int E>
+__global__ void k_element_records(const double *__restrict__ pos, const int *__restrict__ cells, int C, int recn, double *__restrict__ rec) {
+    constexpr int NV = ElemTraits<E>::NV, NL = ElemTraits<E>::NL, DIM = ElemTraits<E>::DIM;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double X[NV][3];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+        const int n = cells[(size_t)c * NL + v];
+        X[v][0] = pos[3 * (size_t)n]; X[v][1] = pos[3 * (size_t)n + 1]; X[v][2] = pos[3 * (size_t)n + 2];
+    }
+    double size, G[NV][NV];
+    simplex_gram<DIM>(X, size, G);
+    double *r = rec + (size_t)c * recn;
+#pragma unroll
+    for (int i = 0; i < NL; i++)
+#pragma unroll
+        for (int j = 0; j < NL; j++) r[i * NL + j] = stiff_entry<E>(i, j, size, G);
+    r[NL * NL] = size;
+    for (int x = NL * NL + 1; x < recn; x++) r[x] = 0.0;
+}
+template <int E>
+__global__ void k_mass_unit_table(double *__restrict__ mu) {
+    constexpr int NL = ElemTraits<E>::NL;
+    const int t = threadIdx.x;
+    if (t < NL * NL) mu[t] = mass_unit<E>(t / NL, t % NL);
+}
+// basis potentials: UD[node][k][i] = U[node][a_i + nE k] - U[node][b_i + nE k]  (b_i < 0: electrode basis / pole);
+// columns nL..nLp-1 of every k-block are zero padding
+__global__ void k_basis_pots(const double *__restrict__ U, size_t ld, int N, int nE, int nK, const int *__restrict__ la,
+                             const int *__restrict__ lb, int nL, int nLp, double *__restrict__ UD, size_t ldUD) {
+    const int x = blockIdx.y * blockDim.x + threadIdx.x;          // k * nLp + i
+    const int node = blockIdx.x * blockDim.y + threadIdx.y;
+    if (x >= nK * nLp || node >= N) return;
+    const int kk = x / nLp, i = x - kk * nLp;
+    double v = 0.0;
+    if (i < nL) {
+        const int a = la[i], b = lb[i];
+        v = U[(size_t)node * ld + a + nE * kk];
+        if (b >= 0) v -= U[(size_t)node * ld + b + nE * kk];
+    }
+    UD[(size_t)node * ldUD + x] = v;
+}
+
+struct Jac2Args {
+    const int *cells; int C;
+    const int *jac_cells; const int *jac_col_ptr; const int *cta_col_ptr;
+    const double *erec; int recn; const double *mu;            // element records, unit mass matrix
+    const double *UDp, *UDq; size_t ldUDp, ldUDq; int nPp, nQp, shared; // basis potentials [N][nK][nPp] / [N][nK][nQp]; shared: Q list == P list
+    int nK; const double *kvals, *kw;
+    const unsigned short *tile_tp, *tile_tq; int n_tiles, PL, mt;   // Gram tiles; PL: plane stride of a Gram buffer
+    const unsigned short *toff; int terms;                      // [nd][terms] pre-resolved offsets into a Gram buffer
+    const double *kfac; const int *out_row; int nd, out_identity, out_base, off_in_smem, kfac_in_smem;
+    const double *rho_col; double *Jt; size_t ldJ;
+    uint32_t slot_bytes, uq_off;                                // ring slot: [record | U_P rows | U_Q rows]; uq_off: byte offset of U_Q
+    uint32_t rec_bytes;
+};
+
+template <int E, int MT, int TERMS>
+__global__ void __launch_bounds__(J2_THREADS, 1)
+k_jacobian2(const Jac2Args A) {
+    constexpr int NL = ElemTraits<E>::NL;
+    extern __shared__ __align__(128) unsigned char j2_smem[];
+    __shared__ __align__(8) uint64_t full[J2_SLOTS], empty[J2_SLOTS], gfull[2], gempty[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    // shared-memory map
+    unsigned char *ring = j2_smem;
+    double *sV = reinterpret_cast<double *>(ring + (size_t)J2_SLOTS * A.slot_bytes);          // [2][NL][nQp]
+    double *sG = sV + 2 * NL * A.nQp;                                                         // [2][16 PL + 2]
+    const int gsz = 16 * A.PL + 2;
+    double *sKf = sG + 2 * gsz;                                                               // [nd] (optional)
+    unsigned short *sOff = reinterpret_cast<unsigned short *>(sKf + (A.kfac_in_smem ? ((A.nd + 1) & ~1) : 0));   // [nd][TERMS] (optional)
+    if (tid == 0) {
+        for (int s = 0; s < J2_SLOTS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&gfull[b], 1); mbar_init(&gempty[b], J2_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sG[16 * A.PL] = 0.0; sG[gsz + 16 * A.PL] = 0.0;                                        // zero slots of both buffers
+    }
+    // tables shared by the epilogue warps (read-only afterwards)
+    if (A.kfac_in_smem) for (int d = tid; d < A.nd; d += J2_THREADS) sKf[d] = A.kfac[d];
+    if (A.off_in_smem) for (int x = tid; x < A.nd * TERMS; x += J2_THREADS) sOff[x] = A.toff[x];
+    __syncthreads();
+    const int my_lo = A.cta_col_ptr[blockIdx.x], my_hi = A.cta_col_ptr[blockIdx.x + 1];
+    const int ci_lo = A.jac_col_ptr[my_lo], ci_hi = A.jac_col_ptr[my_hi];
+    const int nK = A.nK;
+    const uint32_t rowP = (uint32_t)A.nPp * 8u, rowQ = (uint32_t)A.nQp * 8u;
+
+    if (warp == J2_GRAM_WARPS + J2_EPI_WARPS) {
+        // ------------------------------- producer -------------------------------
+        const uint32_t bytes = A.rec_bytes + NL * rowP + (A.shared ? 0u : NL * rowQ);
+        uint32_t n = 0;
+        for (int base = ci_lo; base < ci_hi; base += 32) {
+            // this batch: lane l holds the cell and node ids of cell base + l
+            const int ci = base + lane;
+            int cell = 0, nodes[NL];
+            if (ci < ci_hi) {
+                cell = __ldg(A.jac_cells + ci);
+#pragma unroll
+                for (int i = 0; i < NL; i++) nodes[i] = __ldg(A.cells + (size_t)cell * NL + i);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NL; i++) nodes[i] = 0;
+            }
+            const int nb = min(32, ci_hi - base);
+            for (int jj = 0; jj < nb; jj++) {
+                const int cj = __shfl_sync(0xffffffffu, cell, jj);
+                int mynode = 0;
+#pragma unroll
+                for (int i = 0; i < NL; i++) { const int v = __shfl_sync(0xffffffffu, nodes[i], jj); if (lane == i || lane == NL + i) mynode = v; }
+                for (int kk = 0; kk < nK; kk++, n++) {
+                    const uint32_t slot = n % J2_SLOTS, use = n / J2_SLOTS;
+                    if (use > 0) mbar_wait(&empty[slot], (use & 1u) ^ 1u);
+                    unsigned char *sb = ring + (size_t)slot * A.slot_bytes;
+                    if (lane == 31) {
+                        mbar_expect_tx(&full[slot], bytes);
+                        tma_bulk_g2s(sb, A.erec + (size_t)cj * A.recn, A.rec_bytes, &full[slot]);
+                    }
+                    __syncwarp();
+                    if (lane < NL) tma_bulk_g2s(sb + A.rec_bytes + lane * rowP, A.UDp + (size_t)mynode * A.ldUDp + (size_t)kk * A.nPp, rowP, &full[slot]);
+                    else if (!A.shared && lane < 2 * NL)
+                        tma_bulk_g2s(sb + A.uq_off + (lane - NL) * rowQ, A.UDq + (size_t)mynode * A.ldUDq + (size_t)kk * A.nQp, rowQ, &full[slot]);
+                }
+            }
+        }
+        return;
+    }
+
+    if (warp >= J2_GRAM_WARPS) {
+        // ------------------------------- epilogue warps -------------------------------
+        const int te = tid - J2_GT;
+        const unsigned short *off = A.off_in_smem ? sOff : A.toff;
+        const double *kfp = A.kfac_in_smem ? sKf : A.kfac;
+        const bool scaled = A.rho_col != nullptr;
+        uint32_t nc = 0;                                         // non-empty columns seen
+        for (int col = my_lo; col < my_hi; col++) {
+            double *out = A.Jt + (size_t)col * A.ldJ;
+            if (A.jac_col_ptr[col] == A.jac_col_ptr[col + 1]) {      // no cells: the column of J is zero
+                for (int d = te; d < A.nd; d += J2_ET) out[A.out_identity ? A.out_base + d : A.out_row[d]] = 0.0;
+                continue;
+            }
+            const uint32_t buf = nc & 1u, use = nc >> 1;
+            mbar_wait(&gfull[buf], use & 1u);
+            const double *G = sG + buf * gsz;
+            double scale = 1.0;
+            if (scaled) { const double r = A.rho_col[col]; scale = 1.0 / (r * r); }
+            if (TERMS == 1 && A.out_identity && scaled && !(A.out_base & 1)) {
+                // the common dipole-dipole case: one look-up per datum, two data per thread and pass, 128-bit stores
+                const uint32_t *off2 = reinterpret_cast<const uint32_t *>(off);
+                const double2 *kf2 = reinterpret_cast<const double2 *>(kfp);
+                double2 *out2 = reinterpret_cast<double2 *>(out + A.out_base);
+                const int np = A.nd >> 1;
+#pragma unroll 4
+                for (int d2 = te; d2 < np; d2 += J2_ET) {
+                    const uint32_t o = off2[d2];
+                    const double2 kf = kf2[d2];
+                    out2[d2] = make_double2(G[o & 0xffffu] * (kf.x * scale), G[o >> 16] * (kf.y * scale));
+                }
+                if ((A.nd & 1) && te == 0) out[A.out_base + A.nd - 1] = G[off[A.nd - 1]] * (kfp[A.nd - 1] * scale);
+            } else {
+#pragma unroll 2
+                for (int d = te; d < A.nd; d += J2_ET) {
+                    const unsigned short *o = off + (size_t)d * TERMS;
+                    double v = G[o[0]];
+                    if (TERMS >= 2) v -= G[o[1]];
+                    if (TERMS == 4) v -= (G[o[2]] - G[o[3]]);
+                    const double kf = scaled ? kfp[d] * scale : 1.0;       // k_i / rho_j^2 only if len(model) == cols (:1377)
+                    out[A.out_identity ? A.out_base + d : A.out_row[d]] = v * kf;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&gempty[buf]);
+            nc++;
+        }
+        return;
+    }
+
+    // ------------------------------- Gram warps -------------------------------
+    int tp[MT], tq[MT]; bool have[MT];
+#pragma unroll
+    for (int m = 0; m < MT; m++) {
+        const int t = tid + m * J2_GT;
+        have[m] = t < A.n_tiles;
+        tp[m] = have[m] ? A.tile_tp[t] : 0; tq[m] = have[m] ? A.tile_tq[t] : 0;
+    }
+    double acc[MT][16];
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+        for (int x = 0; x < 16; x++) acc[m][x] = 0.0;
+    const int szQ = NL * A.nQp;
+    // V(item) = w_k (K + k^2 size mu) U_Q  into sV[which]
+    auto compute_v = [&](uint32_t n_item, int kk) {
+        const unsigned char *sb = ring + (size_t)(n_item % J2_SLOTS) * A.slot_bytes;
+        const double *rec = reinterpret_cast<const double *>(sb);
+        const double *uq = reinterpret_cast<const double *>(sb + (A.shared ? A.rec_bytes : A.uq_off));
+        double *v = sV + (n_item & 1u) * szQ;
+        const double k = A.kvals[kk], wk = A.kw[kk];
+        const double k2s = k * k * rec[NL * NL];
+        for (int x = tid; x < szQ; x += J2_GT) {
+            const int i = x / A.nQp, q = x - i * A.nQp;
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < NL; j++) s = fma(fma(k2s, A.mu[i * NL + j], rec[i * NL + j]), uq[j * A.nQp + q], s);
+            v[x] = s * wk;
+        }
+    };
+    uint32_t n = 0, nc = 0;
+    const uint32_t n_items = (uint32_t)(ci_hi - ci_lo) * (uint32_t)nK;
+    int col = my_lo;
+    while (col < my_hi && A.jac_col_ptr[col] == A.jac_col_ptr[col + 1]) col++;
+    if (n_items > 0) {
+        mbar_wait(&full[0], 0u);
+        compute_v(0u, 0);
+        named_bar_sync(2, J2_GT);
+    }
+    int ci = ci_lo, kk = 0;
+    for (; n < n_items; n++) {
+        // V of the next item while its data are fresh; the register tiles of this one
+        int ci_n = ci, kk_n = kk + 1;
+        if (kk_n == nK) { kk_n = 0; ci_n++; }
+        if (n + 1 < n_items) {
+            const uint32_t sl = (n + 1) % J2_SLOTS, use = (n + 1) / J2_SLOTS;
+            mbar_wait(&full[sl], use & 1u);
+            compute_v(n + 1, kk_n);
+        }
+        {
+            const unsigned char *sb = ring + (size_t)(n % J2_SLOTS) * A.slot_bytes;
+            const double *up = reinterpret_cast<const double *>(sb + A.rec_bytes);
+            const double *v = sV + (n & 1u) * szQ;
+#pragma unroll
+            for (int m = 0; m < MT; m++) {
+                if (have[m]) {
+#pragma unroll
+                    for (int i = 0; i < NL; i++) {
+                        const double2 u01 = *reinterpret_cast<const double2 *>(up + i * A.nPp + 4 * tp[m]);
+                        const double2 u23 = *reinterpret_cast<const double2 *>(up + i * A.nPp + 4 * tp[m] + 2);
+                        const double2 v01 = *reinterpret_cast<const double2 *>(v + i * A.nQp + 4 * tq[m]);
+                        const double2 v23 = *reinterpret_cast<const double2 *>(v + i * A.nQp + 4 * tq[m] + 2);
+                        const double u[4] = {u01.x, u01.y, u23.x, u23.y};
+                        const double w[4] = {v01.x, v01.y, v23.x, v23.y};
+#pragma unroll
+                        for (int a = 0; a < 4; a++)
+#pragma unroll
+                            for (int b = 0; b < 4; b++) acc[m][a * 4 + b] = fma(u[a], w[b], acc[m][a * 4 + b]);
+                    }
+                }
+            }
+        }
+        named_bar_sync(2, J2_GT);                     // V(n+1) visible; everybody is done with item n
+        if (tid == 0) mbar_arrive(&empty[n % J2_SLOTS]);
+        // last item of the column?
+        const bool col_done = (kk == nK - 1) && (ci + 1 == A.jac_col_ptr[col + 1]);
+        if (col_done) {
+            const uint32_t buf = nc & 1u, use = nc >> 1;
+            if (use > 0) mbar_wait(&gempty[buf], (use & 1u) ^ 1u);
+            double *G = sG + buf * gsz;
+#pragma unroll
+            for (int m = 0; m < MT; m++) {
+                if (have[m]) {
+                    const int t = tid + m * J2_GT;
+#pragma unroll
+                    for (int x = 0; x < 16; x++) { G[x * A.PL + t] = acc[m][x]; acc[m][x] = 0.0; }
+                }
+            }
+            named_bar_sync(2, J2_GT);
+            if (tid == 0) mbar_arrive(&gfull[buf]);
+            nc++;
+            col++;
+            while (col < my_hi && A.jac_col_ptr[col] == A.jac_col_ptr[col + 1]) col++;
+        }
+        ci = ci_n; kk = kk_n;
+    }
 }
 
 // y = l .* (J (r .* x))  (J column-major [cols][ld]):  y[d] = l[d] * sum_j Jt[j][d] r[j] x[j];  l, r optional

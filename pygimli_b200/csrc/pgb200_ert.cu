@@ -51,6 +51,12 @@ struct JacChunk {
     size_t smem;
 };
 
+struct Jac2Chunk {
+    int nd, nP, nPp, n_tiles, PL, mt, out_identity, out_base, kfac_in_smem, off_in_smem;
+    size_t data_off, plist_off, tile_off;       // offsets into the concatenated device arrays (data rows, P basis, tiles)
+    size_t smem; unsigned slot_bytes, rec_bytes, uq_off;
+};
+
 enum Phase { PH_MAP = 0, PH_ASM, PH_RHS, PH_SOLVE, PH_EPI, PH_JAC, PH_COUNT };
 
 } // namespace
@@ -120,6 +126,12 @@ struct pgb200_ert {
     DevBuf<int> j_plist, j_qlist, j_out, j_cta_ptr; DevBuf<JacDatum> j_idx; std::vector<int> h_jac_col_ptr; int j_grid = 0;
     DevBuf<double> j_kfac;
     std::vector<JacChunk> chunks; int nQ = 0, nQp = 0;
+    // second-generation Jacobian (k_jacobian2): element records, basis lists, tile lists, pre-resolved term offsets
+    int jac_v2 = 1, recn = 0;
+    DevBuf<double> erec, mu_tab, UDp, UDq, j2_kfac;
+    DevBuf<int> j2_pa, j2_pb, j2_qa, j2_qb, j2_out;
+    DevBuf<unsigned short> j2_tp, j2_tq, j2_off;
+    std::vector<Jac2Chunk> chunks2; int j2_nQ = 0, j2_nQp = 0, j2_shared = 0, j2_terms = 0, j2_grid = 0; bool j2_ok = false;
     size_t ldJ = 0; int j_rows = 0; bool jac_valid = false;
     // multilevel preconditioner
     std::vector<AmgLevel *> amg; int use_amg = 1, coarse_sweeps = 8; DevBuf<double> Z0, X0, dinvw0, vals_dw0; DevBuf<unsigned long long> gmax;
@@ -334,18 +346,17 @@ bool panel_path_ok(const pgb200_ert *h) { return h->use_panels && h->stream.ok; 
 // launch geometry of the flat element-wise kernels (ert_kernels.cuh, flat_map): column chunks of at most FLAT_T columns,
 // rows per CTA = rows per pass x passes
 constexpr int FLAT_MAX_GX = 296;           // 2 CTAs of 512 threads per SM: bounds the partial rows of the deterministic dots
-struct FlatCfg { int cw, rows_cta, nblk; dim3 grid; };
+struct FlatCfg { int cw; dim3 grid; };
 inline FlatCfg flat_cfg(int n_rows, int c0, int c1, int gx_cap = 8 * FLAT_MAX_GX) {
     FlatCfg f;
     const int w = std::max(1, c1 - c0);
     const int nchunk = cdiv(w, FLAT_T);
     f.cw = cdiv(w, nchunk);
     const int rpp = FLAT_T / f.cw;
-    // up to 12 passes per row block, fewer when that would leave less than ~4 CTAs per SM (small levels, narrow shards)
+    // up to 12 passes per CTA, fewer when that would leave less than ~4 CTAs per SM (small levels, narrow shards); the
+    // rows are split evenly over the CTAs (contiguous ranges)
     const int passes = std::max(1, std::min(12, n_rows / (rpp * 600)));
-    f.rows_cta = rpp * passes;
-    f.nblk = cdiv(n_rows, f.rows_cta);
-    f.grid = dim3(std::min(f.nblk, gx_cap), nchunk);           // CTAs walk the row blocks with a grid stride
+    f.grid = dim3(std::max(1, std::min(cdiv(n_rows, rpp * passes), gx_cap)), nchunk);
     return f;
 }
 inline DotOut dot_out(pgb200_ert *h, double *out0, double *out1) {
@@ -457,7 +468,7 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
             CKR(launch_stream<EPI_RESIDUAL>(h, *lv[l].st, lv[l].st->ent_dw.p, lv[l].R, lv[l].X, c0, c1, nullptr, ex));
             AmgLevel *L = h->amg[l];
             const FlatCfg fc = flat_cfg(L->n, c0, c1);
-            k_amg_sum_members<<<fc.grid, FLAT_T, 0, h->st>>>(L->mem_ptr.p, L->mem_idx.p, L->n, lv[l].X, L->R.p, c0, c1, h->ld, fc.cw, fc.rows_cta, fc.nblk); LAUNCH(h);
+            k_amg_sum_members<<<fc.grid, FLAT_T, 0, h->st>>>(L->mem_ptr.p, L->mem_idx.p, L->n, lv[l].X, L->R.p, c0, c1, h->ld, fc.cw); LAUNCH(h);
         } else {
             CKR(amg_restrict(h, lv[l].rowptr, lv[l].colidx, lv[l].vals_dw, lv[l].nnz, lv[l].n, h->amg[l], lv[l].R, c0, c1));
         }
@@ -468,7 +479,7 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
         Lv &c = lv[nl];
         h->cur_tag = nl;
         const FlatCfg fc = flat_cfg(c.n, c0, c1);
-        k_amg_prolong<<<fc.grid, FLAT_T, 0, h->st>>>(c.dinvw, c.n, nullptr, c.R, nullptr, c.X, h->nE, c0, c1, h->ld, fc.cw, fc.rows_cta, fc.nblk); LAUNCH(h);
+        k_amg_prolong<<<fc.grid, FLAT_T, 0, h->st>>>(c.dinvw, c.n, nullptr, c.R, nullptr, c.X, h->nE, c0, c1, h->ld, fc.cw); LAUNCH(h);
         double *a = c.X, *b = c.Z;
         const int sweeps = (nl == 0) ? 1 : h->coarse_sweeps;
         for (int s = 0; s + 1 < sweeps; s++) {
@@ -483,7 +494,7 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
         Lv &f = lv[l];
         h->cur_tag = l;
         const FlatCfg fc = flat_cfg(f.n, c0, c1);
-        k_amg_prolong<<<fc.grid, FLAT_T, 0, h->st>>>(f.dinvw, f.n, h->amg[l]->agg.p, f.R, E, f.X, h->nE, c0, c1, h->ld, fc.cw, fc.rows_cta, fc.nblk); LAUNCH(h);
+        k_amg_prolong<<<fc.grid, FLAT_T, 0, h->st>>>(f.dinvw, f.n, h->amg[l]->agg.p, f.R, E, f.X, h->nE, c0, c1, h->ld, fc.cw); LAUNCH(h);
         if (streamed(l)) {
             PanelExtra ex{}; ex.R = f.R; ex.dinvw = f.dinvw; ex.n = f.n;
             const PanelEntry *ea = (l == 0) ? h->stream.ent_a.p : f.st->ent_a.p;
@@ -513,7 +524,7 @@ int pcg_solve(pgb200_ert *h) {
     FlatCfg fc = flat_cfg(h->N, c0, c1), fd = flat_cfg(h->N, c0, c1, FLAT_MAX_GX);   // per-iteration vector kernels; fd: those with column dots
     auto regrid = [&]() { fc = flat_cfg(h->N, c0, c1); fd = flat_cfg(h->N, c0, c1, FLAT_MAX_GX); };
     const bool amg = h->use_amg && !h->amg.empty();
-    k_pcg_init<<<fd.grid, FLAT_T, 0, h->st>>>(h->B.p, h->dinv.p, h->X.p, h->R.p, h->P.p, h->N, h->nE, c0, c1, ld, fd.cw, fd.rows_cta, fd.nblk,
+    k_pcg_init<<<fd.grid, FLAT_T, 0, h->st>>>(h->B.p, h->dinv.p, h->X.p, h->R.p, h->P.p, h->N, h->nE, c0, c1, ld, fd.cw,
                                               dot_out(h, amg ? nullptr : sc(0), sc(6))); LAUNCH(h);
     if (amg) {
         CKR(amg_vcycle(h, c0, c1, sc(0)));
@@ -538,15 +549,15 @@ int pcg_solve(pgb200_ert *h) {
         if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
         if (amg) {
             k_pcg_update_xr<false><<<fd.grid, FLAT_T, 0, h->st>>>(h->P.p, h->AP.p, nullptr, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
-                                                                 sc(rz_old), sc(3), fd.cw, fd.rows_cta, fd.nblk, dot_out(h, nullptr, sc(rr_cur))); LAUNCH(h);
+                                                                 sc(rz_old), sc(3), fd.cw, dot_out(h, nullptr, sc(rr_cur))); LAUNCH(h);
             CKR(amg_vcycle(h, c0, c1, sc(rz_new)));
             k_pcg_update_p<false><<<fc.grid, FLAT_T, 0, h->st>>>(h->Z0.p, nullptr, h->P.p, h->N, h->nE, c0, c1, ld, sc(rz_old), sc(rz_new),
-                                                                sc(rr_cur), sc(6), tol2, fc.cw, fc.rows_cta, fc.nblk); LAUNCH(h);
+                                                                sc(rr_cur), sc(6), tol2, fc.cw); LAUNCH(h);
         } else {
             k_pcg_update_xr<true><<<fd.grid, FLAT_T, 0, h->st>>>(h->P.p, h->AP.p, h->dinv.p, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
-                                                                sc(rz_old), sc(3), fd.cw, fd.rows_cta, fd.nblk, dot_out(h, sc(rz_new), sc(rr_cur))); LAUNCH(h);
+                                                                sc(rz_old), sc(3), fd.cw, dot_out(h, sc(rz_new), sc(rr_cur))); LAUNCH(h);
             k_pcg_update_p<true><<<fc.grid, FLAT_T, 0, h->st>>>(h->R.p, h->dinv.p, h->P.p, h->N, h->nE, c0, c1, ld, sc(rz_old), sc(rz_new),
-                                                               sc(rr_cur), sc(6), tol2, fc.cw, fc.rows_cta, fc.nblk); LAUNCH(h);
+                                                               sc(rr_cur), sc(6), tol2, fc.cw); LAUNCH(h);
         }
         return 0;
     };
@@ -726,6 +737,8 @@ int finish_response(pgb200_ert *h, double *rhoa_dev) {
     return 0;
 }
 
+int build_jac2_plan(pgb200_ert *h);
+
 int jac_plane(int nPp, int nQp) {               // plane stride of the element-major Gram block: >= #tiles and = 4 (mod 16), so that
     const int nt = (nPp / 4) * (nQp / 4);       // 16 consecutive q of one p hit 16 different 8-byte banks: (q & 3) * 4 + (q >> 2)
     return (nt + 11) / 16 * 16 + 4;
@@ -862,17 +875,250 @@ int launch_jacobian(pgb200_ert *h, const double *rho_col) {
     return 0;
 }
 
+// ---- second-generation Jacobian: host plan ---------------------------------------------------------------------------
+// one side of the measurement in a chosen basis: list of (a, b) basis entries (b = -1: a single electrode) and, per datum,
+// up to two signed indices into the list (dipole basis: one index; electrode basis: + index of a / m, - index of b / n)
+struct JacSide {
+    bool dipole = false;
+    std::vector<std::pair<int, int>> list;
+    std::vector<int> i0, i1;       // per datum; i1 = -1: no second term
+};
+static JacSide jac_side(const std::vector<int> &abmn, int r0, int r1, int t0) {
+    JacSide S;
+    const int nd = r1 - r0;
+    std::vector<std::pair<int, int>> dip; std::vector<int> el;
+    for (int d = r0; d < r1; d++) {
+        const int x = abmn[4 * d + t0], y = abmn[4 * d + t0 + 1];
+        dip.push_back({x, y});
+        if (x >= 0) el.push_back(x);
+        if (y >= 0) el.push_back(y);
+    }
+    std::vector<std::pair<int, int>> ud(dip); std::sort(ud.begin(), ud.end()); ud.erase(std::unique(ud.begin(), ud.end()), ud.end());
+    std::sort(el.begin(), el.end()); el.erase(std::unique(el.begin(), el.end()), el.end());
+    // dipoles whose first electrode is missing cannot be a basis entry (u_a - u_b needs a); fall back to electrodes
+    bool ok = true;
+    for (auto &p : ud) if (p.first < 0) ok = false;
+    S.dipole = ok && ud.size() <= el.size() + el.size() / 4 + 4;
+    S.i0.assign(nd, -1); S.i1.assign(nd, -1);
+    if (S.dipole) {
+        S.list = ud;
+        for (int d = 0; d < nd; d++) S.i0[d] = (int)(std::lower_bound(ud.begin(), ud.end(), dip[d]) - ud.begin());
+    } else {
+        for (int e : el) S.list.push_back({e, -1});
+        for (int d = 0; d < nd; d++) {
+            if (dip[d].first >= 0) S.i0[d] = (int)(std::lower_bound(el.begin(), el.end(), dip[d].first) - el.begin());
+            if (dip[d].second >= 0) S.i1[d] = (int)(std::lower_bound(el.begin(), el.end(), dip[d].second) - el.begin());
+        }
+    }
+    return S;
+}
+
+int build_jac2_plan(pgb200_ert *h) {
+    h->j2_ok = false; h->chunks2.clear();
+    if (!h->jac_v2) return 0;
+    const int NL = h->nloc, r0 = h->row0, r1 = h->row1, nd = r1 - r0;
+    if (nd <= 0) { h->j2_ok = true; return 0; }
+    JacSide P = jac_side(h->h_abmn, r0, r1, 0), Q = jac_side(h->h_abmn, r0, r1, 2);
+    // one shared list (symmetric Gram block) when both sides use the same kind of basis and their union is not much larger
+    bool shared = false;
+    if (P.dipole == Q.dipole) {
+        std::vector<std::pair<int, int>> uni(P.list); uni.insert(uni.end(), Q.list.begin(), Q.list.end());
+        std::sort(uni.begin(), uni.end()); uni.erase(std::unique(uni.begin(), uni.end()), uni.end());
+        if (uni.size() <= std::max(P.list.size(), Q.list.size()) * 6 / 5 + 2) {
+            auto remap = [&](JacSide &S) {
+                std::vector<int> m(S.list.size());
+                for (size_t i = 0; i < S.list.size(); i++) m[i] = (int)(std::lower_bound(uni.begin(), uni.end(), S.list[i]) - uni.begin());
+                for (auto &v : S.i0) if (v >= 0) v = m[v];
+                for (auto &v : S.i1) if (v >= 0) v = m[v];
+                S.list = uni;
+            };
+            remap(P); remap(Q); shared = true;
+        }
+    }
+    const int terms = (P.dipole ? 1 : 2) * (Q.dipole ? 1 : 2);
+    h->j2_terms = terms; h->j2_shared = shared ? 1 : 0;
+    h->j2_nQ = (int)Q.list.size(); h->j2_nQp = std::max(4, (h->j2_nQ + 3) / 4 * 4);
+    const int nQp = h->j2_nQp, tilesQ = nQp / 4;
+    int dev_smem = 0;
+    CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    const size_t cap = (size_t)dev_smem - 1024;
+    const unsigned rec_bytes = (unsigned)h->recn * 8u;
+    // device-side concatenations
+    std::vector<int> pa, pb, outr; std::vector<unsigned short> ttp, ttq, toff; std::vector<double> kf;
+    // a chunk over `rows` (indices relative to r0) with P basis entries `plist` (indices into P.list; identity when shared)
+    auto make_chunk = [&](const std::vector<int> &rows, bool sh, Jac2Chunk &c, bool commit) -> bool {
+        // P sub-list of this chunk
+        std::vector<int> pmap(P.list.size(), -1), plist;
+        if (sh) { plist.resize(P.list.size()); for (size_t i = 0; i < plist.size(); i++) { plist[i] = (int)i; pmap[i] = (int)i; } }
+        else {
+            std::vector<char> used(P.list.size(), 0);
+            for (int d : rows) { if (P.i0[d] >= 0) used[P.i0[d]] = 1; if (P.i1[d] >= 0) used[P.i1[d]] = 1; }
+            for (size_t i = 0; i < used.size(); i++) if (used[i]) { pmap[i] = (int)plist.size(); plist.push_back((int)i); }
+        }
+        c.nP = (int)plist.size(); c.nPp = std::max(4, (c.nP + 3) / 4 * 4);
+        const int tilesP = c.nPp / 4;
+        // tiles that some term needs
+        std::vector<int> tslot((size_t)tilesP * tilesQ, -1);
+        auto canon = [&](int p, int q, int &tp, int &tq, int &e) {
+            tp = p >> 2; tq = q >> 2; e = (p & 3) * 4 + (q & 3);
+            if (sh && tp > tq) { std::swap(tp, tq); e = (q & 3) * 4 + (p & 3); }
+        };
+        std::vector<std::pair<int, int>> tl;
+        auto need = [&](int p, int q) { if (p < 0 || q < 0) return; int tp, tq, e; canon(pmap[p], q, tp, tq, e); int &sl = tslot[(size_t)tp * tilesQ + tq]; if (sl < 0) { sl = (int)tl.size(); tl.push_back({tp, tq}); } };
+        for (int d : rows) { need(P.i0[d], Q.i0[d]); need(P.i0[d], Q.i1[d]); need(P.i1[d], Q.i0[d]); need(P.i1[d], Q.i1[d]); }
+        c.n_tiles = (int)tl.size();
+        if (c.n_tiles > J2_MAX_MT * J2_GT) return false;
+        c.mt = c.n_tiles <= J2_GT ? 1 : 2;
+        c.PL = std::max(1, c.n_tiles) | 1;
+        if (16 * (size_t)c.PL + 2 > 65535) return false;
+        c.nd = (int)rows.size();
+        c.rec_bytes = rec_bytes;
+        c.uq_off = rec_bytes + (unsigned)(NL * c.nPp * 8);
+        c.slot_bytes = (unsigned)up128(rec_bytes + (size_t)NL * c.nPp * 8 + (sh ? 0 : (size_t)NL * nQp * 8));
+        size_t base = (size_t)J2_SLOTS * c.slot_bytes + 2 * (size_t)NL * nQp * 8 + 2 * (16 * (size_t)c.PL + 2) * 8;
+        if (base > cap) return false;
+        c.kfac_in_smem = 0; c.off_in_smem = 0;
+        const size_t kfb = (size_t)((c.nd + 1) & ~1) * 8, ofb = (size_t)c.nd * terms * 2 + 16;
+        if (base + kfb + ofb <= cap) { c.kfac_in_smem = 1; c.off_in_smem = 1; base += kfb + ofb; }
+        else if (base + ofb <= cap) { c.off_in_smem = 1; base += ofb; }
+        c.smem = base;
+        if (!commit) return true;
+        c.data_off = kf.size(); c.plist_off = pa.size(); c.tile_off = ttp.size();
+        for (int i : plist) { pa.push_back(P.list[i].first); pb.push_back(P.list[i].second); }
+        for (auto &t : tl) { ttp.push_back((unsigned short)t.first); ttq.push_back((unsigned short)t.second); }
+        const unsigned short zero = (unsigned short)(16 * c.PL);
+        auto off = [&](int p, int q) -> unsigned short {
+            if (p < 0 || q < 0) return zero;
+            int tp, tq, e; canon(pmap[p], q, tp, tq, e);
+            return (unsigned short)(e * c.PL + tslot[(size_t)tp * tilesQ + tq]);
+        };
+        c.out_identity = 1; c.out_base = (int)c.data_off;
+        for (size_t x = 0; x < rows.size(); x++) {
+            const int d = rows[x];
+            // v = t0 [- t1] [- (t2 - t3)]
+            if (terms == 1) toff.push_back(off(P.i0[d], Q.i0[d]));
+            else if (terms == 2 && P.dipole) { toff.push_back(off(P.i0[d], Q.i0[d])); toff.push_back(off(P.i0[d], Q.i1[d])); }
+            else if (terms == 2) { toff.push_back(off(P.i0[d], Q.i0[d])); toff.push_back(off(P.i1[d], Q.i0[d])); }
+            else { toff.push_back(off(P.i0[d], Q.i0[d])); toff.push_back(off(P.i0[d], Q.i1[d])); toff.push_back(off(P.i1[d], Q.i0[d])); toff.push_back(off(P.i1[d], Q.i1[d])); }
+            outr.push_back(d); kf.push_back(h->h_kfac[r0 + d]);
+            if (d != (int)c.data_off + (int)x) c.out_identity = 0;
+        }
+        return true;
+    };
+    std::vector<int> all(nd);
+    for (int i = 0; i < nd; i++) all[i] = i;
+    Jac2Chunk c{};
+    if (make_chunk(all, shared, c, false)) { make_chunk(all, shared, c, true); h->chunks2.push_back(c); }
+    else {
+        // rows ordered by their first P index; greedy chunks that fit (no symmetry inside a chunk: its P list is a subset)
+        h->j2_shared = 0;
+        std::vector<int> order(all);
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return std::max(P.i0[x], P.i1[x]) < std::max(P.i0[y], P.i1[y]); });
+        size_t i = 0;
+        while (i < order.size()) {
+            // largest prefix [i, j) that fits, by doubling + bisection on the row count
+            size_t lo = i + 1, hi = order.size();
+            auto fits = [&](size_t j) { std::vector<int> rows(order.begin() + i, order.begin() + j); Jac2Chunk t{}; return make_chunk(rows, false, t, false); };
+            if (!fits(lo)) PGB_FAIL("Jacobian: a single data row does not fit the Gram buffers");
+            if (!fits(hi)) { while (hi - lo > 1) { const size_t mid = (lo + hi) / 2; if (fits(mid)) lo = mid; else hi = mid; } } else lo = hi;
+            std::vector<int> rows(order.begin() + i, order.begin() + lo);
+            Jac2Chunk cc{};
+            make_chunk(rows, false, cc, true);
+            h->chunks2.push_back(cc);
+            i = lo;
+        }
+    }
+    std::vector<int> qa, qb;
+    for (auto &e : Q.list) { qa.push_back(e.first); qb.push_back(e.second); }
+    CKR(h->j2_pa.upload(pa.data(), pa.size(), h->st)); CKR(h->j2_pb.upload(pb.data(), pb.size(), h->st));
+    CKR(h->j2_qa.upload(qa.data(), qa.size(), h->st)); CKR(h->j2_qb.upload(qb.data(), qb.size(), h->st));
+    CKR(h->j2_tp.upload(ttp.data(), ttp.size(), h->st)); CKR(h->j2_tq.upload(ttq.data(), ttq.size(), h->st));
+    CKR(h->j2_off.upload(toff.data(), toff.size(), h->st)); CKR(h->j2_out.upload(outr.data(), outr.size(), h->st));
+    CKR(h->j2_kfac.upload(kf.data(), kf.size(), h->st));
+    int maxPp = 4;
+    for (auto &cc : h->chunks2) maxPp = std::max(maxPp, cc.nPp);
+    CKR(h->UDp.alloc((size_t)h->N * h->nK * maxPp));
+    if (!h->j2_shared) CKR(h->UDq.alloc((size_t)h->N * h->nK * nQp));
+    CK(cudaStreamSynchronize(h->st));
+    h->j2_ok = true;
+    return 0;
+}
+
+template <int E, int MT>
+int jac2_go(pgb200_ert *h, const Jac2Args &A, int terms, int grid, size_t smem) {
+#define J2GO(T) do { CK(cudaFuncSetAttribute(k_jacobian2<E, MT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                     k_jacobian2<E, MT, T><<<grid, J2_THREADS, smem, h->st>>>(A); } while (0)
+    if (terms == 1) J2GO(1); else if (terms == 2) J2GO(2); else J2GO(4);
+#undef J2GO
+    LAUNCH(h);
+    return 0;
+}
+
+template <int E>
+int launch_jacobian2(pgb200_ert *h, const double *rho_col) {
+    const int NL = h->nloc, nQp = h->j2_nQp;
+    auto basis = [&](const int *la, const int *lb, int nL, int nLp, double *UD) -> int {
+        dim3 b(32, 8), g(cdiv(h->N, 8), cdiv(h->nK * nLp, 32));
+        k_basis_pots<<<g, b, 0, h->st>>>(h->U.p, h->ld, h->N, h->nE, h->nK, la, lb, nL, nLp, UD, (size_t)h->nK * nLp); LAUNCH(h);
+        return 0;
+    };
+    if (!h->j2_shared) CKR(basis(h->j2_qa.p, h->j2_qb.p, h->j2_nQ, nQp, h->UDq.p));
+    const int grid = std::max(1, std::min(h->M, h->num_sms));
+    if (grid != h->j2_grid) {
+        // contiguous column ranges per CTA, balanced by the number of cells (+1 per column for the epilogue)
+        std::vector<int> ptr(grid + 1, h->M);
+        const long long total = (long long)h->h_jac_col_ptr[h->M] + h->M;
+        int col = 0; ptr[0] = 0;
+        for (int b = 1; b < grid; b++) {
+            const long long target = total * b / grid;
+            while (col < h->M && (long long)h->h_jac_col_ptr[col] + col < target) col++;
+            ptr[b] = col;
+        }
+        CKR(h->j_cta_ptr.upload(ptr.data(), ptr.size(), h->st));
+        h->j2_grid = grid; h->j_grid = 0;
+    }
+    for (auto &c : h->chunks2) {
+        CKR(basis(h->j2_pa.p + c.plist_off, h->j2_pb.p + c.plist_off, c.nP, c.nPp, h->UDp.p));
+        Jac2Args A;
+        A.cells = h->cells.p; A.C = h->C; A.jac_cells = h->jac_cells.p; A.jac_col_ptr = h->jac_col_ptr.p; A.cta_col_ptr = h->j_cta_ptr.p;
+        A.erec = h->erec.p; A.recn = h->recn; A.mu = h->mu_tab.p;
+        A.UDp = h->UDp.p; A.ldUDp = (size_t)h->nK * c.nPp; A.UDq = h->j2_shared ? h->UDp.p : h->UDq.p; A.ldUDq = h->j2_shared ? A.ldUDp : (size_t)h->nK * nQp;
+        A.nPp = c.nPp; A.nQp = h->j2_shared ? c.nPp : nQp; A.shared = h->j2_shared;
+        A.nK = h->nK; A.kvals = h->kvals.p; A.kw = h->kw.p;
+        A.tile_tp = h->j2_tp.p + c.tile_off; A.tile_tq = h->j2_tq.p + c.tile_off; A.n_tiles = c.n_tiles; A.PL = c.PL; A.mt = c.mt;
+        A.toff = h->j2_off.p + c.data_off * h->j2_terms; A.terms = h->j2_terms;
+        A.kfac = h->j2_kfac.p + c.data_off; A.out_row = h->j2_out.p + c.data_off; A.nd = c.nd; A.out_identity = c.out_identity; A.out_base = c.out_base;
+        A.off_in_smem = c.off_in_smem; A.kfac_in_smem = c.kfac_in_smem;
+        A.rho_col = rho_col; A.Jt = h->Jt.p; A.ldJ = h->ldJ;
+        A.slot_bytes = c.slot_bytes; A.uq_off = c.uq_off; A.rec_bytes = c.rec_bytes;
+        if (c.mt == 1) CKR((jac2_go<E, 1>(h, A, h->j2_terms, grid, c.smem)));
+        else CKR((jac2_go<E, 2>(h, A, h->j2_terms, grid, c.smem)));
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int jacobian(pgb200_ert *h, const double *rho_col) {
     if (h->j_rows <= 0) { h->jac_valid = true; return 0; }
     if (h->Jt.n < (size_t)h->M * h->ldJ) CKR(h->Jt.alloc((size_t)h->M * h->ldJ));
     phase_begin(h, PH_JAC);
     if (h->prof) CK(cudaEventRecord(h->jev[0], h->st));
-    switch (h->elem) {
-        case TRI3:  CKR(launch_jacobian<TRI3>(h, rho_col)); break;
-        case TRI6:  CKR(launch_jacobian<TRI6>(h, rho_col)); break;
-        case TET4:  CKR(launch_jacobian<TET4>(h, rho_col)); break;
-        case TET10: CKR(launch_jacobian<TET10>(h, rho_col)); break;
-        default: PGB_FAIL("unknown element type");
+    if (h->jac_v2 && h->j2_ok) {
+        switch (h->elem) {
+            case TRI3:  CKR(launch_jacobian2<TRI3>(h, rho_col)); break;
+            case TRI6:  CKR(launch_jacobian2<TRI6>(h, rho_col)); break;
+            case TET4:  CKR(launch_jacobian2<TET4>(h, rho_col)); break;
+            case TET10: CKR(launch_jacobian2<TET10>(h, rho_col)); break;
+            default: PGB_FAIL("unknown element type");
+        }
+    } else {
+        switch (h->elem) {
+            case TRI3:  CKR(launch_jacobian<TRI3>(h, rho_col)); break;
+            case TRI6:  CKR(launch_jacobian<TRI6>(h, rho_col)); break;
+            case TET4:  CKR(launch_jacobian<TET4>(h, rho_col)); break;
+            case TET10: CKR(launch_jacobian<TET10>(h, rho_col)); break;
+            default: PGB_FAIL("unknown element type");
+        }
     }
     if (h->prof) { CK(cudaEventRecord(h->jev[1], h->st)); h->jac_timed = true; }
     h->jac_valid = true;
@@ -1095,10 +1341,25 @@ int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
         CK(cudaGetLastError());
         h->prim_set = true;
     }
+    // geometry-only element records of the Jacobian kernel: per cell the stiffness matrix and the size
+    if (const char *e = getenv("PGB200_JACOBIAN_V1")) h->jac_v2 = atoi(e) ? 0 : 1;
+    if (h->jac_v2) {
+        h->recn = (NL * NL + 1 + 1) / 2 * 2;                 // [K | size | pad]: a multiple of 16 bytes (one bulk copy)
+        CKR(h->erec.alloc((size_t)C * h->recn)); CKR(h->mu_tab.alloc((size_t)NL * NL));
+        switch (h->elem) {
+            case TRI3:  k_element_records<TRI3><<<cdiv(C, 128), 128, 0, st>>>(h->pos.p, h->cells.p, C, h->recn, h->erec.p); k_mass_unit_table<TRI3><<<1, 128, 0, st>>>(h->mu_tab.p); break;
+            case TRI6:  k_element_records<TRI6><<<cdiv(C, 128), 128, 0, st>>>(h->pos.p, h->cells.p, C, h->recn, h->erec.p); k_mass_unit_table<TRI6><<<1, 128, 0, st>>>(h->mu_tab.p); break;
+            case TET4:  k_element_records<TET4><<<cdiv(C, 128), 128, 0, st>>>(h->pos.p, h->cells.p, C, h->recn, h->erec.p); k_mass_unit_table<TET4><<<1, 128, 0, st>>>(h->mu_tab.p); break;
+            default:    k_element_records<TET10><<<cdiv(C, 128), 128, 0, st>>>(h->pos.p, h->cells.p, C, h->recn, h->erec.p); k_mass_unit_table<TET10><<<1, 128, 0, st>>>(h->mu_tab.p); break;
+        }
+        LAUNCH(h); LAUNCH(h);
+        CK(cudaGetLastError());
+    }
     // rho = 1 matrices: the S1 of the singularity-removal right-hand side, and the (geometry-only) strength
     // information the multilevel hierarchy is built from
     CKR(h->vals1.alloc(h->nnz * nK)); CKR(assemble(h, nullptr, h->vals1.p));
     CKR(build_jac_plan(h));
+    CKR(build_jac2_plan(h));
     CK(cudaStreamSynchronize(st));
     return 0;
 }
@@ -1180,7 +1441,7 @@ int pgb200_ert_set_shard(pgb200_ert *h, int src_begin, int src_end, int row_begi
     if (src_begin < 0 || src_end > h->nS || src_begin > src_end || row_begin < 0 || row_end > h->D || row_begin > row_end) PGB_FAIL("invalid shard");
     CK(cudaSetDevice(h->device));
     h->c0 = src_begin; h->c1 = src_end; h->pots_valid = false; h->shard_solved = false;
-    if (row_begin != h->row0 || row_end != h->row1) { h->row0 = row_begin; h->row1 = row_end; CKR(build_jac_plan(h)); }
+    if (row_begin != h->row0 || row_end != h->row1) { h->row0 = row_begin; h->row1 = row_end; CKR(build_jac_plan(h)); CKR(build_jac2_plan(h)); }
     return 0;
 }
 
@@ -1190,6 +1451,7 @@ int pgb200_ert_set_kfac(pgb200_ert *h, const double *k) {
     h->h_kfac.assign(k, k + h->D);
     CK(cudaMemcpyAsync(h->kfac.p, k, sizeof(double) * h->D, cudaMemcpyHostToDevice, h->st));
     CKR(build_jac_plan(h));
+    CKR(build_jac2_plan(h));
     return 0;
 }
 
@@ -1515,9 +1777,11 @@ int pgb200_ert_path_info(pgb200_ert *h, int *out, int n) {
     if (!h || !out) PGB_FAIL("null argument");
     int mt = 0, res = 1;
     for (auto &c : h->chunks) { mt = std::max(mt, c.mt); res = res && c.resolved; }
+    int nch = (int)h->chunks.size();
+    if (h->jac_v2 && h->j2_ok) { mt = 0; nch = (int)h->chunks2.size(); for (auto &c : h->chunks2) mt = std::max(mt, c.mt); res = 10 * h->j2_terms + h->j2_shared; }
     int sl = 0;
     for (AmgLevel *L : h->amg) sl += (h->use_panels && L->stream.ok) ? 1 : 0;
-    const int v[10] = {h->pi_panel_nc, h->pi_tiles, h->pi_two_k, h->pi_graph_launches, (int)h->chunks.size(), mt, res, (int)h->amg.size(), h->pi_slots, sl};
+    const int v[10] = {h->pi_panel_nc, h->pi_tiles, h->pi_two_k, h->pi_graph_launches, nch, mt, res, (int)h->amg.size(), h->pi_slots, sl};
     for (int i = 0; i < n && i < 10; i++) out[i] = v[i];
     return 0;
 }
