@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libpgb200_ert.so")
+LIB_PATH = os.environ.get("PGB200_LIB") or os.path.join(_PKG, "libpgb200_ert.so")     # PGB200_LIB: A/B builds of the same library
 
 c_int_p = C.POINTER(C.c_int)
 c_dbl_p = C.POINTER(C.c_double)

@@ -387,10 +387,16 @@ struct PanelExtra {
     int n;                    // rows of the level (stride of dinvw per wavenumber)
 };
 
-constexpr int ST_CONSUMER_WARPS = 15;              // + 1 producer warp = 512 threads (128 registers per thread available)
+#ifndef PGB_ST_WARPS
+#define PGB_ST_WARPS 15
+#define PGB_ST_RPW 4
+#define PGB_ST_UNROLL 4
+#endif
+constexpr int ST_CONSUMER_WARPS = PGB_ST_WARPS;    // + 1 producer warp (15 + 1 = 512 threads: 128 registers per thread available)
 constexpr int ST_CONSUMERS = ST_CONSUMER_WARPS * 32;
 constexpr int ST_THREADS = ST_CONSUMERS + 32;      // + the producer warp
-constexpr int ST_RPW = 4;                          // rows per consumer warp: panels have at most 60 rows
+constexpr int ST_UNROLL = PGB_ST_UNROLL;
+constexpr int ST_RPW = PGB_ST_RPW;                 // rows per consumer warp: panels have at most ST_CONSUMER_WARPS * ST_RPW rows
 constexpr int ST_MAX_SLOTS = 4;
 constexpr int ST_MAX_TILE_W = 128;                 // columns per tile (2 column pairs per lane)
 
@@ -534,7 +540,7 @@ k_spmm_stream(const StreamArgs A) {
                     const int r = warp + ST_CONSUMER_WARPS * rr;
                     if (r < nrows) {
                         const int pb = sR[r], pe = sR[r + 1];
-#pragma unroll 4
+#pragma unroll ST_UNROLL
                         for (int e = pb; e < pe; e++) {
                             const int4 raw = *reinterpret_cast<const int4 *>(sE + e);      // one 128-bit broadcast load: {value, row}
                             const double a = __hiloint2double(raw.y, raw.x);

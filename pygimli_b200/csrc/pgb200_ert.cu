@@ -110,7 +110,7 @@ struct pgb200_ert {
         jac_cells, jac_col_ptr, abmn;
     std::vector<int> color_ptr, pro_level_ptr;
     StreamDev stream; int use_panels = 1, use_panels_build = 1;   // streamed row panels of the fine level (use_panels 0: plain gather SpMM, A/B evidence)
-    int stream_rmax = ST_CONSUMER_WARPS * ST_RPW, stream_hc = 104, stream_chunks = 2; // panel limits (stream_panels.h)
+    int stream_rmax = std::min(60, ST_CONSUMER_WARPS * ST_RPW), stream_hc = 104, stream_chunks = 2; // panel limits (stream_panels.h)
     DevBuf<double> dot_part; DevBuf<unsigned> dot_counter;    // deterministic column dots: per-CTA partial rows + tickets
     int dot_slots = 0; size_t smem_optin = 0;
     std::vector<double> h_kvals;
