@@ -112,6 +112,48 @@ typedef struct pgb200_amg_level {
     const int *mem_idx;     /* [n of the finer level] ... as finer-level node ids                        */
 } pgb200_amg_level;
 
+/* ---- compiled plan builder: what the reference takes (mesh + data container) -> plan ---------------------------
+ * ModellingBase::setMesh(mesh) / setData(dataContainer) (core/src/modellingbase.h:68-99) hand the reference a pointer-graph
+ * mesh and a DataContainerERT; the flat-array equivalents below carry the same information (original numbering, the
+ * reference's marker conventions).  pgb200_plan_build does all geometry-only set-up on the host (csrc/plan_builder.cpp:
+ * pattern by sort + unique, colouring, electrode matching, wavenumbers, mixed-BC table, prolongation levels, Jacobian
+ * columns), pgb200_ert_open adds the device side and the aggregation hierarchy -- one call from a reference-side binding. */
+typedef struct pgb200_mesh_in {
+    int dim;                    /* 2 or 3                                                                      */
+    int nloc;                   /* nodes per cell: 3 / 6 / 4 / 10                                              */
+    int n_nodes, n_cells;
+    int n_bounds, nlb;          /* marked boundary faces and nodes per face (2 / 3 edges, 3 / 6 triangles)     */
+    const double *pos;          /* [N*3]                                                                       */
+    const int *node_marker;     /* [N]  -99 electrode, -999 reference, -1000 calibration (bert/bert.h:30-32)   */
+    const int *cells;           /* [C*nloc]                                                                    */
+    const int *cell_marker;     /* [C]  >= 0 model index, < 0 background                                       */
+    const int *bounds;          /* [B*nlb]                                                                     */
+    const int *bound_marker;    /* [B]  -1 Neumann (surface), -2 mixed, -3 Dirichlet (gimli.h:234-240)         */
+} pgb200_mesh_in;
+typedef struct pgb200_scheme_in {
+    int n_elec, n_data;
+    const double *sensors;      /* [nE*3] sensor positions (DataContainer::sensorPositions)                    */
+    const int *abmn;            /* [D*4]  tokens a b m n, -1 = unused                                          */
+    const double *k_fac;        /* [D] token k or NULL: analytic factors on a flat earth, numeric with topography */
+} pgb200_scheme_in;
+typedef struct pgb200_built_plan pgb200_built_plan;     /* owns every array of the plan */
+/* n_k_user > 0: wavenumbers / weights set by the caller (setkValues / setWeights, dcfemmodelling.h:239-243) */
+int pgb200_plan_build(const pgb200_mesh_in *mesh, const pgb200_scheme_in *scheme, int sr, int n_k_user, const double *k_user,
+                      const double *w_user, pgb200_built_plan **out);
+int pgb200_plan_free(pgb200_built_plan *plan);
+const char *pgb200_plan_error(void);
+const pgb200_plan *pgb200_plan_view(const pgb200_built_plan *plan);
+/* named arrays / scalars of a built plan for host-side consumers and tests; type: 0 int32, 1 float64, 2 int64.  Names:
+ * node_perm node_inv pos cells cell_marker rowptr colidx diag_pos ref_rowptr ref_colidx ref_slot color_ptr color_order
+ * cells_col pos_col k w bc_slot bc_ptr bc_owner bc_coef dir_zero_slots dir_diag_slots dir_nodes el_pos sing_val pick_w
+ * min_radius el_node el_node_ref el_cell sing_node pick_ptr pick_idx src_cell_ptr src_cells pro_level_ptr pro_cells pro_nb
+ * pro_w jac_cells jac_col_ptr abmn k_fac, level<l>.{rowptr,colidx,diag_pos,gal_ptr,gal_idx,agg,mem_ptr,mem_idx}      */
+int pgb200_plan_array(const pgb200_built_plan *plan, const char *name, const void **ptr, long long *count, int *type);
+int pgb200_plan_scalar(const pgb200_built_plan *plan, const char *name, double *out);
+/* aggregation hierarchy from the rho = 1 values of the first wavenumber (host); returns the number of levels, < 0 on error */
+int pgb200_plan_build_hierarchy(pgb200_built_plan *plan, const double *vals1, double theta, int passes, int min_size, int max_levels);
+const pgb200_amg_level *pgb200_plan_levels(const pgb200_built_plan *plan);
+
 /* ---- host-only helpers (no GPU needed) -------------------------------------------- */
 const char *pgb200_last_error(void);
 int pgb200_version(void);
@@ -137,6 +179,13 @@ int pgb200_pairwise_aggregate(int n, const int *rowptr, const int *colidx, const
 
 /* ---- life cycle ------------------------------------------------------------------- */
 int pgb200_ert_create(const pgb200_plan *plan, int device, pgb200_ert **out);
+/* mesh + scheme -> ready handle: pgb200_plan_build + pgb200_ert_create + aggregation hierarchy (multilevel = 1) in one call.
+ * The handle owns the built plan (pgb200_ert_plan); n_k_user / k_user / w_user as in pgb200_plan_build.           */
+int pgb200_ert_open(const pgb200_mesh_in *mesh, const pgb200_scheme_in *scheme, int sr, int n_k_user, const double *k_user,
+                    const double *w_user, int multilevel, int device, pgb200_ert **out);
+/* the same for a plan the caller built and keeps alive (takes no ownership): device set-up + hierarchy */
+int pgb200_ert_open_plan(pgb200_built_plan *plan, int multilevel, int device, pgb200_ert **out);
+const pgb200_built_plan *pgb200_ert_plan(const pgb200_ert *h);
 int pgb200_ert_destroy(pgb200_ert *h);
 /* Install (n_levels > 0) or remove the aggregation hierarchy of the multilevel preconditioner.  */
 int pgb200_ert_set_hierarchy(pgb200_ert *h, int n_levels, const pgb200_amg_level *levels);

@@ -40,6 +40,16 @@ class Plan(C.Structure):
     ]
 
 
+class MeshIn(C.Structure):
+    _fields_ = [("dim", C.c_int), ("nloc", C.c_int), ("n_nodes", C.c_int), ("n_cells", C.c_int), ("n_bounds", C.c_int), ("nlb", C.c_int),
+                ("pos", c_dbl_p), ("node_marker", c_int_p), ("cells", c_int_p), ("cell_marker", c_int_p), ("bounds", c_int_p),
+                ("bound_marker", c_int_p)]
+
+
+class SchemeIn(C.Structure):
+    _fields_ = [("n_elec", C.c_int), ("n_data", C.c_int), ("sensors", c_dbl_p), ("abmn", c_int_p), ("k_fac", c_dbl_p)]
+
+
 class AmgLevel(C.Structure):
     _fields_ = [("n", C.c_int), ("nnz", C.c_int), ("rowptr", c_int_p), ("colidx", c_int_p), ("diag_pos", c_int_p),
                 ("gal_ptr", c_int_p), ("gal_idx", c_int_p), ("agg", c_int_p), ("mem_ptr", c_int_p), ("mem_idx", c_int_p)]
@@ -56,6 +66,8 @@ EXPORTS = [
     "pgb200_ert_pack_potentials", "pgb200_ert_get", "pgb200_ert_stats", "pgb200_ert_reset_stats", "pgb200_ert_set_profile",
     "pgb200_spmm", "pgb200_ert_get_trace", "pgb200_ert_set_primary_dev", "pgb200_ert_fill_matrix", "pgb200_ert_jacobian_mult_lr", "pgb200_ert_jacobian_tmult_lr", "pgb200_ert_coverage_trans",
     "pgb200_ert_path_info", "pgb200_ert_potentials_state",
+    "pgb200_plan_build", "pgb200_plan_free", "pgb200_plan_error", "pgb200_plan_view", "pgb200_plan_array", "pgb200_plan_scalar",
+    "pgb200_plan_build_hierarchy", "pgb200_plan_levels", "pgb200_ert_open", "pgb200_ert_open_plan", "pgb200_ert_plan",
 ]
 
 _lib = None
@@ -106,6 +118,20 @@ def lib():
         L.pgb200_ert_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.pgb200_ert_set_profile.argtypes = [C.c_void_p, C.c_int]
         L.pgb200_ert_path_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.pgb200_plan_error.restype = C.c_char_p
+        L.pgb200_plan_build.argtypes = [C.POINTER(MeshIn), C.POINTER(SchemeIn), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.pgb200_plan_free.argtypes = [C.c_void_p]
+        L.pgb200_plan_view.argtypes = [C.c_void_p]
+        L.pgb200_plan_view.restype = C.POINTER(Plan)
+        L.pgb200_plan_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), c_int_p]
+        L.pgb200_plan_scalar.argtypes = [C.c_void_p, C.c_char_p, c_dbl_p]
+        L.pgb200_plan_build_hierarchy.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int]
+        L.pgb200_plan_levels.argtypes = [C.c_void_p]
+        L.pgb200_plan_levels.restype = C.c_void_p
+        L.pgb200_ert_open.argtypes = [C.POINTER(MeshIn), C.POINTER(SchemeIn), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.pgb200_ert_open_plan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.pgb200_ert_plan.argtypes = [C.c_void_p]
+        L.pgb200_ert_plan.restype = C.c_void_p
         L.pgb200_color_cells.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.pgb200_build_stream_panels.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 11
         L.pgb200_ert_set_spmm_variant.argtypes = [C.c_void_p, C.c_int]
@@ -198,6 +224,100 @@ def set_hierarchy(handle, levels):
             setattr(a, name, v.ctypes.data_as(c_int_p))
     check(lib().pgb200_ert_set_hierarchy(handle, len(levels), C.cast(arr, C.c_void_p)))
     return keep
+
+
+class NativePlan:
+    """A plan built by the compiled builder (csrc/plan_builder.cpp, pgb200_plan_build).  Attribute access mirrors
+    host_setup.ERTPlan for everything the Python layer reads: sizes (N C nnz nE nK nS M dim nloc), flags (topography
+    has_background), and arrays by name (k w rowptr colidx ref_rowptr ref_colidx ref_slot node_perm node_inv ...), fetched
+    lazily as numpy copies."""
+
+    _SCALARS = dict(N="N", C="C", nnz="nnz", nE="nE", nK="nK", M="M", dim="dim", nloc="nloc", n_colors="n_colors", pro_nf="pro_nf")
+
+    def __init__(self, ptr, mesh, scheme, keep):
+        self._ptr, self.mesh_ref, self.scheme, self._keep, self._cache = ptr, mesh, scheme, keep, {}
+
+    def free(self):
+        if self._ptr:
+            lib().pgb200_plan_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def scalar(self, name):
+        v = C.c_double()
+        if lib().pgb200_plan_scalar(self._ptr, name.encode(), C.byref(v)) != 0:
+            raise PGB200Error(lib().pgb200_plan_error().decode())
+        return v.value
+
+    def array(self, name):
+        if name in self._cache:
+            return self._cache[name]
+        ptr, n, t = C.c_void_p(), C.c_longlong(), C.c_int()
+        if lib().pgb200_plan_array(self._ptr, name.encode(), C.byref(ptr), C.byref(n), C.byref(t)) != 0:
+            raise AttributeError(lib().pgb200_plan_error().decode())
+        dt = {0: np.int32, 1: np.float64, 2: np.int64}[t.value]
+        if n.value == 0:
+            out = np.zeros(0, dt)
+        else:
+            out = np.ctypeslib.as_array(C.cast(ptr, C.POINTER({0: C.c_int, 1: C.c_double, 2: C.c_longlong}[t.value])), shape=(n.value,)).copy()
+        self._cache[name] = out
+        return out
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        if name in NativePlan._SCALARS:
+            return int(self.scalar(NativePlan._SCALARS[name]))
+        if name == "nS":
+            return int(self.scalar("nK")) * int(self.scalar("nE"))
+        if name in ("topography", "has_background", "neumann_domain", "k_missing"):
+            return bool(self.scalar(name))
+        if name == "surface_z":
+            return self.scalar("surface_z")
+        if name == "dir_zero_slots" or name == "dir_diag_slots":
+            return self.array(name)
+        return self.array(name)
+
+    def view(self):
+        return lib().pgb200_plan_view(self._ptr)
+
+
+def plan_build(mesh, scheme, sr=True, k_values=None, weights=None) -> NativePlan:
+    """mesh (MeshArrays) + scheme (SchemeArrays) -> NativePlan through pgb200_plan_build (compiled, OpenMP)"""
+    keep = [np.ascontiguousarray(mesh.pos, np.float64), np.ascontiguousarray(mesh.node_marker, np.int32),
+            np.ascontiguousarray(mesh.cells, np.int32), np.ascontiguousarray(mesh.cell_marker, np.int32),
+            np.ascontiguousarray(mesh.bounds, np.int32).reshape(mesh.bound_marker.size, -1),
+            np.ascontiguousarray(mesh.bound_marker, np.int32),
+            np.ascontiguousarray(scheme.sensors, np.float64), np.ascontiguousarray(scheme.abmn(), np.int32)]
+    m = MeshIn()
+    m.dim, m.nloc, m.n_nodes, m.n_cells = mesh.dim, mesh.cells.shape[1], mesh.pos.shape[0], mesh.cells.shape[0]
+    m.n_bounds, m.nlb = keep[5].size, (keep[4].shape[1] if keep[4].size else mesh.dim)
+    m.pos, m.node_marker, m.cells, m.cell_marker, m.bounds, m.bound_marker = _dp(keep[0]), _ip(keep[1]), _ip(keep[2]), _ip(keep[3]), _ip(keep[4]), _ip(keep[5])
+    sc = SchemeIn()
+    sc.n_elec, sc.n_data, sc.sensors, sc.abmn = keep[6].shape[0], keep[7].shape[0], _dp(keep[6]), _ip(keep[7])
+    if scheme.k is not None:
+        kf = np.ascontiguousarray(scheme.k, np.float64)
+        keep.append(kf)
+        sc.k_fac = _dp(kf)
+    nk, kp, wp = 0, None, None
+    if k_values is not None and weights is not None:
+        ka, wa = np.ascontiguousarray(k_values, np.float64), np.ascontiguousarray(weights, np.float64)
+        keep.extend([ka, wa])
+        nk, kp, wp = ka.size, ka.ctypes.data, wa.ctypes.data
+    out = C.c_void_p()
+    if lib().pgb200_plan_build(C.byref(m), C.byref(sc), 1 if sr else 0, nk, kp, wp, C.byref(out)) != 0:
+        msg = lib().pgb200_plan_error().decode()
+        if "not on the B200 path" in msg or "not supported" in msg:
+            raise NotImplementedError(msg)
+        if "does not match the given mesh" in msg:
+            raise ValueError(msg)
+        raise PGB200Error(msg)
+    return NativePlan(out, mesh, scheme, keep)
 
 
 def _ip(a):

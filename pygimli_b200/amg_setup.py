@@ -39,7 +39,11 @@ def _coarsen(rowptr, colidx, agg, nc):
 
 
 def _sum_values(vals, gal_ptr, gal_idx):
-    return np.add.reduceat(vals[gal_idx], gal_ptr[:-1])
+    # sequential sums in gather order (np.bincount accumulates in index order), the order csrc/plan_builder.cpp and the
+    # k_galerkin kernel use; np.add.reduceat would switch to pairwise blocks for segments of 8 and more entries, and the
+    # last-bit differences flip ties of the strength-based matching
+    seg = np.repeat(np.arange(gal_ptr.size - 1), np.diff(gal_ptr))
+    return np.bincount(seg, weights=vals[gal_idx], minlength=gal_ptr.size - 1)
 
 
 def _diag_pos(rowptr, colidx):

@@ -639,11 +639,14 @@ k_spmm_stream(const StreamArgs A) {
             named_bar_sync(1, ST_CONSUMERS);
             if (s_ticket == nslot - 1) {
                 __threadfence();
-                for (int i = threadIdx.x; i < wc; i += ST_CONSUMERS) {
-                    const int cc = cs + i;
-                    if (cc >= v0 && cc < v1) {
-                        A.dots[cc] = ordered_row_sum(A.dot_part + cc, A.ld, 0, 1, nslot);
-                    }
+                // 4 threads per column add every 4th partial row, then the four sums are added in order
+                const int i = threadIdx.x >> 2, part4 = threadIdx.x & 3;
+                for (int i0 = 0; i0 < wc; i0 += ST_CONSUMERS / 4) {
+                    const int cc = cs + i0 + i;
+                    const bool okc = (i0 + i) < wc && cc >= v0 && cc < v1;
+                    double s4 = okc ? ordered_row_sum(A.dot_part + cc, A.ld, part4, 4, nslot) : 0.0;
+                    const double s1 = __shfl_down_sync(0xffffffffu, s4, 1), s2 = __shfl_down_sync(0xffffffffu, s4, 2), s3 = __shfl_down_sync(0xffffffffu, s4, 3);
+                    if (okc && part4 == 0) A.dots[cc] = ((s4 + s1) + s2) + s3;
                 }
                 if (threadIdx.x == 0) A.dot_counter[t] = 0u;
             }

@@ -149,6 +149,7 @@ struct pgb200_ert {
     cudaEvent_t jev[2]; bool jac_timed = false; int jac_launches = 0; long long total_iters = 0; int solves = 0;
     double *h_pinned = nullptr; size_t h_pinned_n = 0;
     int num_sms = 148;
+    pgb200_built_plan *built = nullptr; bool owns_built = false;    // pgb200_ert_open: the plan the handle was built from
     // which code paths the last solve / Jacobian took (pgb200_ert_path_info)
     int pi_panel_nc = 0, pi_tiles = 0, pi_two_k = 0, pi_graph_launches = 0, pi_slots = 0, pi_stream_levels = 0;
 };
@@ -1364,6 +1365,35 @@ int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
     return 0;
 }
 
+int pgb200_ert_open_plan(pgb200_built_plan *plan, int multilevel, int device, pgb200_ert **out) {
+    if (!plan || !out) PGB_FAIL("null argument");
+    const pgb200_plan *v = pgb200_plan_view(plan);
+    CKR(pgb200_ert_create(v, device, out));
+    pgb200_ert *h = *out;
+    h->built = plan;
+    if (multilevel) {
+        // aggregation hierarchy from the rho = 1 matrix of the smallest wavenumber (geometry only)
+        std::vector<double> v1((size_t)h->nnz);
+        CK(cudaMemcpy(v1.data(), h->vals1.p, sizeof(double) * h->nnz, cudaMemcpyDeviceToHost));
+        const int nl = pgb200_plan_build_hierarchy(plan, v1.data(), 0.25, 2, 256, 12);
+        if (nl < 0) PGB_FAIL(std::string("hierarchy: ") + pgb200_plan_error());
+        CKR(pgb200_ert_set_hierarchy(h, nl, pgb200_plan_levels(plan)));
+        CKR(pgb200_ert_set_preconditioner(h, nl > 0 ? 1 : 0, 8));
+    } else CKR(pgb200_ert_set_preconditioner(h, 0, 8));
+    return 0;
+}
+int pgb200_ert_open(const pgb200_mesh_in *mesh, const pgb200_scheme_in *scheme, int sr, int n_k_user, const double *k_user,
+                    const double *w_user, int multilevel, int device, pgb200_ert **out) {
+    if (!out) PGB_FAIL("null argument");
+    pgb200_built_plan *plan = nullptr;
+    if (pgb200_plan_build(mesh, scheme, sr, n_k_user, k_user, w_user, &plan)) PGB_FAIL(std::string(pgb200_plan_error()));
+    const int rc = pgb200_ert_open_plan(plan, multilevel, device, out);
+    if (rc) { if (*out) { (*out)->built = nullptr; pgb200_ert_destroy(*out); *out = nullptr; } pgb200_plan_free(plan); return rc; }
+    (*out)->owns_built = true;
+    return 0;
+}
+const pgb200_built_plan *pgb200_ert_plan(const pgb200_ert *h) { return h ? h->built : nullptr; }
+
 int pgb200_ert_destroy(pgb200_ert *h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
@@ -1375,6 +1405,7 @@ int pgb200_ert_destroy(pgb200_ert *h) {
     for (AmgLevel *L : h->amg) delete L;
     if (h->gexec) cudaGraphExecDestroy(h->gexec);
     if (h->own_st) cudaStreamDestroy(h->own_st);
+    if (h->built && h->owns_built) pgb200_plan_free(h->built);
     delete h;
     return 0;
 }

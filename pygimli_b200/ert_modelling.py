@@ -30,6 +30,9 @@ from .mesh import MeshArrays, from_pg_mesh, create_p2
 from .scheme import SchemeArrays, geometric_factors, electrode_matrix_data
 
 
+DEFAULT_PCG_TOL = 1e-12
+
+
 def _as_mesh(mesh) -> MeshArrays:
     if isinstance(mesh, MeshArrays):
         return mesh
@@ -212,6 +215,7 @@ class CoreB200:
         if preconditioner not in ("multilevel", "jacobi"):
             raise ValueError("preconditioner must be 'multilevel' or 'jacobi'")
         self.preconditioner = preconditioner
+        self.plan_builder = os.environ.get("PGB200_PLAN", "native")
         self.hierarchy = None
         self.sr = bool(sr)
         self.verbose = bool(verbose)
@@ -223,7 +227,9 @@ class CoreB200:
         self._keep = None
         self._k = None
         self._w = None
-        self._tol, self._maxit, self._check = 1e-12, 50000, 25
+        # stated relative residual tolerance of the block-PCG, ||r|| <= tol * ||b|| per source column (PGB200_TOL overrides
+        # the default for tolerance studies)
+        self._tol, self._maxit, self._check = float(os.environ.get("PGB200_TOL", DEFAULT_PCG_TOL)), 50000, 25
         self._stream = None
         self._shard = None
         self._prim_pm = None
@@ -308,6 +314,8 @@ class CoreB200:
         if self._h:
             _capi.lib().pgb200_ert_destroy(self._h)
         self._h = None
+        if isinstance(self._plan, _capi.NativePlan):
+            self._plan.free()
         self._plan = None
         self._keep = None
         self._prim_pm = None
@@ -328,8 +336,13 @@ class CoreB200:
                 raise RuntimeError("Found no mesh, so cannot calculate a response.")
             if self._scheme is None:
                 raise RuntimeError("no response without data container")
-            # the plan is geometry only; missing k-factors are resolved at the first response()/createJacobian()
-            self._plan = build_plan(self._mesh, self._scheme, self._k, self._w, color_fn=_capi.color_cells)
+            # the plan is geometry only; missing k-factors are resolved at the first response()/createJacobian().
+            # Built by the compiled builder (csrc/plan_builder.cpp, pgb200_plan_build); PGB200_PLAN=python selects the
+            # numpy twin (host_setup.build_plan) the tests compare it with
+            if self.plan_builder == "python":
+                self._plan = build_plan(self._mesh, self._scheme, self._k, self._w, color_fn=_capi.color_cells)
+            else:
+                self._plan = _capi.plan_build(self._mesh, self._scheme, self.sr, self._k, self._w)
             self._placeholder_k = not self._have_k()
         return self._plan
 
@@ -390,9 +403,15 @@ class CoreB200:
     def _ensure_handle(self):
         if self._h is None:
             P = self._ensure_plan()
-            s, keep = _capi.make_plan_struct(P, self.sr)
             h = C.c_void_p()
-            rc = _capi.lib().pgb200_ert_create(C.byref(s), self.device, C.byref(h))
+            native = isinstance(P, _capi.NativePlan)
+            if native:
+                # device set-up + aggregation hierarchy in the library (pgb200_ert_open_plan)
+                rc = _capi.lib().pgb200_ert_open_plan(P._ptr, 1 if self.preconditioner == "multilevel" else 0, self.device, C.byref(h))
+                keep = None
+            else:
+                s, keep = _capi.make_plan_struct(P, self.sr)
+                rc = _capi.lib().pgb200_ert_create(C.byref(s), self.device, C.byref(h))
             if rc != 0:
                 msg = _capi.last_error()
                 if h:
@@ -404,7 +423,9 @@ class CoreB200:
                 _capi.check(_capi.lib().pgb200_ert_set_stream(h, C.c_void_p(self._stream)))
             if self._shard:
                 _capi.check(_capi.lib().pgb200_ert_set_shard(h, *self._shard))
-            if self.preconditioner == "multilevel":
+            if native:
+                pass
+            elif self.preconditioner == "multilevel":
                 # aggregation hierarchy from the rho = 1 matrix of the smallest wavenumber (geometry only)
                 v1 = self.get("vals1", raw=True).reshape(P.nK, P.nnz)[0]
                 self.hierarchy = build_hierarchy(P.rowptr, P.colidx, v1, _capi.pairwise_aggregate)
