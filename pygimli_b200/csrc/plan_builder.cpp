@@ -18,7 +18,17 @@
 #include <string>
 #include <vector>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 namespace {
+
+struct StageTimer {
+    bool on; std::chrono::steady_clock::time_point t;
+    StageTimer() : on(getenv("PGB200_VERBOSE") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void lap(const char *what) { if (!on) return; auto n = std::chrono::steady_clock::now(); fprintf(stderr, "[plan_build] %-28s %.3f s\n", what, std::chrono::duration<double>(n - t).count()); t = n; }
+};
 
 constexpr double TOLERANCE = 1e-12;
 constexpr int MARKER_NODE_ELECTRODE = -99, MARKER_NODE_REFERENCE = -999, MARKER_NODE_CALIBRATION = -1000;
@@ -344,6 +354,7 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
     if (N <= 0 || C <= 0) PLAN_FAIL("Found no mesh, so cannot calculate a response.");
     P.dim = dim; P.nloc = nloc; P.N = N; P.C = C; P.nlb = nlb; P.n_bounds = nB;
     const int nvert = dim + 1;
+    StageTimer tm;
 
     // ---- internal node order: Morton curve of rank-quantised coordinates ------------------------------------------
     {
@@ -379,6 +390,7 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
     const double *pos = P.pos.data();
     const int *cells = P.cells.data();
 
+    tm.lap("node order + renumber");
     // ---- boundary classification / topography (dcfemmodelling.cpp:725-765) -----------------------------------------
     bool any_mixed_dir = false;
     for (int b = 0; b < nB; b++) if (P.bound_marker[b] == MARKER_BOUND_MIXED || P.bound_marker[b] == MARKER_BOUND_DIRICHLET) any_mixed_dir = true;
@@ -402,6 +414,7 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
     for (int i = 0; i < N; i++) nc_ptr[i + 1] += nc_ptr[i];
     { IVec fill(nc_ptr.begin(), nc_ptr.end() - 1); for (int c = 0; c < C; c++) for (int j = 0; j < nloc; j++) nc_cells[fill[cells[(size_t)c * nloc + j]]++] = c; }
 
+    tm.lap("boundary + incidence");
     // ---- CSR pattern (sparsematrix.h:966-1032): union of all node pairs per cell, columns ascending -----------------
     P.rowptr.assign(N + 1, 0);
     {
@@ -421,12 +434,14 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
         P.nnz = tot;
     }
     const IVec &rowptr = P.rowptr, &colidx = P.colidx;
+    tm.lap("pattern");
     // per-cell scatter map
     IVec cpos((size_t)C * nloc * nloc);
 #pragma omp parallel for schedule(static)
     for (int c = 0; c < C; c++)
         for (int i = 0; i < nloc; i++)
             for (int j = 0; j < nloc; j++) cpos[((size_t)c * nloc + i) * nloc + j] = csr_find(rowptr, colidx, cells[(size_t)c * nloc + i], cells[(size_t)c * nloc + j]);
+    tm.lap("scatter map");
     // colours
     {
         IVec color(C);
@@ -446,6 +461,7 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
             for (int x = 0; x < nloc * nloc; x++) P.pos_col[(size_t)x * C + s] = cpos[(size_t)c * nloc * nloc + x];
         }
     }
+    tm.lap("colours");
     P.diag_pos.resize(N);
     for (int i = 0; i < N; i++) { P.diag_pos[i] = csr_find(rowptr, colidx, i, i); if (P.diag_pos[i] < 0) PLAN_FAIL("matrix row without diagonal entry"); }
     // the reference's pattern (original numbering) and the slot correspondence
@@ -462,6 +478,7 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
         }
     }
 
+    tm.lap("diag + reference pattern");
     // ---- electrodes (dcfemmodelling.cpp:845-940) -------------------------------------------------------------------------
     const int nE = si->n_elec, D = si->n_data;
     if (nE <= 0) PLAN_FAIL("no response without data container");
@@ -559,6 +576,7 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
         }
     }
 
+    tm.lap("electrodes");
     // ---- wavenumbers ------------------------------------------------------------------------------------------------------
     if (k_user && w_user && n_k_user > 0) { P.kv.assign(k_user, k_user + n_k_user); P.kw.assign(w_user, w_user + n_k_user); }
     else { const std::string e = init_kwave_list(dim, nE, si->sensors, P.kv, P.kw); if (!e.empty()) PLAN_FAIL(e); }
@@ -573,6 +591,7 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
             P.sing_val[(size_t)kk * nE + i] = kv > 0.0 ? bessel_k0(P.min_radius[i] / 6.0 * kv) / M_PI : 1.0 / (2.0 * M_PI * P.min_radius[i] / 2.0);
         }
 
+    tm.lap("wavenumbers");
     // ---- boundary faces: owner cells, mixed-BC coefficient table, Dirichlet nodes ----------------------------------------
     IVec owner(nB, -1);
     {
@@ -628,6 +647,7 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
             for (int i = 0; i < N; i++) for (int p = rowptr[i]; p < rowptr[i + 1]; p++) if (isd[i] || isd[colidx[p]]) P.dir_zero.push_back(p);
     }
 
+    tm.lap("boundary tables");
     // ---- model mapping (modellingbase.cpp:401-497, mesh.cpp:2247-2316) ---------------------------------------------------
     int maxm = -1;
     for (int c = 0; c < C; c++) { if (P.cell_marker[c] <= -1000000) PLAN_FAIL("fixed-value regions are not supported on the B200 path"); maxm = std::max(maxm, P.cell_marker[c]); }
@@ -641,23 +661,25 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
         static const int fl2[3][2] = {{0, 1}, {1, 2}, {2, 0}}, fl3[4][3] = {{0, 1, 2}, {0, 1, 3}, {1, 2, 3}, {2, 0, 3}};
         const int nf = dim == 2 ? 3 : 4;
         P.pro_nf = nf;
-        // face-sharing neighbours through sorted corner-node keys
-        struct FK { long long key; int cf; };
-        std::vector<FK> fk((size_t)C * nf);
+        // face-sharing neighbours through the node -> cells incidence (each face: the other cell that holds all its corners)
+        IVec nb((size_t)C * nf, -1);
+#pragma omp parallel for schedule(static)
         for (int c = 0; c < C; c++)
             for (int f = 0; f < nf; f++) {
                 int v[3];
                 for (int a = 0; a < dim; a++) v[a] = cells[(size_t)c * nloc + (dim == 2 ? fl2[f][a] : fl3[f][a])];
-                std::sort(v, v + dim);
-                long long key = v[0];
-                for (int a = 1; a < dim; a++) key = key * N + v[a];
-                fk[(size_t)c * nf + f] = {key, c * nf + f};
+                for (int q = nc_ptr[v[0]]; q < nc_ptr[v[0] + 1]; q++) {
+                    const int c2 = nc_cells[q];
+                    if (c2 == c) continue;
+                    bool all = true;
+                    for (int a = 1; a < dim && all; a++) { bool fnd = false; for (int j = 0; j < nvert; j++) if (cells[(size_t)c2 * nloc + j] == v[a]) fnd = true; all = fnd; }
+                    bool first = false; for (int j = 0; j < nvert; j++) if (cells[(size_t)c2 * nloc + j] == v[0]) first = true;
+                    if (all && first) { nb[(size_t)c * nf + f] = c2; break; }
+                }
             }
-        std::sort(fk.begin(), fk.end(), [](const FK &a, const FK &b) { return a.key < b.key || (a.key == b.key && a.cf < b.cf); });
-        IVec nb((size_t)C * nf, -1);
-        for (size_t x = 0; x + 1 < fk.size(); x++) if (fk[x].key == fk[x + 1].key) { nb[fk[x].cf] = fk[x + 1].cf / nf; nb[fk[x + 1].cf] = fk[x].cf / nf; }
         DVec zw((size_t)C * nf);
         const double xy[3] = {1.0, dim == 3 ? 1.0 : 0.0, 0.0};
+#pragma omp parallel for schedule(static)
         for (int c = 0; c < C; c++)
             for (int f = 0; f < nf; f++) {
                 int v[3];
@@ -668,17 +690,19 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
             }
         IVec lvl(C);
         for (int c = 0; c < C; c++) lvl[c] = P.cell_marker[c] < 0 ? -1 : 0;
-        int cur = 0;
-        IVec todo;
-        for (int c = 0; c < C; c++) if (lvl[c] < 0) todo.push_back(c);
-        while (!todo.empty()) {
-            IVec now, rest;
-            for (int c : todo) {
-                bool has = false;
-                for (int f = 0; f < nf; f++) { const int n = nb[(size_t)c * nf + f]; if (n >= 0 && lvl[n] >= 0 && lvl[n] <= cur) has = true; }
-                (has ? now : rest).push_back(c);
-            }
+        // level l = the empty cells with a neighbour filled at a level < l (mesh.cpp:2276-2306, one recursion per level);
+        // frontier search: the candidates of a level are the empty neighbours of the cells filled one level before
+        int cur = 0, remaining = 0;
+        std::vector<char> queued((size_t)C, 0);
+        IVec now;
+        for (int c = 0; c < C; c++) {
+            if (lvl[c] >= 0) continue;
+            remaining++;
+            for (int f = 0; f < nf; f++) { const int n = nb[(size_t)c * nf + f]; if (n >= 0 && lvl[n] >= 0) { now.push_back(c); queued[c] = 1; break; } }
+        }
+        while (remaining > 0) {
             if (now.empty()) PLAN_FAIL("cannot fill empty cells: disconnected background region");
+            std::sort(now.begin(), now.end());
             for (int c : now) {
                 double wsum = 0.0, wv[4]; int nv[4];
                 for (int f = 0; f < nf; f++) {
@@ -692,8 +716,12 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
             }
             cur++;
             for (int c : now) lvl[c] = cur;
+            remaining -= (int)now.size();
             P.pro_level_ptr.push_back((int)P.pro_cells.size());
-            todo.swap(rest);
+            IVec next;
+            for (int c : now)
+                for (int f = 0; f < nf; f++) { const int n = nb[(size_t)c * nf + f]; if (n >= 0 && lvl[n] < 0 && !queued[n]) { queued[n] = 1; next.push_back(n); } }
+            now.swap(next);
         }
     }
 
@@ -725,6 +753,7 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
         for (int d = 0; d < D; d++) { const int a = P.abmn[4 * d], b = P.abmn[4 * d + 1], m = P.abmn[4 * d + 2], n = P.abmn[4 * d + 3]; P.kfac[d] = 1.0 / (u(a, m) - u(b, m) - u(a, n) + u(b, n)); }
     } else { P.kfac.assign(D, 0.0); P.k_missing = 1; }
 
+    tm.lap("jacobian columns + data");
     // ---- the flat view ----------------------------------------------------------------------------------------------------------
     pgb200_plan &V = P.view;
     V.dim = dim; V.nloc = nloc; V.n_nodes = N; V.n_cells = C; V.nnz = (int)P.nnz; V.n_elec = nE; V.n_k = nK; V.n_model = M; V.n_data = D; V.sr = sr ? 1 : 0;
