@@ -194,6 +194,10 @@ int pgb200_ert_set_hierarchy(pgb200_ert *h, int n_levels, const pgb200_amg_level
 int pgb200_ert_set_preconditioner(pgb200_ert *h, int multilevel, int coarse_sweeps);
 /* replay blocks of 6 multilevel-PCG iterations as one CUDA graph (default on; off while profiling) */
 int pgb200_ert_set_graph(pgb200_ert *h, int on);
+/* on != 0: the block-PCG starts from the potentials of the previous solve on this handle instead of zero (Gauss-Newton /
+ * time-lapse loops, where consecutive models differ little).  Off by default; the convergence criterion is unchanged
+ * (||r|| <= tol ||b|| per source column).                                                      */
+int pgb200_ert_set_warm_start(pgb200_ert *h, int on);
 /* CUDA stream (cudaStream_t) all work is enqueued on; 0/NULL = the handle's own blocking stream,
  * which is implicitly ordered with the legacy default stream.                                */
 int pgb200_ert_set_stream(pgb200_ert *h, void *stream);

@@ -66,6 +66,7 @@ EXPORTS = [
     "pgb200_ert_pack_potentials", "pgb200_ert_get", "pgb200_ert_stats", "pgb200_ert_reset_stats", "pgb200_ert_set_profile",
     "pgb200_spmm", "pgb200_ert_get_trace", "pgb200_ert_set_primary_dev", "pgb200_ert_fill_matrix", "pgb200_ert_jacobian_mult_lr", "pgb200_ert_jacobian_tmult_lr", "pgb200_ert_coverage_trans",
     "pgb200_ert_path_info", "pgb200_ert_potentials_state",
+    "pgb200_ert_set_warm_start",
     "pgb200_plan_build", "pgb200_plan_free", "pgb200_plan_error", "pgb200_plan_view", "pgb200_plan_array", "pgb200_plan_scalar",
     "pgb200_plan_build_hierarchy", "pgb200_plan_levels", "pgb200_ert_open", "pgb200_ert_open_plan", "pgb200_ert_plan",
 ]
@@ -138,6 +139,7 @@ def lib():
         L.pgb200_ert_set_hierarchy.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.pgb200_ert_set_preconditioner.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.pgb200_ert_set_graph.argtypes = [C.c_void_p, C.c_int]
+        L.pgb200_ert_set_warm_start.argtypes = [C.c_void_p, C.c_int]
         L.pgb200_ert_map_model.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.pgb200_pairwise_aggregate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         L.pgb200_spmm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,

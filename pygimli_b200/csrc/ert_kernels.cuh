@@ -727,9 +727,10 @@ __device__ __forceinline__ void flat_col_finalize(double v0, double v1, const Fl
 }
 
 // x = 0; r = b; p = z = Dinv r (Jacobi; with the multilevel preconditioner p is set by the first cycle); rz = r.z; bb = b.b
+// AX != nullptr: warm start from the x the buffer already holds (the potentials of the previous model): r = b - A x
 __global__ void __launch_bounds__(FLAT_T)
 k_pcg_init(const double *__restrict__ B, const double *__restrict__ dinv, double *__restrict__ Xv, double *__restrict__ R,
-           double *__restrict__ P, int N, int nE, int c0, int c1, size_t ld, int cw, const DotOut D) {
+           double *__restrict__ P, const double *__restrict__ AX, int N, int nE, int c0, int c1, size_t ld, int cw, const DotOut D) {
     const FlatMap f = flat_map(c0, c1, cw);
     double s0 = 0.0, s1 = 0.0;
     if (f.active) {
@@ -738,9 +739,11 @@ k_pcg_init(const double *__restrict__ B, const double *__restrict__ dinv, double
         for (int row = lo + f.roff; row < hi; row += f.rpp) {
             const size_t o = (size_t)row * ld + f.col;
             const double b = B[o];
-            const double z = dk[row] * b;
-            Xv[o] = 0.0; R[o] = b; P[o] = z;
-            s0 = fma(b, z, s0); s1 = fma(b, b, s1);
+            double r = b;
+            if (AX) r = b - AX[o]; else Xv[o] = 0.0;
+            const double z = dk[row] * r;
+            R[o] = r; P[o] = z;
+            s0 = fma(r, z, s0); s1 = fma(b, b, s1);
         }
     }
     flat_col_finalize(s0, s1, f, D);

@@ -149,6 +149,7 @@ struct pgb200_ert {
     cudaEvent_t jev[2]; bool jac_timed = false; int jac_launches = 0; long long total_iters = 0; int solves = 0;
     double *h_pinned = nullptr; size_t h_pinned_n = 0;
     int num_sms = 148;
+    int warm_start = 0, warm_used = 0; bool x_warm_ok = false;   // initial guess = previous solution (Gauss-Newton loops)
     pgb200_built_plan *built = nullptr; bool owns_built = false;    // pgb200_ert_open: the plan the handle was built from
     // which code paths the last solve / Jacobian took (pgb200_ert_path_info)
     int pi_panel_nc = 0, pi_tiles = 0, pi_two_k = 0, pi_graph_launches = 0, pi_slots = 0, pi_stream_levels = 0;
@@ -525,7 +526,17 @@ int pcg_solve(pgb200_ert *h) {
     FlatCfg fc = flat_cfg(h->N, c0, c1), fd = flat_cfg(h->N, c0, c1, FLAT_MAX_GX);   // per-iteration vector kernels; fd: those with column dots
     auto regrid = [&]() { fc = flat_cfg(h->N, c0, c1); fd = flat_cfg(h->N, c0, c1, FLAT_MAX_GX); };
     const bool amg = h->use_amg && !h->amg.empty();
-    k_pcg_init<<<fd.grid, FLAT_T, 0, h->st>>>(h->B.p, h->dinv.p, h->X.p, h->R.p, h->P.p, h->N, h->nE, c0, c1, ld, fd.cw,
+    // warm start (opt-in, pgb200_ert_set_warm_start): X still holds the secondary potentials of the previous model on this
+    // shard; a Gauss-Newton step changes the model little, so r0 = b - A x is small compared with b
+    const double *ax = nullptr;
+    if (h->warm_start && h->x_warm_ok) {
+        if (panel_path_ok(h)) { PanelExtra ex{}; CKR(launch_stream<EPI_SPMM>(h, h->stream, h->stream.ent_a.p, h->X.p, h->AP.p, c0, c1, nullptr, ex)); }
+        else CKR((launch_spmm<0, false>(h, h->vals.p, nullptr, nullptr, h->X.p, h->AP.p, c0, c1, nullptr)));
+        ax = h->AP.p;
+        h->warm_used++;
+    }
+    h->x_warm_ok = false;
+    k_pcg_init<<<fd.grid, FLAT_T, 0, h->st>>>(h->B.p, h->dinv.p, h->X.p, h->R.p, h->P.p, ax, h->N, h->nE, c0, c1, ld, fd.cw,
                                               dot_out(h, amg ? nullptr : sc(0), sc(6))); LAUNCH(h);
     if (amg) {
         CKR(amg_vcycle(h, c0, c1, sc(0)));
@@ -594,7 +605,7 @@ int pcg_solve(pgb200_ert *h) {
     // Removes the launch gaps of the ~27 kernels per multilevel iteration (matters most for narrow multi-GPU shards).
     const bool graph_mode = h->use_graph && amg && !h->prof && h->st != 0;
     if (graph_mode) {
-        const int blocks_per_check = std::max(1, h->check_every / 6);
+        const int blocks_per_check = ax ? 1 : std::max(1, h->check_every / 6);      // warm starts can be done after a few iterations
         int blocks = 0;
         while (it < h->max_iter && !converged) {
             GraphKey key{c0, c1, h->tol, h->use_panels, (int)h->amg.size(), h->coarse_sweeps, (void *)h->st, (void *)h->vals.p};
@@ -639,6 +650,7 @@ int pcg_solve(pgb200_ert *h) {
     }
     CK(cudaGetLastError());
     h->last_iters = it; h->total_iters += it; h->solves++;
+    h->x_warm_ok = converged;
     if (!converged) {
         char buf[256];
         snprintf(buf, sizeof buf, "block-PCG did not reach rel. residual %.1e in %d iterations (worst column %.3e)", h->tol, it, h->last_relres);
@@ -1452,6 +1464,8 @@ int pgb200_ert_set_preconditioner(pgb200_ert *h, int multilevel, int coarse_swee
     return 0;
 }
 
+int pgb200_ert_set_warm_start(pgb200_ert *h, int on) { if (!h) PGB_FAIL("null handle"); h->warm_start = on != 0; if (!on) h->x_warm_ok = false; return 0; }
+
 int pgb200_ert_set_stream(pgb200_ert *h, void *stream) {
     if (!h) PGB_FAIL("null handle");
     // NULL / legacy default stream: keep the handle's own blocking stream (implicitly ordered with the legacy stream;
@@ -1471,7 +1485,7 @@ int pgb200_ert_set_shard(pgb200_ert *h, int src_begin, int src_end, int row_begi
     if (!h) PGB_FAIL("null handle");
     if (src_begin < 0 || src_end > h->nS || src_begin > src_end || row_begin < 0 || row_end > h->D || row_begin > row_end) PGB_FAIL("invalid shard");
     CK(cudaSetDevice(h->device));
-    h->c0 = src_begin; h->c1 = src_end; h->pots_valid = false; h->shard_solved = false;
+    h->c0 = src_begin; h->c1 = src_end; h->pots_valid = false; h->shard_solved = false; h->x_warm_ok = false;
     if (row_begin != h->row0 || row_end != h->row1) { h->row0 = row_begin; h->row1 = row_end; CKR(build_jac_plan(h)); CKR(build_jac2_plan(h)); }
     return 0;
 }
@@ -1613,7 +1627,7 @@ int pgb200_ert_set_primary_dev(pgb200_ert *h, const double *src_dev, long long s
     k_gather_rows<<<g, b, 0, h->st>>>(src_dev, (size_t)src_ld, map.p, h->N, h->nS, h->ld, h->prim.p); LAUNCH(h);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->st));
-    h->prim_set = true; h->pots_valid = false; h->shard_solved = false; h->jac_valid = false;
+    h->prim_set = true; h->pots_valid = false; h->shard_solved = false; h->jac_valid = false; h->x_warm_ok = false;
     return 0;
 }
 

@@ -231,6 +231,7 @@ class CoreB200:
         # the default for tolerance studies)
         self._tol, self._maxit, self._check = float(os.environ.get("PGB200_TOL", DEFAULT_PCG_TOL)), 50000, 25
         self._stream = None
+        self._warm = False
         self._shard = None
         self._prim_pm = None
         self._placeholder_k = False
@@ -272,6 +273,12 @@ class CoreB200:
         self._tol, self._maxit, self._check = float(rel_tol), int(max_iter), int(check_every)
         if self._h:
             _capi.check(_capi.lib().pgb200_ert_set_solver(self._h, self._tol, self._maxit, self._check))
+
+    def setWarmStart(self, on=True):
+        """start every block-PCG solve from the potentials of the previous one (Gauss-Newton / time-lapse loops)"""
+        self._warm = bool(on)
+        if self._h:
+            _capi.check(_capi.lib().pgb200_ert_set_warm_start(self._h, 1 if self._warm else 0))
 
     def setStream(self, stream_ptr):
         """CUDA stream handle (int, e.g. torch.cuda.current_stream().cuda_stream)"""
@@ -423,6 +430,8 @@ class CoreB200:
                 _capi.check(_capi.lib().pgb200_ert_set_stream(h, C.c_void_p(self._stream)))
             if self._shard:
                 _capi.check(_capi.lib().pgb200_ert_set_shard(h, *self._shard))
+            if self._warm:
+                _capi.check(_capi.lib().pgb200_ert_set_warm_start(h, 1))
             if native:
                 pass
             elif self.preconditioner == "multilevel":

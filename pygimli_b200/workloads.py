@@ -74,10 +74,10 @@ def c4_3d_crosshole(scale: float = 1.0):
     # snap the borehole positions to the grid so that electrodes sit on nodes
     bx = np.round(R * np.cos(ang) / h) * h
     by = np.round(R * np.sin(ang) / h) * h
-    lo, hi = -R - 4.0, R + 4.0
+    lo, hi = -R - 6.0, R + 6.0                       # fine region sized for ~4M tetrahedra (BASELINE.json configs[3])
     xs = graded_axis(lo, hi, h, 1.5, 300.0)
-    zs = -graded_axis(0.0, 30.0, h, 1.5, 300.0, both=False)
-    mesh = grid_mesh_3d(xs, xs, zs, para_box=(lo, hi, lo, hi, -30.0), marker_per="cube")
+    zs = -graded_axis(0.0, 33.0, h, 1.5, 300.0, both=False)
+    mesh = grid_mesh_3d(xs, xs, zs, para_box=(lo, hi, lo, hi, -33.0), marker_per="cube")
     sens = np.array([[bx[b], by[b], -2.0 - i] for b in range(nb) for i in range(ne_b)])
     ids = mark_electrode_nodes(mesh, sens)
     assert np.all(ids >= 0), "crosshole electrodes must coincide with grid nodes"
