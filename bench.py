@@ -321,7 +321,7 @@ def run_b200(args):
     barrier()
     stp = fop.core.stats()
     fop.core.setProfile(False)
-    for key in ("spmm_timed", "spmm_ms_total", "jacobian_kernel_ms", "jacobian_timed"):
+    for key in ("spmm_timed", "spmm_ms_total", "spmm_bytes_total", "jacobian_kernel_ms", "jacobian_timed"):
         st[key] = stp[key]
 
     # end-to-end through the host-buffer API
@@ -365,7 +365,9 @@ def run_b200(args):
         # dominant kernel: the SpMM inside block-PCG.  Algorithmic bytes per launch:
         # 12 nnz + 4 (N+1) + 16 N s  (values + column indices + row pointers; X read once, Y written once)
         ncols = fop.n_local_sources
-        spmm_bytes = 12.0 * P.nnz * (P.nK if ncols >= P.nS else max(1, ncols // P.nE)) + 4.0 * (P.N + 1) + 16.0 * P.N * ncols
+        # per launch, summed by the library with the ACTIVE column window of each timed launch (2.5-D windows shrink as
+        # wavenumber groups converge), divided by the launches: average algorithmic bytes of a timed launch
+        spmm_bytes = st["spmm_bytes_total"] / max(1.0, st["spmm_timed"])
         spmm_ms = st["spmm_ms_total"] / max(1.0, st["spmm_timed"])
         ach = spmm_bytes / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0
         d_local = fop.rows[1] - fop.rows[0]

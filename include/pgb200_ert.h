@@ -283,7 +283,8 @@ long long pgb200_ert_get(pgb200_ert *h, const char *what, double *out_host, long
 /* stats[0]=PCG iterations of the last solve, [1]=max relative residual, [2]=kernel launches
  * since create/reset, [3..8] = accumulated ms since reset: map, assemble, rhs, solve, epilogue,
  * jacobian, [9]=SpMM launches timed, [10]=their total ms, [11]=Jacobian kernel ms (total),
- * [12]=Jacobian passes timed, [13]=PCG iterations since reset, [14]=solves since reset       */
+ * [12]=Jacobian passes timed, [13]=PCG iterations since reset, [14]=solves since reset, [15]=algorithmic bytes of
+ * the timed SpMM launches (each with its own active column window), [16]=warm-started solves since reset   */
 int pgb200_ert_stats(pgb200_ert *h, double *stats, int n);
 int pgb200_ert_reset_stats(pgb200_ert *h);
 /* which code paths the last solve / Jacobian plan took (parity tests assert that the kernels the benchmark times are

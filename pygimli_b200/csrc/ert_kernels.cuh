@@ -1106,6 +1106,153 @@ k_amg_prolong(const double *__restrict__ dinvw, int n, const int *__restrict__ a
     }
 }
 
+// ---------------------------------------------------------------------------------
+// Small levels of the multilevel cycle, fused: ONE launch runs the whole sub-cycle of the levels below STREAM_MIN_ROWS
+// (restrict ... coarsest sweeps ... prolongate + post-smooth) for a slice of CPC source columns per CTA.
+//   The source columns are independent, so a CTA that owns a column slice needs no grid-wide synchronisation: every
+//   vector of every small level (R, X, Z of its columns) lives in shared memory for the whole sub-cycle, the level
+//   matrices stream from L2 (coalesced: half a warp per matrix row, lanes = consecutive CSR entries, shuffle reduction).
+//   Replaces ~20 latency-bound launches per PCG iteration (8-16 us each on levels of a few thousand rows and fewer).
+// ---------------------------------------------------------------------------------
+constexpr int SUB_MAX_LEVELS = 8;
+constexpr int SUB_THREADS = 512;
+struct SubLevel {
+    const int *rowptr, *colidx, *mem_ptr, *mem_idx, *agg;      // mem/agg: transfer to the NEXT (coarser) sub-level
+    const double *vals, *vals_dw, *dinvw;                       // [nK][nnz], [nK][nnz], [nK][n]
+    int n; size_t nnz;
+    int off;                                                    // offset (in rows) of this level inside a column's shared vectors
+};
+struct SubArgs {
+    SubLevel lv[SUB_MAX_LEVELS]; int nl;                        // nl sub-levels, the last one is the coarsest
+    int rows_total;                                             // sum of n over the sub-levels
+    const double *Rin; double *Zout; size_t ld;                 // residual of the first sub-level in, its correction out
+    int nE, c0, c1, sweeps;
+};
+
+template <int CPC>
+__device__ __forceinline__ void sub_half_reduce(double (&v)[CPC]) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+        for (int c = 0; c < CPC; c++) v[c] += __shfl_xor_sync(0xffffffffu, v[c], o);
+}
+
+template <int CPC>
+__global__ void __launch_bounds__(SUB_THREADS)
+k_amg_subcycle(const SubArgs A) {
+    extern __shared__ __align__(16) double sub_sm[];
+    // column slice of this CTA: slices never straddle a wavenumber group
+    const int spk = (A.nE + CPC - 1) / CPC;                      // slices per wavenumber group
+    const int kk = blockIdx.x / spk, cs = kk * A.nE + (blockIdx.x - kk * spk) * CPC;
+    const int ce = min(cs + CPC, (kk + 1) * A.nE);
+    const int v0 = max(cs, A.c0), v1 = min(ce, A.c1);
+    if (v1 <= v0) return;
+    const int RT = A.rows_total;
+    double *sR = sub_sm, *sX = sub_sm + (size_t)CPC * RT, *sZ = sub_sm + 2 * (size_t)CPC * RT;     // [CPC][rows_total] each
+    const int tid = threadIdx.x, half = tid >> 4, hl = tid & 15, nhalf = SUB_THREADS / 16;
+    // 1. residual of the first sub-level
+    for (int x = tid; x < A.lv[0].n * CPC; x += SUB_THREADS) {
+        const int row = x / CPC, c = x - row * CPC;
+        sR[(size_t)c * RT + row] = (cs + c >= v0 && cs + c < v1) ? A.Rin[(size_t)row * A.ld + cs + c] : 0.0;
+    }
+    __syncthreads();
+    // 2. downward: residual after one damped-Jacobi sweep from zero, restricted (k_amg_restrict)
+    for (int l = 0; l + 1 < A.nl; l++) {
+        const SubLevel &L = A.lv[l], &Lc = A.lv[l + 1];
+        const double *vdw = L.vals_dw + (size_t)kk * L.nnz;
+        for (int base = 0; base < Lc.n; base += nhalf) {           // uniform trip count: the half-warp reductions need whole warps
+            const int I = base + half;
+            const bool act = I < Lc.n;
+            double acc[CPC];
+#pragma unroll
+            for (int c = 0; c < CPC; c++) acc[c] = 0.0;
+            for (int q = act ? L.mem_ptr[I] : 0, qe = act ? L.mem_ptr[I + 1] : 0; q < qe; q++) {
+                const int i = L.mem_idx[q];
+                if (hl == 0) {
+#pragma unroll
+                    for (int c = 0; c < CPC; c++) acc[c] += sR[(size_t)c * RT + L.off + i];
+                }
+                for (int p = L.rowptr[i] + hl; p < L.rowptr[i + 1]; p += 16) {
+                    const double a = vdw[p]; const int j = L.colidx[p];
+#pragma unroll
+                    for (int c = 0; c < CPC; c++) acc[c] = fma(-a, sR[(size_t)c * RT + L.off + j], acc[c]);
+                }
+            }
+            sub_half_reduce<CPC>(acc);
+            if (act && hl == 0) {
+#pragma unroll
+                for (int c = 0; c < CPC; c++) sR[(size_t)c * RT + Lc.off + I] = acc[c];
+            }
+        }
+        __syncthreads();
+    }
+    // 3. coarsest level: x = dw r, then sweeps - 1 damped-Jacobi sweeps
+    {
+        const SubLevel &L = A.lv[A.nl - 1];
+        const double *dw = L.dinvw + (size_t)kk * L.n, *va = L.vals + (size_t)kk * L.nnz;
+        for (int x = tid; x < L.n * CPC; x += SUB_THREADS) { const int row = x % L.n, c = x / L.n; sX[(size_t)c * RT + L.off + row] = dw[row] * sR[(size_t)c * RT + L.off + row]; }
+        __syncthreads();
+        double *a = sX, *b = sZ;
+        const int sw = A.sweeps;
+        for (int s = 0; s + 1 < sw; s++) {
+            for (int base = 0; base < L.n; base += nhalf) {
+                const int row = base + half;
+                const bool act = row < L.n;
+                double acc[CPC];
+#pragma unroll
+                for (int c = 0; c < CPC; c++) acc[c] = 0.0;
+                for (int p = act ? L.rowptr[row] + hl : 0, pe = act ? L.rowptr[row + 1] : 0; p < pe; p += 16) {
+                    const double e = va[p]; const int j = L.colidx[p];
+#pragma unroll
+                    for (int c = 0; c < CPC; c++) acc[c] = fma(e, a[(size_t)c * RT + L.off + j], acc[c]);
+                }
+                sub_half_reduce<CPC>(acc);
+                if (act && hl == 0) {
+#pragma unroll
+                    for (int c = 0; c < CPC; c++) { const size_t o = (size_t)c * RT + L.off + row; b[o] = fma(dw[row], sR[o] - acc[c], a[o]); }
+                }
+            }
+            __syncthreads();
+            double *t = a; a = b; b = t;
+        }
+        // the coarsest result must sit in sZ for the upward pass (E of the next finer level)
+        if (a != sZ) { for (int x = tid; x < L.n * CPC; x += SUB_THREADS) { const int row = x % L.n, c = x / L.n; sZ[(size_t)c * RT + L.off + row] = a[(size_t)c * RT + L.off + row]; } __syncthreads(); }
+    }
+    // 4. upward: x = dw r + E[agg];  z = x + dw (r - A x)
+    for (int l = A.nl - 2; l >= 0; l--) {
+        const SubLevel &L = A.lv[l], &Lc = A.lv[l + 1];
+        const double *dw = L.dinvw + (size_t)kk * L.n, *va = L.vals + (size_t)kk * L.nnz;
+        for (int x = tid; x < L.n * CPC; x += SUB_THREADS) {
+            const int row = x % L.n, c = x / L.n;
+            sX[(size_t)c * RT + L.off + row] = fma(dw[row], sR[(size_t)c * RT + L.off + row], sZ[(size_t)c * RT + Lc.off + L.agg[row]]);
+        }
+        __syncthreads();
+        for (int base = 0; base < L.n; base += nhalf) {
+            const int row = base + half;
+            const bool act = row < L.n;
+            double acc[CPC];
+#pragma unroll
+            for (int c = 0; c < CPC; c++) acc[c] = 0.0;
+            for (int p = act ? L.rowptr[row] + hl : 0, pe = act ? L.rowptr[row + 1] : 0; p < pe; p += 16) {
+                const double e = va[p]; const int j = L.colidx[p];
+#pragma unroll
+                for (int c = 0; c < CPC; c++) acc[c] = fma(e, sX[(size_t)c * RT + L.off + j], acc[c]);
+            }
+            sub_half_reduce<CPC>(acc);
+            if (act && hl == 0) {
+#pragma unroll
+                for (int c = 0; c < CPC; c++) { const size_t o = (size_t)c * RT + L.off + row; sZ[o] = fma(dw[row], sR[o] - acc[c], sX[o]); }
+            }
+        }
+        __syncthreads();
+    }
+    // 5. correction of the first sub-level back to HBM
+    for (int x = tid; x < A.lv[0].n * CPC; x += SUB_THREADS) {
+        const int row = x / CPC, c = x - row * CPC;
+        if (cs + c >= v0 && cs + c < v1) A.Zout[(size_t)row * A.ld + cs + c] = sZ[(size_t)c * RT + row];
+    }
+}
+
 // numeric primary potentials: prim[i][c] = SRC[map[i]][c]  (rows of the P2 primary solve at this mesh's nodes)
 __global__ void k_gather_rows(const double *__restrict__ SRC, size_t ld_src, const int *__restrict__ map, int n, int ncols,
                               size_t ld, double *__restrict__ OUT) {

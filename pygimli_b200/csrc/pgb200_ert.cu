@@ -145,10 +145,11 @@ struct pgb200_ert {
     bool ph_rec[PH_COUNT + 1] = {false};
     std::vector<cudaEvent_t> tev; std::vector<int> tline; int n_tev = 0; int trace = 0; int cur_tag = 0;   // tag: multilevel level of the launch
     int cur_role = 0;   // trace only: epilogue role of a streamed SpMM launch (1 SpMM, 2 post-smoothing, 3 residual)
-    int prof = 0; std::vector<cudaEvent_t> pev; int n_pev = 0; double spmm_ms = 0.0; int spmm_timed = 0; double jac_ms = 0.0;
+    int prof = 0; std::vector<cudaEvent_t> pev; int n_pev = 0; double spmm_ms = 0.0, spmm_bytes = 0.0; int spmm_timed = 0; double jac_ms = 0.0;
     cudaEvent_t jev[2]; bool jac_timed = false; int jac_launches = 0; long long total_iters = 0; int solves = 0;
     double *h_pinned = nullptr; size_t h_pinned_n = 0;
     int num_sms = 148;
+    int use_subcycle = 1; size_t sub_smem[5] = {0, 0, 0, 0, 0};      // fused small multigrid levels (k_amg_subcycle)
     int warm_start = 0, warm_used = 0; bool x_warm_ok = false;   // initial guess = previous solution (Gauss-Newton loops)
     pgb200_built_plan *built = nullptr; bool owns_built = false;    // pgb200_ert_open: the plan the handle was built from
     // which code paths the last solve / Jacobian took (pgb200_ert_path_info)
@@ -451,17 +452,56 @@ int amg_setup_values(pgb200_ert *h) {
     return 0;
 }
 
+// fused sub-cycle over the levels lv[g0..nl] (ert_kernels.cuh k_amg_subcycle); returns false if it does not apply
+struct LvRef { const int *rowptr, *colidx; const double *vals, *vals_dw; size_t nnz; const double *dinvw; int n; const double *R; double *X, *Z; const StreamDev *st; };
+int amg_subcycle(pgb200_ert *h, const std::vector<LvRef> &lv, int g0, int c0, int c1, bool &done) {
+    done = false;
+    const int nl = (int)lv.size() - 1, nsub = nl - g0 + 1;
+    if (!h->use_subcycle || g0 < 1 || nsub < 1 || nsub > SUB_MAX_LEVELS || c1 <= c0) return 0;
+    SubArgs A{};
+    A.nl = nsub; A.sweeps = h->coarse_sweeps; A.ld = h->ld; A.nE = h->nE; A.c0 = c0; A.c1 = c1;
+    int off = 0;
+    for (int s2 = 0; s2 < nsub; s2++) {
+        const LvRef &L = lv[g0 + s2];
+        SubLevel &S = A.lv[s2];
+        S.rowptr = L.rowptr; S.colidx = L.colidx; S.vals = L.vals; S.vals_dw = L.vals_dw; S.dinvw = L.dinvw; S.n = L.n; S.nnz = L.nnz; S.off = off;
+        if (s2 + 1 < nsub) { AmgLevel *T = h->amg[g0 + s2]; S.mem_ptr = T->mem_ptr.p; S.mem_idx = T->mem_idx.p; S.agg = T->agg.p; }
+        off += L.n;
+    }
+    A.rows_total = off;
+    A.Rin = lv[g0].R; A.Zout = lv[g0].Z;
+    const int ncols = c1 - c0;
+    int cpc = ncols <= 160 ? 1 : (ncols <= 320 ? 2 : 4);
+    while (cpc > 1 && 3 * (size_t)cpc * off * 8 > h->smem_optin) cpc >>= 1;
+    const size_t smem = 3 * (size_t)cpc * off * 8;
+    if (smem > h->smem_optin) return 0;
+    const int spk = cdiv(h->nE, cpc), k_lo = c0 / h->nE, k_hi = (c1 - 1) / h->nE;
+    (void)k_lo;
+    const int grid = (k_hi + 1) * spk;                 // CTAs of wavenumber groups below the window exit at once
+#define SUBGO(C) do { if (smem > h->sub_smem[C]) { CK(cudaFuncSetAttribute(k_amg_subcycle<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); h->sub_smem[C] = smem; } \
+                      k_amg_subcycle<C><<<grid, SUB_THREADS, smem, h->st>>>(A); } while (0)
+    if (cpc == 1) SUBGO(1); else if (cpc == 2) SUBGO(2); else SUBGO(4);
+#undef SUBGO
+    LAUNCH(h);
+    done = true;
+    return 0;
+}
+
 // one V(1,1) cycle: Z0 = M^-1 R (level 0 residual = h->R); dots != nullptr: dots[c] = R.Z per column (deterministic on the
 // streamed path)
 int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
     const int nl = (int)h->amg.size();
-    struct Lv { const int *rowptr, *colidx; const double *vals, *vals_dw; size_t nnz; const double *dinvw; int n; const double *R; double *X, *Z; const StreamDev *st; };
+    typedef LvRef Lv;
     std::vector<Lv> lv(nl + 1);
     lv[0] = {h->rowptr.p, h->colidx.p, h->vals.p, h->vals_dw0.p, h->nnz, h->dinvw0.p, h->N, h->R.p, h->X0.p, h->Z0.p, &h->stream};
     for (int l = 0; l < nl; l++) { AmgLevel *L = h->amg[l]; lv[l + 1] = {L->rowptr.p, L->colidx.p, L->vals.p, L->vals_dw.p, L->nnz, L->dinvw.p, L->n, L->R.p, L->X.p, L->Z.p, &L->stream}; }
     auto streamed = [&](int l) { return h->use_panels && lv[l].st->ok; };
+    // the levels below STREAM_MIN_ROWS run as ONE fused launch (g0 = first of them); everything above goes level by level
+    int g0 = nl + 1;
+    if (nl > 0 && h->use_panels) { g0 = 1; while (g0 <= nl && lv[g0].st->ok) g0++; }
+    const int down_to = std::min(nl, g0);
     // downward: residual after one damped-Jacobi sweep from zero, restricted
-    for (int l = 0; l < nl; l++) {
+    for (int l = 0; l < down_to; l++) {
         h->cur_tag = l;
         if (streamed(l)) {
             // residual through the streamed kernel (into X of this level, free until the prolongation), then a
@@ -476,8 +516,15 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
         }
     }
     // coarsest level: fixed number of Jacobi sweeps
-    const double *E;
-    {
+    const double *E = nullptr;
+    bool fused = false;
+    if (g0 <= nl) { h->cur_tag = g0; CKR(amg_subcycle(h, lv, g0, c0, c1, fused)); }
+    if (fused) E = lv[g0].Z;
+    else {
+        for (int l = down_to; l < nl; l++) {
+            h->cur_tag = l;
+            CKR(amg_restrict(h, lv[l].rowptr, lv[l].colidx, lv[l].vals_dw, lv[l].nnz, lv[l].n, h->amg[l], lv[l].R, c0, c1));
+        }
         Lv &c = lv[nl];
         h->cur_tag = nl;
         const FlatCfg fc = flat_cfg(c.n, c0, c1);
@@ -492,7 +539,7 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
         E = a;
     }
     // upward: prolongate, post-smooth
-    for (int l = nl - 1; l >= 0; l--) {
+    for (int l = (fused ? g0 : nl) - 1; l >= 0; l--) {
         Lv &f = lv[l];
         h->cur_tag = l;
         const FlatCfg fc = flat_cfg(f.n, c0, c1);
@@ -558,7 +605,13 @@ int pcg_solve(pgb200_ert *h) {
             CK(cudaMemsetAsync(sc(3) + c0, 0, sizeof(double) * (c1 - c0), h->st));
             CKR((launch_spmm<0, true>(h, h->vals.p, nullptr, nullptr, h->P.p, h->AP.p, c0, c1, sc(3))));
         }
-        if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
+        if (timed) {
+            CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
+            // algorithmic bytes of THIS launch: the CSR of the wavenumber groups inside the active window, X read
+            // and Y written once for the window's columns
+            const int nkw = (c1 - 1) / h->nE - c0 / h->nE + 1;
+            h->spmm_bytes += 12.0 * (double)h->nnz * nkw + 4.0 * (h->N + 1) + 16.0 * (double)h->N * (c1 - c0);
+        }
         if (amg) {
             k_pcg_update_xr<false><<<fd.grid, FLAT_T, 0, h->st>>>(h->P.p, h->AP.p, nullptr, h->X.p, h->R.p, h->N, h->nE, c0, c1, ld,
                                                                  sc(rz_old), sc(3), fd.cw, dot_out(h, nullptr, sc(rr_cur))); LAUNCH(h);
@@ -1812,10 +1865,10 @@ long long pgb200_ert_get(pgb200_ert *h, const char *what, double *out, long long
 
 int pgb200_ert_stats(pgb200_ert *h, double *s, int n) {
     if (!h || !s) PGB_FAIL("null argument");
-    double v[15] = {(double)h->last_iters, h->last_relres, (double)h->launches, h->ph_ms[PH_MAP], h->ph_ms[PH_ASM], h->ph_ms[PH_RHS],
+    double v[17] = {(double)h->last_iters, h->last_relres, (double)h->launches, h->ph_ms[PH_MAP], h->ph_ms[PH_ASM], h->ph_ms[PH_RHS],
                     h->ph_ms[PH_SOLVE], h->ph_ms[PH_EPI], h->ph_ms[PH_JAC], (double)h->spmm_timed, h->spmm_ms, h->jac_ms,
-                    (double)h->jac_launches, (double)h->total_iters, (double)h->solves};
-    for (int i = 0; i < n && i < 15; i++) s[i] = v[i];
+                    (double)h->jac_launches, (double)h->total_iters, (double)h->solves, h->spmm_bytes, (double)h->warm_used};
+    for (int i = 0; i < n && i < 17; i++) s[i] = v[i];
     return 0;
 }
 int pgb200_ert_path_info(pgb200_ert *h, int *out, int n) {
@@ -1832,7 +1885,7 @@ int pgb200_ert_path_info(pgb200_ert *h, int *out, int n) {
 }
 int pgb200_ert_reset_stats(pgb200_ert *h) {
     if (!h) PGB_FAIL("null handle");
-    h->launches = 0; h->spmm_ms = 0.0; h->spmm_timed = 0; h->jac_ms = 0.0; h->n_pev = 0; h->jac_launches = 0; h->total_iters = 0; h->solves = 0;
+    h->launches = 0; h->spmm_ms = 0.0; h->spmm_bytes = 0.0; h->warm_used = 0; h->spmm_timed = 0; h->jac_ms = 0.0; h->n_pev = 0; h->jac_launches = 0; h->total_iters = 0; h->solves = 0;
     for (int p = 0; p < PH_COUNT; p++) h->ph_ms[p] = 0.f;
     return 0;
 }

@@ -541,11 +541,11 @@ class CoreB200:
         return out
 
     def stats(self) -> dict:
-        s = np.zeros(15)
-        _capi.check(_capi.lib().pgb200_ert_stats(self._ensure_handle(), s.ctypes.data, 15))
+        s = np.zeros(17)
+        _capi.check(_capi.lib().pgb200_ert_stats(self._ensure_handle(), s.ctypes.data, 17))
         keys = ["pcg_iterations", "max_rel_residual", "launches", "ms_map", "ms_assemble", "ms_rhs", "ms_solve",
                 "ms_epilogue", "ms_jacobian", "spmm_timed", "spmm_ms_total", "jacobian_kernel_ms", "jacobian_timed",
-                "pcg_iterations_total", "solves"]
+                "pcg_iterations_total", "solves", "spmm_bytes_total", "warm_started_solves"]
         return dict(zip(keys, s.tolist()))
 
     def pathInfo(self) -> dict:
