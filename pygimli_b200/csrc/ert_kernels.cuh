@@ -1127,6 +1127,7 @@ struct SubArgs {
     int rows_total;                                             // sum of n over the sub-levels
     const double *Rin; double *Zout; size_t ld;                 // residual of the first sub-level in, its correction out
     int nE, c0, c1, sweeps;
+    int cache_last;                                             // stage the coarsest level's matrix in shared memory (it is applied `sweeps` times)
 };
 
 template <int CPC>
@@ -1190,6 +1191,16 @@ k_amg_subcycle(const SubArgs A) {
     {
         const SubLevel &L = A.lv[A.nl - 1];
         const double *dw = L.dinvw + (size_t)kk * L.n, *va = L.vals + (size_t)kk * L.nnz;
+        const int *rp = L.rowptr, *cj = L.colidx;
+        if (A.cache_last) {
+            // the matrix of the coarsest level is applied sweeps - 1 times: from shared memory the dependent
+            // index -> value -> x chain costs tens of cycles instead of L2 round trips
+            double *cv = sub_sm + 3 * (size_t)CPC * RT;
+            int *cc = reinterpret_cast<int *>(cv + L.nnz), *cr = cc + L.nnz;
+            for (size_t x = tid; x < L.nnz; x += SUB_THREADS) { cv[x] = va[x]; cc[x] = L.colidx[x]; }
+            for (int x = tid; x <= L.n; x += SUB_THREADS) cr[x] = L.rowptr[x];
+            va = cv; cj = cc; rp = cr;
+        }
         for (int x = tid; x < L.n * CPC; x += SUB_THREADS) { const int row = x % L.n, c = x / L.n; sX[(size_t)c * RT + L.off + row] = dw[row] * sR[(size_t)c * RT + L.off + row]; }
         __syncthreads();
         double *a = sX, *b = sZ;
@@ -1201,8 +1212,8 @@ k_amg_subcycle(const SubArgs A) {
                 double acc[CPC];
 #pragma unroll
                 for (int c = 0; c < CPC; c++) acc[c] = 0.0;
-                for (int p = act ? L.rowptr[row] + hl : 0, pe = act ? L.rowptr[row + 1] : 0; p < pe; p += 16) {
-                    const double e = va[p]; const int j = L.colidx[p];
+                for (int p = act ? rp[row] + hl : 0, pe = act ? rp[row + 1] : 0; p < pe; p += 16) {
+                    const double e = va[p]; const int j = cj[p];
 #pragma unroll
                     for (int c = 0; c < CPC; c++) acc[c] = fma(e, a[(size_t)c * RT + L.off + j], acc[c]);
                 }

@@ -149,7 +149,8 @@ struct pgb200_ert {
     cudaEvent_t jev[2]; bool jac_timed = false; int jac_launches = 0; long long total_iters = 0; int solves = 0;
     double *h_pinned = nullptr; size_t h_pinned_n = 0;
     int num_sms = 148;
-    int use_subcycle = 1; size_t sub_smem[5] = {0, 0, 0, 0, 0};      // fused small multigrid levels (k_amg_subcycle)
+    int use_subcycle = 1;      // 1: coarsest level fused (default), 2: all levels below STREAM_MIN_ROWS, 0: off
+    size_t sub_smem[5] = {0, 0, 0, 0, 0};      // fused small multigrid levels (k_amg_subcycle)
     int warm_start = 0, warm_used = 0; bool x_warm_ok = false;   // initial guess = previous solution (Gauss-Newton loops)
     pgb200_built_plan *built = nullptr; bool owns_built = false;    // pgb200_ert_open: the plan the handle was built from
     // which code paths the last solve / Jacobian took (pgb200_ert_path_info)
@@ -473,8 +474,12 @@ int amg_subcycle(pgb200_ert *h, const std::vector<LvRef> &lv, int g0, int c0, in
     const int ncols = c1 - c0;
     int cpc = ncols <= 160 ? 1 : (ncols <= 320 ? 2 : 4);
     while (cpc > 1 && 3 * (size_t)cpc * off * 8 > h->smem_optin) cpc >>= 1;
-    const size_t smem = 3 * (size_t)cpc * off * 8;
+    size_t smem = 3 * (size_t)cpc * off * 8;
     if (smem > h->smem_optin) return 0;
+    const LvRef &last = lv[nl];
+    const size_t cache = last.nnz * 12 + ((size_t)last.n + 1) * 4 + 16;
+    A.cache_last = (smem + cache <= h->smem_optin) ? 1 : 0;
+    if (A.cache_last) smem += cache;
     const int spk = cdiv(h->nE, cpc), k_lo = c0 / h->nE, k_hi = (c1 - 1) / h->nE;
     (void)k_lo;
     const int grid = (k_hi + 1) * spk;                 // CTAs of wavenumber groups below the window exit at once
@@ -497,12 +502,20 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
     for (int l = 0; l < nl; l++) { AmgLevel *L = h->amg[l]; lv[l + 1] = {L->rowptr.p, L->colidx.p, L->vals.p, L->vals_dw.p, L->nnz, L->dinvw.p, L->n, L->R.p, L->X.p, L->Z.p, &L->stream}; }
     auto streamed = [&](int l) { return h->use_panels && lv[l].st->ok; };
     // the levels below STREAM_MIN_ROWS run as ONE fused launch (g0 = first of them); everything above goes level by level
+    // (measured on the 1M-tet case: fusing all levels below 6000 rows into one launch is SLOWER than one launch per
+    //  operator application -- 214 us against 140 us: with one CTA per column slice the dependent index -> value -> x
+    //  chains of the few-thousand-row levels are L2-latency-bound, while the per-level kernels spread every level over
+    //  all SMs.  The coarsest level alone, with its matrix staged in shared memory, is where fusion pays: 7 launches -> 1)
     int g0 = nl + 1;
-    if (nl > 0 && h->use_panels) { g0 = 1; while (g0 <= nl && lv[g0].st->ok) g0++; }
+    if (nl > 0 && h->use_panels) {
+        if (h->use_subcycle == 2) { g0 = 1; while (g0 <= nl && lv[g0].st->ok) g0++; }
+        else if (h->use_subcycle == 1) g0 = std::max(1, nl);
+    }
     const int down_to = std::min(nl, g0);
     // downward: residual after one damped-Jacobi sweep from zero, restricted
     for (int l = 0; l < down_to; l++) {
         h->cur_tag = l;
+        if (!streamed(l)) { CKR(amg_restrict(h, lv[l].rowptr, lv[l].colidx, lv[l].vals_dw, lv[l].nnz, lv[l].n, h->amg[l], lv[l].R, c0, c1)); continue; }
         if (streamed(l)) {
             // residual through the streamed kernel (into X of this level, free until the prolongation), then a
             // deterministic member sum
@@ -1366,6 +1379,7 @@ int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
     CKR(h->pro_w.upload(p->pro_w, npro * p->pro_nf, st));
     // streamed row panels of the fine matrix (internal layout, built here from the pattern), their kernels' shared-memory
     // opt-in, and the partial rows / tickets of the deterministic column dots
+    if (const char *e = getenv("PGB200_SUBCYCLE")) h->use_subcycle = atoi(e);
     if (const char *e = getenv("PGB200_STREAM_HC")) h->stream_hc = std::max(h->stream_rmax, atoi(e));
     if (const char *e = getenv("PGB200_STREAM_CHUNKS")) h->stream_chunks = std::max(1, atoi(e));
     if (const char *e = getenv("PGB200_STREAM_ROWS")) h->stream_rmax = std::min(ST_CONSUMER_WARPS * ST_RPW, std::max(1, atoi(e)));
