@@ -240,6 +240,10 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL's version banner, the reference C++) write to stdout: keep fd 1 on stderr until the one JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -428,7 +432,10 @@ def run_b200(args):
                     line["cpu_baseline"] = {"value": None, "unit": "s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
             except Exception as exc:  # the baseline must never take the bench line down
                 line["cpu_baseline"] = {"value": None, "unit": "s", "cores": 0, "kind": "reference", "sample": f"failed: {exc}"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

@@ -355,6 +355,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -412,6 +415,7 @@ struct StreamArgs {
     int nE, c0, c1;                               // active column window [c0, c1)
     int k_lo, tpk, pw, n_tiles, cpt;              // tile geometry: first wavenumber, tiles per wavenumber, tile width, tiles, CTAs per tile
     int slots; uint32_t slot_bytes, x_bytes, ent_bytes;    // slot = [X rows | entries | row ranges]
+    int fullrows;                                 // every tile spans whole rows of X (one wavenumber, whole window): run-merged bulk copies
     double *dot_part; unsigned *dot_counter; double *dots;  // deterministic dots (DOT kernels)
     PanelExtra ex;
 };
@@ -439,7 +443,8 @@ k_spmm_stream(const StreamArgs A) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = A.slots;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], ST_CONSUMER_WARPS); }
+        // full: one arrival from the producer's expect_tx (+ one per producer lane when the X rows come by cp.async)
+        for (int s = 0; s < S; s++) { mbar_init(&full[s], A.fullrows ? 1 : 33); mbar_init(&empty[s], ST_CONSUMER_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -457,7 +462,7 @@ k_spmm_stream(const StreamArgs A) {
             int kk, cs, wc, v0, v1;
             if (!stream_tile(A, t, kk, cs, wc, v0, v1)) continue;
             const uint32_t rowb = (uint32_t)wc * 8u;
-            const bool fullrows = (cs == 0 && wc == (int)A.ld);
+            const bool fullrows = A.fullrows != 0;
             const PanelEntry *entk = A.ent + (size_t)kk * A.nnz;
             for (int p = j; p < L.n_panels; p += pstep) {
                 const int ch0 = L.panel_chunk_ptr[p], ch1 = L.panel_chunk_ptr[p + 1];
@@ -485,15 +490,35 @@ k_spmm_stream(const StreamArgs A) {
                     }
                     if (use > 0) mbar_wait(&empty[slot], (use & 1u) ^ 1u);
                     if (lane == 0) {
-                        mbar_expect_tx(&full[slot], (uint32_t)hn * rowb + (uint32_t)ne * 16u + (uint32_t)L.crp_stride * 4u);
+                        mbar_expect_tx(&full[slot], (fullrows ? (uint32_t)hn * rowb : 0u) + (uint32_t)ne * 16u + (uint32_t)L.crp_stride * 4u);
                         if (ne > 0) tma_bulk_g2s(sb + A.x_bytes, entk + e0, (uint32_t)ne * 16u, &full[slot]);
                         tma_bulk_g2s(sb + A.x_bytes + A.ent_bytes, L.crp + (size_t)ch * L.crp_stride, (uint32_t)L.crp_stride * 4u, &full[slot]);
                     }
                     __syncwarp();
+                    if (fullrows) {
 #pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (u < ncopy)
-                            tma_bulk_g2s(sb + (size_t)dst_row[u] * rowb, A.X + (size_t)src_row[u] * A.ld + cs, (uint32_t)len[u] * rowb, &full[slot]);
+                        for (int u = 0; u < 4; u++)
+                            if (u < ncopy)
+                                tma_bulk_g2s(sb + (size_t)dst_row[u] * rowb, A.X + (size_t)src_row[u] * A.ld + cs, (uint32_t)len[u] * rowb, &full[slot]);
+                    } else {
+                        // partial-width tiles (2.5-D wavenumber groups, multi-GPU column shards): the rows are short and
+                        // strided, a bulk copy per row would be bound by the copy engine's per-request cost.  One
+                        // 16-byte cp.async (LDGSTS) per lane moves a whole row per warp instruction; completion is
+                        // tracked by the same mbarrier (cp.async.mbarrier.arrive.noinc, one arrival per lane).
+                        const bool l0 = 16u * lane < rowb, l1 = NCP == 2 && 512u + 16u * lane < rowb;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int nrow = min(32, hn - 32 * u);
+                            for (int jj = 0; jj < nrow; jj++) {
+                                const int src = __shfl_sync(0xffffffffu, src_row[u], jj);
+                                const double *g = A.X + (size_t)src * A.ld + cs + 2 * lane;
+                                unsigned char *d = sb + (size_t)(32 * u + jj) * rowb + 16 * lane;
+                                if (l0) cp_async16(d, g);
+                                if (l1) cp_async16(d + 512, g + 64);
+                            }
+                        }
+                        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[slot])) : "memory");
+                    }
                 }
             }
         }

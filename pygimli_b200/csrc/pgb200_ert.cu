@@ -338,6 +338,7 @@ int launch_stream(pgb200_ert *h, const StreamDev &D, const PanelEntry *ent, cons
     const size_t smem = (size_t)A.slots * A.slot_bytes;
     const int G = h->num_sms;
     A.cpt = A.n_tiles <= G ? std::max(1, G / A.n_tiles) : 1;
+    A.fullrows = (A.n_tiles == 1 && (c0 & ~1) == 0 && A.pw == (int)h->ld) ? 1 : 0;
     A.dot_part = h->dot_part.p; A.dot_counter = h->dot_counter.p; A.dots = dots;
     if (dots && A.n_tiles > (int)h->dot_counter.n) PGB_FAIL("streamed SpMM: too many column tiles for the dot tickets");
     h->pi_panel_nc = A.pw > 64 ? 2 : 1; h->pi_tiles = std::max(h->pi_tiles, A.n_tiles); h->pi_slots = A.slots;
