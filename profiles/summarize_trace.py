@@ -17,6 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--cols", type=int, nargs=2, default=None, help="solve only the source columns [c0, c1) (what one rank of an N-GPU run does)")
     args = ap.parse_args()
     from pygimli_b200 import workloads
     from pygimli_b200.dist import ShardedERT
@@ -24,6 +25,8 @@ def main():
     r = workloads.WORKLOADS[args.workload](args.scale)
     mesh, scheme, kw = r[0], r[1], (r[3] if len(r) > 3 else None)
     fop = ShardedERT(mesh, scheme, kw=kw)
+    if args.cols:
+        fop.core.setShard(args.cols[0], args.cols[1], 0, fop.D * (args.cols[1] - args.cols[0]) // fop.nS)
     model = workloads.model_for(fop.M)
     fop.response(model)                                   # warm-up (graph mode)
     fop.create_jacobian(model)

@@ -505,16 +505,22 @@ k_spmm_stream(const StreamArgs A) {
                         // strided, a bulk copy per row would be bound by the copy engine's per-request cost.  One
                         // 16-byte cp.async (LDGSTS) per lane moves a whole row per warp instruction; completion is
                         // tracked by the same mbarrier (cp.async.mbarrier.arrive.noinc, one arrival per lane).
+                        // (kept lean on purpose: one warp issues every row of the stage, so each instruction in this loop
+                        //  costs ~100 issue slots per stage -- 32-bit shared addresses, one wide multiply-add per row)
                         const bool l0 = 16u * lane < rowb, l1 = NCP == 2 && 512u + 16u * lane < rowb;
+                        const uint32_t ldb = (uint32_t)A.ld * 8u;
+                        const unsigned char *gl = reinterpret_cast<const unsigned char *>(A.X + cs) + 16 * lane;
+                        uint32_t d = smem_u32(sb) + 16u * lane;
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
                             const int nrow = min(32, hn - 32 * u);
+#pragma unroll 4
                             for (int jj = 0; jj < nrow; jj++) {
-                                const int src = __shfl_sync(0xffffffffu, src_row[u], jj);
-                                const double *g = A.X + (size_t)src * A.ld + cs + 2 * lane;
-                                unsigned char *d = sb + (size_t)(32 * u + jj) * rowb + 16 * lane;
-                                if (l0) cp_async16(d, g);
-                                if (l1) cp_async16(d + 512, g + 64);
+                                const uint32_t src = (uint32_t)__shfl_sync(0xffffffffu, src_row[u], jj);
+                                const unsigned char *g = gl + (size_t)src * ldb;          // one IMAD.WIDE
+                                if (l0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+                                if (l1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u), "l"(g + 512) : "memory");
+                                d += rowb;
                             }
                         }
                         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[slot])) : "memory");
