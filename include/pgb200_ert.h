@@ -169,6 +169,15 @@ int pgb200_build_stream_panels(int n_rows, const int *rowptr, const int *colidx,
                                int *panel_row_ptr, int *panel_chunk_ptr, int *chunk_halo_ptr, int *halo_cols, int *chunk_ent_ptr,
                                int *ent_src, unsigned *ent_idx, int *crp, int *chunk_run_ptr, int *runs);
 
+/* The same panels in the 8-row-group form of the FP64 tensor-core SpMM (k_spmm_mma): rows of a panel in groups of 8, per
+ * (chunk, group) k-steps of 4 union columns.  counts[8] = {panels, chunks, halo entries, k-steps, meta words, meta group
+ * stride, max k-steps per chunk, max meta words per chunk}; a_src[32 * k-steps] = CSR slot of A-fragment element
+ * (4 * row-in-group + column-in-step) or -1; meta per chunk = [k-step range start per group | one word per k-step with the
+ * four staged-row indices, one byte each].  Host-side tests only.  Returns 0 on success.                        */
+int pgb200_build_mma_panels(int n_rows, const int *rowptr, const int *colidx, int groups, int hc, int max_chunks, int rowb_hint,
+                            int *counts, int *panel_row_ptr, int *panel_chunk_ptr, int *chunk_halo_ptr, int *halo_cols,
+                            int *chunk_ks_ptr, int *a_src, int *chunk_meta_ptr, unsigned *meta);
+
 /* Greedy pairwise aggregation along the strongest negative coupling (multilevel preconditioner set-up); a pair is
  * formed only if the coupling is at least theta times the strongest coupling of BOTH nodes, left-over nodes join a
  * neighbouring aggregate only across such a strong coupling (theta = 0: unconditional matching).  agg[n] receives the
@@ -293,6 +302,9 @@ int pgb200_ert_reset_stats(pgb200_ert *h);
  * thread of the widest chunk, [6] 1 if every chunk uses pre-resolved Gram offsets, [7] coarse levels of the multilevel
  * preconditioner, [8] shared-memory slots of the streamed kernel's ring, [9] coarse levels on the streamed kernel  */
 int pgb200_ert_path_info(pgb200_ert *h, int *out, int n);
+/* Measurement aid: `reps` back-to-back launches of the fine-level streamed SpMM (role 0: SpMM + p.Ap, 1: post-smoothing +
+ * r.z, 2: residual) on the assembled matrix and the PCG work vectors (overwritten); CUDA-event time per launch in ms. */
+int pgb200_ert_bench_spmm(pgb200_ert *h, int role, int reps, double *ms_per_launch);
 int pgb200_ert_set_profile(pgb200_ert *h, int on);
 /* on == 2 additionally records one CUDA event per kernel launch (no CUDA graph); pgb200_ert_get_trace returns, for the
  * launches since then, (source line in csrc/pgb200_ert.cu) * 256 + 16 * role + multilevel level of each launch (role of a

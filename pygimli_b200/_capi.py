@@ -57,7 +57,7 @@ class AmgLevel(C.Structure):
 
 # every symbol include/pgb200_ert.h declares (checked by tests/test_capi_symbols.py)
 EXPORTS = [
-    "pgb200_last_error", "pgb200_version", "pgb200_color_cells", "pgb200_build_stream_panels", "pgb200_ert_set_spmm_variant", "pgb200_pairwise_aggregate", "pgb200_ert_set_hierarchy", "pgb200_ert_set_preconditioner", "pgb200_ert_set_graph", "pgb200_ert_map_model",
+    "pgb200_last_error", "pgb200_version", "pgb200_color_cells", "pgb200_build_stream_panels", "pgb200_build_mma_panels", "pgb200_ert_set_spmm_variant", "pgb200_pairwise_aggregate", "pgb200_ert_set_hierarchy", "pgb200_ert_set_preconditioner", "pgb200_ert_set_graph", "pgb200_ert_map_model",
     "pgb200_ert_create", "pgb200_ert_destroy", "pgb200_ert_set_stream", "pgb200_ert_set_solver", "pgb200_ert_set_shard",
     "pgb200_ert_set_kfac", "pgb200_ert_response", "pgb200_ert_create_jacobian", "pgb200_ert_jacobian_copy",
     "pgb200_ert_jacobian_mult", "pgb200_ert_jacobian_tmult", "pgb200_ert_response_dev", "pgb200_ert_create_jacobian_dev",
@@ -65,7 +65,7 @@ EXPORTS = [
     "pgb200_ert_mark_potentials_valid", "pgb200_ert_forward_dev", "pgb200_ert_pm_info", "pgb200_ert_finish_response_dev",
     "pgb200_ert_pack_potentials", "pgb200_ert_get", "pgb200_ert_stats", "pgb200_ert_reset_stats", "pgb200_ert_set_profile",
     "pgb200_spmm", "pgb200_ert_get_trace", "pgb200_ert_set_primary_dev", "pgb200_ert_fill_matrix", "pgb200_ert_jacobian_mult_lr", "pgb200_ert_jacobian_tmult_lr", "pgb200_ert_coverage_trans",
-    "pgb200_ert_path_info", "pgb200_ert_potentials_state",
+    "pgb200_ert_path_info", "pgb200_ert_bench_spmm", "pgb200_ert_potentials_state",
     "pgb200_ert_set_warm_start",
     "pgb200_plan_build", "pgb200_plan_free", "pgb200_plan_error", "pgb200_plan_view", "pgb200_plan_array", "pgb200_plan_scalar",
     "pgb200_plan_build_hierarchy", "pgb200_plan_levels", "pgb200_ert_open", "pgb200_ert_open_plan", "pgb200_ert_plan",
@@ -119,6 +119,7 @@ def lib():
         L.pgb200_ert_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.pgb200_ert_set_profile.argtypes = [C.c_void_p, C.c_int]
         L.pgb200_ert_path_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.pgb200_ert_bench_spmm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.pgb200_plan_error.restype = C.c_char_p
         L.pgb200_plan_build.argtypes = [C.POINTER(MeshIn), C.POINTER(SchemeIn), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         L.pgb200_plan_free.argtypes = [C.c_void_p]
@@ -135,6 +136,7 @@ def lib():
         L.pgb200_ert_plan.restype = C.c_void_p
         L.pgb200_color_cells.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.pgb200_build_stream_panels.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 11
+        L.pgb200_build_mma_panels.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 9
         L.pgb200_ert_set_spmm_variant.argtypes = [C.c_void_p, C.c_int]
         L.pgb200_ert_set_hierarchy.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.pgb200_ert_set_preconditioner.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -186,6 +188,27 @@ def pairwise_aggregate(rowptr, colidx, vals, group=None, theta=None):
     if na < 0:
         raise PGB200Error(last_error())
     return agg, int(na)
+
+
+def build_mma_panels(rowptr: np.ndarray, colidx: np.ndarray, groups: int = 12, hc: int = 104, max_chunks: int = 8, rowb_hint: int = 800) -> dict:
+    """8-row-group form of the streamed panels (k_spmm_mma, csrc/stream_panels.h) -- host-side tests"""
+    rowptr = np.ascontiguousarray(rowptr, np.int32)
+    colidx = np.ascontiguousarray(colidx, np.int32)
+    n = rowptr.size - 1
+    counts = np.zeros(8, np.int32)
+    args = [n, rowptr.ctypes.data, colidx.ctypes.data, int(groups), int(hc), int(max_chunks), int(rowb_hint), counts.ctypes.data]
+    if lib().pgb200_build_mma_panels(*args, *([None] * 8)) != 0:
+        raise PGB200Error(last_error())
+    npan, nch, nh, nks, nmeta, gstride, mks, mmeta = (int(x) for x in counts)
+    out = dict(panel_row_ptr=np.zeros(npan + 1, np.int32), panel_chunk_ptr=np.zeros(npan + 1, np.int32),
+               chunk_halo_ptr=np.zeros(nch + 1, np.int32), halo_cols=np.zeros(max(1, nh), np.int32),
+               chunk_ks_ptr=np.zeros(nch + 1, np.int32), a_src=np.zeros(max(1, 32 * nks), np.int32),
+               chunk_meta_ptr=np.zeros(nch + 1, np.int32), meta=np.zeros(max(1, nmeta), np.uint32))
+    if lib().pgb200_build_mma_panels(*args, *(out[k].ctypes.data for k in ("panel_row_ptr", "panel_chunk_ptr", "chunk_halo_ptr", "halo_cols",
+                                                                          "chunk_ks_ptr", "a_src", "chunk_meta_ptr", "meta"))) != 0:
+        raise PGB200Error(last_error())
+    out.update(n_panels=npan, n_chunks=nch, n_ks=nks, meta_gstride=gstride, max_chunk_ks=mks, max_chunk_meta=mmeta, groups=int(groups))
+    return out
 
 
 def build_stream_panels(rowptr: np.ndarray, colidx: np.ndarray, rmax: int = 64, hc: int = 104, max_chunks: int = 2) -> dict:

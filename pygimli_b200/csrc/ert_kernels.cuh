@@ -355,6 +355,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// L2 prefetch of a global range (no shared-memory destination): the ring of k_spmm_mma asks for the NEXT stage's data
+// while the current one is being copied, so that the copy into the freed slot later is served by L2 and not by DRAM
+__device__ __forceinline__ void tma_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
@@ -682,6 +687,458 @@ k_spmm_stream(const StreamArgs A) {
                 if (threadIdx.x == 0) A.dot_counter[t] = 0u;
             }
             named_bar_sync(1, ST_CONSUMERS);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K2'': the same streamed row-panel SpMM with the products on the FP64 tensor-core pipe (DMMA m8n8k4).
+//
+//   Why: k_spmm_stream needs 8 distinct bytes of X from shared memory per DFMA lane (9 wavefronts per CSR entry for 100
+//   columns) and is bound by the shared-memory pipe at ~30 % of the HBM roofline.  A DMMA holds its operands in register
+//   FRAGMENTS that are reused across the 8 x 8 outputs: one k-step of the layout below (8 rows x 4 columns of A against 4
+//   staged rows of X, all source columns) costs 2 wavefronts for A and 2 per 8 source columns for X = 28 wavefronts for 100
+//   columns and ~10 CSR entries' worth of work, i.e. ~3 per entry.  The zeros of the 8 x 4 blocks are multiplied too
+//   (~3x the flops of the CSR form), which the otherwise idle FP64 tensor pipe (64 FMA/clk/SM, measured) absorbs.
+//
+//   Layout (stream_panels.h, "8-row-group form"): a panel has up to 8 * MM_CONSUMER_WARPS rows; consumer warp w owns rows
+//   [8w, 8w+8) of the panel and keeps their sums for all columns of the tile in C fragments (lane: row lane/4, columns
+//   8t + 2(lane%4) + {0,1} of n-tile t) across the chunks.  Per (chunk, group) the host lists the k-steps: 32 packed A
+//   values in fragment order (lane = 4 * row + column) and one word with the 4 staged-row indices.
+//   Producer warp, ring of slots, tiles, deterministic dots: as k_spmm_stream.
+// ---------------------------------------------------------------------------------
+#ifndef PGB_MM_WARPS
+#define PGB_MM_WARPS 12      // 3 consumer warpgroups + 1 producer warpgroup = 16 warps, on every SM sub-partition 3 consumers (the DMMA
+#define PGB_MM_PRODUCERS 4   // pipe is per sub-partition) and 1 producer.  The kernel starts with 128 registers per thread; the
+#endif                       // producers shrink to 56 and the consumers grow to 152 (setmaxnreg).  Issuing a bulk copy costs the
+                             // issuing warp ~65 cycles (measured, ab/dmma/tma_fill2.cu): the copies of a stage are split over the producers
+constexpr int MM_CONSUMER_WARPS = PGB_MM_WARPS;
+constexpr int MM_PRODUCER_WARPS = PGB_MM_PRODUCERS;
+constexpr int MM_CONSUMERS = MM_CONSUMER_WARPS * 32;
+constexpr int MM_THREADS = MM_CONSUMERS + 32 * MM_PRODUCER_WARPS;
+constexpr int MM_PRODUCER_REGS = 56, MM_CONSUMER_REGS = 152;       // 12 * 32 * 152 + 4 * 32 * 56 = 65536
+static_assert(MM_CONSUMER_WARPS % 4 == 0 && MM_PRODUCER_WARPS == 4, "setmaxnreg works on warpgroups of 4 warps");
+constexpr int MM_ROWS = 8 * MM_CONSUMER_WARPS;         // rows per panel
+constexpr int MM_GSTRIDE = (MM_CONSUMER_WARPS + 1 + 3) / 4 * 4;
+
+// packed A fragments of one matrix: aval[k][i] = vals[k][a_src[i]] (0 where a_src[i] < 0)
+__global__ void k_pack_mma(const int *__restrict__ a_src, size_t n_frag, size_t nnz, int nK, const double *__restrict__ vals,
+                           double *__restrict__ aval) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_frag) return;
+    const int src = a_src[i];
+    for (int kk = 0; kk < nK; kk++) aval[(size_t)kk * n_frag + i] = src >= 0 ? vals[(size_t)kk * nnz + src] : 0.0;
+}
+
+struct MmaLevel {
+    const int *panel_row_ptr, *panel_chunk_ptr, *chunk_halo_ptr, *halo_cols, *chunk_ks_ptr, *chunk_meta_ptr, *chunk_run_ptr, *runs;
+    const int4 *cdesc;            // per chunk two int4: {first halo entry, halo entries, first k-step, k-steps}, {first meta word, meta words, first run, runs}
+    const unsigned *meta;
+    int n_panels;
+};
+struct MmaArgs {
+    MmaLevel L;
+    const double *aval; size_t n_frag;            // packed A fragments [nK][n_frag], n_frag = 32 * k-steps
+    const double *X; double *Y; size_t ld;
+    int nE, c0, c1;
+    int k_lo, tpk, pw, n_tiles, cpt;
+    int slots; uint32_t slot_bytes, x_bytes, a_bytes;      // slot = [X rows | A fragments | meta]
+    int fullrows;
+    int dbg;                                      // measurement only: 1 = skip the k-step loop, 2 = skip the X copies, 4 = skip the epilogue,
+    long long *dbg_buf;                           //                   8 = per-stage clock stamps of CTA 0 into dbg_buf[stage * 8 + i]
+    double *dot_part; unsigned *dot_counter; double *dots;
+    PanelExtra ex;
+};
+__device__ __forceinline__ bool mma_tile(const MmaArgs &A, int t, int &kk, int &cs, int &wc, int &v0, int &v1) {
+    const int q = t / A.tpk, j = t - q * A.tpk;
+    kk = A.k_lo + q;
+    const int gb = max(kk * A.nE, A.c0), ge = min((kk + 1) * A.nE, A.c1);
+    cs = (gb & ~1) + j * A.pw;
+    const int ce = min(cs + A.pw, (ge + 1) & ~1);
+    v0 = max(cs, gb); v1 = min(ce, ge);
+    if (v1 <= v0) return false;
+    wc = ce - cs;
+    return true;
+}
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// wait for the phase of a full-barrier; the returned token orders the stage's shared-memory reads behind the wait
+__device__ __forceinline__ uint32_t mbar_wait_tok(uint64_t *bar, uint32_t phase) {
+    // test_wait in a spin loop: try_wait may suspend the warp for an implementation-defined time, which adds its wake-up
+    // latency to every stage of the ring
+    uint32_t tok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "mov.u32 %0, %2;\n"
+        "}\n" : "=r"(tok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    return tok;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr, uint32_t tok) {
+    double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr), "r"(tok)); return v;
+}
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr, uint32_t tok) {
+    double2 v; asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "r"(tok)); return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr, uint32_t tok) {
+    uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr), "r"(tok)); return v;
+}
+
+template <int NT, int EPI, bool DOT>
+__global__ void __launch_bounds__(MM_THREADS, 1)
+k_spmm_mma(const MmaArgs A) {
+    extern __shared__ __align__(128) unsigned char st_smem[];
+    __shared__ __align__(8) uint64_t full[ST_MAX_SLOTS], empty[ST_MAX_SLOTS];
+    __shared__ double sdot[ST_MAX_TILE_W];
+    __shared__ int s_ticket;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = A.slots;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) { mbar_init(&full[s], MM_PRODUCER_WARPS * (A.fullrows ? 1 : 33)); mbar_init(&empty[s], MM_CONSUMER_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int t_first, t_step, j;
+    if (A.n_tiles <= (int)gridDim.x) { t_first = blockIdx.x / A.cpt; t_step = A.n_tiles; j = blockIdx.x - t_first * A.cpt; }
+    else { t_first = blockIdx.x; t_step = gridDim.x; j = 0; }
+    const int pstep = A.cpt;
+    const MmaLevel &L = A.L;
+
+    if (warp >= MM_CONSUMER_WARPS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MM_PRODUCER_REGS));
+        // ------------------------------- producers -------------------------------
+        // producer pw issues every MM_PRODUCER_WARPS-th copy of a stage (the first one also the A fragments and the meta
+        // block) and arms the stage's barrier with the bytes of its own copies.  What to copy is fetched AHEAD of the ring:
+        // the chunk record two stages ahead, the copy list one stage ahead -- when the ring is the bottleneck (the usual
+        // case) no index load sits between a slot becoming free and its copies being issued.
+        const int pw = warp - MM_CONSUMER_WARPS;
+        constexpr int P = MM_PRODUCER_WARPS;
+        constexpr int U = (4 + P - 1) / P;          // up to 128 copies per stage over P warps
+        uint32_t slot = 0, use = 0;
+        int dbg_stage = 0;
+        for (int t = t_first; t < A.n_tiles; t += t_step) {
+            int kk, cs, wc, v0, v1;
+            if (!mma_tile(A, t, kk, cs, wc, v0, v1)) continue;
+            if (j >= L.n_panels) continue;
+            const uint32_t rowb = (uint32_t)wc * 8u;
+            const bool fullrows = A.fullrows != 0;
+            const double *avk = A.aval + (size_t)kk * A.n_frag;
+            // position of the record fetch (two stages ahead): panel pp, its chunk range, chunk pc counting down
+            int pp = j, pc0 = L.panel_chunk_ptr[pp], pc = L.panel_chunk_ptr[pp + 1] - 1;
+            int pn0 = 0, pn1 = 0;
+            if (pp + pstep < L.n_panels) { pn0 = L.panel_chunk_ptr[pp + pstep]; pn1 = L.panel_chunk_ptr[pp + pstep + 1]; }
+            bool more = true;                              // the position (pp, pc) is a stage
+            auto fetch_rec = [&](int4 &ra, int4 &rb, bool &ok) {
+                ok = more;
+                if (!more) return;
+                ra = __ldg(L.cdesc + 2 * pc); rb = __ldg(L.cdesc + 2 * pc + 1);
+                if (pc > pc0) pc--;
+                else {
+                    pp += pstep;
+                    if (pp < L.n_panels) {
+                        pc0 = pn0; pc = pn1 - 1;
+                        if (pp + pstep < L.n_panels) { pn0 = L.panel_chunk_ptr[pp + pstep]; pn1 = L.panel_chunk_ptr[pp + pstep + 1]; }
+                    } else more = false;
+                }
+            };
+            struct Copies { int src[U], dst[U], len[U], n, rows; };
+            auto fetch_copies = [&](const int4 &ra, const int4 &rb, Copies &C) {
+                C.n = 0; C.rows = 0;
+                if (fullrows) {
+                    const int q0 = rb.z, q1 = (A.dbg & 2) ? q0 : q0 + rb.w;
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int i = q0 + pw + P * (lane + 32 * u);
+                        if (i < q1) { C.dst[u] = __ldg(L.runs + 3 * i); C.src[u] = __ldg(L.runs + 3 * i + 1); C.len[u] = __ldg(L.runs + 3 * i + 2); C.n = u + 1; C.rows += C.len[u]; }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int i = pw + P * (lane + 32 * u);
+                        if (i < ra.y) { C.dst[u] = i; C.src[u] = __ldg(L.halo_cols + ra.x + i); C.len[u] = 1; C.n = u + 1; }
+                    }
+                }
+            };
+            int4 a0, b0, a1, b1, a2, b2; bool ok0, ok1, ok2;
+            Copies C0, C1;
+            fetch_rec(a0, b0, ok0);
+            fetch_rec(a1, b1, ok1);
+            fetch_copies(a0, b0, C0);
+            while (ok0) {
+                // ahead of the ring: record of stage + 2, copy list of stage + 1
+                fetch_rec(a2, b2, ok2);
+                if (ok1) fetch_copies(a1, b1, C1);
+                // this stage
+                unsigned char *sb = st_smem + (size_t)slot * A.slot_bytes;
+                const int hn = a0.y, k0 = a0.z, nks = a0.w, m0 = b0.x, nm = b0.y;
+                int rows_mine = C0.rows;
+                if (fullrows) {
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) rows_mine += __shfl_xor_sync(0xffffffffu, rows_mine, o);
+                }
+                const bool stamp = (A.dbg & 8) && blockIdx.x == 0 && pw == 0 && lane == 0;
+                if (stamp) A.dbg_buf[(size_t)dbg_stage * 8 + 0] = clock64();
+                if (use > 0) mbar_wait_spin(&empty[slot], (use & 1u) ^ 1u);
+                if (stamp) A.dbg_buf[(size_t)dbg_stage * 8 + 1] = clock64();
+                if (lane == 0) {
+                    mbar_expect_tx(&full[slot], (uint32_t)rows_mine * rowb + (pw == 0 ? (uint32_t)nks * 256u + (uint32_t)nm * 4u : 0u));
+                    if (pw == 0) {
+                        if (nks > 0) tma_bulk_g2s(sb + A.x_bytes, avk + (size_t)k0 * 32, (uint32_t)nks * 256u, &full[slot]);
+                        tma_bulk_g2s(sb + A.x_bytes + A.a_bytes, L.meta + m0, (uint32_t)nm * 4u, &full[slot]);
+                    }
+                }
+                __syncwarp();
+                if (fullrows) {
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+                        if (u < C0.n)
+                            tma_bulk_g2s(sb + (size_t)C0.dst[u] * rowb, A.X + (size_t)C0.src[u] * A.ld + cs, (uint32_t)C0.len[u] * rowb, &full[slot]);
+                } else {
+                    // partial-width tiles: one 16-byte cp.async per lane moves a row per warp instruction (see k_spmm_stream);
+                    // this warp's rows are pw, pw + P, ...
+                    const bool l0 = 16u * lane < rowb, l1 = 512u + 16u * lane < rowb;
+                    const uint32_t ldb = (uint32_t)A.ld * 8u;
+                    const unsigned char *gl = reinterpret_cast<const unsigned char *>(A.X + cs) + 16 * lane;
+                    uint32_t d = smem_u32(sb) + 16u * lane + (uint32_t)pw * rowb;
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int nrow = min(32, (hn - pw + P - 1) / P - 32 * u);
+#pragma unroll 4
+                        for (int jj = 0; jj < nrow; jj++) {
+                            const uint32_t src = (uint32_t)__shfl_sync(0xffffffffu, C0.src[u], jj);
+                            const unsigned char *g = gl + (size_t)src * ldb;
+                            if (l0) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+                            if (l1) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u), "l"(g + 512) : "memory");
+                            d += P * rowb;
+                        }
+                    }
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[slot])) : "memory");
+                }
+                // the next stage goes to L2 now (its slot is still in use): DRAM latency leaves the ring's critical path
+                if (ok1 && !(A.dbg & 32)) {
+                    if (lane == 0 && pw == 0) {
+                        if (a1.w > 0) tma_prefetch_l2(avk + (size_t)a1.z * 32, (uint32_t)a1.w * 256u);
+                        tma_prefetch_l2(L.meta + b1.x, (uint32_t)b1.y * 4u);
+                    }
+                    if (fullrows) {
+#pragma unroll
+                        for (int u = 0; u < U; u++)
+                            if (u < C1.n) tma_prefetch_l2(A.X + (size_t)C1.src[u] * A.ld + cs, (uint32_t)C1.len[u] * rowb);
+                    }
+                }
+                if (stamp) A.dbg_buf[(size_t)dbg_stage * 8 + 2] = clock64();
+                dbg_stage++;
+                if (++slot == (uint32_t)S) { slot = 0; use++; }
+                a0 = a1; b0 = b1; ok0 = ok1; C0 = C1;
+                a1 = a2; b1 = b2; ok1 = ok2;
+            }
+        }
+        return;
+    }
+
+    // ------------------------------- consumers -------------------------------
+    // All shared-memory reads of the inner loop go through 32-bit shared addresses and non-volatile asm (the compiler may
+    // interleave them with the DMMAs as it likes); every read carries the token the full-barrier wait of its stage
+    // returned, so it can neither move above that wait nor be merged with a read of the same address in another stage.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MM_CONSUMER_REGS));
+    const int lr = lane >> 2, lk = lane & 3;      // fragment coordinates: row / B column n = lr, k index / C column pair = lk
+    const uint32_t smem0 = smem_u32(st_smem);
+    uint32_t slot = 0, phase = 0;
+    int dbg_stage = 0;
+    for (int t = t_first; t < A.n_tiles; t += t_step) {
+        int kk, cs, wc, v0, v1;
+        if (!mma_tile(A, t, kk, cs, wc, v0, v1)) continue;
+        const uint32_t rowb = (uint32_t)wc * 8u;
+        const int nt = (wc + 7) >> 3;             // n-tiles of 8 source columns in use (<= NT; the others compute on whatever
+                                                  // follows the row in the slot and are never stored)
+        double part[DOT ? NT : 1][2];
+#pragma unroll
+        for (int q = 0; q < (DOT ? NT : 1); q++) { part[q][0] = 0.0; part[q][1] = 0.0; }
+        const double *dwk = (EPI == EPI_POST) ? A.ex.dinvw + (size_t)kk * A.ex.n : nullptr;
+
+        int p = j;
+        int r0 = 0, r1 = 0, ch0 = 0, ch1 = 0, hc0 = 0;
+        if (p < L.n_panels) {
+            r0 = L.panel_row_ptr[p]; r1 = L.panel_row_ptr[p + 1]; ch0 = L.panel_chunk_ptr[p]; ch1 = L.panel_chunk_ptr[p + 1];
+            hc0 = L.chunk_halo_ptr[ch0 + 1] - L.chunk_halo_ptr[ch0];
+        }
+        while (p < L.n_panels) {
+            const int nrows = r1 - r0, nch = ch1 - ch0, row_base = r0;
+            const int n0 = min(nrows, hc0);           // own rows staged with chunk 0; the others are the first rows of chunk 1
+            // the next panel's extents are fetched now: their latency hides behind this panel's work
+            const int pn = p + pstep;
+            if (pn < L.n_panels) {
+                r0 = L.panel_row_ptr[pn]; r1 = L.panel_row_ptr[pn + 1]; ch0 = L.panel_chunk_ptr[pn]; ch1 = L.panel_chunk_ptr[pn + 1];
+                hc0 = L.chunk_halo_ptr[ch0 + 1] - L.chunk_halo_ptr[ch0];
+            }
+            uint32_t sb1 = 0, slot1 = 0;              // chunk 1 stays resident until the epilogue when it holds own rows
+            double acc[NT][2];
+#pragma unroll
+            for (int q = 0; q < NT; q++) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+            for (int c = nch - 1; c >= 0; c--) {
+                const bool stamp = (A.dbg & 8) && blockIdx.x == 0 && threadIdx.x == 0;
+                if (stamp) A.dbg_buf[(size_t)dbg_stage * 8 + 3] = clock64();
+                const uint32_t tok = mbar_wait_tok(&full[slot], phase);
+                if (stamp) A.dbg_buf[(size_t)dbg_stage * 8 + 4] = clock64();
+                const uint32_t sb = smem0 + slot * A.slot_bytes;
+                const uint32_t sM = sb + A.x_bytes + A.a_bytes;
+                const int ks0 = (int)lds_u32(sM + 4u * warp, tok), ks1 = (A.dbg & 1) ? ks0 : (int)lds_u32(sM + 4u * warp + 4u, tok);
+                uint32_t aA = sb + A.x_bytes + 8u * lane + 256u * (uint32_t)ks0;
+                uint32_t aK = sM + 4u * MM_GSTRIDE + 4u * (uint32_t)ks0;
+                const uint32_t xb = sb + 8u * lr;
+#pragma unroll 2
+                for (int ks = ks0; ks < ks1; ks++, aA += 256u, aK += 4u) {
+                    const double a = lds_f64(aA, tok);
+                    const uint32_t idx = __byte_perm(lds_u32(aK, tok), 0u, 0x4440u + lk);     // byte lk of the word
+                    const uint32_t xr = xb + idx * rowb;
+                    double b[NT];
+#pragma unroll
+                    for (int q = 0; q < NT; q++) b[q] = lds_f64(xr + 64u * q, tok);
+#pragma unroll
+                    for (int q = 0; q < NT; q++) dmma884(acc[q][0], acc[q][1], a, b[q]);
+                }
+                if (stamp) A.dbg_buf[(size_t)dbg_stage * 8 + 5] = clock64();
+                // epilogue after the panel's last chunk (c == 0): the results are formed IN PLACE in the accumulators while the
+                // slot is still held (own X rows from shared memory), then the slot is released, then Y is stored -- the burst
+                // of stores (a whole panel of Y) no longer sits between two stages of the ring
+                const int r = 8 * warp + lr;
+                const bool epi = c == 0 && !(A.dbg & 4) && r < nrows;
+                const int row = row_base + r;
+                if (epi) {
+                    const uint32_t xs = (r < n0 ? sb + (uint32_t)r * rowb : sb1 + (uint32_t)(r - n0) * rowb) + 16u * lk;
+                    if (EPI == EPI_POST) {
+                        // R in two batches (registers: a batch of R + accumulators + dot partials), each one L2 round trip
+                        const double dw = __ldg(dwk + row);
+                        constexpr int H = (NT + 1) / 2;
+#pragma unroll
+                        for (int half = 0; half < 2; half++) {
+                            double rres[H][2];
+#pragma unroll
+                            for (int qq = 0; qq < H; qq++) {
+                                const int q = half * H + qq;
+                                rres[qq][0] = 0.0; rres[qq][1] = 0.0;
+                                if (q < NT && q < nt) {
+                                    const int lc = 8 * q + 2 * lk, col = cs + lc;
+                                    const bool ok0 = lc < wc && col >= v0 && col < v1, ok1 = lc + 1 < wc && col + 1 >= v0 && col + 1 < v1;
+                                    const size_t o = (size_t)row * A.ld + col;
+                                    if (ok0 && ok1) { const double2 rv = __ldg(reinterpret_cast<const double2 *>(A.ex.R + o)); rres[qq][0] = rv.x; rres[qq][1] = rv.y; }
+                                    else { if (ok0) rres[qq][0] = __ldg(A.ex.R + o); if (ok1) rres[qq][1] = __ldg(A.ex.R + o + 1); }
+                                }
+                            }
+#pragma unroll
+                            for (int qq = 0; qq < H; qq++) {
+                                const int q = half * H + qq;
+                                if (q < NT && q < nt) {
+                                    const int lc = 8 * q + 2 * lk, col = cs + lc;
+                                    const bool ok0 = lc < wc && col >= v0 && col < v1, ok1 = lc + 1 < wc && col + 1 >= v0 && col + 1 < v1;
+                                    const double2 x = lds_f64x2(xs + 64u * q, tok);
+                                    acc[q][0] = fma(dw, rres[qq][0] - acc[q][0], x.x);
+                                    acc[q][1] = fma(dw, rres[qq][1] - acc[q][1], x.y);
+                                    if (DOT) { if (ok0) part[q][0] = fma(rres[qq][0], acc[q][0], part[q][0]); if (ok1) part[q][1] = fma(rres[qq][1], acc[q][1], part[q][1]); }
+                                }
+                            }
+                        }
+                    } else if (EPI == EPI_RESIDUAL || DOT) {
+#pragma unroll
+                        for (int q = 0; q < NT; q++) {
+                            if (q < nt) {
+                                const int lc = 8 * q + 2 * lk, col = cs + lc;
+                                const bool ok0 = lc < wc && col >= v0 && col < v1, ok1 = lc + 1 < wc && col + 1 >= v0 && col + 1 < v1;
+                                const double2 x = lds_f64x2(xs + 64u * q, tok);
+                                if (EPI == EPI_RESIDUAL) { acc[q][0] = x.x - acc[q][0]; acc[q][1] = x.y - acc[q][1]; }
+                                else { if (ok0) part[q][0] = fma(acc[q][0], x.x, part[q][0]); if (ok1) part[q][1] = fma(acc[q][1], x.y, part[q][1]); }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (c == 1 && n0 < nrows) { sb1 = sb; slot1 = slot; }        // released after the epilogue
+                else if (lane == 0) {
+                    mbar_arrive(&empty[slot]);
+                    if (c == 0 && n0 < nrows) mbar_arrive(&empty[slot1]);
+                }
+                if (epi && !(A.dbg & 16)) {
+#pragma unroll
+                    for (int q = 0; q < NT; q++) {
+                        if (q < nt) {
+                            const int lc = 8 * q + 2 * lk, col = cs + lc;
+                            const bool ok0 = lc < wc && col >= v0 && col < v1, ok1 = lc + 1 < wc && col + 1 >= v0 && col + 1 < v1;
+                            const size_t o = (size_t)row * A.ld + col;
+                            if (ok0 && ok1) *reinterpret_cast<double2 *>(A.Y + o) = make_double2(acc[q][0], acc[q][1]);
+                            else { if (ok0) A.Y[o] = acc[q][0]; if (ok1) A.Y[o + 1] = acc[q][1]; }
+                        }
+                    }
+                }
+                if (stamp) A.dbg_buf[(size_t)dbg_stage * 8 + 6] = clock64();
+                dbg_stage++;
+                if (++slot == (uint32_t)S) { slot = 0; phase ^= 1u; }
+            }
+            p = pn;
+        }
+        if (DOT) {
+            // rows of the fragment first (lanes with equal lk, fixed shuffle order), then a fixed-order sum over the warps,
+            // one partial row per CTA, the last CTA of the tile adds the rows in index order
+#pragma unroll
+            for (int q = 0; q < NT; q++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    double v = part[q][h];
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    part[q][h] = v;
+                }
+            }
+            const int nslot = (A.n_tiles <= (int)gridDim.x) ? A.cpt : 1;
+            for (int w = 0; w < MM_CONSUMER_WARPS; w++) {
+                if (warp == w && lr == 0) {
+#pragma unroll
+                    for (int q = 0; q < NT; q++) {
+                        if (q < nt) {
+                            const int i = 8 * q + 2 * lk;
+                            sdot[i] = (w == 0 ? 0.0 : sdot[i]) + part[q][0];
+                            sdot[i + 1] = (w == 0 ? 0.0 : sdot[i + 1]) + part[q][1];
+                        }
+                    }
+                }
+                named_bar_sync(1, MM_CONSUMERS);
+            }
+            double *mine = A.dot_part + (size_t)j * A.ld;
+            for (int i = threadIdx.x; i < wc; i += MM_CONSUMERS) if (cs + i >= v0 && cs + i < v1) mine[cs + i] = sdot[i];
+            __threadfence();
+            named_bar_sync(1, MM_CONSUMERS);
+            if (threadIdx.x == 0) s_ticket = (int)atomicAdd(A.dot_counter + t, 1u);
+            named_bar_sync(1, MM_CONSUMERS);
+            if (s_ticket == nslot - 1) {
+                __threadfence();
+                const int i = threadIdx.x >> 2, part4 = threadIdx.x & 3;
+                for (int i0 = 0; i0 < wc; i0 += MM_CONSUMERS / 4) {
+                    const int cc = cs + i0 + i;
+                    const bool okc = (i0 + i) < wc && cc >= v0 && cc < v1;
+                    double s4 = okc ? ordered_row_sum(A.dot_part + cc, A.ld, part4, 4, nslot) : 0.0;
+                    const double s1 = __shfl_down_sync(0xffffffffu, s4, 1), s2 = __shfl_down_sync(0xffffffffu, s4, 2), s3 = __shfl_down_sync(0xffffffffu, s4, 3);
+                    if (okc && part4 == 0) A.dots[cc] = ((s4 + s1) + s2) + s3;
+                }
+                if (threadIdx.x == 0) A.dot_counter[t] = 0u;
+            }
+            named_bar_sync(1, MM_CONSUMERS);
         }
     }
 }

@@ -76,6 +76,16 @@ struct StreamDev {
     DevBuf<int> panel_row_ptr, panel_chunk_ptr, chunk_halo_ptr, halo_cols, chunk_ent_ptr, crp, ent_src, chunk_run_ptr, runs;
     DevBuf<unsigned> ent_idx;
     DevBuf<PanelEntry> ent_a, ent_dw;       // [nK][nnz]: A (SpMM, post-smoothing) and A * diag(dw) (pre-smoothing residual)
+    // 8-row-group form (k_spmm_mma): when mma is set the arrays above that describe single entries are not allocated
+    bool mma = false; int max_chunk_ks = 0, max_chunk_meta = 0, hc_used = 0; size_t n_frag = 0;
+    DevBuf<int> chunk_ks_ptr, chunk_meta_ptr, a_src, cdesc; DevBuf<unsigned> meta;
+    DevBuf<double> av_a, av_dw;             // [nK][n_frag] packed A fragments of the two value sets
+    MmaLevel mlevel() const {
+        MmaLevel L; L.panel_row_ptr = panel_row_ptr.p; L.panel_chunk_ptr = panel_chunk_ptr.p; L.chunk_halo_ptr = chunk_halo_ptr.p;
+        L.halo_cols = halo_cols.p; L.chunk_ks_ptr = chunk_ks_ptr.p; L.chunk_meta_ptr = chunk_meta_ptr.p; L.chunk_run_ptr = chunk_run_ptr.p;
+        L.runs = runs.p; L.meta = meta.p; L.n_panels = n_panels; L.cdesc = reinterpret_cast<const int4 *>(cdesc.p);
+        return L;
+    }
     StreamLevel level() const {
         StreamLevel L; L.panel_row_ptr = panel_row_ptr.p; L.panel_chunk_ptr = panel_chunk_ptr.p; L.chunk_halo_ptr = chunk_halo_ptr.p;
         L.halo_cols = halo_cols.p; L.chunk_ent_ptr = chunk_ent_ptr.p; L.crp = crp.p; L.n_panels = n_panels; L.crp_stride = crp_stride;
@@ -111,6 +121,7 @@ struct pgb200_ert {
     std::vector<int> color_ptr, pro_level_ptr;
     StreamDev stream; int use_panels = 1, use_panels_build = 1;   // streamed row panels of the fine level (use_panels 0: plain gather SpMM, A/B evidence)
     int stream_rmax = std::min(60, ST_CONSUMER_WARPS * ST_RPW), stream_hc = 104, stream_chunks = 2; // panel limits (stream_panels.h)
+    int use_mma = 1, mma_hc = 104, mma_chunks = 10, mma_dbg = 0; DevBuf<long long> mma_dbg_buf;      // FP64 tensor-core form of the streamed SpMM (k_spmm_mma); 0: k_spmm_stream
     DevBuf<double> dot_part; DevBuf<unsigned> dot_counter;    // deterministic column dots: per-CTA partial rows + tickets
     int dot_slots = 0; size_t smem_optin = 0;
     std::vector<double> h_kvals;
@@ -247,20 +258,44 @@ int launch_spmm(pgb200_ert *h, const double *vals, const double *vals1, const do
 // ---- streamed row-panel SpMM (the PCG hot kernel; ert_kernels.cuh k_spmm_stream) -------------------------------------
 // host layout -> device, once per pattern
 int stream_upload(pgb200_ert *h, StreamDev &D, int n, const int *rowptr_host, const int *colidx_host) {
-    D.ok = false;
+    D.ok = false; D.mma = false;
     if (!h->use_panels_build) return 0;
     StreamPanelsHost S;
-    const std::string err = build_stream_panels(n, rowptr_host, colidx_host, h->stream_rmax, h->stream_hc, h->stream_chunks, S);
+    std::string err = "off";
+    if (h->use_mma) {
+        // staged-row pitch of the most common launch: the whole source block for one wavenumber, else one electrode group
+        const int rowb_hint = 8 * (h->nK == 1 ? (int)h->ld : ((h->nE + 1) & ~1));
+        D.hc_used = std::max(h->mma_hc, (MM_ROWS + 1) / 2);
+        err = build_stream_panels(n, rowptr_host, colidx_host, MM_ROWS, D.hc_used, h->mma_chunks, S, MM_CONSUMER_WARPS, rowb_hint);
+        D.mma = err.empty() && S.max_chunk_halo <= 128;
+    }
+    if (!D.mma) err = build_stream_panels(n, rowptr_host, colidx_host, h->stream_rmax, h->stream_hc, h->stream_chunks, S);
     if (!err.empty()) return 0;                  // (a row wider than the halo limit) -> plain kernels for this level
     cudaStream_t st = h->st;
     CKR(D.panel_row_ptr.upload(S.panel_row_ptr.data(), S.panel_row_ptr.size(), st));
     CKR(D.panel_chunk_ptr.upload(S.panel_chunk_ptr.data(), S.panel_chunk_ptr.size(), st));
     CKR(D.chunk_halo_ptr.upload(S.chunk_halo_ptr.data(), S.chunk_halo_ptr.size(), st));
     CKR(D.halo_cols.upload(S.halo_cols.data(), S.halo_cols.size(), st));
-    CKR(D.chunk_ent_ptr.upload(S.chunk_ent_ptr.data(), S.chunk_ent_ptr.size(), st));
-    CKR(D.crp.upload(S.crp.data(), S.crp.size(), st));
-    CKR(D.ent_src.upload(S.ent_src.data(), S.ent_src.size(), st));
-    CKR(D.ent_idx.upload(S.ent_idx.data(), S.ent_idx.size(), st));
+    if (D.mma) {
+        CKR(D.chunk_ks_ptr.upload(S.chunk_ks_ptr.data(), S.chunk_ks_ptr.size(), st));
+        CKR(D.chunk_meta_ptr.upload(S.chunk_meta_ptr.data(), S.chunk_meta_ptr.size(), st));
+        CKR(D.a_src.upload(S.a_src.data(), S.a_src.size(), st));
+        CKR(D.meta.upload(S.meta.data(), S.meta.size(), st));
+        std::vector<int> cd(8 * (size_t)S.n_chunks);
+        for (int c = 0; c < S.n_chunks; c++) {
+            int *d = cd.data() + 8 * (size_t)c;
+            d[0] = S.chunk_halo_ptr[c]; d[1] = S.chunk_halo_ptr[c + 1] - S.chunk_halo_ptr[c];
+            d[2] = S.chunk_ks_ptr[c]; d[3] = S.chunk_ks_ptr[c + 1] - S.chunk_ks_ptr[c];
+            d[4] = S.chunk_meta_ptr[c]; d[5] = S.chunk_meta_ptr[c + 1] - S.chunk_meta_ptr[c];
+            d[6] = S.chunk_run_ptr[c]; d[7] = S.chunk_run_ptr[c + 1] - S.chunk_run_ptr[c];
+        }
+        CKR(D.cdesc.upload(cd.data(), cd.size(), st));
+    } else {
+        CKR(D.chunk_ent_ptr.upload(S.chunk_ent_ptr.data(), S.chunk_ent_ptr.size(), st));
+        CKR(D.crp.upload(S.crp.data(), S.crp.size(), st));
+        CKR(D.ent_src.upload(S.ent_src.data(), S.ent_src.size(), st));
+        CKR(D.ent_idx.upload(S.ent_idx.data(), S.ent_idx.size(), st));
+    }
     CKR(D.chunk_run_ptr.upload(S.chunk_run_ptr.data(), S.chunk_run_ptr.size(), st));
     std::vector<int> runs(3 * S.run_start.size());
     for (size_t i = 0; i < S.run_start.size(); i++) { runs[3 * i] = S.run_start[i]; runs[3 * i + 1] = S.run_col[i]; runs[3 * i + 2] = S.run_len[i]; }
@@ -269,13 +304,24 @@ int stream_upload(pgb200_ert *h, StreamDev &D, int n, const int *rowptr_host, co
     CK(cudaStreamSynchronize(st));               // the host vectors go out of scope
     D.n_panels = S.n_panels; D.n_chunks = S.n_chunks; D.crp_stride = S.crp_stride; D.max_chunk_halo = S.max_chunk_halo;
     D.max_chunk_ent = S.max_chunk_ent; D.nnz = (size_t)S.nnz;
-    CKR(D.ent_a.alloc(D.nnz * h->nK)); CKR(D.ent_dw.alloc(D.nnz * h->nK));
+    if (D.mma) {
+        D.max_chunk_ks = S.max_chunk_ks; D.max_chunk_meta = S.max_chunk_meta; D.n_frag = (size_t)S.n_ks * 32;
+        CKR(D.av_a.alloc(std::max<size_t>(1, D.n_frag * h->nK))); CKR(D.av_dw.alloc(std::max<size_t>(1, D.n_frag * h->nK)));
+    } else {
+        CKR(D.ent_a.alloc(D.nnz * h->nK)); CKR(D.ent_dw.alloc(D.nnz * h->nK));
+    }
     D.ok = true;
     return 0;
 }
-int stream_pack(pgb200_ert *h, StreamDev &D, const double *vals, PanelEntry *ent) {
+// which: 0 = A (SpMM, post-smoothing), 1 = A * diag(dw) (pre-smoothing residual)
+int stream_pack(pgb200_ert *h, StreamDev &D, const double *vals, int which) {
     if (!D.ok || D.nnz == 0) return 0;
-    k_pack_entries<<<cdiv((long long)D.nnz, 256), 256, 0, h->st>>>(D.ent_src.p, D.ent_idx.p, D.nnz, h->nK, vals, ent); LAUNCH(h);
+    if (D.mma) {
+        if (D.n_frag == 0) return 0;
+        k_pack_mma<<<cdiv((long long)D.n_frag, 256), 256, 0, h->st>>>(D.a_src.p, D.n_frag, D.nnz, h->nK, vals, which ? D.av_dw.p : D.av_a.p); LAUNCH(h);
+        return 0;
+    }
+    k_pack_entries<<<cdiv((long long)D.nnz, 256), 256, 0, h->st>>>(D.ent_src.p, D.ent_idx.p, D.nnz, h->nK, vals, which ? D.ent_dw.p : D.ent_a.p); LAUNCH(h);
     return 0;
 }
 inline size_t up128(size_t x) { return (x + 127) / 128 * 128; }
@@ -307,11 +353,100 @@ int stream_configure(pgb200_ert *h) {
     return 0;
 }
 
-// Y = op(A X) on the column window [c0, c1); dots != nullptr: deterministic per-column dot of the epilogue
+template <int NT, int EPI, bool DOT>
+int mma_go(pgb200_ert *h, const MmaArgs &A, size_t smem) {
+    k_spmm_mma<NT, EPI, DOT><<<h->num_sms, MM_THREADS, smem, h->st>>>(A);
+    h->cur_role = EPI + 1; LAUNCH(h); h->cur_role = 0;
+    return 0;
+}
+template <int NT, int EPI>
+int mma_configure_nt(size_t smem) {
+    CK(cudaFuncSetAttribute(k_spmm_mma<NT, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_spmm_mma<NT, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return 0;
+}
 template <int EPI>
-int launch_stream(pgb200_ert *h, const StreamDev &D, const PanelEntry *ent, const double *X, double *Y, int c0, int c1, double *dots,
+int mma_configure_epi(size_t smem) {
+    CKR((mma_configure_nt<2, EPI>(smem))); CKR((mma_configure_nt<4, EPI>(smem))); CKR((mma_configure_nt<7, EPI>(smem)));
+    CKR((mma_configure_nt<10, EPI>(smem))); CKR((mma_configure_nt<13, EPI>(smem))); CKR((mma_configure_nt<16, EPI>(smem)));
+    return 0;
+}
+int mma_configure(pgb200_ert *h) {
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, k_spmm_mma<16, EPI_POST, true>));
+    int optin = 0;
+    CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    h->smem_optin = std::min(h->smem_optin, (size_t)optin - fa.sharedSizeBytes - 256);
+    CKR(mma_configure_epi<EPI_SPMM>(h->smem_optin));
+    CKR(mma_configure_epi<EPI_POST>(h->smem_optin));
+    CKR(mma_configure_epi<EPI_RESIDUAL>(h->smem_optin));
+    return 0;
+}
+
+// tile geometry shared by the two streamed kernels: tiles per wavenumber, tile width
+struct TileGeo { int k_lo, n_k, tpk, pw, n_tiles; };
+inline TileGeo tile_geo(int nE, int c0, int c1, int wmax) {
+    TileGeo g;
+    g.k_lo = c0 / nE;
+    const int k_hi = (c1 - 1) / nE;
+    // widest column span of one wavenumber group inside the window, from an even start
+    int span;
+    if (k_hi == g.k_lo) span = ((c1 + 1) & ~1) - (c0 & ~1);
+    else span = nE + ((nE & 1) ? 1 : 0);
+    g.n_k = k_hi - g.k_lo + 1;
+    g.tpk = cdiv(span, wmax);
+    g.pw = (cdiv(span, g.tpk) + 1) & ~1;
+    g.n_tiles = g.n_k * g.tpk;
+    return g;
+}
+
+template <int EPI>
+int launch_mma(pgb200_ert *h, const StreamDev &D, int which, const double *X, double *Y, int c0, int c1, double *dots, const PanelExtra &ex) {
+    MmaArgs A;
+    A.L = D.mlevel(); A.aval = which ? D.av_dw.p : D.av_a.p; A.n_frag = D.n_frag; A.X = X; A.Y = Y; A.ld = h->ld; A.nE = h->nE; A.c0 = c0; A.c1 = c1; A.ex = ex;
+    // slot = [X rows | A fragments | meta]; the B fragments of the last n-tile may read up to 56 bytes past a row: the X
+    // region is followed by the A region of the same slot, so those reads stay inside the slot
+    const size_t a_b = up128((size_t)std::max(1, D.max_chunk_ks) * 256), m_b = up128((size_t)std::max(4, D.max_chunk_meta) * 4);
+    const size_t per_col = (size_t)D.max_chunk_halo * 8;
+    // chunk 1 stays resident through chunk 0 when the panel's own rows span both: at least 3 slots then
+    const int min_slots = D.hc_used < MM_ROWS ? 3 : 2;
+    long long wfit = ((long long)(h->smem_optin / min_slots) - (long long)a_b - (long long)m_b - 128) / (long long)per_col;
+    int wmax = (int)std::min<long long>(ST_MAX_TILE_W, wfit) & ~1;
+    if (wmax < 2) PGB_FAIL("streamed SpMM: a halo chunk does not fit shared memory");
+    const TileGeo g = tile_geo(h->nE, c0, c1, wmax);
+    A.k_lo = g.k_lo; A.tpk = g.tpk; A.pw = g.pw; A.n_tiles = g.n_tiles;
+    A.x_bytes = (uint32_t)up128((size_t)D.max_chunk_halo * A.pw * 8);
+    A.a_bytes = (uint32_t)a_b;
+    A.slot_bytes = (uint32_t)(A.x_bytes + a_b + m_b);
+    A.slots = (int)std::min<size_t>(ST_MAX_SLOTS, h->smem_optin / A.slot_bytes);
+    if (A.slots < min_slots) PGB_FAIL("streamed SpMM: internal slot sizing error");
+    const size_t smem = (size_t)A.slots * A.slot_bytes;
+    const int G = h->num_sms;
+    A.cpt = A.n_tiles <= G ? std::max(1, G / A.n_tiles) : 1;
+    A.fullrows = (A.n_tiles == 1 && (c0 & ~1) == 0 && A.pw == (int)h->ld) ? 1 : 0;
+    A.dot_part = h->dot_part.p; A.dot_counter = h->dot_counter.p; A.dots = dots;
+    A.dbg = h->mma_dbg; A.dbg_buf = h->mma_dbg_buf.p;
+    if (dots && A.n_tiles > (int)h->dot_counter.n) PGB_FAIL("streamed SpMM: too many column tiles for the dot tickets");
+    const int nt = cdiv(A.pw, 8);
+    h->pi_panel_nc = 100 + nt; h->pi_tiles = std::max(h->pi_tiles, A.n_tiles); h->pi_slots = A.slots;
+#define MMA_GO(NT) { if (dots) return mma_go<NT, EPI, true>(h, A, smem); return mma_go<NT, EPI, false>(h, A, smem); }
+    if (nt <= 2) MMA_GO(2)
+    if (nt <= 4) MMA_GO(4)
+    if (nt <= 7) MMA_GO(7)
+    if (nt <= 10) MMA_GO(10)
+    if (nt <= 13) MMA_GO(13)
+    MMA_GO(16)
+#undef MMA_GO
+}
+
+// Y = op(A X) on the column window [c0, c1); dots != nullptr: deterministic per-column dot of the epilogue
+// which: 0 = the level's matrix A, 1 = A * diag(dw)
+template <int EPI>
+int launch_stream(pgb200_ert *h, const StreamDev &D, int which, const double *X, double *Y, int c0, int c1, double *dots,
                   const PanelExtra &ex) {
     if (c1 <= c0) return 0;
+    if (D.mma) return launch_mma<EPI>(h, D, which, X, Y, c0, c1, dots, ex);
+    const PanelEntry *ent = which ? D.ent_dw.p : D.ent_a.p;
     const int nE = h->nE;
     StreamArgs A;
     A.L = D.level(); A.ent = ent; A.nnz = D.nnz; A.X = X; A.Y = Y; A.ld = h->ld; A.nE = nE; A.c0 = c0; A.c1 = c1; A.ex = ex;
@@ -441,13 +576,13 @@ int amg_setup_values(pgb200_ert *h) {
         return 0;
     };
     CKR(smoother(h->rowptr.p, h->colidx.p, h->diag_pos.p, h->N, h->nnz, h->vals.p, h->dinvw0.p, h->vals_dw0.p));
-    CKR(stream_pack(h, h->stream, h->vals_dw0.p, h->stream.ent_dw.p));
+    CKR(stream_pack(h, h->stream, h->vals_dw0.p, 1));
     const double *vf = h->vals.p; size_t nnz_f = h->nnz;
     for (AmgLevel *L : h->amg) {
         k_galerkin<<<cdiv((long long)L->nnz, 128), 128, 0, h->st>>>(L->gal_ptr.p, L->gal_idx.p, (int)L->nnz, nK, nnz_f, L->nnz, vf, L->vals.p); LAUNCH(h);
         CKR(smoother(L->rowptr.p, L->colidx.p, L->diag_pos.p, L->n, L->nnz, L->vals.p, L->dinvw.p, L->vals_dw.p));
-        CKR(stream_pack(h, L->stream, L->vals.p, L->stream.ent_a.p));
-        CKR(stream_pack(h, L->stream, L->vals_dw.p, L->stream.ent_dw.p));
+        CKR(stream_pack(h, L->stream, L->vals.p, 0));
+        CKR(stream_pack(h, L->stream, L->vals_dw.p, 1));
         vf = L->vals.p; nnz_f = L->nnz;
     }
     CK(cudaGetLastError());
@@ -521,7 +656,7 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
             // residual through the streamed kernel (into X of this level, free until the prolongation), then a
             // deterministic member sum
             PanelExtra ex{};
-            CKR(launch_stream<EPI_RESIDUAL>(h, *lv[l].st, lv[l].st->ent_dw.p, lv[l].R, lv[l].X, c0, c1, nullptr, ex));
+            CKR(launch_stream<EPI_RESIDUAL>(h, *lv[l].st, 1, lv[l].R, lv[l].X, c0, c1, nullptr, ex));
             AmgLevel *L = h->amg[l];
             const FlatCfg fc = flat_cfg(L->n, c0, c1);
             k_amg_sum_members<<<fc.grid, FLAT_T, 0, h->st>>>(L->mem_ptr.p, L->mem_idx.p, L->n, lv[l].X, L->R.p, c0, c1, h->ld, fc.cw); LAUNCH(h);
@@ -560,8 +695,7 @@ int amg_vcycle(pgb200_ert *h, int c0, int c1, double *dots) {
         k_amg_prolong<<<fc.grid, FLAT_T, 0, h->st>>>(f.dinvw, f.n, h->amg[l]->agg.p, f.R, E, f.X, h->nE, c0, c1, h->ld, fc.cw); LAUNCH(h);
         if (streamed(l)) {
             PanelExtra ex{}; ex.R = f.R; ex.dinvw = f.dinvw; ex.n = f.n;
-            const PanelEntry *ea = (l == 0) ? h->stream.ent_a.p : f.st->ent_a.p;
-            CKR(launch_stream<EPI_POST>(h, *f.st, ea, f.X, f.Z, c0, c1, l == 0 ? dots : nullptr, ex));
+            CKR(launch_stream<EPI_POST>(h, *f.st, 0, f.X, f.Z, c0, c1, l == 0 ? dots : nullptr, ex));
         } else {
             CKR(amg_post(h, f.rowptr, f.colidx, f.vals, f.nnz, f.dinvw, f.n, f.X, f.R, f.Z, c0, c1, l == 0 ? dots : nullptr));
         }
@@ -591,7 +725,7 @@ int pcg_solve(pgb200_ert *h) {
     // shard; a Gauss-Newton step changes the model little, so r0 = b - A x is small compared with b
     const double *ax = nullptr;
     if (h->warm_start && h->x_warm_ok) {
-        if (panel_path_ok(h)) { PanelExtra ex{}; CKR(launch_stream<EPI_SPMM>(h, h->stream, h->stream.ent_a.p, h->X.p, h->AP.p, c0, c1, nullptr, ex)); }
+        if (panel_path_ok(h)) { PanelExtra ex{}; CKR(launch_stream<EPI_SPMM>(h, h->stream, 0, h->X.p, h->AP.p, c0, c1, nullptr, ex)); }
         else CKR((launch_spmm<0, false>(h, h->vals.p, nullptr, nullptr, h->X.p, h->AP.p, c0, c1, nullptr)));
         ax = h->AP.p;
         h->warm_used++;
@@ -614,7 +748,7 @@ int pcg_solve(pgb200_ert *h) {
         if (timed) CK(cudaEventRecord(h->pev[h->n_pev++], h->st));
         if (panel_path_ok(h)) {
             PanelExtra ex{};
-            CKR(launch_stream<EPI_SPMM>(h, h->stream, h->stream.ent_a.p, h->P.p, h->AP.p, c0, c1, sc(3), ex));
+            CKR(launch_stream<EPI_SPMM>(h, h->stream, 0, h->P.p, h->AP.p, c0, c1, sc(3), ex));
         } else {
             CK(cudaMemsetAsync(sc(3) + c0, 0, sizeof(double) * (c1 - c0), h->st));
             CKR((launch_spmm<0, true>(h, h->vals.p, nullptr, nullptr, h->P.p, h->AP.p, c0, c1, sc(3))));
@@ -755,7 +889,7 @@ int forward_solve(pgb200_ert *h) {
     k_count_singular<<<cdiv(h->N, 256), 256, 0, h->st>>>(h->diag_pos.p, h->N, h->nK, h->nnz, h->vals.p, h->flags.p + 1); LAUNCH(h);
     k_inv_diag<<<cdiv(h->N, 256), 256, 0, h->st>>>(h->diag_pos.p, h->N, h->nK, h->nnz, h->vals.p, h->dinv.p); LAUNCH(h);
     h->have_vals = true;
-    CKR(stream_pack(h, h->stream, h->vals.p, h->stream.ent_a.p));
+    CKR(stream_pack(h, h->stream, h->vals.p, 0));
     if (h->use_amg) CKR(amg_setup_values(h));
     phase_begin(h, PH_RHS);
     const int c0 = h->c0, c1 = h->c1;
@@ -1283,6 +1417,31 @@ int pgb200_build_stream_panels(int n_rows, const int *rowptr, const int *colidx,
     return 0;
 }
 
+// 8-row-group form of the streamed panels (k_spmm_mma) -- exported for the host-side tests.  Two calls like above:
+// counts[8] = {n_panels, n_chunks, halo entries, k-steps, meta words, meta_gstride, max k-steps per chunk, max meta words per
+// chunk}; arrays: panel_row_ptr[n_panels+1], panel_chunk_ptr[n_panels+1], chunk_halo_ptr[n_chunks+1], halo_cols[halo entries],
+// chunk_ks_ptr[n_chunks+1], a_src[32 * k-steps], chunk_meta_ptr[n_chunks+1], meta[meta words].
+int pgb200_build_mma_panels(int n_rows, const int *rowptr, const int *colidx, int groups, int hc, int max_chunks, int rowb_hint,
+                            int *counts, int *panel_row_ptr, int *panel_chunk_ptr, int *chunk_halo_ptr, int *halo_cols,
+                            int *chunk_ks_ptr, int *a_src, int *chunk_meta_ptr, unsigned *meta) {
+    if (!rowptr || !colidx || !counts) { g_err = "null argument"; return 1; }
+    StreamPanelsHost S;
+    const std::string err = build_stream_panels(n_rows, rowptr, colidx, 8 * groups, hc, max_chunks, S, groups, rowb_hint);
+    if (!err.empty()) { g_err = err; return 1; }
+    const int c[8] = {S.n_panels, S.n_chunks, (int)S.halo_cols.size(), (int)S.n_ks, (int)S.meta.size(), S.meta_gstride, S.max_chunk_ks, S.max_chunk_meta};
+    for (int i = 0; i < 8; i++) counts[i] = c[i];
+    if (!panel_row_ptr) return 0;
+    std::copy(S.panel_row_ptr.begin(), S.panel_row_ptr.end(), panel_row_ptr);
+    std::copy(S.panel_chunk_ptr.begin(), S.panel_chunk_ptr.end(), panel_chunk_ptr);
+    std::copy(S.chunk_halo_ptr.begin(), S.chunk_halo_ptr.end(), chunk_halo_ptr);
+    std::copy(S.halo_cols.begin(), S.halo_cols.end(), halo_cols);
+    std::copy(S.chunk_ks_ptr.begin(), S.chunk_ks_ptr.end(), chunk_ks_ptr);
+    std::copy(S.a_src.begin(), S.a_src.end(), a_src);
+    std::copy(S.chunk_meta_ptr.begin(), S.chunk_meta_ptr.end(), chunk_meta_ptr);
+    std::copy(S.meta.begin(), S.meta.end(), meta);
+    return 0;
+}
+
 // Pairwise aggregation for the multilevel preconditioner: nodes are visited in order; an unaggregated node is matched
 // with the unaggregated neighbour it is most strongly coupled to (most negative off-diagonal), provided the coupling is
 // STRONG for both of them: -a_ij >= theta * max_k(-a_ik) and >= theta * max_k(-a_jk).  Nodes left alone join the
@@ -1385,7 +1544,10 @@ int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
     if (const char *e = getenv("PGB200_STREAM_CHUNKS")) h->stream_chunks = std::max(1, atoi(e));
     if (const char *e = getenv("PGB200_STREAM_ROWS")) h->stream_rmax = std::min(ST_CONSUMER_WARPS * ST_RPW, std::max(1, atoi(e)));
     h->stream_hc = std::max(h->stream_hc, h->stream_rmax);
+    if (const char *e = getenv("PGB200_SPMM_MMA")) h->use_mma = atoi(e);
+    if (const char *e = getenv("PGB200_MMA_HC")) h->mma_hc = std::min(128, std::max((MM_ROWS + 1) / 2, atoi(e)));
     CKR(stream_configure(h));
+    CKR(mma_configure(h));
     CKR(stream_upload(h, h->stream, N, p->rowptr, p->colidx));
     h->dot_slots = std::max(FLAT_MAX_GX, h->num_sms);
     CKR(h->dot_part.alloc(2 * (size_t)h->dot_slots * h->ld));
@@ -1904,6 +2066,43 @@ int pgb200_ert_reset_stats(pgb200_ert *h) {
     for (int p = 0; p < PH_COUNT; p++) h->ph_ms[p] = 0.f;
     return 0;
 }
+// Measurement aid: `reps` back-to-back launches of the fine-level streamed SpMM in epilogue role `role` (0 SpMM + p.Ap,
+// 1 post-smoothing + r.z, 2 residual) on the current matrix and the PCG work vectors (their contents are overwritten);
+// ms_per_launch = CUDA-event time / reps.  The matrix must have been assembled (any response() call).
+int pgb200_ert_bench_spmm(pgb200_ert *h, int role, int reps, double *ms_per_launch) {
+    if (!h || !ms_per_launch || reps < 1) { g_err = "null argument"; return 1; }
+    if (!h->have_vals || !panel_path_ok(h)) PGB_FAIL("bench_spmm: no assembled matrix / streamed path off");
+    CK(cudaSetDevice(h->device));
+    const int c0 = h->c0, c1 = h->c1;
+    double *S = h->scal.p;
+    if (const char *e = getenv("PGB200_MMA_DBG_LATE")) h->mma_dbg = atoi(e);     // ablation runs (ab/bench_spmm.py): results are wrong
+    if (h->mma_dbg & 8) { CKR(h->mma_dbg_buf.alloc(8 * 4096)); CK(cudaMemsetAsync(h->mma_dbg_buf.p, 0, 8 * 4096 * sizeof(long long), h->st)); }
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = -2; i < reps; i++) {
+        if (i == 0) CK(cudaEventRecord(e0, h->st));
+        PanelExtra ex{};
+        if (role == 1) { ex.R = h->R.p; ex.dinvw = h->dinvw0.p ? h->dinvw0.p : h->dinv.p; ex.n = h->N; CKR(launch_stream<EPI_POST>(h, h->stream, 0, h->P.p, h->AP.p, c0, c1, S + 3 * h->ld, ex)); }
+        else if (role == 2) CKR(launch_stream<EPI_RESIDUAL>(h, h->stream, 0, h->P.p, h->AP.p, c0, c1, nullptr, ex));
+        else CKR(launch_stream<EPI_SPMM>(h, h->stream, 0, h->P.p, h->AP.p, c0, c1, S + 3 * h->ld, ex));
+    }
+    CK(cudaEventRecord(e1, h->st));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f; CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (h->mma_dbg & 8) {
+        std::vector<long long> v(8 * 4096);
+        CK(cudaMemcpy(v.data(), h->mma_dbg_buf.p, v.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        const long long t0 = v[0];
+        for (int st = 0; st < 4096 && v[8 * st + 0]; st++) {
+            fprintf(stderr, "stage %3d  prod: wait %6lld issued %6lld (+%lld)   cons: wait %6lld got %6lld loop %6lld done %6lld\n", st, v[8 * st] - t0, v[8 * st + 1] - t0,
+                    v[8 * st + 2] - v[8 * st + 1], v[8 * st + 3] - t0, v[8 * st + 4] - t0, v[8 * st + 5] - t0, v[8 * st + 6] - t0);
+        }
+    }
+    h->mma_dbg = 0;
+    *ms_per_launch = (double)ms / reps;
+    return 0;
+}
+
 int pgb200_ert_set_spmm_variant(pgb200_ert *h, int panel_staged) {
     if (!h) PGB_FAIL("null handle");
     h->use_panels = panel_staged != 0;

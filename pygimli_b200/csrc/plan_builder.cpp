@@ -366,10 +366,13 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
             std::vector<double> us(u);
             std::sort(us.begin(), us.end());
             us.erase(std::unique(us.begin(), us.end()), us.end());
+            // structured meshes (few distinct coordinates per axis): the rank itself, so that 2^d consecutive nodes of the
+            // curve are the corners of one grid cell -- the 8-row groups of k_spmm_mma then share most of their columns
+            const bool raw = us.size() <= ((size_t)1 << bits);
             const double factor = (double)(1 << bits) / (double)std::max<size_t>(1, us.size());
             for (int i = 0; i < N; i++) {
                 const uint64_t rank = (uint64_t)(std::lower_bound(us.begin(), us.end(), u[i]) - us.begin());
-                const uint64_t q = (uint64_t)((double)rank * factor);
+                const uint64_t q = raw ? rank : (uint64_t)((double)rank * factor);
                 code[i] |= spread_bits(q, dim, bits) << ax;
             }
         }

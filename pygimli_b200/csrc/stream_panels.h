@@ -34,13 +34,34 @@ struct StreamPanelsHost {
     std::vector<int> run_col;           // ... its column
     std::vector<int> run_len;           // ... number of consecutive columns
     int max_chunk_runs = 0;
+    // ---- dense 8-row-group form for the FP64 tensor-core kernel (k_spmm_mma; built when mma_groups > 0) ----
+    // Rows of a panel are cut into GROUPS of 8 consecutive rows (one per consumer warp).  Per (chunk, group) the distinct
+    // halo entries the group's rows touch inside that chunk (the "union columns") are cut into K-STEPS of 4: one k-step is
+    // one DMMA m8n8k4 per 8 source columns, A = the group's 8 x 4 block of matrix values (zeros where a row has no entry).
+    int mma_groups = 0, meta_gstride = 0, max_chunk_ks = 0, max_chunk_meta = 0;
+    long long n_ks = 0;                 // k-steps in total
+    std::vector<int> chunk_ks_ptr;      // [n_chunks + 1] first k-step of a chunk
+    std::vector<int> a_src;             // [n_ks * 32] CSR slot of A-fragment element (lane = 4 * row-in-group + column-in-step), -1 = zero
+    std::vector<int> chunk_meta_ptr;    // [n_chunks + 1] offset (in 32-bit words, multiple of 4) of the chunk's meta block
+    std::vector<unsigned> meta;         // per chunk: [k-step range start of every group (meta_gstride words) | one word per k-step:
+                                        //             the 4 staged-row indices of its columns, one byte each]
 };
 
 // rmax: rows per panel (<= hc), hc: halo entries per chunk, max_chunks: chunks per panel.  Returns "" or an error text.
+// mma_groups > 0: additionally build the 8-row-group form (rmax <= 8 * mma_groups, hc <= 255); rowb_hint = bytes of one
+// staged X row in the most common launch (orders the columns of a k-step so that the four 64-byte B-fragment spans fall
+// into different shared-memory banks).
 inline std::string build_stream_panels(int n, const int *rowptr, const int *colidx, int rmax, int hc, int max_chunks,
-                                       StreamPanelsHost &S) {
-    if (n < 0 || rmax < 1 || hc < rmax || max_chunks < 1) return "invalid stream-panel limits";
+                                       StreamPanelsHost &S, int mma_groups = 0, int rowb_hint = 800) {
+    // 8-row-group form: the panel's own rows may span chunks 0 AND 1 (the kernel keeps both resident for the epilogue), so
+    // chunks can be half a panel: a deeper ring of smaller stages
+    if (n < 0 || rmax < 1 || max_chunks < 1 || (mma_groups > 0 ? 2 * hc < rmax : hc < rmax)) return "invalid stream-panel limits";
+    if (mma_groups > 0 && (rmax > 8 * mma_groups || hc > 255 || max_chunks < 2)) return "invalid stream-panel limits (8-row groups)";
     S = StreamPanelsHost();
+    S.mma_groups = mma_groups;
+    S.meta_gstride = mma_groups > 0 ? (mma_groups + 1 + 3) / 4 * 4 : 0;
+    if (mma_groups > 0) { S.chunk_ks_ptr.push_back(0); S.chunk_meta_ptr.push_back(0); }
+    std::vector<int> upos((size_t)std::max(hc, 1), -1), ulist, usrc, order;
     S.n_rows = n; S.nnz = n > 0 ? rowptr[n] : 0;
     S.crp_stride = (rmax + 1 + 3) / 4 * 4;                       // 16-byte multiple: one bulk copy
     const int hmax = hc * max_chunks;
@@ -88,7 +109,16 @@ inline std::string build_stream_panels(int n, const int *rowptr, const int *coli
         // chunk boundaries: balanced, chunk 0 holds at least the own rows
         std::vector<int> cb((size_t)nch + 1, hn);
         cb[0] = 0;
-        if (nch > 1) {
+        if (nch > 1 && mma_groups > 0 && nrows > hc) {
+            // more own rows than a chunk holds: chunks 0 and 1 share them (both at least half the panel), the rest is balanced
+            const int c01 = std::max((hn + nch - 1) / nch, (nrows + 1) / 2);
+            cb[1] = std::min(hn, c01);
+            if (nch > 2) {
+                cb[2] = std::min(hn, 2 * c01);
+                const int rem = hn - cb[2], per = (rem + nch - 3) / (nch - 2);
+                for (int c = 3; c < nch; c++) cb[c] = std::min(hn, cb[2] + (c - 2) * per);
+            }
+        } else if (nch > 1) {
             const int c0size = std::max((hn + nch - 1) / nch, nrows);
             const int rem = hn - c0size, per = (rem + nch - 2) / (nch - 1);
             for (int c = 1; c < nch; c++) cb[c] = std::min(hn, c0size + (c - 1) * per);
@@ -125,6 +155,73 @@ inline std::string build_stream_panels(int n, const int *rowptr, const int *coli
             for (int i = nrows; i < S.crp_stride; i++) S.crp[crp0 + (size_t)i] = cnt;
             S.chunk_ent_ptr.push_back((int)ent_pos);
             S.max_chunk_ent = std::max(S.max_chunk_ent, cnt);
+            if (mma_groups > 0) {
+                const size_t m0 = S.meta.size();
+                S.meta.resize(m0 + (size_t)S.meta_gstride, 0u);
+                int ks_chunk = 0;
+                for (int g = 0; g < mma_groups; g++) {
+                    S.meta[m0 + (size_t)g] = (unsigned)ks_chunk;
+                    const int ra = start + 8 * g, rb = std::min(row, ra + 8);
+                    if (ra >= row) continue;
+                    // union of the group's columns inside this chunk, in first-touch order; usrc[u * 8 + r] = CSR slot or -1
+                    ulist.clear(); usrc.clear();
+                    for (int r = ra; r < rb; r++)
+                        for (int p = rowptr[r]; p < rowptr[r + 1]; p++) {
+                            const int s = slot[colidx[p]];
+                            if (s < cb[c] || s >= cb[c + 1]) continue;
+                            const int i = s - cb[c];
+                            if (upos[(size_t)i] < 0) { upos[(size_t)i] = (int)ulist.size(); ulist.push_back(i); usrc.insert(usrc.end(), 8, -1); }
+                            usrc[(size_t)upos[(size_t)i] * 8 + (size_t)(r - ra)] = p;
+                        }
+                    const int nu = (int)ulist.size();
+                    for (int i : ulist) upos[(size_t)i] = -1;
+                    if (nu == 0) continue;
+                    // order the columns: a 64-bit LDS is served per half-warp, i.e. per k-step four 32-byte segments (one per
+                    // column, start = idx * rowb mod 128, in units of 16 bytes: classes 0..7, a segment covers 2 consecutive
+                    // classes): every k-step takes 4 columns whose segments overlap as little as possible
+                    std::vector<int> bucket[8];
+                    for (int u = nu - 1; u >= 0; u--) bucket[((long long)ulist[(size_t)u] * rowb_hint % 128) / 16].push_back(u);
+                    const int nks = (nu + 3) / 4;
+                    order.assign((size_t)nks * 4, -1);
+                    int left = nu;
+                    for (int k = 0; k < nks; k++) {
+                        int cover[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                        for (int j = 0; j < 4 && left > 0; j++) {
+                            int best = -1, best_max = 1 << 30; size_t best_size = 0;
+                            for (int cl = 0; cl < 8; cl++) {
+                                if (bucket[cl].empty()) continue;
+                                int mx = 0;
+                                for (int q = 0; q < 8; q++) { const int add = (((q - cl) & 7) < 2) ? 1 : 0; mx = std::max(mx, cover[q] + add); }
+                                if (mx < best_max || (mx == best_max && bucket[cl].size() > best_size)) { best = cl; best_max = mx; best_size = bucket[cl].size(); }
+                            }
+                            for (int q = 0; q < 8; q++) if (((q - best) & 7) < 2) cover[q]++;
+                            order[(size_t)k * 4 + (size_t)j] = bucket[best].back(); bucket[best].pop_back(); left--;
+                        }
+                    }
+                    for (int k = 0; k < nks; k++) {
+                        unsigned word = 0;
+                        const size_t a0 = S.a_src.size();
+                        S.a_src.resize(a0 + 32, -1);
+                        for (int j = 0; j < 4; j++) {
+                            const int u = order[(size_t)k * 4 + (size_t)j];
+                            const int idx = u >= 0 ? ulist[(size_t)u] : ulist[(size_t)order[(size_t)k * 4]];   // padding: any staged row, zero values
+                            word |= (unsigned)idx << (8 * j);
+                            if (u >= 0) for (int r = 0; r < 8; r++) S.a_src[a0 + (size_t)(4 * r + j)] = usrc[(size_t)u * 8 + (size_t)r];
+                        }
+                        S.meta.push_back(word);
+                    }
+                    ks_chunk += nks;
+                }
+                for (int g = mma_groups; g < S.meta_gstride; g++) S.meta[m0 + (size_t)g] = (unsigned)ks_chunk;
+                // groups without rows point at the end too (written as 'continue' above left them at their running value)
+                for (int g = 0; g < mma_groups; g++) if (start + 8 * g >= row) S.meta[m0 + (size_t)g] = (unsigned)ks_chunk;
+                while (S.meta.size() % 4) S.meta.push_back(0u);
+                S.n_ks += ks_chunk;
+                S.chunk_ks_ptr.push_back((int)S.n_ks);
+                S.chunk_meta_ptr.push_back((int)S.meta.size());
+                S.max_chunk_ks = std::max(S.max_chunk_ks, ks_chunk);
+                S.max_chunk_meta = std::max(S.max_chunk_meta, (int)(S.meta.size() - m0));
+            }
         }
         S.n_chunks += nch;
         S.max_rows = std::max(S.max_rows, nrows);

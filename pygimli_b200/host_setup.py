@@ -397,7 +397,10 @@ def node_ordering(mesh: MeshArrays) -> np.ndarray:
     code = np.zeros(mesh.node_count, np.uint64)
     for ax in range(dim):
         u, inv = np.unique(mesh.pos[:, ax], return_inverse=True)
-        q = (inv.astype(np.float64) * ((1 << bits) / max(1, u.size))).astype(np.uint64)
+        if u.size <= (1 << bits):     # structured meshes: the rank itself, 2^d consecutive nodes = one grid cell (k_spmm_mma groups)
+            q = inv.astype(np.uint64)
+        else:
+            q = (inv.astype(np.float64) * ((1 << bits) / max(1, u.size))).astype(np.uint64)
         code |= _spread_bits(q, dim, bits) << np.uint64(ax)
     return np.argsort(code, kind="stable").astype(np.int64)
 

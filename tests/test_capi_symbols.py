@@ -115,3 +115,63 @@ def test_compute_fails_loudly_without_gpu():
     fop.setData(scheme)
     with pytest.raises(_capi.PGB200Error, match="no CUDA device"):
         fop.response(model)
+
+
+def _replay_mma_spmm(pan, vals, X):
+    """CPU replay of k_spmm_mma: per panel, chunks last to first; per (chunk, group) the k-steps: an 8 x 4 block of A
+    values (fragment order: element 4 * row + column) times the 4 staged rows the k-step's word names"""
+    N = X.shape[0]
+    Y = np.zeros_like(X)
+    G, gs = pan["groups"], pan["meta_gstride"]
+    for p in range(pan["n_panels"]):
+        r0, r1 = pan["panel_row_ptr"][p], pan["panel_row_ptr"][p + 1]
+        acc = np.zeros((8 * G, X.shape[1]))
+        for ch in range(pan["panel_chunk_ptr"][p + 1] - 1, pan["panel_chunk_ptr"][p] - 1, -1):
+            h0, h1 = pan["chunk_halo_ptr"][ch], pan["chunk_halo_ptr"][ch + 1]
+            staged = X[pan["halo_cols"][h0:h1]]
+            k0 = pan["chunk_ks_ptr"][ch]
+            m0 = pan["chunk_meta_ptr"][ch]
+            gptr = pan["meta"][m0:m0 + gs].astype(np.int64)
+            words = pan["meta"][m0 + gs:pan["chunk_meta_ptr"][ch + 1]]
+            assert gptr[G] == pan["chunk_ks_ptr"][ch + 1] - k0
+            for g in range(G):
+                for ks in range(gptr[g], gptr[g + 1]):
+                    src = pan["a_src"][32 * (k0 + ks):32 * (k0 + ks + 1)].reshape(8, 4)
+                    a = np.where(src >= 0, vals[np.maximum(src, 0)], 0.0)
+                    idx = [(int(words[ks]) >> (8 * j)) & 0xff for j in range(4)]
+                    assert max(idx) < h1 - h0
+                    acc[8 * g:8 * g + 8] += a @ staged[idx]
+            if ch == pan["panel_chunk_ptr"][p]:
+                assert np.array_equal(pan["halo_cols"][h0:h0 + (r1 - r0)], np.arange(r0, r1))
+        Y[r0:r1] = acc[:r1 - r0]
+        assert not np.any(acc[r1 - r0:])
+    return Y
+
+
+@pytest.mark.parametrize("name,limits", [("3d_p1", (12, 104, 8, 800)), ("3d_p2", (12, 104, 8, 800)), ("2d_p1", (12, 104, 8, 336)),
+                                         ("3d_p1", (12, 52, 10, 800)), ("3d_p2", (12, 48, 16, 800)), ("2d_p2", (12, 52, 10, 400)),
+                                         ("3d_p1", (2, 40, 6, 96)), ("2d_p2", (1, 30, 8, 400))])
+def test_mma_panels_reproduce_spmm(name, limits):
+    """the 8-row-group form (k_spmm_mma) uses every CSR entry exactly once and its dense 8 x 4 blocks times the staged rows
+    equal A @ X"""
+    import scipy.sparse as sp
+    from cases import make_case
+    from pygimli_b200.host_setup import build_pattern
+    mesh, _, _ = make_case(name)
+    rowptr, colidx, _ = build_pattern(mesh)
+    groups, hc, nch, rowb = limits
+    pan = _capi.build_mma_panels(rowptr, colidx, groups, hc, nch, rowb)
+    N = mesh.node_count
+    pr = pan["panel_row_ptr"]
+    assert pr[0] == 0 and pr[-1] == N and np.all(np.diff(pr) > 0) and np.all(np.diff(pr) <= 8 * groups)
+    assert np.all(np.diff(pan["chunk_halo_ptr"]) <= hc) and np.all(np.diff(pan["panel_chunk_ptr"]) <= nch)
+    assert np.all(pan["chunk_meta_ptr"] % 4 == 0)
+    used = pan["a_src"][:32 * pan["n_ks"]]
+    assert np.array_equal(np.sort(used[used >= 0]), np.arange(colidx.size))       # every CSR slot exactly once
+    rng = np.random.default_rng(0)
+    vals = rng.standard_normal(colidx.size)
+    X = rng.standard_normal((N, 5))
+    A = sp.csr_matrix((vals, colidx, rowptr), shape=(N, N))
+    Y = _replay_mma_spmm(pan, vals, X)
+    ref = A @ X
+    assert np.max(np.abs(Y - ref)) <= 1e-12 * np.max(np.abs(ref))
