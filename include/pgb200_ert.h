@@ -302,6 +302,22 @@ int pgb200_ert_reset_stats(pgb200_ert *h);
  * thread of the widest chunk, [6] 1 if every chunk uses pre-resolved Gram offsets, [7] coarse levels of the multilevel
  * preconditioner, [8] shared-memory slots of the streamed kernel's ring, [9] coarse levels on the streamed kernel  */
 int pgb200_ert_path_info(pgb200_ert *h, int *out, int n);
+/* ---- complex resistivity (induced polarisation): DCMultiElectrodeModelling with setComplex(true) ------------------------
+ * Replaces CSparseMatrix assembly (core/src/bert/dcfemmodelling.cpp:235-242), the complex total-field solves (:1755-1925,
+ * cholmodWrapper.cpp:167-222) and createJacobian_(CVector, CMatrix) (:1410-1444).  The handle must be opened as a TOTAL-FIELD
+ * problem (sr = 0) on a scheme that lists every electrode twice (sensors = [s_0..s_{n-1}, s_0..s_{n-1}]) and whose rows are the
+ * four real blocks of the complex sensitivity -- (a,b,m,n), (a+n,b+n,m+n,n+n), (a,b,m+n,n+n), (a+n,b+n,m,n) for every datum --,
+ * with the wavenumbers of the original electrode list; pygimli_b200.CoreB200.setComplex(True) builds exactly that.  Inside a
+ * wavenumber group the first n source columns carry the real parts of the potentials, the next n the imaginary parts.
+ * S = S_r + i S_i is complex symmetric: conjugate-orthogonal CG preconditioned by the real multilevel cycle of S_r.      */
+int pgb200_ert_set_complex(pgb200_ert *h, int on);
+/* model_host = [Re rho (n_in) | Im rho (n_in)].  After the call pgb200_ert_pm_info holds the doubled electrode matrix
+ * (row i < n: real part of the potentials of source i at the electrodes, row n + i: imaginary part).              */
+int pgb200_ert_complex_forward(pgb200_ert *h, const double *model_host, int n_in);
+/* j_host: D x M complex values (D = scheme rows / 4), row-major, interleaved (re, im); rows scaled by kfac_host[d] / m_j^2
+ * when n_in == M.  Solves first if the handle has no potentials of a complex forward call.                        */
+int pgb200_ert_complex_jacobian(pgb200_ert *h, const double *model_host, int n_in, const double *kfac_host, double *j_host);
+
 /* Measurement aid: `reps` back-to-back launches of the fine-level streamed SpMM (role 0: SpMM + p.Ap, 1: post-smoothing +
  * r.z, 2: residual) on the assembled matrix and the PCG work vectors (overwritten); CUDA-event time per launch in ms. */
 int pgb200_ert_bench_spmm(pgb200_ert *h, int role, int reps, double *ms_per_launch);

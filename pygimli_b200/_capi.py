@@ -65,7 +65,7 @@ EXPORTS = [
     "pgb200_ert_mark_potentials_valid", "pgb200_ert_forward_dev", "pgb200_ert_pm_info", "pgb200_ert_finish_response_dev",
     "pgb200_ert_pack_potentials", "pgb200_ert_get", "pgb200_ert_stats", "pgb200_ert_reset_stats", "pgb200_ert_set_profile",
     "pgb200_spmm", "pgb200_ert_get_trace", "pgb200_ert_set_primary_dev", "pgb200_ert_fill_matrix", "pgb200_ert_jacobian_mult_lr", "pgb200_ert_jacobian_tmult_lr", "pgb200_ert_coverage_trans",
-    "pgb200_ert_path_info", "pgb200_ert_bench_spmm", "pgb200_ert_potentials_state",
+    "pgb200_ert_path_info", "pgb200_ert_bench_spmm", "pgb200_ert_set_complex", "pgb200_ert_complex_forward", "pgb200_ert_complex_jacobian", "pgb200_ert_potentials_state",
     "pgb200_ert_set_warm_start",
     "pgb200_plan_build", "pgb200_plan_free", "pgb200_plan_error", "pgb200_plan_view", "pgb200_plan_array", "pgb200_plan_scalar",
     "pgb200_plan_build_hierarchy", "pgb200_plan_levels", "pgb200_ert_open", "pgb200_ert_open_plan", "pgb200_ert_plan",
@@ -120,6 +120,9 @@ def lib():
         L.pgb200_ert_set_profile.argtypes = [C.c_void_p, C.c_int]
         L.pgb200_ert_path_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.pgb200_ert_bench_spmm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.pgb200_ert_set_complex.argtypes = [C.c_void_p, C.c_int]
+        L.pgb200_ert_complex_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.pgb200_ert_complex_jacobian.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.pgb200_plan_error.restype = C.c_char_p
         L.pgb200_plan_build.argtypes = [C.POINTER(MeshIn), C.POINTER(SchemeIn), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
         L.pgb200_plan_free.argtypes = [C.c_void_p]

@@ -1285,6 +1285,149 @@ k_pcg_update_p(const double *__restrict__ R, const double *__restrict__ dinv, do
 }
 
 // ---------------------------------------------------------------------------------
+// complex resistivity (reference: DCMultiElectrodeModelling with setComplex(true),
+// dcfemmodelling.cpp:235-242 CSparseMatrix assembly, :1755-1925 complex total-field solves, :1410-1444 complex Jacobian).
+// S = S_r + i S_i is complex SYMMETRIC (sigma = 1/rho complex per cell, real element matrices): solved by COCG
+// (conjugate orthogonal CG: the CG recurrence with the unconjugated product x^T y) preconditioned by the real multilevel
+// cycle of S_r applied to real and imaginary parts alike.  Layout: the handle is built with every electrode listed twice
+// (plan with 2 nE "electrodes"): inside wavenumber group k, columns [0, nE) hold the REAL parts and [nE, 2 nE) the IMAGINARY
+// parts of the nE complex sources, so every real kernel of the path (SpMM, multilevel cycle, pick-up, Jacobian) runs
+// unchanged on the 2 nS real columns.  The kernels below work per COMPLEX source j (flat mapping over [0, nS/2)).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ int cplx_col(int j, int nEc) { return (j / nEc) * 2 * nEc + (j % nEc); }   // real part; imaginary: + nEc
+
+// 1 / sigma_r and 1 / sigma_i per cell for the two assembly passes (sigma = 1 / (rho_r + i rho_i)); flag: |rho| <= 1e-12
+__global__ void k_cplx_sigma(const double *__restrict__ rr, const double *__restrict__ ri, int C, double *__restrict__ inv_sr,
+                             double *__restrict__ inv_si, int *flag) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double a = rr[c], b = ri[c], d = a * a + b * b;
+    if (!(d > 1e-24)) { atomicOr(flag, 1); inv_sr[c] = 0.0; inv_si[c] = 0.0; return; }     // both passes skip the cell
+    inv_sr[c] = d / a;            // sigma_r =  a / d
+    inv_si[c] = -d / b;           // sigma_i = -b / d   (b == 0: -inf -> contributes 0)
+}
+__global__ void k_set_slots(const int *__restrict__ slots, int n, int nK, size_t nnz, double value, double *__restrict__ vals) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) for (int kk = 0; kk < nK; kk++) vals[(size_t)kk * nnz + slots[t]] = value;
+}
+// right-hand sides: the imaginary-part columns of the doubled layout are zero (real unit currents)
+__global__ void k_cplx_zero_imag_cols(double *__restrict__ B, int N, int nEc, int nS2, size_t ld) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * nS2) return;
+    const int row = (int)(i / nS2), c = (int)(i % nS2);
+    if ((c % (2 * nEc)) >= nEc) B[(size_t)row * ld + c] = 0.0;
+}
+// out0[j] + i out1[j] = sum_rows a b (unconjugated);  NORM: out0[j] = sum |a|^2 (b unused)
+template <bool NORM>
+__global__ void __launch_bounds__(FLAT_T)
+k_cplx_dot(const double *__restrict__ Av, const double *__restrict__ Bv, int N, int nEc, int nSc, size_t ld, int cw, const DotOut D) {
+    const FlatMap f = flat_map(0, nSc, cw);
+    double s0 = 0.0, s1 = 0.0;
+    if (f.active) {
+        const int cr = cplx_col(f.col, nEc), ci = cr + nEc;
+        int lo, hi; flat_rows(N, lo, hi);
+        for (int row = lo + f.roff; row < hi; row += f.rpp) {
+            const size_t o = (size_t)row * ld;
+            const double ar = Av[o + cr], ai = Av[o + ci];
+            if (NORM) { s0 = fma(ar, ar, s0); s0 = fma(ai, ai, s0); }
+            else { const double br = Bv[o + cr], bi = Bv[o + ci]; s0 += ar * br - ai * bi; s1 += ar * bi + ai * br; }
+        }
+    }
+    flat_col_finalize(s0, s1, f, D);
+}
+// q = (S_r + i S_i) p from Y1 = S_r [p_r | p_i] and Y2 = S_i [p_r | p_i]:  q_r = Y1_r - Y2_i,  q_i = Y2_r + Y1_i  (written
+// over Y1);  out = p^T q
+__global__ void __launch_bounds__(FLAT_T)
+k_cplx_combine(double *__restrict__ Y1, const double *__restrict__ Y2, const double *__restrict__ P, int N, int nEc, int nSc, size_t ld,
+               int cw, const DotOut D) {
+    const FlatMap f = flat_map(0, nSc, cw);
+    double s0 = 0.0, s1 = 0.0;
+    if (f.active) {
+        const int cr = cplx_col(f.col, nEc), ci = cr + nEc;
+        int lo, hi; flat_rows(N, lo, hi);
+        for (int row = lo + f.roff; row < hi; row += f.rpp) {
+            const size_t o = (size_t)row * ld;
+            const double qr = Y1[o + cr] - Y2[o + ci], qi = Y2[o + cr] + Y1[o + ci];
+            Y1[o + cr] = qr; Y1[o + ci] = qi;
+            const double pr = P[o + cr], pi = P[o + ci];
+            s0 += pr * qr - pi * qi; s1 += pr * qi + pi * qr;
+        }
+    }
+    flat_col_finalize(s0, s1, f, D);
+}
+// alpha = rho / (p^T q);  x += alpha p;  r -= alpha q;  out1 = |r|^2     (scalars: [re | im] at j and ldS + j)
+__global__ void __launch_bounds__(FLAT_T)
+k_cplx_update_xr(const double *__restrict__ P, const double *__restrict__ Q, double *__restrict__ Xv, double *__restrict__ R, int N, int nEc,
+                 int nSc, size_t ld, const double *__restrict__ rho, const double *__restrict__ pq, size_t ldS, int cw, const DotOut D) {
+    const FlatMap f = flat_map(0, nSc, cw);
+    double s1 = 0.0;
+    if (f.active) {
+        const int cr = cplx_col(f.col, nEc), ci = cr + nEc;
+        const double nr = rho[f.col], ni = rho[ldS + f.col], dr = pq[f.col], di = pq[ldS + f.col];
+        const double dd = dr * dr + di * di;
+        const double ar = dd > 0.0 ? (nr * dr + ni * di) / dd : 0.0, ai = dd > 0.0 ? (ni * dr - nr * di) / dd : 0.0;
+        int lo, hi; flat_rows(N, lo, hi);
+        for (int row = lo + f.roff; row < hi; row += f.rpp) {
+            const size_t o = (size_t)row * ld;
+            const double pr = P[o + cr], pi = P[o + ci], qr = Q[o + cr], qi = Q[o + ci];
+            Xv[o + cr] += ar * pr - ai * pi; Xv[o + ci] += ar * pi + ai * pr;
+            const double rr = R[o + cr] - (ar * qr - ai * qi), ri = R[o + ci] - (ar * qi + ai * qr);
+            R[o + cr] = rr; R[o + ci] = ri;
+            s1 = fma(rr, rr, s1); s1 = fma(ri, ri, s1);
+        }
+    }
+    flat_col_finalize(0.0, s1, f, D);
+}
+// beta = rho_new / rho;  p = z + beta p   (p = 0 once the column has converged)
+__global__ void __launch_bounds__(FLAT_T)
+k_cplx_update_p(const double *__restrict__ Z, double *__restrict__ P, int N, int nEc, int nSc, size_t ld, const double *__restrict__ rho,
+                const double *__restrict__ rho_new, size_t ldS, const double *__restrict__ rr, const double *__restrict__ bb, double tol2, int cw) {
+    const FlatMap f = flat_map(0, nSc, cw);
+    if (!f.active) return;
+    const int cr = cplx_col(f.col, nEc), ci = cr + nEc;
+    const bool done = !(rr[f.col] > tol2 * bb[f.col]);
+    const double nr = rho_new[f.col], ni = rho_new[ldS + f.col], dr = rho[f.col], di = rho[ldS + f.col];
+    const double dd = dr * dr + di * di;
+    const double br = dd > 0.0 ? (nr * dr + ni * di) / dd : 0.0, bi = dd > 0.0 ? (ni * dr - nr * di) / dd : 0.0;
+    int lo, hi; flat_rows(N, lo, hi);
+    for (int row = lo + f.roff; row < hi; row += f.rpp) {
+        const size_t o = (size_t)row * ld;
+        const double pr = P[o + cr], pi = P[o + ci];
+        P[o + cr] = done ? 0.0 : Z[o + cr] + (br * pr - bi * pi);
+        P[o + ci] = done ? 0.0 : Z[o + ci] + (br * pi + bi * pr);
+    }
+}
+// complex Jacobian from the four real blocks of the doubled scheme (rows [0,D): ab_r.mn_r, [D,2D): ab_i.mn_i, [2D,3D):
+// ab_r.mn_i, [3D,4D): ab_i.mn_r):  J = ((J0 - J1) + i (J2 + J3)) * k_d / m_col^2   (:1410-1444, no conjugation);
+// out: row-major [D][M] interleaved (re, im).  scale == 0: unscaled (model length != columns)
+__global__ void k_cplx_jacobian(const double *__restrict__ Jt, size_t ldJ, int D, int M, const double *__restrict__ kfac,
+                                const double *__restrict__ m_re, const double *__restrict__ m_im, int scale, double *__restrict__ out) {
+    __shared__ double t0[32][33], t1[32][33];
+    const int c0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+        const int col = c0 + jj, d = d0 + threadIdx.x;
+        double re = 0.0, im = 0.0;
+        if (col < M && d < D) {
+            const double *cj = Jt + (size_t)col * ldJ;
+            re = cj[d] - cj[D + d]; im = cj[2 * D + d] + cj[3 * D + d];
+            if (scale) {
+                const double a = m_re[col], b = m_im[col];
+                const double sr = a * a - b * b, si = 2.0 * a * b, dd = sr * sr + si * si;      // m^2
+                const double k = kfac[d];
+                const double xr = (re * sr + im * si) / dd * k, xi = (im * sr - re * si) / dd * k;
+                re = xr; im = xi;
+            }
+        }
+        t0[jj][threadIdx.x] = re; t1[jj][threadIdx.x] = im;
+    }
+    __syncthreads();
+    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+        const int d = d0 + jj, col = c0 + threadIdx.x;
+        if (d < D && col < M) { out[2 * ((size_t)d * M + col)] = t0[threadIdx.x][jj]; out[2 * ((size_t)d * M + col) + 1] = t1[threadIdx.x][jj]; }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // multilevel preconditioner (unsmoothed aggregation, V(1,1), damped Jacobi) -- see amg_setup.py
 // All kernels work on node-major block vectors of one level and the column window [c0,c1).
 // ---------------------------------------------------------------------------------

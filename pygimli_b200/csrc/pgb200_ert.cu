@@ -121,7 +121,9 @@ struct pgb200_ert {
     std::vector<int> color_ptr, pro_level_ptr;
     StreamDev stream; int use_panels = 1, use_panels_build = 1;   // streamed row panels of the fine level (use_panels 0: plain gather SpMM, A/B evidence)
     int stream_rmax = std::min(60, ST_CONSUMER_WARPS * ST_RPW), stream_hc = 104, stream_chunks = 2; // panel limits (stream_panels.h)
-    int use_mma = 1, mma_hc = 104, mma_chunks = 10, mma_dbg = 0; DevBuf<long long> mma_dbg_buf;      // FP64 tensor-core form of the streamed SpMM (k_spmm_mma); 0: k_spmm_stream
+    int use_mma = 1, mma_hc = 104, mma_chunks = 10, mma_dbg = 0; DevBuf<long long> mma_dbg_buf;
+    // complex resistivity (pgb200_ert_set_complex): plan built with every electrode listed twice, see ert_kernels.cuh
+    int is_complex = 0; DevBuf<double> c_rho_r, c_y2, c_scal, c_model, c_out;      // FP64 tensor-core form of the streamed SpMM (k_spmm_mma); 0: k_spmm_stream
     DevBuf<double> dot_part; DevBuf<unsigned> dot_counter;    // deterministic column dots: per-CTA partial rows + tickets
     int dot_slots = 0; size_t smem_optin = 0;
     std::vector<double> h_kvals;
@@ -2100,6 +2102,169 @@ int pgb200_ert_bench_spmm(pgb200_ert *h, int role, int reps, double *ms_per_laun
     }
     h->mma_dbg = 0;
     *ms_per_launch = (double)ms / reps;
+    return 0;
+}
+
+// ---- complex resistivity -------------------------------------------------------------------------------
+// The handle must come from a plan that lists every electrode twice (sensors = [sensors | sensors], total-field scheme, sr = 0):
+// within a wavenumber group the first nE/2 source columns carry real parts, the others imaginary parts.
+int pgb200_ert_set_complex(pgb200_ert *h, int on) {
+    if (!h) PGB_FAIL("null handle");
+    if (on && (h->sr || (h->nE & 1))) PGB_FAIL("complex resistivity needs a total-field handle (sr = 0) built with every electrode listed twice");
+    h->is_complex = on != 0;
+    h->pots_valid = false; h->shard_solved = false; h->jac_valid = false;
+    return 0;
+}
+
+namespace {
+// z = D^-1 r on all columns (levels without a hierarchy: Jacobi)
+__global__ void k_cplx_jacobi(const double *__restrict__ R, const double *__restrict__ dinv, double *__restrict__ Z, int N, int nE, int nS, size_t ld) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)N * nS) return;
+    const int row = (int)(i / nS), c = (int)(i % nS);
+    Z[(size_t)row * ld + c] = dinv[(size_t)(c / nE) * N + row] * R[(size_t)row * ld + c];
+}
+
+// model_dev: [re (n_in) | im (n_in)];  assemble S_r, S_i, solve all sources by COCG, potentials -> U
+int complex_forward(pgb200_ert *h, const double *model_dev, int n_in) {
+    if (!h->is_complex) PGB_FAIL("pgb200_ert_set_complex(h, 1) first");
+    if (h->c0 != 0 || h->c1 != h->nS) PGB_FAIL("complex resistivity: source shards are not supported");
+    const int N = h->N, nE = h->nE, nEc = nE / 2, nS = h->nS, nSc = nS / 2;
+    const size_t ld = h->ld;
+    cudaStream_t st = h->st;
+    if (!h->c_rho_r.p) {
+        CKR(h->c_rho_r.alloc((size_t)h->C)); CKR(h->c_y2.alloc((size_t)N * ld)); CKR(h->c_scal.alloc(8 * ld));
+        if (!h->vals1.p) CKR(h->vals1.alloc(h->nnz * h->nK));
+    }
+    // mapERTModel(CVector) (:1199-1208): real and imaginary parts are mapped and prolongated separately
+    phase_begin(h, PH_MAP);
+    CKR(map_model(h, model_dev, n_in));
+    CK(cudaMemcpyAsync(h->c_rho_r.p, h->rho.p, sizeof(double) * h->C, cudaMemcpyDeviceToDevice, st));
+    CKR(map_model(h, model_dev + n_in, n_in));
+    CK(cudaMemsetAsync(h->flags.p, 0, sizeof(int) * 4, st));              // the positivity check of the real path does not apply
+    k_cplx_sigma<<<cdiv(h->C, 256), 256, 0, st>>>(h->c_rho_r.p, h->rho.p, h->C, h->c_rho_r.p, h->rho.p, h->flags.p); LAUNCH(h);
+    // S_r and S_i (:235-242): two real assembly passes with 1/sigma_r and 1/sigma_i as "resistivities"
+    phase_begin(h, PH_ASM);
+    CKR(assemble(h, h->c_rho_r.p, h->vals.p));
+    CKR(assemble(h, h->rho.p, h->vals1.p));
+    if (h->n_dir_nodes) { k_set_slots<<<cdiv(h->n_dir_nodes, 128), 128, 0, st>>>(h->dir_diag.p, h->n_dir_nodes, h->nK, h->nnz, 0.0, h->vals1.p); LAUNCH(h); }
+    k_count_singular<<<cdiv(N, 256), 256, 0, st>>>(h->diag_pos.p, N, h->nK, h->nnz, h->vals.p, h->flags.p + 1); LAUNCH(h);
+    k_inv_diag<<<cdiv(N, 256), 256, 0, st>>>(h->diag_pos.p, N, h->nK, h->nnz, h->vals.p, h->dinv.p); LAUNCH(h);
+    h->have_vals = true;
+    CKR(stream_pack(h, h->stream, h->vals.p, 0));
+    if (h->use_amg) CKR(amg_setup_values(h));
+    phase_begin(h, PH_RHS);
+    CK(cudaMemsetAsync(h->B.p, 0, sizeof(double) * N * ld, st));
+    k_delta_rhs<<<cdiv(nS, 128), 128, 0, st>>>(h->pick_ptr.p, h->pick_idx.p, h->pick_w.p, nE, 0, nS, ld, h->B.p); LAUNCH(h);
+    k_cplx_zero_imag_cols<<<cdiv((long long)N * nS, 256), 256, 0, st>>>(h->B.p, N, nEc, nS, ld); LAUNCH(h);
+    int hf[4];
+    CK(cudaMemcpyAsync(hf, h->flags.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (hf[0]) PGB_FAIL("complex response for abs model with negative or zero resistivity is not defined");
+    if (hf[1]) PGB_FAIL("stiffness matrix has rows with diagonal < 1e-12 (the reference would force them to homogeneous Dirichlet); unsupported model");
+    // ---- COCG ----
+    phase_begin(h, PH_SOLVE);
+    const bool amg = h->use_amg && !h->amg.empty();
+    double *S = h->c_scal.p;
+    auto row = [&](int i) { return S + (size_t)i * ld; };      // 0,1 rho | 2,3 rho' | 4,5 p^T q | 6 |r|^2 | 7 |b|^2
+    const FlatCfg fd = flat_cfg(N, 0, nSc, FLAT_MAX_GX), fc = flat_cfg(N, 0, nSc);
+    CK(cudaMemsetAsync(S, 0, sizeof(double) * 8 * ld, st));
+    CK(cudaMemsetAsync(h->X.p, 0, sizeof(double) * N * ld, st));
+    CK(cudaMemcpyAsync(h->R.p, h->B.p, sizeof(double) * N * ld, cudaMemcpyDeviceToDevice, st));
+    auto precond = [&]() -> int {
+        if (amg) return amg_vcycle(h, 0, nS, nullptr);
+        k_cplx_jacobi<<<cdiv((long long)N * nS, 256), 256, 0, st>>>(h->R.p, h->dinv.p, h->Z0.p, N, nE, nS, ld); LAUNCH(h);
+        return 0;
+    };
+    if (!h->Z0.p) CKR(h->Z0.alloc((size_t)N * ld));
+    k_cplx_dot<true><<<fd.grid, FLAT_T, 0, st>>>(h->B.p, nullptr, N, nEc, nSc, ld, fd.cw, dot_out(h, row(7), nullptr)); LAUNCH(h);
+    CKR(precond());
+    CK(cudaMemcpyAsync(h->P.p, h->Z0.p, sizeof(double) * N * ld, cudaMemcpyDeviceToDevice, st));
+    k_cplx_dot<false><<<fd.grid, FLAT_T, 0, st>>>(h->R.p, h->Z0.p, N, nEc, nSc, ld, fd.cw, dot_out(h, row(0), row(1))); LAUNCH(h);
+    CKR(ensure_pinned(h, 2 * ld));
+    const double tol2 = h->tol * h->tol;
+    int it = 0; bool converged = false; int cur = 0;
+    while (it < h->max_iter && !converged) {
+        double *rho = row(2 * cur), *rho_new = row(2 * (1 - cur));
+        // q = (S_r + i S_i) p
+        if (panel_path_ok(h)) { PanelExtra ex{}; CKR(launch_stream<EPI_SPMM>(h, h->stream, 0, h->P.p, h->AP.p, 0, nS, nullptr, ex)); }
+        else CKR((launch_spmm<0, false>(h, h->vals.p, nullptr, nullptr, h->P.p, h->AP.p, 0, nS, nullptr)));
+        CKR((launch_spmm<0, false>(h, h->vals1.p, nullptr, nullptr, h->P.p, h->c_y2.p, 0, nS, nullptr)));
+        k_cplx_combine<<<fd.grid, FLAT_T, 0, st>>>(h->AP.p, h->c_y2.p, h->P.p, N, nEc, nSc, ld, fd.cw, dot_out(h, row(4), row(5))); LAUNCH(h);
+        k_cplx_update_xr<<<fd.grid, FLAT_T, 0, st>>>(h->P.p, h->AP.p, h->X.p, h->R.p, N, nEc, nSc, ld, rho, row(4), ld, fd.cw, dot_out(h, nullptr, row(6))); LAUNCH(h);
+        CKR(precond());
+        k_cplx_dot<false><<<fd.grid, FLAT_T, 0, st>>>(h->R.p, h->Z0.p, N, nEc, nSc, ld, fd.cw, dot_out(h, rho_new, rho_new + ld)); LAUNCH(h);
+        k_cplx_update_p<<<fc.grid, FLAT_T, 0, st>>>(h->Z0.p, h->P.p, N, nEc, nSc, ld, rho, rho_new, ld, row(6), row(7), tol2, fc.cw); LAUNCH(h);
+        cur = 1 - cur;
+        it++;
+        if (it % 6 == 0 || it >= h->max_iter) {
+            CK(cudaMemcpyAsync(h->h_pinned, row(6), sizeof(double) * 2 * ld, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            double worst = 0.0;
+            for (int j = 0; j < nSc; j++) {
+                const double rr = h->h_pinned[j], bb = h->h_pinned[ld + j];
+                double rel = bb > 0.0 ? std::sqrt(rr / bb) : (rr > 0.0 ? INFINITY : 0.0);
+                if (!(rr == rr)) rel = INFINITY;
+                worst = std::max(worst, rel);
+            }
+            h->last_relres = worst;
+            converged = worst <= h->tol;
+        }
+    }
+    CK(cudaGetLastError());
+    h->last_iters = it; h->total_iters += it; h->solves++;
+    h->x_warm_ok = false;
+    if (!converged) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "complex block-COCG did not reach rel. residual %.1e in %d iterations (worst column %.3e)", h->tol, it, h->last_relres);
+        PGB_FAIL(buf);
+    }
+    phase_begin(h, PH_EPI);
+    {
+        dim3 b(32, 8), g(cdiv(N, 8), cdiv(nS, 32));
+        k_finalize_pots<<<g, b, 0, st>>>(h->X.p, nullptr, nullptr, 0.0, N, nE, 0, nS, ld, h->U.p); LAUNCH(h);
+    }
+    h->shard_solved = true; h->pots_valid = true;
+    CKR(pickup(h));              // electrode matrix of the doubled layout: pM[i][j], i < nE/2 real part, i >= nE/2 imaginary part
+    return 0;
+}
+}  // namespace
+
+// model_host = [re (n_in) | im (n_in)] (n_in = model cells or cells).  Solves; the electrode matrix (pgb200_ert_pm_info) and the
+// potentials (pgb200_ert_potentials_info) are then those of the doubled layout.
+int pgb200_ert_complex_forward(pgb200_ert *h, const double *model_host, int n_in) {
+    if (!h || !model_host) PGB_FAIL("null argument");
+    CK(cudaSetDevice(h->device));
+    if (n_in != h->M && n_in != h->C) PGB_FAIL("model length must equal the number of model cells (max marker + 1) or the cell count");
+    if (h->c_model.n < (size_t)2 * n_in) CKR(h->c_model.alloc((size_t)2 * std::max(h->M, h->C)));
+    CK(cudaMemcpyAsync(h->c_model.p, model_host, sizeof(double) * 2 * n_in, cudaMemcpyHostToDevice, h->st));
+    h->model_len = n_in;
+    CKR(complex_forward(h, h->c_model.p, n_in));
+    CKR(finish_timing(h));
+    return 0;
+}
+
+// complex Jacobian: the handle's scheme holds the four real blocks (4 D rows, see k_cplx_jacobian); j_host receives D x M
+// complex values, row-major, interleaved (re, im); kfac_host[D]; scaling by k_d / m_j^2 when n_in == M (:1377, :1420-1428)
+int pgb200_ert_complex_jacobian(pgb200_ert *h, const double *model_host, int n_in, const double *kfac_host, double *j_host) {
+    if (!h || !model_host || !kfac_host || !j_host) PGB_FAIL("null argument");
+    CK(cudaSetDevice(h->device));
+    if (!h->is_complex) PGB_FAIL("pgb200_ert_set_complex(h, 1) first");
+    if (h->D % 4) PGB_FAIL("complex Jacobian: the scheme must hold four blocks of rows");
+    if (n_in != h->M && n_in != h->C) PGB_FAIL("model length must equal the number of model cells (max marker + 1) or the cell count");
+    const int D = h->D / 4, M = h->M;
+    if (h->c_model.n < (size_t)2 * n_in) CKR(h->c_model.alloc((size_t)2 * std::max(h->M, h->C)));
+    CK(cudaMemcpyAsync(h->c_model.p, model_host, sizeof(double) * 2 * n_in, cudaMemcpyHostToDevice, h->st));
+    if (!h->pots_valid) CKR(complex_forward(h, h->c_model.p, n_in));       // prepareJacobianT_: numeric potentials of this model
+    CKR(jacobian(h, nullptr));                                            // four real blocks, unscaled
+    if (h->c_out.n < (size_t)2 * D * M + D) CKR(h->c_out.alloc((size_t)2 * D * M + D));
+    double *kf = h->c_out.p + (size_t)2 * D * M;
+    CK(cudaMemcpyAsync(kf, kfac_host, sizeof(double) * D, cudaMemcpyHostToDevice, h->st));
+    dim3 b(32, 8), g(cdiv(M, 32), cdiv(D, 32));
+    k_cplx_jacobian<<<g, b, 0, h->st>>>(h->Jt.p, h->ldJ, D, M, kf, h->c_model.p, h->c_model.p + n_in, n_in == M ? 1 : 0, h->c_out.p); LAUNCH(h);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(j_host, h->c_out.p, sizeof(double) * 2 * D * M, cudaMemcpyDeviceToHost, h->st));
+    CKR(finish_timing(h));
     return 0;
 }
 

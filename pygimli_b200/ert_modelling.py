@@ -209,6 +209,28 @@ def managerCoverage(S, para_mesh, response, model):
         return np.log10(cov_trans / param_sizes)[marker]
 
 
+class ComplexJacobianB200:
+    """Complex sensitivity matrix of the complex-resistivity path (the reference's ``CMatrix`` jacobian,
+    dcfemmodelling.cpp:1446-1461): ``numpy()`` is the D x M complex matrix, ``squeezed(conj)`` the real 2D x 2M block matrix
+    ``pg.utils.squeezeComplex`` / ``toRealMatrix`` hands to the inversion (pygimli/utils/complex.py:79-111)."""
+
+    def __init__(self, J):
+        self._J = J
+
+    def rows(self):
+        return self._J.shape[0]
+
+    def cols(self):
+        return self._J.shape[1]
+
+    def numpy(self):
+        return self._J
+
+    def squeezed(self, conj=False):
+        re, im = self._J.real, self._J.imag
+        return np.block([[re, im], [-im, re]]) if conj else np.block([[re, -im], [im, re]])
+
+
 class CoreB200:
     """Replacement for ``pg.core.DCSRMultiElectrodeModelling`` (sr=True) /
     ``DCMultiElectrodeModelling`` (sr=False) on one B200."""
@@ -238,6 +260,9 @@ class CoreB200:
         self._prim_pm = None
         self._placeholder_k = False
         self._J = JacobianB200(self)
+        self._complex = False       # complex resistivity (setComplex): an inner total-field core on the doubled electrode list
+        self._cx = None
+        self._Jc = None
 
     # ---- reference-style setters -----------------------------------------------------
     def setVerbose(self, v):
@@ -245,6 +270,57 @@ class CoreB200:
 
     def setThreadCount(self, n):   # CPU threads of the reference's sensitivity loop; nothing to do on the GPU
         pass
+
+    def setComplex(self, c=True):
+        """complex resistivity (induced polarisation), DCMultiElectrodeModelling::setComplex: models and responses are
+        [real part | imaginary part] vectors, the Jacobian is complex (ertModelling.py:204-238, dcfemmodelling.cpp:1103-1118,
+        1446-1461).  Total-field fop only: the reference's singularity-removal class refuses complex models (:2156)."""
+        if c and self.sr:
+            raise _capi.PGB200Error("complex resistivity needs the total-field operator (sr=False); the reference's "
+                                    "DCSRMultiElectrodeModelling::calculateK throws for complex models")
+        self._complex = bool(c)
+        self._drop_complex()
+
+    def complex(self):
+        return self._complex
+
+    def _drop_complex(self):
+        if self._cx is not None:
+            self._cx.close()
+        self._cx = None
+        self._Jc = None
+
+    def _ensure_complex(self):
+        """inner core: same mesh, every electrode listed twice (source column i: real part, i + nE: imaginary part), scheme =
+        the four real blocks of the complex sensitivity, wavenumbers of the ORIGINAL electrode list (include/pgb200_ert.h)"""
+        if self._cx is None:
+            P = self._ensure_plan()                       # wavenumbers and weights of the original layout
+            sch = self._scheme
+            nE = sch.sensors.shape[0]
+
+            def off(v):
+                return np.where(v >= 0, v + nE, v)
+            a, b, m, n = sch.a, sch.b, sch.m, sch.n
+            sch4 = SchemeArrays(np.vstack([sch.sensors, sch.sensors]),
+                                np.concatenate([a, off(a), a, off(a)]), np.concatenate([b, off(b), b, off(b)]),
+                                np.concatenate([m, off(m), off(m), m]), np.concatenate([n, off(n), off(n), n]),
+                                np.ones(4 * sch.size))
+            cx = CoreB200(sr=False, verbose=self.verbose, device=self.device)
+            cx.setMesh(self._mesh)
+            cx.setData(sch4)
+            cx.setkValues(P.k)
+            cx.setWeights(P.w)
+            cx.setSolverTolerance(self._tol, self._maxit, self._check)
+            h = cx._ensure_handle()
+            _capi.check(_capi.lib().pgb200_ert_set_complex(h, 1))
+            self._cx = cx
+        return self._cx
+
+    def _complex_model(self, model):
+        m = np.ascontiguousarray(model, np.float64).ravel()
+        if m.size % 2:
+            raise _capi.PGB200Error("complex model: expected [real part | imaginary part]")
+        return m, m.size // 2
 
     def setMesh(self, mesh, ignoreRegionManager=True):
         self._mesh = _as_mesh(mesh)
@@ -322,6 +398,7 @@ class CoreB200:
 
     # ---- life cycle -------------------------------------------------------------------
     def _invalidate(self):
+        self._drop_complex()
         if self._h:
             _capi.lib().pgb200_ert_destroy(self._h)
         self._h = None
@@ -455,6 +532,17 @@ class CoreB200:
 
     # ---- the path ---------------------------------------------------------------------
     def response(self, model):
+        if self._complex:
+            # response() of a complex fop (dcfemmodelling.cpp:1103-1118): (u_re + i u_im) k, no rounding, no reciprocity mean
+            cx = self._ensure_complex()
+            m, n_in = self._complex_model(model)
+            _capi.check(_capi.lib().pgb200_ert_complex_forward(cx._h, m.ctypes.data, n_in))
+            nE = self._scheme.sensors.shape[0]
+            pm = cx.get("pm").reshape(2 * nE, 2 * nE)
+            u = electrode_matrix_data(pm[:nE, :nE] + 1j * pm[nE:, :nE], self._scheme)
+            self._resolve_k_complex()
+            resp = u * self._scheme.k
+            return np.concatenate([resp.real, resp.imag])
         h = self._ensure_handle()
         self._resolve_k()
         m = np.ascontiguousarray(model, np.float64)
@@ -468,6 +556,16 @@ class CoreB200:
             self.setGeometricFactors(self.calcGeometricFactor(nModel=int(n_model)))
 
     def createJacobian(self, model):
+        if self._complex:
+            cx = self._ensure_complex()
+            m, n_in = self._complex_model(model)
+            self._resolve_k_complex()
+            D, M = self._scheme.size, self._ensure_plan().M
+            J = np.zeros((D, M), np.complex128)
+            k = np.ascontiguousarray(self._scheme.k, np.float64)
+            _capi.check(_capi.lib().pgb200_ert_complex_jacobian(cx._h, m.ctypes.data, n_in, k.ctypes.data, J.ctypes.data))
+            self._Jc = ComplexJacobianB200(J)
+            return None
         h = self._ensure_handle()
         self._jacobian_k(np.size(model))
         m = np.ascontiguousarray(model, np.float64)
@@ -485,9 +583,21 @@ class CoreB200:
         _capi.check(_capi.lib().pgb200_ert_create_jacobian_dev(self._ensure_handle(), C.c_void_p(model_ptr), int(n)))
 
     def jacobian(self):
+        if self._complex:
+            if self._Jc is None:
+                raise _capi.PGB200Error("no Jacobian: call createJacobian first")
+            return self._Jc
         return self._J
 
+    def _resolve_k_complex(self):
+        if self._scheme.k is None:
+            if self._ensure_plan().topography:
+                raise _capi.PGB200Error(" data contains no K-factors ")
+            self._scheme.k = geometric_factors(self._scheme, self._mesh.dim)
+
     def clearPotentials(self):
+        if self._cx is not None and self._cx._h:
+            _capi.check(_capi.lib().pgb200_ert_clear_potentials(self._cx._h))
         if self._h:
             _capi.check(_capi.lib().pgb200_ert_clear_potentials(self._h))
 
@@ -605,11 +715,10 @@ class ERTModellingB200:
         self.mapERTModel = self._core.mapERTModel
 
     def complex(self):
-        return False
+        return self._core.complex()
 
     def setComplex(self, c):
-        if c:
-            raise NotImplementedError("complex resistivity is outside the B200 path (SURVEY §8(f) item 3)")
+        self._core.setComplex(c)
 
     def setVerbose(self, v):
         self._core.setVerbose(v)
@@ -652,7 +761,14 @@ class ERTModellingB200:
         return self._core.response(mod)
 
     def createJacobian(self, mod):
+        if self._core.complex():
+            # ertModelling.py:221-236: the complex Jacobian is handed on as the real block matrix [[Re, -Im], [Im, Re]]
+            self._core.createJacobian(mod)
+            self._Jsq = self._core.jacobian().squeezed(conj=False)
+            return self._Jsq
         return self._core.createJacobian(mod)
 
     def jacobian(self):
+        if self._core.complex():
+            return self._Jsq
         return self._core.jacobian()
