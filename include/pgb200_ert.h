@@ -95,6 +95,12 @@ typedef struct pgb200_plan {
     int topography;             /* 1: non-flat surface or pure-Neumann domain (dcfemmodelling.cpp:718-754): no analytic
                                  * primary potentials / analytic branches; with sr = 1 the primary potentials must be
                                  * supplied through pgb200_ert_set_primary_dev before the first solve (:2009-2056)  */
+    int ref_node;               /* reference-electrode node (marker -999, bert/bert.h:31) in the internal numbering or -1:
+                                 * every current pattern is the dipole (electrode, reference), the right-hand side gets -1
+                                 * there (dcfemmodelling.cpp:1009-1015, 1517-1523, 1868-1870)                     */
+    int ref_last;               /* 1: pure-Neumann domain without a -999 node -- the LAST electrode is the current reference
+                                 * (:1054-1064): its own pattern does not exist (zero potentials) and createJacobian fails
+                                 * with the reference's length error (bertJacobian.cpp:283-291)                  */
 } pgb200_plan;
 
 /* One coarse level of the aggregation hierarchy of the multilevel preconditioner (host pointers, copied).

@@ -36,7 +36,7 @@ class Plan(C.Structure):
         ("pro_w", c_dbl_p),
         ("n_jac_cells", C.c_int), ("jac_cells", c_int_p), ("jac_col_ptr", c_int_p),
         ("abmn", c_int_p), ("k_fac", c_dbl_p),
-        ("topography", C.c_int),
+        ("topography", C.c_int), ("ref_node", C.c_int), ("ref_last", C.c_int),
     ]
 
 
@@ -305,6 +305,8 @@ class NativePlan:
             return int(self.scalar("nK")) * int(self.scalar("nE"))
         if name in ("topography", "has_background", "neumann_domain", "k_missing"):
             return bool(self.scalar(name))
+        if name in ("ref_node", "ref_last"):
+            return int(self.scalar(name))
         if name == "surface_z":
             return self.scalar("surface_z")
         if name == "dir_zero_slots" or name == "dir_diag_slots":
@@ -376,6 +378,7 @@ def make_plan_struct(P, sr: bool):
     s.fullspace = 1 if P.surface_z <= -1e300 else 0
     s.surface_z = 0.0 if s.fullspace else P.surface_z
     s.topography = 1 if getattr(P, "topography", False) else 0
+    s.ref_node, s.ref_last = int(getattr(P, "ref_node", -1)), int(getattr(P, "ref_last", 0))
     s.pos, s.cells, s.cell_marker = D(P.mesh.pos), I(P.mesh.cells), I(P.cell_marker)
     s.rowptr, s.colidx, s.diag_pos = I(P.rowptr), I(P.colidx), I(P.diag_pos)
     s.n_colors, s.color_ptr, s.color_order = P.n_colors, I(P.color_ptr), I(P.color_order)

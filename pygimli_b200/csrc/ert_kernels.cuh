@@ -1933,6 +1933,21 @@ __global__ void k_delta_rhs(const int *__restrict__ pick_ptr, const int *__restr
     for (int t = pick_ptr[e]; t < pick_ptr[e + 1]; t++) B[(size_t)pick_idx[t] * ld + col] = pick_w[t];
 }
 
+// current reference of the dipole patterns (dcfemmodelling.cpp:1517-1523, 1868-1870): a reference-electrode node (-999)
+// takes -1 in every pattern; without one on a pure-Neumann domain the LAST electrode is the reference (:1054-1064) and
+// its own pattern does not exist (zero right-hand side, zero potentials)
+__global__ void k_ref_rhs(const int *__restrict__ pick_ptr, const int *__restrict__ pick_idx, const double *__restrict__ pick_w,
+                          int nE, int c0, int c1, size_t ld, int ref_node, int ref_last, double *__restrict__ B) {
+    const int col = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= c1) return;
+    const int e = col % nE;
+    if (ref_node >= 0) B[(size_t)ref_node * ld + col] = -1.0;
+    if (ref_last) {
+        if (e == nE - 1) { for (int t = pick_ptr[e]; t < pick_ptr[e + 1]; t++) B[(size_t)pick_idx[t] * ld + col] = 0.0; }
+        else for (int t = pick_ptr[nE - 1]; t < pick_ptr[nE]; t++) B[(size_t)pick_idx[t] * ld + col] = -pick_w[t];
+    }
+}
+
 // ---------------------------------------------------------------------------------
 // forward epilogue (dcfemmodelling.cpp:1707-1729, datamap.cpp:57-97, :159-231, :1140-1196)
 // ---------------------------------------------------------------------------------

@@ -104,6 +104,7 @@ struct AmgLevel {      // one coarse level of the aggregation hierarchy (device 
 struct pgb200_ert {
     // sizes
     int dim = 0, nloc = 0, elem = 0, N = 0, C = 0, nE = 0, nK = 0, nS = 0, M = 0, D = 0, sr = 1, fullspace = 0, topography = 0;
+    int ref_node = -1, ref_last = 0;          // current reference of the dipole patterns (plan.ref_node / plan.ref_last)
     bool prim_set = false;
     size_t nnz = 0, ld = 0;
     double surface_z = 0.0;
@@ -901,6 +902,9 @@ int forward_solve(pgb200_ert *h) {
     } else {
         CK(cudaMemsetAsync(h->B.p, 0, sizeof(double) * h->N * h->ld, h->st));
         if (c1 > c0) { k_delta_rhs<<<cdiv(c1 - c0, 128), 128, 0, h->st>>>(h->pick_ptr.p, h->pick_idx.p, h->pick_w.p, h->nE, c0, c1, h->ld, h->B.p); LAUNCH(h); }
+        if (c1 > c0 && (h->ref_node >= 0 || h->ref_last)) {
+            k_ref_rhs<<<cdiv(c1 - c0, 128), 128, 0, h->st>>>(h->pick_ptr.p, h->pick_idx.p, h->pick_w.p, h->nE, c0, c1, h->ld, h->ref_node, h->ref_last, h->B.p); LAUNCH(h);
+        }
     }
     // NB: the reference zeroes right-hand-side rows only for calibration nodes (:2281-2283), which never exist on
     // the non-Neumann domains handled here; rows of -3 Dirichlet faces keep S1*p/rho_s - S*p = p (1 - rho_s).
@@ -1505,6 +1509,11 @@ int pgb200_ert_create(const pgb200_plan *p, int device, pgb200_ert **out) {
     h->dim = p->dim; h->nloc = p->nloc; h->N = p->n_nodes; h->C = p->n_cells; h->nnz = (size_t)p->nnz;
     h->nE = p->n_elec; h->nK = p->n_k; h->nS = h->nE * h->nK; h->M = p->n_model; h->D = p->n_data; h->sr = p->sr;
     h->fullspace = p->fullspace; h->surface_z = p->surface_z; h->topography = p->topography;
+    h->ref_node = p->ref_node; h->ref_last = p->ref_last;
+    if (h->ref_node >= p->n_nodes) PGB_FAIL("plan.ref_node out of range");
+    if (p->sr && (h->ref_node >= 0 || h->ref_last))
+        PGB_FAIL("singularity removal with a current reference electrode (reference-electrode node -999 or pure-Neumann domain: dipole patterns, "
+                 "dcfemmodelling.cpp:1054-1064, 1517-1523) is not on the B200 path; use the total-field operator (sr = 0)");
     if (p->dim == 2 && p->nloc == 3) h->elem = TRI3; else if (p->dim == 2 && p->nloc == 6) h->elem = TRI6;
     else if (p->dim == 3 && p->nloc == 4) h->elem = TET4; else if (p->dim == 3 && p->nloc == 10) h->elem = TET10;
     else PGB_FAIL("unsupported cell type (need Tri3/Tri6/Tet4/Tet10)");
@@ -1865,6 +1874,13 @@ int pgb200_ert_set_primary_dev(pgb200_ert *h, const double *src_dev, long long s
 
 // ---- Jacobian -------------------------------------------------------------------------
 static int create_jacobian_common(pgb200_ert *h, int n_in) {
+    if (h->ref_last) {
+        // the reference fails here too: nE - 1 current patterns, createSensitivityCol wants nE rows (bertJacobian.cpp:283-291)
+        char buf[200];
+        snprintf(buf, sizeof buf, "potential matrix rowsize to small. %d < %d (the last electrode is the current reference of this pure-Neumann "
+                                  "domain; add a reference-electrode node, marker -999)", h->nS - h->nK, h->nS);
+        PGB_FAIL(buf);
+    }
     const double *rho_col = (n_in == h->M) ? h->model.p : nullptr;      // scaling only if len(model) == J.cols (:1377)
     if (!h->pots_valid) {
         // prepareJacobianT_ (:1246-1309): no potentials yet -> solve, analytically for a homogeneous model
@@ -2156,6 +2172,8 @@ int complex_forward(pgb200_ert *h, const double *model_dev, int n_in) {
     phase_begin(h, PH_RHS);
     CK(cudaMemsetAsync(h->B.p, 0, sizeof(double) * N * ld, st));
     k_delta_rhs<<<cdiv(nS, 128), 128, 0, st>>>(h->pick_ptr.p, h->pick_idx.p, h->pick_w.p, nE, 0, nS, ld, h->B.p); LAUNCH(h);
+    if (h->ref_node >= 0) { k_ref_rhs<<<cdiv(nS, 128), 128, 0, st>>>(h->pick_ptr.p, h->pick_idx.p, h->pick_w.p, nE, 0, nS, ld, h->ref_node, 0, h->B.p); LAUNCH(h); }
+    if (h->ref_last) PGB_FAIL("complex resistivity on a pure-Neumann domain needs a reference-electrode node (marker -999)");
     k_cplx_zero_imag_cols<<<cdiv((long long)N * nS, 256), 256, 0, st>>>(h->B.p, N, nEc, nS, ld); LAUNCH(h);
     int hf[4];
     CK(cudaMemcpyAsync(hf, h->flags.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));

@@ -228,7 +228,7 @@ struct pgb200_built_plan {
     // geometry in the internal numbering
     int dim = 0, nloc = 0, N = 0, C = 0, nE = 0, nK = 0, M = 0, D = 0, nlb = 0, n_bounds = 0;
     long long nnz = 0;
-    int topography = 0, neumann_domain = 0, has_background = 0, k_missing = 0;
+    int topography = 0, neumann_domain = 0, has_background = 0, k_missing = 0, ref_node = -1, ref_last = 0;
     double surface_z = 0.0;
     IVec node_perm, node_inv;                     // perm[new] = old, inv[old] = new
     DVec pos; IVec node_marker, cells, cell_marker, bounds, bound_marker;
@@ -335,7 +335,7 @@ int pgb200_plan_scalar(const pgb200_built_plan *P, const char *name, double *out
     const std::string s(name);
     if (s == "N") *out = P->N; else if (s == "C") *out = P->C; else if (s == "nnz") *out = (double)P->nnz; else if (s == "nE") *out = P->nE;
     else if (s == "nK") *out = P->nK; else if (s == "M") *out = P->M; else if (s == "D") *out = P->D; else if (s == "dim") *out = P->dim;
-    else if (s == "nloc") *out = P->nloc; else if (s == "topography") *out = P->topography; else if (s == "neumann_domain") *out = P->neumann_domain;
+    else if (s == "nloc") *out = P->nloc; else if (s == "topography") *out = P->topography; else if (s == "neumann_domain") *out = P->neumann_domain; else if (s == "ref_node") *out = P->ref_node; else if (s == "ref_last") *out = P->ref_last;
     else if (s == "has_background") *out = P->has_background; else if (s == "k_missing") *out = P->k_missing; else if (s == "n_colors") *out = P->n_colors;
     else if (s == "n_levels") *out = (double)P->levels.size(); else if (s == "surface_z") *out = P->surface_z; else if (s == "pro_nf") *out = P->pro_nf;
     else { g_plan_err = "unknown plan scalar: " + s; return 1; }
@@ -409,7 +409,10 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
     }
     if (neumann_domain) { topography = true; if (dim == 2) neumann_domain = false; }
     P.topography = topography ? 1 : 0; P.surface_z = surface_z; P.neumann_domain = neumann_domain ? 1 : 0;
-    if (neumann_domain) PLAN_FAIL("pure-Neumann 3-D domains (no mixed/Dirichlet boundary) need the calibration-node handling of dcfemmodelling.cpp:1040-1075; not on the B200 path");
+    // reference-electrode node (-999): the first one in the reference's node order (:1009-1015); a pure-Neumann domain without
+    // one takes the last electrode as current reference (:1054-1064)
+    for (int R = 0; R < N && P.ref_node < 0; R++) if (mi->node_marker[R] == MARKER_NODE_REFERENCE) P.ref_node = inv[R];
+    if (neumann_domain && P.ref_node < 0) P.ref_last = 1;
 
     // ---- node -> cells incidence --------------------------------------------------------------------------------------
     IVec nc_ptr(N + 1, 0), nc_cells((size_t)C * nloc);
@@ -497,7 +500,6 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
         const bool zvar = (zmax - zmin) > 0 || zabs > 0, yflat = (ymax - ymin) == 0 && yabs < 1e-8;
         if (zvar && yflat) for (int i = 0; i < nE; i++) std::swap(sens[3 * i + 1], sens[3 * i + 2]);
     }
-    for (int i = 0; i < N; i++) if (P.node_marker[i] == MARKER_NODE_REFERENCE) PLAN_FAIL("reference-electrode nodes (-999) are not supported on the B200 path");
     IVec src_nodes;                         // electrode-node candidates in the REFERENCE's node order
     for (int R = 0; R < N; R++) if (mi->node_marker[R] == MARKER_NODE_ELECTRODE) src_nodes.push_back(inv[R]);
     P.el_node.assign(nE, -1); P.el_cell.assign(nE, -1); P.sing_node.assign(nE, -1); P.el_pos.assign(3 * (size_t)nE, 0.0);
@@ -645,6 +647,13 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
     {
         std::vector<char> isd((size_t)N, 0);
         for (int b = 0; b < nB; b++) if (P.bound_marker[b] == MARKER_BOUND_DIRICHLET) for (int v = 0; v < nlb; v++) isd[P.bounds[(size_t)b * nlb + v]] = 1;
+        if (P.neumann_domain) {
+            // calibration nodes (-1000) pin the potential of a pure-Neumann domain; without one the reference takes its node 0
+            // (:1044-1052).  On other domains calibration nodes are ignored (:1066-1070).
+            bool any = false;
+            for (int i = 0; i < N; i++) if (P.node_marker[i] == MARKER_NODE_CALIBRATION) { isd[i] = 1; any = true; }
+            if (!any) isd[inv[0]] = 1;
+        }
         for (int i = 0; i < N; i++) if (isd[i]) { P.dir_nodes.push_back(i); P.dir_diag.push_back(P.diag_pos[i]); }
         if (!P.dir_nodes.empty())
             for (int i = 0; i < N; i++) for (int p = rowptr[i]; p < rowptr[i + 1]; p++) if (isd[i] || isd[colidx[p]]) P.dir_zero.push_back(p);
@@ -771,7 +780,7 @@ int pgb200_plan_build(const pgb200_mesh_in *mi, const pgb200_scheme_in *si, int 
     V.n_pro_levels = (int)P.pro_level_ptr.size() - 1; V.pro_nf = V.n_pro_levels ? P.pro_nf : 0; V.pro_level_ptr = P.pro_level_ptr.data(); V.pro_cells = P.pro_cells.data();
     V.pro_nb = P.pro_nb.data(); V.pro_w = P.pro_w.data();
     V.n_jac_cells = (int)P.jac_cells.size(); V.jac_cells = P.jac_cells.data(); V.jac_col_ptr = P.jac_col_ptr.data();
-    V.abmn = P.abmn.data(); V.k_fac = P.kfac.data(); V.topography = P.topography;
+    V.abmn = P.abmn.data(); V.k_fac = P.kfac.data(); V.topography = P.topography; V.ref_node = P.ref_node; V.ref_last = P.ref_last;
 #undef PLAN_FAIL
     *out = Pp;
     return 0;

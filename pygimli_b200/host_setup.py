@@ -455,10 +455,11 @@ def build_plan(mesh: MeshArrays, scheme, k_values=None, weights=None, color_fn=N
         if dim == 2:
             neumann_domain = False
     P.topography, P.surface_z, P.neumann_domain = topography, surface_z, neumann_domain
-    if neumann_domain:
-        raise NotImplementedError(
-            "pure-Neumann 3-D domains (no mixed/Dirichlet boundary) need the calibration-node handling of "
-            "dcfemmodelling.cpp:1040-1075; not on the B200 path (SURVEY §8(f) item 2)")
+    # reference-electrode node (-999): the first one in the reference's node order (:1009-1015); a pure-Neumann domain
+    # without one takes the last electrode as current reference (:1054-1064)
+    ref_nodes = np.nonzero(P.mesh_ref.node_marker == MARKER_NODE_REFERENCE)[0]
+    P.ref_node = int(inv[ref_nodes[0]]) if ref_nodes.size else -1
+    P.ref_last = 1 if (neumann_domain and P.ref_node < 0) else 0
     # topography: the plan is the same; analytic primary potentials / analytic branches are switched off in the library
     # and CoreB200 supplies numeric primary potentials from a P2 total-field solve (dcfemmodelling.cpp:2009-2056)
 
@@ -494,8 +495,6 @@ def build_plan(mesh: MeshArrays, scheme, k_values=None, weights=None, color_fn=N
     nE = sens.shape[0]
     P.nE = nE
     src_nodes = [int(i) for i in inv[src_order_ref]]          # candidates in the reference's node order
-    if np.any(mesh.node_marker == MARKER_NODE_REFERENCE):
-        raise NotImplementedError("reference-electrode nodes (-999) are not supported on the B200 path")
     el_node = np.full(nE, -1, np.int64)          # mID: node id for node electrodes
     el_pos = np.zeros((nE, 3))
     el_cell = np.full(nE, -1, np.int64)
@@ -612,6 +611,13 @@ def build_plan(mesh: MeshArrays, scheme, k_values=None, weights=None, color_fn=N
     # ---- homogeneous Dirichlet nodes (-3 faces; calibration nodes are ignored on
     #      non-Neumann domains, dcfemmodelling.cpp:1066-1070) -------------------------
     dn = np.unique(mesh.bounds[bm == MARKER_BOUND_DIRICHLET].ravel()) if np.any(bm == MARKER_BOUND_DIRICHLET) else np.zeros(0, np.int64)
+    if neumann_domain:
+        # calibration nodes (-1000) pin the potential of a pure-Neumann domain; without one the reference takes its node 0
+        # (dcfemmodelling.cpp:1044-1052)
+        cal = np.nonzero(mesh.node_marker == MARKER_NODE_CALIBRATION)[0]
+        if cal.size == 0:
+            cal = np.array([inv[0]], np.int64)
+        dn = np.unique(np.concatenate([dn, cal]))
     P.dir_nodes = dn.astype(np.int32)
     rowof = np.repeat(np.arange(N, dtype=np.int64), np.diff(P.rowptr))
     isd = np.zeros(N, bool)

@@ -195,3 +195,32 @@ def complex_model(model, seed: int = 7):
     -10 ... -20 mrad per model cell"""
     rng = np.random.default_rng(seed)
     return model * np.exp(-0.01j * (1.0 + rng.random(model.size)))
+
+
+def make_tank_case(ref_node: bool = True, calib_node: bool = True):
+    """closed 3-D tank (every boundary face homogeneous Neumann): 8 electrodes on the top face, a
+    reference-electrode node (-999) and a calibration node (-1000) as in doc/examples/3_ert/plot_modTank3d.py:50-63
+    (dcfemmodelling.cpp:1009-1064).  -> (mesh, scheme without k, model)"""
+    from pygimli_b200.scheme import SchemeArrays
+    xs = np.linspace(0.0, 1.0, 9)
+    zs = -np.linspace(0.0, 0.5, 5)
+    mesh = grid_mesh_3d(xs, xs, zs, para_box=(-1.0, 2.0, -1.0, 2.0, -1.0), marker_per="cube")
+    mesh.bound_marker[:] = -1                                  # closed box
+    sens = np.array([[0.25, 0.25, 0.0], [0.5, 0.25, 0.0], [0.75, 0.25, 0.0], [0.75, 0.5, 0.0],
+                     [0.75, 0.75, 0.0], [0.5, 0.75, 0.0], [0.25, 0.75, 0.0], [0.25, 0.5, 0.0]])
+    ids = mark_electrode_nodes(mesh, sens)
+    assert np.all(ids >= 0)
+
+    def node_at(p):
+        return int(np.argmin(np.sum((mesh.pos - np.asarray(p)) ** 2, axis=1)))
+    if ref_node:
+        mesh.node_marker[node_at([0.5, 0.5, -0.5])] = -999
+    if calib_node:
+        mesh.node_marker[node_at([0.875, 0.125, -0.25])] = -1000
+    rows = np.array([(0, 1, 2, 3), (0, 1, 4, 5), (1, 2, 5, 6), (2, 3, 6, 7), (3, 4, 7, 0), (0, 3, 1, 6), (1, 5, 2, 3), (0, 1, 6, 7),
+                     (7, 1, 5, 3), (6, 5, 1, 2)], np.int32)
+    scheme = SchemeArrays(sens, rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3])
+    M = int(mesh.cell_marker.max()) + 1
+    rng = np.random.default_rng(11)
+    model = 10.0 ** (1.5 + 0.3 * rng.standard_normal(M))
+    return mesh, scheme, model

@@ -5,7 +5,7 @@ the golden-vector tests pin to the reference: every index array bit-exact, float
 import numpy as np
 import pytest
 
-from cases import CASES, WIDE_CASES, TOPO_CASES, make_case, make_wide_case, make_topo_case, make_pole_case
+from cases import CASES, WIDE_CASES, TOPO_CASES, make_case, make_wide_case, make_topo_case, make_pole_case, make_tank_case
 from pygimli_b200 import _capi, amg_setup, host_setup as hs
 from pygimli_b200.scheme import geometric_factors
 
@@ -33,6 +33,9 @@ def _variants():
     sch.sensors[:, 0] += 0.13
     sch.k = geometric_factors(sch, 2)
     yield "free", (mesh, sch), {}
+    for nm, flags in (("tank_ref_cal", (True, True)), ("tank_ref", (True, False)), ("tank_last", (False, True))):
+        mesh, scheme, _ = make_tank_case(*flags)              # pure-Neumann tank: calibration node, reference electrode
+        yield nm, (mesh, scheme), {}
     mesh, scheme, _ = make_case("2d_p1")                      # user wavenumbers
     yield "user_k", (mesh, scheme), dict(k_values=np.array([0.01, 0.05, 0.2, 0.8, 2.5]), weights=np.array([0.02, 0.05, 0.2, 0.6, 1.1]))
 
@@ -45,6 +48,7 @@ def test_native_plan_equals_numpy_twin(name, ms, kw):
     for s in ("N", "C", "nnz", "nE", "nK", "M", "dim", "nloc", "n_colors"):
         assert getattr(Q, s) == getattr(P, s), s
     assert Q.topography == P.topography and Q.has_background == P.has_background
+    assert Q.ref_node == P.ref_node and Q.ref_last == P.ref_last and Q.neumann_domain == P.neumann_domain
     for nm in INT_ARRAYS:
         a, b = np.asarray(getattr(P, nm)), Q.array(nm)
         assert a.shape == b.shape and np.array_equal(a.astype(np.int64), b.astype(np.int64)), nm
@@ -89,10 +93,6 @@ def test_native_hierarchy_equals_numpy_twin(name):
 
 
 def test_plan_builder_error_behaviour():
-    mesh, scheme, _ = make_case("3d_p1")
-    mesh.bound_marker[:] = -1                       # no mixed / Dirichlet boundary: pure-Neumann 3-D domain
-    with pytest.raises(NotImplementedError, match="Neumann"):
-        _capi.plan_build(mesh, scheme)
     mesh, scheme, _ = make_case("2d_p1")
     mesh.node_marker[:] = 0
     scheme.sensors[0, 0] = -1e6                    # an electrode outside the mesh
