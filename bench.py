@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 def _traffic(workload, kernel):
     """DRAM bytes per launch from the committed ncu capture (profiles/r02_traffic.json), or None"""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             t = json.load(f)[workload][kernel]
         return float(t["dram_read_bytes"] + t["dram_write_bytes"])
     except Exception:
@@ -391,10 +391,10 @@ def run_b200(args):
             "gauss_newton_loop": ("every step a different model (30 % -> 0.3 % log-resistivity updates), block-PCG warm-started from the "
                                   "previous potentials" if gn_loop else None),
             "phase_ms_per_step": {k: st[k] / args.steps for k in ("ms_map", "ms_assemble", "ms_rhs", "ms_solve", "ms_epilogue", "ms_jacobian")},
-            "roofline": {"kernel": ("k_spmm_stream (persistent, warp-specialised, TMA-staged row panels" if args.spmm != "plain" else "k_spmm (plain gather") + ", CSR x dense block, inside block-PCG)", "bound": "hbm", "achieved": ach, "peak": peak,
+            "roofline": {"kernel": ("k_spmm_mma (persistent, warp-specialised, TMA-staged row panels, 8-row groups on the FP64 DMMA pipe" if args.spmm != "plain" else "k_spmm (plain gather") + ", CSR x dense block, inside block-PCG)", "bound": "hbm", "achieved": ach, "peak": peak,
                          "unit": "GB/s", "frac": ach / peak if peak else None,
                          "peak_nominal": 8000.0, "frac_nominal": ach / 8000.0,
-                         "traffic": _traffic(args.workload, "k_spmm_stream") if (world == 1 and args.scale == 1.0 and args.spmm == "stream") else None, "peak_source": peak_src,
+                         "traffic": _traffic(args.workload, "k_spmm_mma") if (world == 1 and args.scale == 1.0 and args.spmm == "stream") else None, "peak_source": peak_src,
                          "launches_timed": st["spmm_timed"], "avg_launch_ms": spmm_ms, "algorithmic_bytes_per_launch": spmm_bytes},
             "roofline_jacobian": {"kernel": "k_jacobian", "bound": "hbm", "achieved": jac_bytes / (jac_ms * 1e-3) / 1e9 if jac_ms > 0 else None,
                                   "peak": peak, "unit": "GB/s", "frac": (jac_bytes / (jac_ms * 1e-3) / 1e9 / peak) if jac_ms > 0 else None,

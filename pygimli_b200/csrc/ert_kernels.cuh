@@ -1144,6 +1144,154 @@ k_spmm_mma(const MmaArgs A) {
 }
 
 // ---------------------------------------------------------------------------------
+// K2-narrow: the SpMM of NARROW column windows (the source shards of a multi-GPU run: 13 - 32 of 100 columns).  A narrow block
+// vector fits L2 many times over and a stage of the streamed kernels would carry a few KB, so their per-stage latencies
+// dominate (measured: 86 us for 13 columns against 124 us for 100).  Here nothing is staged: a warp takes an 8-row group,
+// walks its k-steps (stream_panels.h, gather form) -- A fragment from global memory, the four rows of X through the read-only
+// path -- and feeds the same DMMA m8n8k4 tiles; 32 warps per SM hide the L2 latency.  Same three epilogues, same
+// deterministic dots (per-CTA partial rows, last ticket adds them in order).
+// ---------------------------------------------------------------------------------
+struct GatherArgs {
+    const int *ks_ptr, *cols;            // gather form of the level
+    const double *aval; size_t n_frag;   // packed A fragments [nK][n_frag]
+    int n_groups, n_rows;
+    const double *X; double *Y; size_t ld;
+    int kk, cs, wc, v0, v1;              // wavenumber group; copied columns [cs, cs + wc) with cs even; valid columns [v0, v1)
+    double *dot_part; unsigned *dot_counter; double *dots;
+    PanelExtra ex;
+};
+constexpr int GA_THREADS = 256;
+template <int NT, int EPI, bool DOT>
+__global__ void __launch_bounds__(GA_THREADS, 3)
+k_spmm_gather(const GatherArgs A) {
+    __shared__ double sdot[8 * NT];
+    __shared__ int s_ticket;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lr = lane >> 2, lk = lane & 3;
+    const int nwarps = GA_THREADS / 32;
+    const double *av = A.aval + (size_t)A.kk * A.n_frag + lane;
+    const int ldm1 = (int)A.ld - 1;
+    // column of the lane's B element in n-tile q (clamped: the values of columns outside the window are never stored)
+    int bcol[NT];
+#pragma unroll
+    for (int q = 0; q < NT; q++) bcol[q] = min(A.cs + 8 * q + lr, ldm1);
+    double part[DOT ? NT : 1][2];
+#pragma unroll
+    for (int q = 0; q < (DOT ? NT : 1); q++) { part[q][0] = 0.0; part[q][1] = 0.0; }
+    const double *dwk = (EPI == EPI_POST) ? A.ex.dinvw + (size_t)A.kk * A.ex.n : nullptr;
+    const int gstep = gridDim.x * nwarps;
+    int g = blockIdx.x * nwarps + warp;
+    int k0 = 0, k1 = 0;
+    if (g < A.n_groups) { k0 = __ldg(A.ks_ptr + g); k1 = __ldg(A.ks_ptr + g + 1); }
+    for (; g < A.n_groups; g += gstep) {
+        // the NEXT group of this warp: its k-step range is fetched now, and once it is known its A fragments and column
+        // lists are prefetched into L2 (they stream from DRAM exactly once; the demand loads then see L2 latency)
+        int k0n = 0, k1n = 0;
+        if (g + gstep < A.n_groups) { k0n = __ldg(A.ks_ptr + g + gstep); k1n = __ldg(A.ks_ptr + g + gstep + 1); }
+        double acc[NT][2];
+#pragma unroll
+        for (int q = 0; q < NT; q++) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+        constexpr int KU = NT <= 2 ? 4 : 2;          // k-steps in flight per warp
+        for (int ks = k0; ks < k1; ks += KU) {
+            int col[KU]; double a[KU]; double b[KU][NT];
+#pragma unroll
+            for (int u = 0; u < KU; u++) {
+                const bool ok = ks + u < k1;
+                col[u] = ok ? __ldg(A.cols + 4 * (size_t)(ks + u) + lk) : 0;
+                a[u] = ok ? __ldcs(av + 32 * (size_t)(ks + u)) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < KU; u++) {
+                const double *xr = A.X + (size_t)col[u] * A.ld;
+#pragma unroll
+                for (int q = 0; q < NT; q++) b[u][q] = __ldg(xr + bcol[q]);
+            }
+#pragma unroll
+            for (int u = 0; u < KU; u++)
+#pragma unroll
+                for (int q = 0; q < NT; q++) dmma884(acc[q][0], acc[q][1], a[u], b[u][q]);
+        }
+        {
+            // 128-byte lines of the next group's A fragments (2 per k-step) and column list (1 per 8 k-steps)
+            const int nl = 2 * (k1n - k0n);
+            for (int i = lane; i < nl; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.aval + (size_t)A.kk * A.n_frag + 32 * (size_t)k0n + 16 * (size_t)i));
+            if (lane < (k1n - k0n + 7) / 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cols + 4 * (size_t)k0n + 32 * (size_t)lane));
+        }
+        const int row = 8 * g + lr;
+        if (row < A.n_rows) {
+            const double dw = (EPI == EPI_POST) ? __ldg(dwk + row) : 0.0;
+#pragma unroll
+            for (int q = 0; q < NT; q++) {
+                const int lc = 8 * q + 2 * lk, colq = A.cs + lc;
+                const bool ok0 = lc < A.wc && colq >= A.v0 && colq < A.v1, ok1 = lc + 1 < A.wc && colq + 1 >= A.v0 && colq + 1 < A.v1;
+                if (!(ok0 || ok1)) continue;
+                const size_t o = (size_t)row * A.ld + colq;
+                double x0 = 0.0, x1 = 0.0, r0 = 0.0, r1 = 0.0;
+                if (EPI != EPI_SPMM || DOT) { if (ok0) x0 = __ldg(A.X + o); if (ok1) x1 = __ldg(A.X + o + 1); }
+                if (EPI == EPI_POST) { if (ok0) r0 = __ldg(A.ex.R + o); if (ok1) r1 = __ldg(A.ex.R + o + 1); }
+                double y0, y1;
+                if (EPI == EPI_POST) {
+                    y0 = fma(dw, r0 - acc[q][0], x0); y1 = fma(dw, r1 - acc[q][1], x1);
+                    if (DOT) { if (ok0) part[q][0] = fma(r0, y0, part[q][0]); if (ok1) part[q][1] = fma(r1, y1, part[q][1]); }
+                } else if (EPI == EPI_RESIDUAL) {
+                    y0 = x0 - acc[q][0]; y1 = x1 - acc[q][1];
+                } else {
+                    y0 = acc[q][0]; y1 = acc[q][1];
+                    if (DOT) { if (ok0) part[q][0] = fma(y0, x0, part[q][0]); if (ok1) part[q][1] = fma(y1, x1, part[q][1]); }
+                }
+                if (ok0 && ok1) *reinterpret_cast<double2 *>(A.Y + o) = make_double2(y0, y1);
+                else { if (ok0) A.Y[o] = y0; if (ok1) A.Y[o + 1] = y1; }
+            }
+        }
+        k0 = k0n; k1 = k1n;
+    }
+    if (DOT) {
+#pragma unroll
+        for (int q = 0; q < NT; q++)
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                double v = part[q][hh];
+                v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+                part[q][hh] = v;
+            }
+        for (int w = 0; w < nwarps; w++) {
+            if (warp == w && lr == 0) {
+#pragma unroll
+                for (int q = 0; q < NT; q++) {
+                    const int i = 8 * q + 2 * lk;
+                    sdot[i] = (w == 0 ? 0.0 : sdot[i]) + part[q][0];
+                    sdot[i + 1] = (w == 0 ? 0.0 : sdot[i + 1]) + part[q][1];
+                }
+            }
+            __syncthreads();
+        }
+        double *mine = A.dot_part + (size_t)blockIdx.x * A.ld;
+        for (int i = threadIdx.x; i < A.wc; i += GA_THREADS) if (A.cs + i >= A.v0 && A.cs + i < A.v1) mine[A.cs + i] = sdot[i];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket = (int)atomicAdd(A.dot_counter, 1u);
+        __syncthreads();
+        if (s_ticket == (int)gridDim.x - 1) {
+            // last CTA: GA_THREADS / (8 NT) threads per column add interleaved slices of the partial rows (fixed order), then
+            // one thread per column adds the slice sums in order
+            __threadfence();
+            __shared__ double sfin[GA_THREADS];
+            constexpr int WP = 8 * NT, SL = GA_THREADS / WP;
+            const int c = threadIdx.x % WP, sl = threadIdx.x / WP, cc = A.cs + c;
+            const bool okc = c < A.wc && cc >= A.v0 && cc < A.v1;
+            sfin[threadIdx.x] = okc ? ordered_row_sum(A.dot_part + cc, A.ld, sl, SL, (int)gridDim.x) : 0.0;
+            __syncthreads();
+            if (sl == 0 && okc) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < SL; j++) v += sfin[j * WP + c];
+                A.dots[cc] = v;
+            }
+            if (threadIdx.x == 0) *A.dot_counter = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // block-PCG vector kernels (one independent CG per source column, all columns advance in the same launches).
 // Flat mapping: the FLAT_T threads of a CTA tile the column window [c0,c1) (chunks of at most cw columns along
 // blockIdx.y) as rpp = FLAT_T / w consecutive rows of w columns, so that a warp touches 32 consecutive elements of the

@@ -80,6 +80,9 @@ struct StreamDev {
     bool mma = false; int max_chunk_ks = 0, max_chunk_meta = 0, hc_used = 0; size_t n_frag = 0;
     DevBuf<int> chunk_ks_ptr, chunk_meta_ptr, a_src, cdesc; DevBuf<unsigned> meta;
     DevBuf<double> av_a, av_dw;             // [nK][n_frag] packed A fragments of the two value sets
+    // gather form (k_spmm_gather): built by pgb200_ert_set_shard for narrow source shards
+    bool g_ok = false; int g_groups = 0, g_rows = 0; size_t g_frag = 0;
+    DevBuf<int> g_ks_ptr, g_cols, g_a_src; DevBuf<double> g_av_a, g_av_dw;
     MmaLevel mlevel() const {
         MmaLevel L; L.panel_row_ptr = panel_row_ptr.p; L.panel_chunk_ptr = panel_chunk_ptr.p; L.chunk_halo_ptr = chunk_halo_ptr.p;
         L.halo_cols = halo_cols.p; L.chunk_ks_ptr = chunk_ks_ptr.p; L.chunk_meta_ptr = chunk_meta_ptr.p; L.chunk_run_ptr = chunk_run_ptr.p;
@@ -319,6 +322,9 @@ int stream_upload(pgb200_ert *h, StreamDev &D, int n, const int *rowptr_host, co
 // which: 0 = A (SpMM, post-smoothing), 1 = A * diag(dw) (pre-smoothing residual)
 int stream_pack(pgb200_ert *h, StreamDev &D, const double *vals, int which) {
     if (!D.ok || D.nnz == 0) return 0;
+    if (D.g_ok && D.g_frag) {
+        k_pack_mma<<<cdiv((long long)D.g_frag, 256), 256, 0, h->st>>>(D.g_a_src.p, D.g_frag, D.nnz, h->nK, vals, which ? D.g_av_dw.p : D.g_av_a.p); LAUNCH(h);
+    }
     if (D.mma) {
         if (D.n_frag == 0) return 0;
         k_pack_mma<<<cdiv((long long)D.n_frag, 256), 256, 0, h->st>>>(D.a_src.p, D.n_frag, D.nnz, h->nK, vals, which ? D.av_dw.p : D.av_a.p); LAUNCH(h);
@@ -442,12 +448,54 @@ int launch_mma(pgb200_ert *h, const StreamDev &D, int which, const double *X, do
 #undef MMA_GO
 }
 
+// ---- narrow column windows: gather form (k_spmm_gather) ---------------------------------------------------------------
+constexpr int GATHER_MAX_W = 32;
+int gather_upload(pgb200_ert *h, StreamDev &D, int n, const int *rowptr_dev, const int *colidx_dev, size_t nnz) {
+    D.g_ok = false;
+    if (!D.ok || n <= 0) return 0;
+    std::vector<int> rp((size_t)n + 1), ci(nnz);
+    CK(cudaMemcpyAsync(rp.data(), rowptr_dev, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(ci.data(), colidx_dev, sizeof(int) * nnz, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    GatherGroupsHost G;
+    build_gather_groups(n, rp.data(), ci.data(), G);
+    CKR(D.g_ks_ptr.upload(G.ks_ptr.data(), G.ks_ptr.size(), h->st));
+    CKR(D.g_cols.upload(G.cols.data(), G.cols.size(), h->st));
+    CKR(D.g_a_src.upload(G.a_src.data(), G.a_src.size(), h->st));
+    CK(cudaStreamSynchronize(h->st));
+    D.g_groups = G.n_groups; D.g_rows = n; D.g_frag = (size_t)G.n_ks * 32;
+    CKR(D.g_av_a.alloc(std::max<size_t>(1, D.g_frag * h->nK))); CKR(D.g_av_dw.alloc(std::max<size_t>(1, D.g_frag * h->nK)));
+    D.g_ok = true;
+    return 0;
+}
+template <int NT, int EPI, bool DOT>
+int gather_go(pgb200_ert *h, const GatherArgs &A, int grid) {
+    k_spmm_gather<NT, EPI, DOT><<<grid, GA_THREADS, 0, h->st>>>(A);
+    h->cur_role = EPI + 1; LAUNCH(h); h->cur_role = 0;
+    return 0;
+}
+template <int EPI>
+int launch_gather(pgb200_ert *h, const StreamDev &D, int which, const double *X, double *Y, int c0, int c1, double *dots, const PanelExtra &ex) {
+    GatherArgs A;
+    A.ks_ptr = D.g_ks_ptr.p; A.cols = D.g_cols.p; A.aval = which ? D.g_av_dw.p : D.g_av_a.p; A.n_frag = D.g_frag;
+    A.n_groups = D.g_groups; A.n_rows = D.g_rows; A.X = X; A.Y = Y; A.ld = h->ld;
+    A.kk = c0 / h->nE; A.cs = c0 & ~1; A.wc = ((c1 + 1) & ~1) - A.cs; A.v0 = c0; A.v1 = c1;
+    A.dot_part = h->dot_part.p; A.dot_counter = h->dot_counter.p; A.dots = dots; A.ex = ex;
+    const int grid = std::max(1, std::min(std::min(3 * h->num_sms, 2 * h->dot_slots), cdiv(D.g_groups, GA_THREADS / 32)));
+    h->pi_panel_nc = 200 + cdiv(A.wc, 8); h->pi_tiles = std::max(h->pi_tiles, 1);
+    if (A.wc <= 16) { if (dots) return gather_go<2, EPI, true>(h, A, grid); return gather_go<2, EPI, false>(h, A, grid); }
+    if (dots) return gather_go<4, EPI, true>(h, A, grid);
+    return gather_go<4, EPI, false>(h, A, grid);
+}
+
 // Y = op(A X) on the column window [c0, c1); dots != nullptr: deterministic per-column dot of the epilogue
 // which: 0 = the level's matrix A, 1 = A * diag(dw)
 template <int EPI>
 int launch_stream(pgb200_ert *h, const StreamDev &D, int which, const double *X, double *Y, int c0, int c1, double *dots,
                   const PanelExtra &ex) {
     if (c1 <= c0) return 0;
+    if (D.g_ok && c0 / h->nE == (c1 - 1) / h->nE && ((c1 + 1) & ~1) - (c0 & ~1) <= GATHER_MAX_W)
+        return launch_gather<EPI>(h, D, which, X, Y, c0, c1, dots, ex);
     if (D.mma) return launch_mma<EPI>(h, D, which, X, Y, c0, c1, dots, ex);
     const PanelEntry *ent = which ? D.ent_dw.p : D.ent_a.p;
     const int nE = h->nE;
@@ -1727,6 +1775,16 @@ int pgb200_ert_set_shard(pgb200_ert *h, int src_begin, int src_end, int row_begi
     if (src_begin < 0 || src_end > h->nS || src_begin > src_end || row_begin < 0 || row_end > h->D || row_begin > row_end) PGB_FAIL("invalid shard");
     CK(cudaSetDevice(h->device));
     h->c0 = src_begin; h->c1 = src_end; h->pots_valid = false; h->shard_solved = false; h->x_warm_ok = false;
+    {
+        // narrow source shard inside one wavenumber group: the levels that run on the streamed kernels get the gather form
+        const bool narrow = src_end > src_begin && src_begin / h->nE == (src_end - 1) / h->nE &&
+                            ((src_end + 1) & ~1) - (src_begin & ~1) <= GATHER_MAX_W && !getenv("PGB200_NO_GATHER");
+        if (narrow && h->use_panels && !h->stream.g_ok) {
+            CKR(gather_upload(h, h->stream, h->N, h->rowptr.p, h->colidx.p, h->nnz));
+            for (AmgLevel *L : h->amg) if (L->stream.ok) CKR(gather_upload(h, L->stream, L->n, L->rowptr.p, L->colidx.p, L->nnz));
+            h->have_vals = false;                  // the packed fragments are filled by the next assembly
+        }
+    }
     if (row_begin != h->row0 || row_end != h->row1) { h->row0 = row_begin; h->row1 = row_end; CKR(build_jac_plan(h)); CKR(build_jac2_plan(h)); }
     return 0;
 }

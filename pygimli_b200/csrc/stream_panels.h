@@ -234,4 +234,39 @@ inline std::string build_stream_panels(int n, const int *rowptr, const int *coli
     return "";
 }
 
+// ---- gather form (k_spmm_gather): narrow column windows (multi-GPU source shards) -------------------------------------
+// No shared-memory staging: the block vectors of a narrow window stay in L2, so every 8-row group simply lists its k-steps --
+// 32 A-fragment slots and the four GLOBAL column indices of the k-step -- over the union of its rows' columns (ascending).
+struct GatherGroupsHost {
+    int n_groups = 0; long long n_ks = 0;
+    std::vector<int> ks_ptr;     // [n_groups + 1]
+    std::vector<int> cols;       // [4 * n_ks] column of X of every k-step slot (padding: the group's first row)
+    std::vector<int> a_src;      // [32 * n_ks] CSR slot of fragment element (4 * row-in-group + slot) or -1
+};
+inline void build_gather_groups(int n, const int *rowptr, const int *colidx, GatherGroupsHost &G) {
+    G = GatherGroupsHost();
+    G.n_groups = (n + 7) / 8;
+    G.ks_ptr.assign(1, 0);
+    std::vector<int> ucols, pos((size_t)std::max(n, 1), -1);
+    for (int g = 0; g < G.n_groups; g++) {
+        const int ra = 8 * g, rb = std::min(n, ra + 8);
+        ucols.clear();
+        for (int r = ra; r < rb; r++) for (int p = rowptr[r]; p < rowptr[r + 1]; p++) if (pos[(size_t)colidx[p]] < 0) { pos[(size_t)colidx[p]] = 0; ucols.push_back(colidx[p]); }
+        std::sort(ucols.begin(), ucols.end());
+        for (size_t u = 0; u < ucols.size(); u++) pos[(size_t)ucols[u]] = (int)u;
+        const int nks = ((int)ucols.size() + 3) / 4;
+        const size_t c0 = G.cols.size(), a0 = G.a_src.size();
+        G.cols.resize(c0 + (size_t)4 * nks, ra); G.a_src.resize(a0 + (size_t)32 * nks, -1);
+        for (size_t u = 0; u < ucols.size(); u++) G.cols[c0 + u] = ucols[u];
+        for (int r = ra; r < rb; r++)
+            for (int p = rowptr[r]; p < rowptr[r + 1]; p++) {
+                const int u = pos[(size_t)colidx[p]];
+                G.a_src[a0 + (size_t)(u / 4) * 32 + (size_t)(4 * (r - ra) + (u & 3))] = p;
+            }
+        for (int c : ucols) pos[(size_t)c] = -1;
+        G.n_ks += nks;
+        G.ks_ptr.push_back((int)G.n_ks);
+    }
+}
+
 } // namespace pgb
