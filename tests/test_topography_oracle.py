@@ -61,9 +61,11 @@ def test_forward_without_primary_is_refused():
         OracleERT(mesh, scheme).forward(model)
 
 
-def test_pure_neumann_3d_is_refused():
-    """no mixed/Dirichlet face at all: the reference needs calibration nodes (dcfemmodelling.cpp:1040-1075)"""
+def test_pure_neumann_3d_plan():
+    """no mixed/Dirichlet face at all: topography branch, the reference's node 0 becomes the calibration node and the last
+    electrode the current reference (dcfemmodelling.cpp:1040-1075)"""
     mesh, scheme, _ = make_case("3d_p1")
     mesh.bound_marker[:] = -1
-    with pytest.raises(NotImplementedError):
-        build_plan(mesh, scheme)
+    P = build_plan(mesh, scheme)
+    assert P.topography and P.neumann_domain and P.ref_last == 1 and P.ref_node == -1
+    assert list(P.dir_nodes) == [int(P.node_inv[0])]
