@@ -14,6 +14,7 @@ One JSON line on stdout (rank 0).
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -354,6 +355,26 @@ def run_b200(args):
         jops["bytes_per_pass"] = 8.0 * Jop.rows() * Jop.cols()
         jops["GBps"] = {k[:-3]: jops["bytes_per_pass"] / (v * 1e-3) / 1e9 for k, v in jops.items() if k.endswith("_ms")}
 
+    # what a caller pays who wants the reference's RMatrix on the HOST: the same step plus pgb200_ert_jacobian_copy into
+    # pinned host memory (transposed to row-major on the GPU, then D x M x 8 bytes over PCIe); once, not per step
+    e2e_jcopy = None
+    if world == 1:
+        try:
+            Jop = fop.core.jacobian()
+            nbytes = 8 * Jop.rows() * Jop.cols()
+            if 0 < nbytes <= 24e9:
+                jh = torch.empty(Jop.rows() * Jop.cols(), dtype=torch.float64, pin_memory=True)
+                from pygimli_b200 import _capi as _c
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                step_e2e()
+                _c.check(_c.lib().pgb200_ert_jacobian_copy(fop.core._h, ctypes.c_void_p(jh.data_ptr())))
+                e2e_jcopy = {"value": time.perf_counter() - t0, "unit": "s", "d2h_bytes": int(nbytes),
+                             "note": "one e2e step + the whole Jacobian copied to pinned host memory (row-major, as the reference's RMatrix)"}
+                del jh
+        except Exception as exc:
+            e2e_jcopy = {"value": None, "note": f"failed: {exc}"}
+
     # checksums that tie an N-rank result to the N = 1 result: same model, same x
     r_chk, jx_chk, _ = step_e2e()
     checks = {"rhoa_l2": float(np.linalg.norm(r_chk)), "rhoa_sum": float(np.sum(r_chk)), "Jx_l2": float(np.linalg.norm(jx_chk))}
@@ -403,6 +424,7 @@ def run_b200(args):
             "e2e": {"value": ms_e2e / 1e3 / args.steps, "unit": "s", "h2d_bytes_per_step": 8 * (2 * M + M + D),
                     "d2h_bytes_per_step": 8 * (D + D + M),
                     "note": "host-buffer C ABI: response + createJacobian + one J.x and one J^T.y; J stays in HBM"},
+            "e2e_with_J_copy": e2e_jcopy,
             "gpu_launches": int(st["launches"]),
             "checksums": checks,
             "clocks": clocks,

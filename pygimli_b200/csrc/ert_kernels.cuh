@@ -716,7 +716,10 @@ constexpr int MM_CONSUMER_WARPS = PGB_MM_WARPS;
 constexpr int MM_PRODUCER_WARPS = PGB_MM_PRODUCERS;
 constexpr int MM_CONSUMERS = MM_CONSUMER_WARPS * 32;
 constexpr int MM_THREADS = MM_CONSUMERS + 32 * MM_PRODUCER_WARPS;
-constexpr int MM_PRODUCER_REGS = 56, MM_CONSUMER_REGS = 152;       // 12 * 32 * 152 + 4 * 32 * 56 = 65536
+#ifndef PGB_MM_CREGS
+#define PGB_MM_CREGS 152
+#endif
+constexpr int MM_PRODUCER_REGS = 56, MM_CONSUMER_REGS = PGB_MM_CREGS;       // 12 * 32 * 152 + 4 * 32 * 56 = 65536
 static_assert(MM_CONSUMER_WARPS % 4 == 0 && MM_PRODUCER_WARPS == 4, "setmaxnreg works on warpgroups of 4 warps");
 constexpr int MM_ROWS = 8 * MM_CONSUMER_WARPS;         // rows per panel
 constexpr int MM_GSTRIDE = (MM_CONSUMER_WARPS + 1 + 3) / 4 * 4;
@@ -1092,7 +1095,7 @@ k_spmm_mma(const MmaArgs A) {
             }
             p = pn;
         }
-        if (DOT) {
+        if (DOT && !(A.dbg & 64)) {
             // rows of the fragment first (lanes with equal lk, fixed shuffle order), then a fixed-order sum over the warps,
             // one partial row per CTA, the last CTA of the tile adds the rows in index order
 #pragma unroll
