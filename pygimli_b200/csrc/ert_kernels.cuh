@@ -2433,9 +2433,11 @@ k_jacobian(const JacArgs A) {
 //                       pre-resolved 16-bit offsets, times k_d / rho^2, 128-bit stores -- while the Gram warps are
 //                       already working on the next column.
 // ---------------------------------------------------------------------------------
-constexpr int J2_THREADS = 512;
-constexpr int J2_GRAM_WARPS = 11, J2_EPI_WARPS = 4;            // + 1 producer warp = 16 warps
-constexpr int J2_GT = J2_GRAM_WARPS * 32, J2_ET = J2_EPI_WARPS * 32;
+constexpr int J2_GRAM_WARPS = 11;                              // + EW epilogue warps + 1 producer warp
+constexpr int J2_GT = J2_GRAM_WARPS * 32;
+// EW = epilogue warps (template parameter of k_jacobian2): 4 where the Gram blocks bound the kernel (many tiles per written
+// byte: crosshole c4), 8 where the store of J does (complete schemes on many rows: c3, measured 5.8 -> 4.7 ms)
+__host__ __device__ constexpr int j2_threads(int ew) { return 32 * (J2_GRAM_WARPS + ew + 1); }
 constexpr int J2_SLOTS = 3;
 constexpr int J2_MAX_MT = 2;                                   // register tiles per Gram thread
 
@@ -2498,9 +2500,10 @@ struct Jac2Args {
     uint32_t rec_bytes;
 };
 
-template <int E, int MT, int TERMS>
-__global__ void __launch_bounds__(J2_THREADS, 1)
+template <int E, int MT, int TERMS, int EW>
+__global__ void __launch_bounds__(j2_threads(EW), 1)
 k_jacobian2(const Jac2Args A) {
+    constexpr int J2_EPI_WARPS = EW, J2_THREADS = j2_threads(EW), J2_ET = 32 * EW;
     constexpr int NL = ElemTraits<E>::NL;
     extern __shared__ __align__(128) unsigned char j2_smem[];
     __shared__ __align__(8) uint64_t full[J2_SLOTS], empty[J2_SLOTS], gfull[2], gempty[2];

@@ -1312,14 +1312,25 @@ int build_jac2_plan(pgb200_ert *h) {
     return 0;
 }
 
-template <int E, int MT>
-int jac2_go(pgb200_ert *h, const Jac2Args &A, int terms, int grid, size_t smem) {
-#define J2GO(T) do { CK(cudaFuncSetAttribute(k_jacobian2<E, MT, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-                     k_jacobian2<E, MT, T><<<grid, J2_THREADS, smem, h->st>>>(A); } while (0)
+template <int E, int MT, int EW>
+int jac2_go_ew(pgb200_ert *h, const Jac2Args &A, int terms, int grid, size_t smem) {
+#define J2GO(T) do { CK(cudaFuncSetAttribute(k_jacobian2<E, MT, T, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                     k_jacobian2<E, MT, T, EW><<<grid, j2_threads(EW), smem, h->st>>>(A); } while (0)
     if (terms == 1) J2GO(1); else if (terms == 2) J2GO(2); else J2GO(4);
 #undef J2GO
     LAUNCH(h);
     return 0;
+}
+// epilogue warps: 8 when the store of J bounds the kernel, 4 when the Gram blocks do -- bytes of J written per (tile, cell) of
+// Gram work; c3: 9700 rows x 8 B / (325 tiles x 4 cells) = 60, c4: 3320 x 8 / (384 x 6) = 11.5
+template <int E, int MT>
+int jac2_go(pgb200_ert *h, const Jac2Args &A, int terms, int grid, size_t smem) {
+    const double cells_per_col = std::max(1.0, (double)h->n_jac_cells / std::max(1, h->M));
+    const double bytes_per_work = 8.0 * A.nd / (std::max(1, A.n_tiles) * cells_per_col * h->nK);
+    static const int force = getenv("PGB200_J2_EPI") ? atoi(getenv("PGB200_J2_EPI")) : 0;
+    const bool wide = force ? force >= 8 : bytes_per_work > 45.0;     // c5 (30) is faster with 4 warps: 4.77 vs 5.08 ms
+    if (wide) return jac2_go_ew<E, MT, 8>(h, A, terms, grid, smem);
+    return jac2_go_ew<E, MT, 4>(h, A, terms, grid, smem);
 }
 
 template <int E>
