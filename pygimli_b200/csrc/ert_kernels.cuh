@@ -1165,7 +1165,7 @@ struct GatherArgs {
 };
 constexpr int GA_THREADS = 256;
 template <int NT, int EPI, bool DOT>
-__global__ void __launch_bounds__(GA_THREADS, 3)
+__global__ void __launch_bounds__(GA_THREADS, NT <= 2 ? 4 : 3)       // latency-bound: as many warps per SM as the registers allow
 k_spmm_gather(const GatherArgs A) {
     __shared__ double sdot[8 * NT];
     __shared__ int s_ticket;
@@ -1229,8 +1229,14 @@ k_spmm_gather(const GatherArgs A) {
                 if (!(ok0 || ok1)) continue;
                 const size_t o = (size_t)row * A.ld + colq;
                 double x0 = 0.0, x1 = 0.0, r0 = 0.0, r1 = 0.0;
-                if (EPI != EPI_SPMM || DOT) { if (ok0) x0 = __ldg(A.X + o); if (ok1) x1 = __ldg(A.X + o + 1); }
-                if (EPI == EPI_POST) { if (ok0) r0 = __ldg(A.ex.R + o); if (ok1) r1 = __ldg(A.ex.R + o + 1); }
+                if (EPI != EPI_SPMM || DOT) {
+                    if (ok0 && ok1) { const double2 v = __ldg(reinterpret_cast<const double2 *>(A.X + o)); x0 = v.x; x1 = v.y; }
+                    else { if (ok0) x0 = __ldg(A.X + o); if (ok1) x1 = __ldg(A.X + o + 1); }
+                }
+                if (EPI == EPI_POST) {
+                    if (ok0 && ok1) { const double2 v = __ldg(reinterpret_cast<const double2 *>(A.ex.R + o)); r0 = v.x; r1 = v.y; }
+                    else { if (ok0) r0 = __ldg(A.ex.R + o); if (ok1) r1 = __ldg(A.ex.R + o + 1); }
+                }
                 double y0, y1;
                 if (EPI == EPI_POST) {
                     y0 = fma(dw, r0 - acc[q][0], x0); y1 = fma(dw, r1 - acc[q][1], x1);
