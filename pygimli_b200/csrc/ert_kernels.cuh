@@ -864,7 +864,14 @@ k_spmm_mma(const MmaArgs A) {
             struct Copies { int src[U], dst[U], len[U], n, rows; };
             auto fetch_copies = [&](const int4 &ra, const int4 &rb, Copies &C) {
                 C.n = 0; C.rows = 0;
-                if (fullrows) {
+                if (A.fullrows == 2) {
+                    // partial-width tile, one bulk copy per halo row (the rows are not contiguous in memory)
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int i = pw + P * (lane + 32 * u);
+                        if (i < ra.y && !(A.dbg & 2)) { C.dst[u] = i; C.src[u] = __ldg(L.halo_cols + ra.x + i); C.len[u] = 1; C.n = u + 1; C.rows += 1; }
+                    }
+                } else if (fullrows) {
                     const int q0 = rb.z, q1 = (A.dbg & 2) ? q0 : q0 + rb.w;
 #pragma unroll
                     for (int u = 0; u < U; u++) {
@@ -940,7 +947,7 @@ k_spmm_mma(const MmaArgs A) {
                         if (a1.w > 0) tma_prefetch_l2(avk + (size_t)a1.z * 32, (uint32_t)a1.w * 256u);
                         tma_prefetch_l2(L.meta + b1.x, (uint32_t)b1.y * 4u);
                     }
-                    if (fullrows) {
+                    if (A.fullrows == 1) {
 #pragma unroll
                         for (int u = 0; u < U; u++)
                             if (u < C1.n) tma_prefetch_l2(A.X + (size_t)C1.src[u] * A.ld + cs, (uint32_t)C1.len[u] * rowb);
