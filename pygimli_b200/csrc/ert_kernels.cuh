@@ -1167,6 +1167,7 @@ struct GatherArgs {
     int n_groups, n_rows;
     const double *X; double *Y; size_t ld;
     int kk, cs, wc, v0, v1;              // wavenumber group; copied columns [cs, cs + wc) with cs even; valid columns [v0, v1)
+    int dbg;                             // measurement only (profiles/bench_spmm.py): 64 = no dot tail, 256 = no final sum of the last CTA
     double *dot_part; unsigned *dot_counter; double *dots;
     PanelExtra ex;
 };
@@ -1260,7 +1261,7 @@ k_spmm_gather(const GatherArgs A) {
         }
         k0 = k0n; k1 = k1n;
     }
-    if (DOT) {
+    if (DOT && !(A.dbg & 64)) {
 #pragma unroll
         for (int q = 0; q < NT; q++)
 #pragma unroll
@@ -1286,7 +1287,7 @@ k_spmm_gather(const GatherArgs A) {
         __syncthreads();
         if (threadIdx.x == 0) s_ticket = (int)atomicAdd(A.dot_counter, 1u);
         __syncthreads();
-        if (s_ticket == (int)gridDim.x - 1) {
+        if (s_ticket == (int)gridDim.x - 1 && !(A.dbg & 256)) {
             // last CTA: GA_THREADS / (8 NT) threads per column add interleaved slices of the partial rows (fixed order), then
             // one thread per column adds the slice sums in order
             __threadfence();

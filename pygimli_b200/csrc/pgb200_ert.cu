@@ -483,7 +483,7 @@ int launch_gather(pgb200_ert *h, const StreamDev &D, int which, const double *X,
     A.ks_ptr = D.g_ks_ptr.p; A.cols = D.g_cols.p; A.aval = which ? D.g_av_dw.p : D.g_av_a.p; A.n_frag = D.g_frag;
     A.n_groups = D.g_groups; A.n_rows = D.g_rows; A.X = X; A.Y = Y; A.ld = h->ld;
     A.kk = c0 / h->nE; A.cs = c0 & ~1; A.wc = ((c1 + 1) & ~1) - A.cs; A.v0 = c0; A.v1 = c1;
-    A.dot_part = h->dot_part.p; A.dot_counter = h->dot_counter.p; A.dots = dots; A.ex = ex;
+    A.dot_part = h->dot_part.p; A.dot_counter = h->dot_counter.p; A.dots = dots; A.ex = ex; A.dbg = h->mma_dbg;
     static const int force_per_sm = getenv("PGB200_GATHER_CTAS") ? atoi(getenv("PGB200_GATHER_CTAS")) : 0;
     const int per_sm = force_per_sm ? force_per_sm : (A.wc <= 16 ? 4 : 3);
     const int grid = std::max(1, std::min(std::min(per_sm * h->num_sms, 2 * h->dot_slots), cdiv(D.g_groups, GA_THREADS / 32)));
