@@ -1340,7 +1340,7 @@ int jac2_go(pgb200_ert *h, const Jac2Args &A, int terms, int grid, size_t smem) 
 
 template <int E>
 int launch_jacobian2(pgb200_ert *h, const double *rho_col) {
-    const int NL = h->nloc, nQp = h->j2_nQp;
+    const int nQp = h->j2_nQp;
     auto basis = [&](const int *la, const int *lb, int nL, int nLp, double *UD) -> int {
         dim3 b(32, 8), g(cdiv(h->N, 8), cdiv(h->nK * nLp, 32));
         k_basis_pots<<<g, b, 0, h->st>>>(h->U.p, h->ld, h->N, h->nE, h->nK, la, lb, nL, nLp, UD, (size_t)h->nK * nLp); LAUNCH(h);
